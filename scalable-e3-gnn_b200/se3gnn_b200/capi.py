@@ -1,0 +1,149 @@
+"""ctypes binding of ``include/se3gnn_b200.h`` (the C ABI of the CUDA library).
+
+There is no CPU fallback: if the shared library is missing, or a call fails,
+this module raises.  PyTorch is used by callers only for device memory and
+streams; pointers cross this boundary as plain integers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libse3gnn_b200.so")
+
+MAX_SEG = 4
+EPI_RAW, EPI_GATE = 0, 1
+GRAD_NONE, GRAD_STORE, GRAD_ATOMIC, GRAD_SORTED = 0, 1, 2, 3
+
+_i32p = C.POINTER(C.c_int32)
+_f32p = C.c_void_p  # device pointers travel as integers
+
+
+class L1tpDesc(C.Structure):
+    _fields_ = [
+        ("d_in1", C.c_int32), ("d_out", C.c_int32),
+        ("n", C.c_int32 * 4), ("m", C.c_int32 * 4),
+        ("in_cols", _i32p * 4), ("out_cols", _i32p * 4),
+    ]
+
+
+class RowSeg(C.Structure):
+    _fields_ = [("base", C.c_void_p), ("idx", C.c_void_p), ("width", C.c_int32), ("ld", C.c_int32)]
+
+
+class L1tpFwdArgs(C.Structure):
+    _fields_ = [
+        ("rows", C.c_int64), ("nseg", C.c_int32), ("seg", RowSeg * MAX_SEG),
+        ("in2", C.c_void_p), ("w", C.c_void_p * 4), ("norm", C.c_void_p * 4),
+        ("epilogue", C.c_int32), ("gate_ns", C.c_int32), ("gate_cs", C.c_float), ("gate_cg", C.c_float),
+        ("out_raw", C.c_void_p), ("out_post", C.c_void_p), ("resid", C.c_void_p),
+        ("seg_idx", C.c_void_p), ("out_seg", C.c_void_p),
+    ]
+
+
+class L1tpBwdArgs(C.Structure):
+    _fields_ = [
+        ("rows", C.c_int64), ("nseg", C.c_int32), ("seg", RowSeg * MAX_SEG),
+        ("in2", C.c_void_p), ("w", C.c_void_p * 4), ("norm", C.c_void_p * 4),
+        ("epilogue", C.c_int32), ("gate_ns", C.c_int32), ("gate_cs", C.c_float), ("gate_cg", C.c_float),
+        ("raw", C.c_void_p), ("gout", C.c_void_p), ("gout_idx", C.c_void_p),
+        ("gseg", C.c_void_p * MAX_SEG), ("gseg_mode", C.c_int32 * MAX_SEG),
+        ("gw", C.c_void_p * 4), ("gin2", C.c_void_p),
+    ]
+
+
+EXPORTS = [
+    # name, restype, argtypes  (must list every symbol include/se3gnn_b200.h declares)
+    ("se3_last_error", C.c_char_p, []),
+    ("se3_version", C.c_int, []),
+    ("se3_launch_count", C.c_int64, []),
+    ("se3_l1tp_plan_create", C.c_int, [C.POINTER(L1tpDesc), C.POINTER(C.c_void_p)]),
+    ("se3_l1tp_plan_destroy", None, [C.c_void_p]),
+    ("se3_l1tp_plan_info", C.c_int, [C.c_void_p, _i32p, _i32p, _i32p, _i32p]),
+    ("se3_l1tp_forward", C.c_int, [C.c_void_p, C.POINTER(L1tpFwdArgs), C.c_void_p]),
+    ("se3_l1tp_backward", C.c_int, [C.c_void_p, C.POINTER(L1tpBwdArgs), C.c_void_p]),
+]
+
+_lib = None
+
+
+class Se3Error(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the CUDA library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise Se3Error(
+                f"{LIB_PATH} is missing: build it with `python -m se3gnn_b200.build` "
+                "(nvcc, sm_100a).  se3gnn_b200 has no CPU / eager fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name, res, args in EXPORTS:
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str = "se3gnn_b200"):
+    if rc != 0:
+        msg = lib().se3_last_error().decode(errors="replace")
+        raise Se3Error(f"{what} failed (code {rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(lib().se3_launch_count())
+
+
+def ptr(t) -> Optional[int]:
+    """Device pointer of a torch tensor (or None)."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def current_stream_ptr() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+class L1tpPlan:
+    """Owns a ``se3_l1tp_plan`` (device-side column tables + tiling)."""
+
+    def __init__(self, n: Sequence[int], m: Sequence[int], in_cols, out_cols):
+        self.n = [int(x) for x in n]
+        self.m = [int(x) for x in m]
+        d = L1tpDesc()
+        d.d_in1 = self.n[0] + self.n[1] + 3 * (self.n[2] + self.n[3])
+        d.d_out = self.m[0] + self.m[1] + 3 * (self.m[2] + self.m[3])
+        self.d_in1, self.d_out = d.d_in1, d.d_out
+        self._keep = []
+        for s in range(4):
+            d.n[s] = self.n[s]
+            d.m[s] = self.m[s]
+            a = (C.c_int32 * max(1, self.n[s]))(*[int(c) for c in in_cols[s]])
+            b = (C.c_int32 * max(1, self.m[s]))(*[int(c) for c in out_cols[s]])
+            self._keep += [a, b]
+            d.in_cols[s] = C.cast(a, _i32p)
+            d.out_cols[s] = C.cast(b, _i32p)
+        h = C.c_void_p()
+        check(lib().se3_l1tp_plan_create(C.byref(d), C.byref(h)), "se3_l1tp_plan_create")
+        self.handle = h
+
+    def info(self):
+        v = [C.c_int32() for _ in range(4)]
+        check(lib().se3_l1tp_plan_info(self.handle, *[C.byref(x) for x in v]))
+        return dict(tile_rows=v[0].value, smem_fwd=v[1].value, smem_bwd=v[2].value, weight_floats=v[3].value)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None) and _lib is not None:
+                _lib.se3_l1tp_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass

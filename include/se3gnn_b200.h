@@ -21,6 +21,7 @@
 #ifndef SE3GNN_B200_H
 #define SE3GNN_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -117,6 +118,52 @@ typedef struct se3_l1tp_bwd_args {
 } se3_l1tp_bwd_args;
 
 int se3_l1tp_backward(se3_l1tp_plan* plan, const se3_l1tp_bwd_args* args, void* stream);
+
+/* -------------------------------------------------------------- octree ---- */
+/* Builder-defined API (the reference's numba graph builder is not in the mount; the
+ * specification is oracle/octree_oracle.py).  All arrays are caller-allocated device memory. */
+typedef struct se3_octree {
+    int64_t n;                 /* particles                                          */
+    int32_t leaf_size;         /* a cell splits iff count > leaf_size                */
+    int32_t max_depth;         /* 21 (63-bit Morton keys)                            */
+    int64_t cell_cap;          /* capacity of the cell_* arrays                      */
+    uint64_t* keys;            /* [n]  sorted Morton keys                            */
+    int32_t* order;            /* [n]  rank -> original particle index               */
+    int32_t* cell_start;       /* [cell_cap] first rank of the cell                  */
+    int32_t* cell_count;       /* [cell_cap] particles in the cell                   */
+    int32_t* cell_level;       /* [cell_cap]                                         */
+    int32_t* cell_parent;      /* [cell_cap] -1 for the root                         */
+    int32_t* cell_first_child; /* [cell_cap] -1 for leaves                           */
+    int32_t* cell_nchild;      /* [cell_cap]                                         */
+    uint64_t* cell_key;        /* [cell_cap] Morton prefix (key >> 3*(21-level))     */
+    int32_t* level_ptr;        /* [max_depth+2] first cell id of each level          */
+    int32_t* leaf_of_rank;     /* [n]  leaf cell of each rank                        */
+    int32_t* cell_of_particle; /* [n]  leaf cell of each particle, original order    */
+    float* bbox;               /* [4]  lo.x lo.y lo.z scale                          */
+    void* work;                /* scratch, >= se3_octree_work_bytes()                */
+    size_t work_bytes;
+} se3_octree;
+
+int se3_octree_work_bytes(int64_t n, int64_t cell_cap, size_t* bytes);
+/* keys + stable radix sort + level-synchronous split + leaf assignment.  Synchronises the
+ * stream once to return the number of cells and of non-empty levels. */
+int se3_octree_build(const float* pos /*[n,3]*/, se3_octree* t, int64_t* m_out, int32_t* nlevels_out, void* stream);
+/* 26-neighbour lookup + degrees + exclusive scan.  nbr [m,26], deg [n+m], rowptr [n+m+1],
+ * scan_work [(n+m)/1024+2].  Synchronises once to return the edge count. */
+int se3_graph_degrees(const se3_octree* t, int64_t m, int32_t* nbr, int32_t* deg, int64_t* rowptr,
+                      int64_t* scan_work, int64_t* e_out, void* stream);
+/* CSR emission: col [e] = source node, dst [e] = target node (nodes: ranks 0..n-1, cells n..n+m-1). */
+int se3_graph_emit(const se3_octree* t, int64_t m, const int32_t* nbr, const int64_t* rowptr, int32_t* col,
+                   int32_t* dst, void* stream);
+/* node positions / velocities / masses in node order: particles permuted to rank order, cells = moments. */
+int se3_node_data(const se3_octree* t, int64_t m, int32_t nlevels, const float* pos, const float* vel,
+                  const float* mass, float* npos, float* nvel, float* nmass, void* stream);
+/* edge_attr [e,4] = SH(1)(pos[src]-pos[dst]) ('integral' normalisation), edge_extra [e,2] = (|rel|, m_i m_j),
+ * node_attr [n+m,4] = mean incoming edge_attr + SH(1)(vel), x_in [n+m,8] = (pos-centroid, vel, |vel|, mass). */
+int se3_edge_geometry(int64_t n, int64_t m, int64_t e, const int64_t* rowptr, const int32_t* col,
+                      const int32_t* dst, const float* npos, const float* nvel, const float* nmass,
+                      float mass_scale, float* edge_attr, float* edge_extra, float* node_attr, float* x_in,
+                      void* stream);
 
 #ifdef __cplusplus
 }

@@ -1284,6 +1284,7 @@ static int check_weights(const se3_l1tp_plan* p, const float* const* w) {
 
 extern "C" int se3_l1tp_forward(se3_l1tp_plan* p, const se3_l1tp_fwd_args* a, void* stream) {
     if (!p || !a) { set_error("null argument"); return SE3_ERR_INVALID; }
+    if (a->rows == 0) return SE3_OK;
     if (a->rows < 0 || !a->in2) { set_error("bad rows/in2"); return SE3_ERR_INVALID; }
     FwdK K;
     memset(&K, 0, sizeof(K));
@@ -1298,7 +1299,6 @@ extern "C" int se3_l1tp_forward(se3_l1tp_plan* p, const se3_l1tp_fwd_args* a, vo
     if (a->seg_idx && a->resid) { set_error("resid + segment sum is not supported"); return SE3_ERR_INVALID; }
     if (!a->out_raw && !a->out_post && !a->out_seg) { set_error("no output requested"); return SE3_ERR_INVALID; }
     if (a->out_post && a->epilogue != SE3_EPI_GATE) { set_error("out_post needs the GATE epilogue"); return SE3_ERR_INVALID; }
-    if (a->rows == 0) return SE3_OK;
     K.rows = a->rows; K.in2 = a->in2;
     for (int s = 0; s < 4; ++s) { K.w[s] = a->w[s]; K.norm[s] = a->norm[s]; }
     K.out_raw = a->out_raw; K.out_post = a->out_post; K.resid = a->resid;
@@ -1312,6 +1312,12 @@ extern "C" int se3_l1tp_forward(se3_l1tp_plan* p, const se3_l1tp_fwd_args* a, vo
 
 extern "C" int se3_l1tp_backward(se3_l1tp_plan* p, const se3_l1tp_bwd_args* a, void* stream) {
     if (!p || !a) { set_error("null argument"); return SE3_ERR_INVALID; }
+    if (a->rows == 0) {
+        for (int s = 0; s < 4; ++s)
+            if (a->gw[s] && p->w_cnt[s])
+                SE3_CUDA_TRY(cudaMemsetAsync(a->gw[s], 0, sizeof(float) * p->w_cnt[s], (cudaStream_t)stream));
+        return SE3_OK;
+    }
     if (a->rows < 0 || !a->in2 || !a->gout) { set_error("bad rows/in2/gout"); return SE3_ERR_INVALID; }
     BwdK K;
     memset(&K, 0, sizeof(K));
@@ -1326,11 +1332,6 @@ extern "C" int se3_l1tp_backward(se3_l1tp_plan* p, const se3_l1tp_bwd_args* a, v
     cudaStream_t st = (cudaStream_t)stream;
     bool want_gw = false;
     for (int s = 0; s < 4; ++s) want_gw |= a->gw[s] != nullptr;
-    if (a->rows == 0) {
-        for (int s = 0; s < 4; ++s)
-            if (a->gw[s] && p->w_cnt[s]) SE3_CUDA_TRY(cudaMemsetAsync(a->gw[s], 0, sizeof(float) * p->w_cnt[s], st));
-        return SE3_OK;
-    }
     for (int s = 0; s < a->nseg; ++s) {
         int mode = a->gseg[s] ? a->gseg_mode[s] : SE3_GRAD_NONE;
         if ((mode == SE3_GRAD_ATOMIC || mode == SE3_GRAD_SORTED) && !a->seg[s].idx) mode = SE3_GRAD_STORE;

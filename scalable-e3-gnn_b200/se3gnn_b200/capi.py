@@ -54,6 +54,17 @@ class L1tpBwdArgs(C.Structure):
     ]
 
 
+class Octree(C.Structure):
+    _fields_ = [
+        ("n", C.c_int64), ("leaf_size", C.c_int32), ("max_depth", C.c_int32), ("cell_cap", C.c_int64),
+        ("keys", C.c_void_p), ("order", C.c_void_p),
+        ("cell_start", C.c_void_p), ("cell_count", C.c_void_p), ("cell_level", C.c_void_p),
+        ("cell_parent", C.c_void_p), ("cell_first_child", C.c_void_p), ("cell_nchild", C.c_void_p),
+        ("cell_key", C.c_void_p), ("level_ptr", C.c_void_p), ("leaf_of_rank", C.c_void_p),
+        ("cell_of_particle", C.c_void_p), ("bbox", C.c_void_p), ("work", C.c_void_p), ("work_bytes", C.c_size_t),
+    ]
+
+
 EXPORTS = [
     # name, restype, argtypes  (must list every symbol include/se3gnn_b200.h declares)
     ("se3_last_error", C.c_char_p, []),
@@ -64,6 +75,16 @@ EXPORTS = [
     ("se3_l1tp_plan_info", C.c_int, [C.c_void_p, _i32p, _i32p, _i32p, _i32p]),
     ("se3_l1tp_forward", C.c_int, [C.c_void_p, C.POINTER(L1tpFwdArgs), C.c_void_p]),
     ("se3_l1tp_backward", C.c_int, [C.c_void_p, C.POINTER(L1tpBwdArgs), C.c_void_p]),
+    ("se3_octree_work_bytes", C.c_int, [C.c_int64, C.c_int64, C.POINTER(C.c_size_t)]),
+    ("se3_octree_build", C.c_int, [C.c_void_p, C.POINTER(Octree), C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.c_void_p]),
+    ("se3_graph_degrees", C.c_int, [C.POINTER(Octree), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.POINTER(C.c_int64), C.c_void_p]),
+    ("se3_graph_emit", C.c_int, [C.POINTER(Octree), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("se3_node_data", C.c_int, [C.POINTER(Octree), C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("se3_edge_geometry", C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p]),
 ]
 
 _lib = None

@@ -1,0 +1,108 @@
+"""SEGNN (l_max = 1) on the octree graph, every tensor product running as one fused sm_100a kernel.
+
+The reference mount contains only ``L1TensorProduct``; the layer layout below is
+the public SEGNN one (Brandstetter et al. 2021: embedding -> N x [message(2 gated TPs) -> add
+aggregation -> update(gated TP, TP, residual)] -> 2 read-out TPs) with every
+``O3TensorProduct[SwishGate]`` realised by the reference's ``L1TensorProduct`` (no bias terms).
+It is restated on CPU in ``oracle/segnn_oracle.py``, which is what the GPU tests compare against.
+
+Per layer the kernels are (rows = E edges or Nn nodes):
+    msg1 : gather x[dst] | x[src] | edge_extra  -> TP(edge SH) -> gate                    [E]
+    msg2 : TP(edge SH) -> gate -> sorted-segment sum over dst (no [E,64] message tensor)   [E] -> [Nn]
+    upd1 : x | agg -> TP(node attr) -> gate                                                [Nn]
+    upd2 : TP(node attr) + residual                                                        [Nn]
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import nn
+
+from se3gnn_b200 import capi
+from se3gnn_b200.gate import SIGMOID_CST, SILU_CST
+from se3gnn_b200.irreps import Irreps
+from se3gnn_b200.tp import TPConfig, get_plan, tp_layer
+
+from .l1_tensor_prod import L1TensorProduct, _SP
+
+INPUT_IRREPS = "2x1o+2x0e"   # (pos - centroid, vel, |vel|, mass)   -- x_in of the graph builder
+EXTRA_IRREPS = "2x0e"        # (|rel|, m_i m_j)                      -- edge_extra of the graph builder
+
+
+def gate_irreps(hidden: Irreps) -> Irreps:
+    """TP output that feeds a gate: scalars + one gate scalar per l=1 channel, then the vectors."""
+    ns = hidden.count("0e")
+    nv = hidden.count("1o")
+    if ns + 3 * nv != hidden.dim:
+        raise ValueError("hidden irreps must be of the form  a x0e + b x1o")
+    return Irreps(f"{ns + nv}x0e+{nv}x1o")
+
+
+class SEGNN(nn.Module):
+    def __init__(self, hidden: str = "34x0e+10x1o", num_layers: int = 4, out_irreps: str = "1x1o",
+                 input_irreps: str = INPUT_IRREPS):
+        super().__init__()
+        self.hidden = Irreps(hidden).simplify()
+        self.num_layers = num_layers
+        self.ns = self.hidden.count("0e")
+        self.nv = self.hidden.count("1o")
+        self.d = self.hidden.dim
+        hg = gate_irreps(self.hidden)
+        h = str(self.hidden)
+        self.in_irreps = Irreps(input_irreps)
+        self.out_irreps = Irreps(out_irreps)
+        self.embed = L1TensorProduct(self.in_irreps, self.hidden)
+        self.msg1 = nn.ModuleList(L1TensorProduct(Irreps(f"{h}+{h}+{EXTRA_IRREPS}"), hg) for _ in range(num_layers))
+        self.msg2 = nn.ModuleList(L1TensorProduct(self.hidden, hg) for _ in range(num_layers))
+        self.upd1 = nn.ModuleList(L1TensorProduct(Irreps(f"{h}+{h}"), hg) for _ in range(num_layers))
+        self.upd2 = nn.ModuleList(L1TensorProduct(self.hidden, self.hidden) for _ in range(num_layers))
+        self.pre1 = L1TensorProduct(self.hidden, hg)
+        self.pre2 = L1TensorProduct(self.hidden, self.out_irreps)
+
+    # -------------------------------------------------------------- helpers
+    @staticmethod
+    def _wn(tp: L1TensorProduct):
+        ws = [getattr(tp, f"weights_{s}", None) for s in _SP]
+        ns = []
+        for s in _SP:
+            b = getattr(tp, f"norm_{s}", None)
+            ns.append(b if b is not None and b.numel() > 0 else None)
+        return ws, ns
+
+    def _cfg(self, tp: L1TensorProduct, widths, gate: bool, **kw) -> TPConfig:
+        plan = get_plan(tp.iri1, tp.iro)
+        if gate:
+            return TPConfig(plan=plan, widths=widths, epilogue=capi.EPI_GATE, gate_ns=self.ns,
+                            gate_cs=SILU_CST, gate_cg=SIGMOID_CST, **kw)
+        return TPConfig(plan=plan, widths=widths, **kw)
+
+    # -------------------------------------------------------------- forward
+    def forward(self, x_in, node_attr, edge_attr, edge_extra, dst, src):
+        """x_in [Nn,8], node_attr [Nn,4], edge_attr [E,4], edge_extra [E,2], dst/src [E] int32 (sorted by dst).
+        Returns the per-node output [Nn, out_dim]."""
+        if not x_in.is_cuda:
+            raise RuntimeError("se3gnn_b200.SEGNN runs on CUDA (sm_100a) only; there is no CPU fallback")
+        nn_, e, d = x_in.shape[0], edge_attr.shape[0], self.d
+        ws, ns = self._wn(self.embed)
+        x = tp_layer(self._cfg(self.embed, (self.in_irreps.dim,), False), nn_, [x_in], [None], node_attr, ws, ns)
+        for l in range(self.num_layers):
+            ws, ns = self._wn(self.msg1[l])
+            cfg = self._cfg(self.msg1[l], (d, d, edge_extra.shape[1]), True,
+                            grad_modes=(capi.GRAD_SORTED, capi.GRAD_ATOMIC, capi.GRAD_NONE), share_grad={1: 0})
+            m1 = tp_layer(cfg, e, [x, x, edge_extra], [dst, src, None], edge_attr, ws, ns)
+            ws, ns = self._wn(self.msg2[l])
+            cfg = self._cfg(self.msg2[l], (d,), True, num_segments=nn_)
+            agg = tp_layer(cfg, e, [m1], [None], edge_attr, ws, ns, seg_idx=dst)
+            ws, ns = self._wn(self.upd1[l])
+            u1 = tp_layer(self._cfg(self.upd1[l], (d, d), True), nn_, [x, agg], [None, None], node_attr, ws, ns)
+            ws, ns = self._wn(self.upd2[l])
+            x = tp_layer(self._cfg(self.upd2[l], (d,), False), nn_, [u1], [None], node_attr, ws, ns, resid=x)
+        ws, ns = self._wn(self.pre1)
+        p1 = tp_layer(self._cfg(self.pre1, (d,), True), nn_, [x], [None], node_attr, ws, ns)
+        ws, ns = self._wn(self.pre2)
+        return tp_layer(self._cfg(self.pre2, (d,), False), nn_, [p1], [None], node_attr, ws, ns)
+
+    def forward_graph(self, g):
+        """Convenience: run on an ``OctreeGraph`` from ``se3gnn_b200.octree.build_octree_graph``."""
+        return self.forward(g.x_in, g.node_attr, g.edge_attr, g.edge_extra, g.dst, g.col)

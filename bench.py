@@ -1,0 +1,278 @@
+#!/usr/bin/env python
+"""bench.py — particles/s of the hot path (octree graph build + 4-layer SEGNN l_max=1 fwd/bwd + Adam)
+on synthetic Plummer clouds, BASELINE.json configs[1]: 100k particles per GPU, fp32, leaf size 32.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: reference TP op sequence (torch port)
+                                                             # + self-authored numba octree, host cores
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "scalable-e3-gnn_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "particles/sec for graph build + SEGNN fwd/bwd step"
+UNIT = "particles/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--particles", type=int, default=100_000, help="particles per GPU")
+    ap.add_argument("--kind", default="plummer", choices=["plummer", "uniform", "nfw"])
+    ap.add_argument("--layers", type=int, default=4)
+    ap.add_argument("--leaf", type=int, default=32)
+    ap.add_argument("--cpu-sample", type=int, default=10_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump", default=None, help="write the per-kernel table (JSON) here")
+    return ap.parse_args()
+
+
+def workload(a):
+    return {"workload": f"SEGNN l_max=1, {a.layers} layers, hidden 34x0e+10x1o, {a.particles} particles/GPU "
+                        f"({a.kind} sphere), fp32, octree leaf size {a.leaf} [BASELINE configs[1]]",
+            "particles_per_gpu": a.particles, "leaf_size": a.leaf, "layers": a.layers}
+
+
+# ------------------------------------------------------------------------------- reference (CPU) arm
+def cpu_arm(a, steps, warmup, budget_s=150.0):
+    from oracle.pipeline_oracle import time_cpu
+    from se3gnn_b200.pipeline import synthetic_cloud
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    os.environ.setdefault("NUMBA_NUM_THREADS", str(cores))
+    # bounded sample: ~2e3 particles/s on 8 cores -> keep (steps+warmup) * n / rate within the budget
+    n = int(max(1000, min(a.cpu_sample, 1500.0 * budget_s / max(1, steps + warmup))))
+    pps, ms, edges = time_cpu(n, a.kind, 1, steps=steps, warmup=warmup, threads=cores, make_cloud=synthetic_cloud)
+    return {"value": pps, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n}-particle {a.kind} cloud ({edges} edges), {steps} step(s) after {warmup} warm-up, "
+                      f"torch {torch.__version__} CPU {cores} threads + numba; reference TP op sequence (port) "
+                      f"+ self-authored octree/SEGNN remainder"}, ms
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, a.steps), max(1, a.warmup)
+    cb, ms = cpu_arm(a, steps, warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload(a), "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        # "under load" = samples in the upper half of what we saw
+        med = statistics.median(sm) if sm else None
+        return {"sm_mhz": med, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------- CUDA arm
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    from se3gnn_b200 import capi
+    from se3gnn_b200.pipeline import TrainStep, synthetic_cloud
+    from models.segnn.segnn import SEGNN
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    torch.manual_seed(0)
+    model = SEGNN(num_layers=a.layers).to(dev)
+    ts = TrainStep(model, leaf_size=a.leaf, distributed=world > 1)
+    n = a.particles
+    pos, vel, mass, target = (torch.from_numpy(x) for x in synthetic_cloud(n, a.kind, seed=1 + rank))
+    host = [t.pin_memory() for t in (pos, vel, mass, target)]
+    devt = [t.to(dev) for t in host]
+    K, W = max(1, a.steps), max(3, a.warmup)
+
+    for _ in range(W):
+        loss = ts.step_device(*devt)
+    barrier()
+    g = ts.last_graph
+    edges, cells = g.e, g.m
+
+    # ---- timed region: K steps, inputs resident in HBM
+    clk = ClockSampler(local) if rank == 0 else None
+    l0 = capi.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        loss = ts.step_device(*devt)
+    e1.record()
+    barrier()
+    ms = allmax(e0.elapsed_time(e1))
+    launches = (capi.launch_count() - l0) // K
+    clocks = clk.stop() if clk else None
+    value = n * world * K / (ms * 1e-3)
+
+    # ---- end to end through the public host-buffer API (H2D of the step's inputs + D2H of the loss each step)
+    ts.step_host(*host)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        lossf = ts.step_host(*host)
+    torch.cuda.synchronize()
+    dt = allmax(time.perf_counter() - t0)
+    barrier()
+    e2e = {"value": n * world * K / dt, "unit": UNIT, "h2d_bytes_per_step": int(sum(t.numel() * 4 for t in host)),
+           "d2h_bytes_per_step": 4 + 16, "ms_per_step": dt * 1e3 / K}
+
+    # ---- per-kernel table (CUDA events on the launching stream around every library call), 2 more steps
+    capi.profile_begin()
+    for _ in range(2):
+        ts.step_device(*devt)
+    prof = capi.profile_end()
+    agg = {}
+    for tag, t_ms, nb, fl in prof:
+        r = agg.setdefault(tag, {"ms": 0.0, "bytes": 0.0, "flops": 0.0, "launches": 0})
+        r["ms"] += t_ms
+        r["bytes"] += nb
+        r["flops"] += fl
+        r["launches"] += 1
+    tot_ms = sum(r["ms"] for r in agg.values())
+    top = max(agg.items(), key=lambda kv: kv[1]["ms"])
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    tr = top[1]
+    ach = tr["bytes"] / (tr["ms"] * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(top[0])
+    except Exception:
+        pass
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    roofline = {"kernel": top[0], "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": traffic, "peak_source": peak_src,
+                "bytes_per_launch": tr["bytes"] / tr["launches"], "ms_per_launch": tr["ms"] / tr["launches"],
+                "share_of_step": tr["ms"] / tot_ms,
+                "fp32_tflops": tr["flops"] / (tr["ms"] * 1e-3) / 1e12,
+                "fp32_peak_tflops_at_clock": fp32_peak,
+                "note": "fp32 CUDA-core contraction (1e-5 parity target): FMA-pipe-bound, see DESIGN.md"}
+    table = {k: {"ms_per_step": v["ms"] / 2, "GBps": v["bytes"] / max(v["ms"], 1e-9) / 1e6,
+                 "TFLOPs": v["flops"] / max(v["ms"], 1e-9) / 1e9, "launches_per_step": v["launches"] // 2}
+             for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
+    if a.dump and rank == 0:
+        os.makedirs(os.path.dirname(os.path.abspath(a.dump)), exist_ok=True)
+        json.dump({"kernels": table, "edges": edges, "cells": cells, "particles": n}, open(a.dump, "w"), indent=1)
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cb = None
+    if world == 1 and not a.no_cpu_baseline:
+        cb, _ = cpu_arm(a, steps=2, warmup=1, budget_s=40.0)
+    cfg = workload(a)
+    cfg.update({"edges_per_gpu": edges, "cells_per_gpu": cells,
+                "parallelism": f"dp{world} (one independent cloud per GPU, NCCL all-reduce of weight gradients)",
+                "l2": "no flush: per-step working set (per-edge activations, ~%.1f GB) exceeds the 126 MB L2"
+                      % (edges * 4 * (74 + 64 + 74 + 64 + 8) * a.layers / 1e9),
+                "optimizer": "Adam (torch fused) inside the timed step"})
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": cfg, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cb, "edges_per_s": edges * world * K / (ms * 1e-3),
+            "loss": float(loss.item()), "kernels": table}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)

@@ -70,8 +70,9 @@ class SEGNN(nn.Module):
             ns.append(b if b is not None and b.numel() > 0 else None)
         return ws, ns
 
-    def _cfg(self, tp: L1TensorProduct, widths, gate: bool, **kw) -> TPConfig:
+    def _cfg(self, tp: L1TensorProduct, widths, gate: bool, tag: str = "tp", **kw) -> TPConfig:
         plan = get_plan(tp.iri1, tp.iro)
+        kw["tag"] = tag
         if gate:
             return TPConfig(plan=plan, widths=widths, epilogue=capi.EPI_GATE, gate_ns=self.ns,
                             gate_cs=SILU_CST, gate_cg=SIGMOID_CST, **kw)
@@ -85,23 +86,23 @@ class SEGNN(nn.Module):
             raise RuntimeError("se3gnn_b200.SEGNN runs on CUDA (sm_100a) only; there is no CPU fallback")
         nn_, e, d = x_in.shape[0], edge_attr.shape[0], self.d
         ws, ns = self._wn(self.embed)
-        x = tp_layer(self._cfg(self.embed, (self.in_irreps.dim,), False), nn_, [x_in], [None], node_attr, ws, ns)
+        x = tp_layer(self._cfg(self.embed, (self.in_irreps.dim,), False, "embed"), nn_, [x_in], [None], node_attr, ws, ns)
         for l in range(self.num_layers):
             ws, ns = self._wn(self.msg1[l])
-            cfg = self._cfg(self.msg1[l], (d, d, edge_extra.shape[1]), True,
+            cfg = self._cfg(self.msg1[l], (d, d, edge_extra.shape[1]), True, "msg1",
                             grad_modes=(capi.GRAD_SORTED, capi.GRAD_ATOMIC, capi.GRAD_NONE), share_grad={1: 0})
             m1 = tp_layer(cfg, e, [x, x, edge_extra], [dst, src, None], edge_attr, ws, ns)
             ws, ns = self._wn(self.msg2[l])
-            cfg = self._cfg(self.msg2[l], (d,), True, num_segments=nn_)
+            cfg = self._cfg(self.msg2[l], (d,), True, "msg2", num_segments=nn_)
             agg = tp_layer(cfg, e, [m1], [None], edge_attr, ws, ns, seg_idx=dst)
             ws, ns = self._wn(self.upd1[l])
-            u1 = tp_layer(self._cfg(self.upd1[l], (d, d), True), nn_, [x, agg], [None, None], node_attr, ws, ns)
+            u1 = tp_layer(self._cfg(self.upd1[l], (d, d), True, "upd1"), nn_, [x, agg], [None, None], node_attr, ws, ns)
             ws, ns = self._wn(self.upd2[l])
-            x = tp_layer(self._cfg(self.upd2[l], (d,), False), nn_, [u1], [None], node_attr, ws, ns, resid=x)
+            x = tp_layer(self._cfg(self.upd2[l], (d,), False, "upd2"), nn_, [u1], [None], node_attr, ws, ns, resid=x)
         ws, ns = self._wn(self.pre1)
-        p1 = tp_layer(self._cfg(self.pre1, (d,), True), nn_, [x], [None], node_attr, ws, ns)
+        p1 = tp_layer(self._cfg(self.pre1, (d,), True, "pre1"), nn_, [x], [None], node_attr, ws, ns)
         ws, ns = self._wn(self.pre2)
-        return tp_layer(self._cfg(self.pre2, (d,), False), nn_, [p1], [None], node_attr, ws, ns)
+        return tp_layer(self._cfg(self.pre2, (d,), False, "pre2"), nn_, [p1], [None], node_attr, ws, ns)
 
     def forward_graph(self, g):
         """Convenience: run on an ``OctreeGraph`` from ``se3gnn_b200.octree.build_octree_graph``."""

@@ -121,6 +121,47 @@ def launch_count() -> int:
     return int(lib().se3_launch_count())
 
 
+# ---------------------------------------------------------------- per-launch profiling (bench.py)
+_prof = None
+
+
+def profile_begin():
+    """Start recording one (tag, CUDA-event pair, algorithmic bytes, flops) entry per library call."""
+    global _prof
+    _prof = []
+
+
+def profile_end():
+    """Stop recording; returns [(tag, ms, bytes, flops)] (synchronises)."""
+    global _prof
+    import torch
+    torch.cuda.synchronize()
+    out = [(tag, a.elapsed_time(b), nbytes, flops) for tag, a, b, nbytes, flops in (_prof or [])]
+    _prof = None
+    return out
+
+
+class mark:
+    """Context manager: CUDA events on the launching (current) stream around one library call."""
+
+    def __init__(self, tag: str, nbytes: float = 0.0, flops: float = 0.0):
+        self.tag, self.nbytes, self.flops = tag, nbytes, flops
+
+    def __enter__(self):
+        if _prof is not None:
+            import torch
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _prof is not None:
+            self.b.record()
+            _prof.append((self.tag, self.a, self.b, self.nbytes, self.flops))
+        return False
+
+
 def ptr(t) -> Optional[int]:
     """Device pointer of a torch tensor (or None)."""
     if t is None:

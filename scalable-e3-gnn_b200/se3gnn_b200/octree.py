@@ -99,7 +99,10 @@ def build_octree_graph(pos: torch.Tensor, vel: Optional[torch.Tensor] = None, ma
     t.work, t.work_bytes = work.data_ptr(), wb.value
     st = capi.current_stream_ptr()
     m_out, nlev = C.c_int64(), C.c_int32()
-    capi.check(lib.se3_octree_build(pos.data_ptr(), C.byref(t), C.byref(m_out), C.byref(nlev), st), "se3_octree_build")
+    # algorithmic bytes: keys 12+12 B/particle, 8 sort passes x (8 hist + 12 read + 12 write) B,
+    # split/assign ~ (8 read + 4 write) B per particle per level touched (charged once here)
+    with capi.mark("octree.build", n * (24.0 + 8 * 32.0 + 12.0)):
+        capi.check(lib.se3_octree_build(pos.data_ptr(), C.byref(t), C.byref(m_out), C.byref(nlev), st), "se3_octree_build")
     m = int(m_out.value)
     nn = n + m
     nbr = torch.empty((m, 26), **i32)
@@ -107,13 +110,15 @@ def build_octree_graph(pos: torch.Tensor, vel: Optional[torch.Tensor] = None, ma
     rowptr = torch.empty(nn + 1, device=dev, dtype=torch.int64)
     scan_work = torch.empty(nn // 1024 + 2, device=dev, dtype=torch.int64)
     e_out = C.c_int64()
-    capi.check(lib.se3_graph_degrees(C.byref(t), m, nbr.data_ptr(), deg.data_ptr(), rowptr.data_ptr(),
-                                     scan_work.data_ptr(), C.byref(e_out), st), "se3_graph_degrees")
+    with capi.mark("graph.degrees", m * (8.0 + 104.0 + 4.0) + n * 8.0 + nn * 12.0):
+        capi.check(lib.se3_graph_degrees(C.byref(t), m, nbr.data_ptr(), deg.data_ptr(), rowptr.data_ptr(),
+                                         scan_work.data_ptr(), C.byref(e_out), st), "se3_graph_degrees")
     e = int(e_out.value)
     col = torch.empty(e, **i32)
     dst = torch.empty(e, **i32)
-    capi.check(lib.se3_graph_emit(C.byref(t), m, nbr.data_ptr(), rowptr.data_ptr(), col.data_ptr(), dst.data_ptr(), st),
-               "se3_graph_emit")
+    with capi.mark("graph.emit", e * 8.0 + m * 104.0 + nn * 8.0):
+        capi.check(lib.se3_graph_emit(C.byref(t), m, nbr.data_ptr(), rowptr.data_ptr(), col.data_ptr(), dst.data_ptr(), st),
+                   "se3_graph_emit")
     g = OctreeGraph(n=n, m=m, e=e, nlevels=int(nlev.value), leaf_size=int(leaf_size), keys=keys, order=order,
                     cell_start=cells[0, :m], cell_count=cells[1, :m], cell_level=cells[2, :m], cell_parent=cells[3, :m],
                     cell_first_child=cells[4, :m], cell_nchild=cells[5, :m], cell_key=cell_key[:m], level_ptr=level_ptr,
@@ -131,15 +136,17 @@ def build_octree_graph(pos: torch.Tensor, vel: Optional[torch.Tensor] = None, ma
         g.node_pos = torch.empty((nn, 3), **f32)
         g.node_vel = torch.empty((nn, 3), **f32)
         g.node_mass = torch.empty(nn, **f32)
-        capi.check(lib.se3_node_data(C.byref(t), m, g.nlevels, pos.data_ptr(), vel.data_ptr(), mass.data_ptr(),
-                                     g.node_pos.data_ptr(), g.node_vel.data_ptr(), g.node_mass.data_ptr(), st),
-                   "se3_node_data")
+        with capi.mark("graph.node_data", n * 60.0 + m * 56.0):
+            capi.check(lib.se3_node_data(C.byref(t), m, g.nlevels, pos.data_ptr(), vel.data_ptr(), mass.data_ptr(),
+                                         g.node_pos.data_ptr(), g.node_vel.data_ptr(), g.node_mass.data_ptr(), st),
+                       "se3_node_data")
         g.edge_attr = torch.empty((e, 4), **f32)
         g.edge_extra = torch.empty((e, 2), **f32)
         g.node_attr = torch.empty((nn, 4), **f32)
         g.x_in = torch.empty((nn, 8), **f32)
-        capi.check(lib.se3_edge_geometry(n, m, e, rowptr.data_ptr(), col.data_ptr(), dst.data_ptr(),
-                                         g.node_pos.data_ptr(), g.node_vel.data_ptr(), g.node_mass.data_ptr(),
-                                         C.c_float(float(n)), g.edge_attr.data_ptr(), g.edge_extra.data_ptr(),
-                                         g.node_attr.data_ptr(), g.x_in.data_ptr(), st), "se3_edge_geometry")
+        with capi.mark("graph.edge_geometry", e * (8.0 + 12.0 + 24.0 + 16.0) + nn * (28.0 + 48.0)):
+            capi.check(lib.se3_edge_geometry(n, m, e, rowptr.data_ptr(), col.data_ptr(), dst.data_ptr(),
+                                             g.node_pos.data_ptr(), g.node_vel.data_ptr(), g.node_mass.data_ptr(),
+                                             C.c_float(float(n)), g.edge_attr.data_ptr(), g.edge_extra.data_ptr(),
+                                             g.node_attr.data_ptr(), g.x_in.data_ptr(), st), "se3_edge_geometry")
     return g

@@ -67,11 +67,54 @@ class TPConfig:
     # which of the segments share one gradient buffer (e.g. x gathered by dst and by src)
     share_grad: Dict[int, int] = field(default_factory=dict)
 
+    tag: str = "tp"
+
     @property
     def d_post(self) -> int:
         if self.epilogue == capi.EPI_GATE:
             return self.gate_ns + 3 * self.plan.m[3]
         return self.plan.d_out
+
+    def flops_fwd_per_row(self) -> int:
+        """Minimal (factorised) FMA count x2 of one forward row, see csrc/l1tp.cu header."""
+        n, m = self.plan.n, self.plan.m
+        fe = (n[0] + n[3]) * m[0] + n[0] * m[3] + 3 * (n[3] + n[2]) * m[3]
+        fo = (n[1] + n[2]) * m[1] + n[1] * m[2] + 3 * (n[2] + n[3]) * m[2]
+        return 2 * (fe + fo)
+
+    def algo_bytes(self, rows: int, segs, idxs, backward: bool, nseg_out: int = 0, has_resid: bool = False,
+                   grads=None) -> float:
+        """Algorithmic HBM bytes of one launch: every operand once; a segment gathered through a
+        *sorted* index is charged once per distinct row (segment-cached), an unsorted gather once per row."""
+        b = rows * 4 * 4  # in2
+        for i, s in enumerate(segs):
+            w = self.widths[i]
+            if idxs[i] is None:
+                b += rows * w * 4
+            else:
+                srt = i < len(self.grad_modes) and self.grad_modes[i] == capi.GRAD_SORTED
+                b += (min(rows, s.shape[0]) if srt else rows) * w * 4 + rows * 4
+        gate = self.epilogue == capi.EPI_GATE
+        d_out, d_post = self.plan.d_out, self.d_post
+        if not backward:
+            if nseg_out:
+                b += nseg_out * d_post * 4 + rows * 4
+                if gate:
+                    b += rows * d_out * 4  # pre-activation saved for backward
+            else:
+                b += rows * d_out * 4 + (rows * d_post * 4 if gate else 0)
+            if has_resid:
+                b += rows * d_out * 4
+        else:
+            if gate:
+                b += rows * d_out * 4
+            b += (nseg_out if nseg_out else rows) * d_post * 4 + (rows * 4 if nseg_out else 0)
+            for i, s in enumerate(segs):
+                if grads is not None and grads[i]:
+                    w = self.widths[i]
+                    srt = idxs[i] is not None and i < len(self.grad_modes) and self.grad_modes[i] == capi.GRAD_SORTED
+                    b += (min(rows, s.shape[0]) if srt else rows) * w * 4
+        return float(b)
 
 
 def _chk(t: Optional[torch.Tensor], name: str, dtype=torch.float32):
@@ -136,7 +179,11 @@ class TPLayerFn(torch.autograd.Function):
         if raw is not None:
             a.out_raw = raw.data_ptr()
         a.resid = capi.ptr(resid)
-        capi.check(lib.se3_l1tp_forward(cfg.plan.handle, C.byref(a), capi.current_stream_ptr()), "se3_l1tp_forward")
+        with capi.mark(cfg.tag + ".fwd",
+                       cfg.algo_bytes(rows, segs, idxs, False, cfg.num_segments if seg_idx is not None else 0,
+                                      resid is not None) if capi._prof is not None else 0.0,
+                       float(cfg.flops_fwd_per_row()) * rows):
+            capi.check(lib.se3_l1tp_forward(cfg.plan.handle, C.byref(a), capi.current_stream_ptr()), "se3_l1tp_forward")
         ctx.cfg = cfg
         ctx.rows = rows
         ctx.idxs = idxs
@@ -193,7 +240,7 @@ class TPLayerFn(torch.autograd.Function):
                 buf = gsegs[owner]
             elif idx is None:
                 buf = torch.empty_like(s)
-                if s.shape[-1] != cfg.widths[i]:
+                if s.shape[-1] != cfg.widths[i] or s.shape[0] != ctx.rows:
                     buf.zero_()
             else:
                 buf = torch.zeros_like(s)
@@ -212,7 +259,11 @@ class TPLayerFn(torch.autograd.Function):
         if nig[2] and cfg.need_gin2:
             gin2 = torch.empty_like(in2)
             a.gin2 = gin2.data_ptr()
-        capi.check(lib.se3_l1tp_backward(cfg.plan.handle, C.byref(a), capi.current_stream_ptr()), "se3_l1tp_backward")
+        with capi.mark(cfg.tag + ".bwd",
+                       cfg.algo_bytes(ctx.rows, segs, ctx.idxs, True, cfg.num_segments if ctx.seg_idx is not None else 0,
+                                      False, seg_need) if capi._prof is not None else 0.0,
+                       2.0 * cfg.flops_fwd_per_row() * ctx.rows):
+            capi.check(lib.se3_l1tp_backward(cfg.plan.handle, C.byref(a), capi.current_stream_ptr()), "se3_l1tp_backward")
         gresid = gout if (ctx.has_resid and nig[3]) else None
         out_gsegs = []
         for i in range(nseg):

@@ -39,6 +39,8 @@ const char* se3_last_error(void);
 int se3_version(void);
 /* number of kernels launched by this library in this process since load */
 int64_t se3_launch_count(void);
+/* of those, launches of the tcgen05 (tensor-core) kernels */
+int64_t se3_tc_launch_count(void);
 
 /* ---------------------------------------------------------------- l1tp ---- */
 

@@ -7,6 +7,7 @@ namespace se3 {
 
 static thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
+std::atomic<long long> g_tc_launches{0};
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -30,3 +31,4 @@ int num_sms() {
 extern "C" const char* se3_last_error(void) { return se3::g_err; }
 extern "C" int se3_version(void) { return 100; }
 extern "C" int64_t se3_launch_count(void) { return (int64_t)se3::g_launches.load(); }
+extern "C" int64_t se3_tc_launch_count(void) { return (int64_t)se3::g_tc_launches.load(); }

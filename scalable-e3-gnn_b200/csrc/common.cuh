@@ -12,6 +12,7 @@ namespace se3 {
 
 void set_error(const char* fmt, ...);
 extern std::atomic<long long> g_launches;
+extern std::atomic<long long> g_tc_launches;
 int num_sms();
 
 #define SE3_CUDA_TRY(expr)                                                        \
@@ -49,5 +50,19 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
                  : "memory");
 }
+
+// Row source of a fused TP call: in1 row = virtual concatenation of up to 4 (optionally indexed) segments.
+struct RowSrc {
+    const float* base[SE3_MAX_SEG];
+    const int32_t* idx[SE3_MAX_SEG];
+    int ld[SE3_MAX_SEG];
+    int cum[SE3_MAX_SEG + 1];
+    int nseg;
+};
+
+struct EpiL {
+    int mode, ns_g, nv, d_post;
+    float cs, cg;
+};
 
 }  // namespace se3

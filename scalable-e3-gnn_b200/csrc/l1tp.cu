@@ -62,19 +62,6 @@ struct PlanL {
     int b_y, b_rowoff, b_tab, b_norm, b_gt, smem_bwd;
 };
 
-struct RowSrc {
-    const float* base[SE3_MAX_SEG];
-    const int32_t* idx[SE3_MAX_SEG];
-    int ld[SE3_MAX_SEG];
-    int cum[SE3_MAX_SEG + 1];
-    int nseg;
-};
-
-struct EpiL {
-    int mode, ns_g, nv, d_post;
-    float cs, cg;
-};
-
 struct FwdK {
     long long rows;
     RowSrc src;
@@ -1099,7 +1086,12 @@ struct se3_l1tp_plan {
     int occ_fwd = 1, occ_bwd = 1, maxwj = 2;
     int w_off[4], w_cnt[4];
     int n[4], m[4];
+    int t_in[4], t_out[4];
 };
+
+int se3_l1tp_tc_try_forward(const int n[4], const int m[4], const int t_in[4], const int t_out[4], int ntab,
+                            const int* d_tab, const se3_l1tp_fwd_args* a, const se3::RowSrc& src, const se3::EpiL& epi,
+                            cudaStream_t st, bool* launched);
 
 extern "C" int se3_l1tp_plan_create(const se3_l1tp_desc* d, se3_l1tp_plan** out) {
     if (!d || !out) { set_error("null argument"); return SE3_ERR_INVALID; }
@@ -1128,7 +1120,7 @@ extern "C" int se3_l1tp_plan_create(const se3_l1tp_desc* d, se3_l1tp_plan** out)
         t_out[s] = (int)tab.size();
         for (int k = 0; k < d->m[s]; ++k) tab.push_back(d->out_cols[s][k]);
     }
-    for (int s = 0; s < 4; ++s) { p->n[s] = d->n[s]; p->m[s] = d->m[s]; }
+    for (int s = 0; s < 4; ++s) { p->n[s] = d->n[s]; p->m[s] = d->m[s]; p->t_in[s] = t_in[s]; p->t_out[s] = t_out[s]; }
     L.ntab = (int)tab.size();
     // families: E = (s 0e, dot 1o, cross 1e -> Z 0e, V 1o), O = (s 0o, dot 1e, cross 1o -> Z 0o, V 1e)
     const int fs[2] = {0, 1}, fd[2] = {3, 2}, fx[2] = {2, 3}, fz[2] = {0, 1}, fv[2] = {3, 2};
@@ -1303,6 +1295,13 @@ extern "C" int se3_l1tp_forward(se3_l1tp_plan* p, const se3_l1tp_fwd_args* a, vo
     for (int s = 0; s < 4; ++s) { K.w[s] = a->w[s]; K.norm[s] = a->norm[s]; }
     K.out_raw = a->out_raw; K.out_post = a->out_post; K.resid = a->resid;
     K.seg_idx = a->seg_idx; K.out_seg = a->out_seg; K.tab = p->d_tab;
+    {   // tensor-core (tcgen05) path when the configuration is eligible
+        bool launched = false;
+        rc = se3_l1tp_tc_try_forward(p->n, p->m, p->t_in, p->t_out, p->L.ntab, p->d_tab, a, K.src, K.epi,
+                                     (cudaStream_t)stream, &launched);
+        if (rc) return rc;
+        if (launched) return SE3_OK;
+    }
     const long long ntiles = (a->rows + p->L.TR - 1) / p->L.TR;
     const int grid = (int)std::min<long long>(ntiles, (long long)num_sms() * p->occ_fwd);
     l1tp_fwd_kernel<<<grid, NT, p->L.smem_fwd, (cudaStream_t)stream>>>(p->L, K);

@@ -70,6 +70,7 @@ EXPORTS = [
     ("se3_last_error", C.c_char_p, []),
     ("se3_version", C.c_int, []),
     ("se3_launch_count", C.c_int64, []),
+    ("se3_tc_launch_count", C.c_int64, []),
     ("se3_l1tp_plan_create", C.c_int, [C.POINTER(L1tpDesc), C.POINTER(C.c_void_p)]),
     ("se3_l1tp_plan_destroy", None, [C.c_void_p]),
     ("se3_l1tp_plan_info", C.c_int, [C.c_void_p, _i32p, _i32p, _i32p, _i32p]),
@@ -119,6 +120,10 @@ def check(rc: int, what: str = "se3gnn_b200"):
 
 def launch_count() -> int:
     return int(lib().se3_launch_count())
+
+
+def tc_launch_count() -> int:
+    return int(lib().se3_tc_launch_count())
 
 
 # ---------------------------------------------------------------- per-launch profiling (bench.py)

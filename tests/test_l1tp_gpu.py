@@ -159,7 +159,9 @@ def test_fused_message_layer_vs_oracle():
                     grad_modes=(capi.GRAD_SORTED, capi.GRAD_ATOMIC, capi.GRAD_NONE), share_grad={1: 0})
     cfg2 = TPConfig(plan=get_plan(Irreps(hid), Irreps(out)), widths=(64,), epilogue=capi.EPI_GATE, gate_ns=34,
                     gate_cs=SILU_CST, gate_cg=SIGMOID_CST, num_segments=N)
+    tc0 = capi.tc_launch_count()
     m1t = tp_layer(cfg1, E, [xt, xt, ext], [dt, st, None], yt, ws1, ns1)
+    assert capi.tc_launch_count() == tc0 + 1, "the SEGNN message TP must run on the tcgen05 path"
     _close(m1t, m1, "m1")
     aggt = tp_layer(cfg2, E, [m1t], [None], yt, ws2, ns2, seg_idx=dt)
     _close(aggt, agg, "agg")

@@ -135,7 +135,13 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     lo = x - hi;
 }
 
-__device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// sigmoid with two MUFU ops (ex2.approx, rcp.approx: ~1e-7 relative, far inside the 1e-5 parity budget)
+__device__ __forceinline__ float sigm(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return r;
+}
 
 // byte offset of element (row/col n, k) inside a canonical tile with KQ = K/4 sixteen-byte chunks per row
 __device__ __forceinline__ int canon_off(int n, int k, int KQ) { return (((n >> 3) * KQ + (k >> 2)) << 7) + ((n & 7) << 4) + ((k & 3) << 2); }
@@ -532,27 +538,65 @@ __global__ void __launch_bounds__(TC_THREADS, 1) l1tp_tc_fwd_kernel(const TcArgs
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(B_ACC_EMPTY + b));
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            // ---- finish: one warp per row, lanes over columns
+            // ---- finish (256 threads): raw tile -> global (+residual); gate -> post rows (global and/or post tile)
             const bool to_ptile = gate && A.seg_idx;
-            for (int r = ew; r < nvalid; r += NEPI_WARPS) {
-                const float* orow2 = otile + r * A.dop;
-                if (A.out_raw) {
-                    float* dst = A.out_raw + (row0 + r) * dout;
-                    const float* res = A.resid ? A.resid + (row0 + r) * dout : nullptr;
-                    for (int c = lane; c < dout; c += 32) {
-                        float v = orow2[c];
-                        if (res) v += __ldg(res + c);
-                        dst[c] = v;
+            if (A.out_raw) {
+                float* dst = A.out_raw + row0 * dout;
+                const float* res = A.resid ? A.resid + row0 * dout : nullptr;
+                const int total = nvalid * dout;
+                if (A.dop == dout) {
+                    // the tile is the exact image of the global rows: linear 16-byte copy
+                    const int n4 = total >> 2;
+                    for (int t = et; t < n4; t += 256) {
+                        float4 v = reinterpret_cast<const float4*>(otile)[t];
+                        if (res) {
+                            const float4 q = __ldg(reinterpret_cast<const float4*>(res) + t);
+                            v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+                        }
+                        reinterpret_cast<float4*>(dst)[t] = v;
+                    }
+                    for (int t = (n4 << 2) + et; t < total; t += 256) dst[t] = otile[t] + (res ? __ldg(res + t) : 0.0f);
+                } else {
+                    for (int r = ew; r < nvalid; r += NEPI_WARPS) {
+                        const float* orow2 = otile + r * A.dop;
+                        for (int c = lane; c < dout; c += 32) {
+                            float v = orow2[c];
+                            if (res) v += __ldg(res + r * dout + c);
+                            dst[r * dout + c] = v;
+                        }
                     }
                 }
-                if (gate) {
-                    float* dst = A.out_post ? A.out_post + (row0 + r) * dpost : nullptr;
-                    for (int c = lane; c < dpost; c += 32) {
-                        const float x = orow2[pcol[c]];
-                        const int gc = gcol[c];
-                        const float v = gc < 0 ? A.epi.cs * x * sigm(x) : A.epi.cg * sigm(orow2[gc]) * x;
-                        if (dst) dst[c] = v;
-                        if (to_ptile) ptile[r * A.dpp + c] = v;
+            }
+            if (gate) {
+                float* dstp = A.out_post ? A.out_post + row0 * dpost : nullptr;
+                if ((dpost & 3) == 0) {
+                    const int q4 = dpost >> 2;           // float4 groups per row
+                    const int total4 = nvalid * q4;
+                    for (int t = et; t < total4; t += 256) {
+                        const int r = t / q4, c0 = (t - r * q4) << 2;
+                        const float* orow2 = otile + r * A.dop;
+                        float v[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float x = orow2[pcol[c0 + j]];
+                            const int gc = gcol[c0 + j];
+                            const float gx = gc < 0 ? x : orow2[gc];
+                            v[j] = (gc < 0 ? A.epi.cs : A.epi.cg) * sigm(gx) * x;
+                        }
+                        const float4 o4 = make_float4(v[0], v[1], v[2], v[3]);
+                        if (dstp) reinterpret_cast<float4*>(dstp)[t] = o4;
+                        if (to_ptile) *reinterpret_cast<float4*>(ptile + r * A.dpp + c0) = o4;
+                    }
+                } else {
+                    for (int r = ew; r < nvalid; r += NEPI_WARPS) {
+                        const float* orow2 = otile + r * A.dop;
+                        for (int c = lane; c < dpost; c += 32) {
+                            const float x = orow2[pcol[c]];
+                            const int gc = gcol[c];
+                            const float v = gc < 0 ? A.epi.cs * x * sigm(x) : A.epi.cg * sigm(orow2[gc]) * x;
+                            if (dstp) dstp[r * dpost + c] = v;
+                            if (to_ptile) ptile[r * A.dpp + c] = v;
+                        }
                     }
                 }
             }
@@ -653,8 +697,10 @@ int se3_l1tp_tc_try_forward(const int n[4], const int m[4], const int t_in[4], c
     A.in2off = off;
     off += TM * 4;
     A.slot_floats = off;
-    A.dop = A.d_out | 1;
-    A.dpp = epi.d_post | 1;
+    // raw tile stride: 16 row-lanes write one column at a time -> need stride*r (mod 32) distinct for r < 16,
+    // i.e. stride odd or == 2 (mod 4).  If d_out itself qualifies the tile is the exact image of the global rows.
+    A.dop = ((A.d_out & 1) || (A.d_out & 3) == 2) ? A.d_out : A.d_out + 2;
+    A.dpp = (epi.d_post & 3) == 0 ? tc_stage_stride(epi.d_post) : (epi.d_post | 1);
     auto al = [](int x, int q) { return (x + q - 1) / q * q; };
     int o = 0;
     A.o_b1 = o; o += 2 * A.N1 * A.K1 * 4;
@@ -662,6 +708,7 @@ int se3_l1tp_tc_try_forward(const int n[4], const int m[4], const int t_in[4], c
     A.o_b3 = o; o += 2 * A.N3 * A.K2 * 4;
     o = al(o, 128);
     A.o_stage = o; o += 2 * A.slot_floats * 4;
+    o = al(o, 16);
     A.o_out = o; o += al(TM * A.dop * 4, 16);
     A.o_post = o; o += (epi.mode == SE3_EPI_GATE && a->seg_idx) ? al(TM * A.dpp * 4, 16) : 0;
     A.o_tab = o; o += al(ntab * 4, 16);

@@ -5,14 +5,14 @@
 //     a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi     (a_hi = fp32 truncated to tf32, a_lo = a - a_hi),
 // three `tcgen05.mma.kind::tf32` per K-step with fp32 accumulation in TMEM.
 //
-// One persistent CTA per SM, 16 warps, warp-specialised, everything hand-shaken with mbarriers:
+// One persistent CTA per SM, 24 warps, warp-specialised, everything hand-shaken with mbarriers:
 //   warps 0,2   producers : cp.async (16 B, zero-fill) gather of the tile's rows (virtual concat of indexed
 //                           segments) + in2 into a 2-slot stage ring; index values prefetched one tile ahead
-//   warps 4-7   builders  : stage -> feature chunks in the UMMA canonical K-major layout (64 rows x 24 K,
+//   warps 4-15  builders  : stage -> feature chunks in the UMMA canonical K-major layout (64 rows x 24 K,
 //                           hi and lo halves), chunk ring of <= 7 slots; fence.proxy.async; arrive
 //   warp  1     MMA       : one lane issues 9 MMAs per chunk (3 K-steps x 3xTF32), tcgen05.commit frees the
 //                           chunk slot; after the last chunk of a tile commits the accumulator buffer
-//   warps 8-15  epilogue  : tcgen05.ld (32x32b) -> Y0/Y1 combination, norm, swish/sigmoid gate -> smem tile
+//   warps 16-23 epilogue  : tcgen05.ld (32x32b) -> Y0/Y1 combination, norm, swish/sigmoid gate -> smem tile
 //                           -> coalesced stores / residual / sorted-segment sum; TMEM accumulators are
 //                           double buffered so the epilogue of tile t overlaps the MMAs of tile t+1
 // GEMMs per 64-row tile (M=64; N and K padded with zero weights):
@@ -26,13 +26,14 @@
 
 namespace se3 {
 
-static constexpr int TC_THREADS = 512;
+static constexpr int TC_THREADS = 768;
 static constexpr int TM = 64;
 static constexpr int KC = 24;
 static constexpr int SLOT_HALF = TM * KC * 4;  // bytes of one (hi or lo) 64x24 fp32 chunk
 static constexpr int SLOT_BYTES = 2 * SLOT_HALF;
-static constexpr int NBUILD_WARPS = 4;
+static constexpr int NBUILD_WARPS = 12;  // one 16-row x 2-K-chunk task per warp and chunk
 static constexpr int NEPI_WARPS = 8;
+static constexpr int BUILD_W0 = 4, EPI_W0 = 16;
 static constexpr float C3f = 0.57735026918962576451f;
 
 struct TcArgs {
@@ -191,7 +192,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) l1tp_tc_fwd_kernel(const TcArgs
             int s = 0;
             for (int q = 1; q < SE3_MAX_SEG; ++q)
                 if (q < A.src.nseg && vc >= A.src.cum[q]) s = q;
-            e = (s << 16) | (vc - A.src.cum[s]);
+            e = (A.sstride[s] << 20) | (A.soff[s] + vc - A.src.cum[s]);   // stride | float offset in the stage slot
         }
         stab[k] = e;
     }
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) l1tp_tc_fwd_kernel(const TcArgs
             int s = 0;
             for (int q = 1; q < SE3_MAX_SEG; ++q)
                 if (q < A.src.nseg && vc >= A.src.cum[q]) s = q;
-            e = (s << 16) | (vc - A.src.cum[s]);
+            e = (A.sstride[s] << 20) | (A.soff[s] + vc - A.src.cum[s]);
         }
         vtab[k] = e;
     }
@@ -220,10 +221,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) l1tp_tc_fwd_kernel(const TcArgs
     }
     __syncthreads();
     for (int q = tid; q < 6 * A.nchS; q += TC_THREADS) {
+        // 16-byte fast path: four consecutive, 16-byte aligned columns of one segment
         const int e0 = stab[4 * q];
         int f = -1;
-        if (4 * q + 3 < A.ns && e0 >= 0 && (e0 & 3) == 0 && A.vec16[e0 >> 16] && stab[4 * q + 1] == e0 + 1 &&
-            stab[4 * q + 2] == e0 + 2 && stab[4 * q + 3] == e0 + 3)
+        if (4 * q + 3 < A.ns && e0 >= 0 && (e0 & 3) == 0 && stab[4 * q + 1] == e0 + 1 && stab[4 * q + 2] == e0 + 2 &&
+            stab[4 * q + 3] == e0 + 3)
             f = e0;
         sq[q] = f;
     }
@@ -370,10 +372,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) l1tp_tc_fwd_kernel(const TcArgs
             if (lane == 0) tc_commit(BAR(B_ACC_FULL + b));
             __syncwarp();
         }
-    } else if (warp >= 4 && warp < 4 + NBUILD_WARPS) {
+    } else if (warp >= BUILD_W0 && warp < BUILD_W0 + NBUILD_WARPS) {
         // ================= builders
-        const int bw = warp - 4;
-        const int r16 = lane & 15, khalf = lane >> 4;
+        const int bw = warp - BUILD_W0;
+        const int row = (bw / 3) * 16 + (lane & 15), kc = (bw % 3) * 2 + (lane >> 4);
+        const int o = (((row >> 3) * (KC / 4) + kc) << 7) + ((row & 7) << 4);  // byte offset inside a chunk half
         int it = 0;
         long long g0 = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it, g0 += A.NCH) {
@@ -386,27 +389,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) l1tp_tc_fwd_kernel(const TcArgs
                 const int aslot = (int)(g % A.nslot);
                 mbar_wait(BAR(B_SLOT_EMPTY + aslot), ((uint32_t)(g / A.nslot) & 1) ^ 1);
                 unsigned char* ahi = smraw + A.o_a + aslot * SLOT_BYTES;
-                for (int t = bw; t < 12; t += NBUILD_WARPS) {
-                    const int rg = t / 3, kp = t - rg * 3;
-                    const int row = rg * 16 + r16, kc = kp * 2 + khalf;
+                {
                     const int q = 6 * c + kc;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 v;
                     const int f = sq[q];
                     if (f >= 0) {
-                        const int s = f >> 16;
-                        v = *reinterpret_cast<const float4*>(st + A.soff[s] + row * A.sstride[s] + (f & 0xffff));
+                        v = *reinterpret_cast<const float4*>(st + (f & 0xfffff) + row * (f >> 20));
                     } else {
                         float e[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const int ee = stab[4 * q + j];
-                            e[j] = ee >= 0 ? st[A.soff[ee >> 16] + row * A.sstride[ee >> 16] + (ee & 0xffff)] : 0.0f;
+                            e[j] = ee >= 0 ? st[(ee & 0xfffff) + row * (ee >> 20)] : 0.0f;
                         }
                         v = make_float4(e[0], e[1], e[2], e[3]);
                     }
                     float4 h, l;
                     split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-                    const int o = (((row >> 3) * (KC / 4) + kc) << 7) + ((row & 7) << 4);
                     *reinterpret_cast<float4*>(ahi + o) = h;
                     *reinterpret_cast<float4*>(ahi + SLOT_HALF + o) = l;
                 }
@@ -425,9 +424,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) l1tp_tc_fwd_kernel(const TcArgs
                     mbar_wait(BAR(B_SLOT_EMPTY + aslot), ((uint32_t)(gu / A.nslot) & 1) ^ 1);
                     sl[u] = smraw + A.o_a + aslot * SLOT_BYTES;
                 }
-                for (int t = bw; t < 12; t += NBUILD_WARPS) {
-                    const int rg = t / 3, kp = t - rg * 3;
-                    const int row = rg * 16 + r16, kc = kp * 2 + khalf;
+                {
                     const float4 y = *reinterpret_cast<const float4*>(st + A.in2off + row * 4);
                     const float sy0 = C3f * y.x;
                     float d[4], a0[4], a1[4], a2[4];
@@ -437,13 +434,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) l1tp_tc_fwd_kernel(const TcArgs
                         const int ee = kd < A.K2 ? vtab[kd] : -1;
                         float vx = 0.f, vy = 0.f, vz = 0.f;
                         if (ee >= 0) {
-                            const float* p = st + A.soff[ee >> 16] + row * A.sstride[ee >> 16] + (ee & 0xffff);
+                            const float* p = st + (ee & 0xfffff) + row * (ee >> 20);
                             vx = p[0]; vy = p[1]; vz = p[2];
                         }
                         d[j] = C3f * (vx * y.y + vy * y.z + vz * y.w);
                         a0[j] = sy0 * vx; a1[j] = sy0 * vy; a2[j] = sy0 * vz;
                     }
-                    const int o = (((row >> 3) * (KC / 4) + kc) << 7) + ((row & 7) << 4);
                     float4 h, l;
 #define SE3_PUT(arr, base)                                                                                   \
     split_tf32(arr[0], h.x, l.x); split_tf32(arr[1], h.y, l.y); split_tf32(arr[2], h.z, l.z);                \
@@ -466,14 +462,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) l1tp_tc_fwd_kernel(const TcArgs
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(B_STAGE_EMPTY + slot));
         }
-    } else if (warp >= 8) {
+    } else if (warp >= EPI_W0) {
         // ================= epilogue (8 warps).  Warp w reads TMEM lanes 32(w%4)..; rows 16(w%4)..+15 live in its
         // lanes 0..15.  Warps 8-11 convert the l=0 accumulators, warps 12-15 the l=1 ones, into the raw tile;
         // then all 256 threads finish: coalesced raw store (+residual), gate -> post store / segment sum.
         const int e = warp & 3;
-        const int h = (warp - 8) >> 2;
-        const int ew = warp - 8;           // 0..7
-        const int et = tid - 8 * 32;       // 0..255
+        const int h = (warp - EPI_W0) >> 2;
+        const int ew = warp - EPI_W0;      // 0..7
+        const int et = tid - EPI_W0 * 32;  // 0..255
         const bool rowlane = lane < 16;
         const int row = 16 * e + (lane & 15);
         float* otile = reinterpret_cast<float*>(smraw + A.o_out);

@@ -11,6 +11,7 @@ from typing import Optional
 import numpy as np
 import torch
 
+from .dist import allreduce_mean_, flatten_grads
 from .octree import build_octree_graph
 
 
@@ -56,11 +57,7 @@ class TrainStep:
         self.leaf_size = leaf_size
         self.distributed = distributed
         params = [p for p in model.parameters()]
-        self.flat_grad = torch.zeros(sum(p.numel() for p in params), device=params[0].device, dtype=torch.float32)
-        o = 0
-        for p in params:
-            p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
-            o += p.numel()
+        self.flat_grad = flatten_grads(params)
         self.opt = torch.optim.Adam(params, lr=lr, fused=True)
         self._pin = None
         self.last_graph = None
@@ -76,9 +73,7 @@ class TrainStep:
         loss = (out[:n] - tgt).square().mean()
         loss.backward()
         if self.distributed:
-            import torch.distributed as dist
-            dist.all_reduce(self.flat_grad)
-            self.flat_grad.div_(dist.get_world_size())
+            allreduce_mean_(self.flat_grad)
         self.opt.step()
         return loss.detach()
 

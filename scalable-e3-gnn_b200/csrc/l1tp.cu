@@ -733,7 +733,7 @@ __global__ void __launch_bounds__(NT) l1tp_bwd_kernel(const PlanL P, const BwdK 
         const int nvalid = (int)min((long long)TR, R - row0);
         load_rows(K.src, K.in2, row0, R, TR, rowoff, Yt);
         __syncthreads();
-        build_features(P, K.src, sm, off_az, off_av, tab, rowoff, Yt, row0, R);
+        if (do_gw) build_features(P, K.src, sm, off_az, off_av, tab, rowoff, Yt, row0, R);  // only gW needs A tiles
 
         // ---- cotangent of the raw TP output -> g tile (aliases the input-gradient tile)
         const int dout = P.d_out;
@@ -1089,6 +1089,10 @@ struct se3_l1tp_plan {
     int t_in[4], t_out[4];
 };
 
+int se3_l1tp_tc_try_backward_w(const int n[4], const int m[4], const int t_in[4], const int t_out[4], int ntab,
+                               const int* d_tab, const se3_l1tp_bwd_args* a, const se3::RowSrc& src, const se3::EpiL& epi,
+                               float* partials, int wtot, int gw_z_off, int gw_v_off, int max_grid, cudaStream_t st,
+                               int* grid_out, bool* launched);
 int se3_l1tp_tc_try_forward(const int n[4], const int m[4], const int t_in[4], const int t_out[4], int ntab,
                             const int* d_tab, const se3_l1tp_fwd_args* a, const se3::RowSrc& src, const se3::EpiL& epi,
                             cudaStream_t st, bool* launched);
@@ -1343,23 +1347,35 @@ extern "C" int se3_l1tp_backward(se3_l1tp_plan* p, const se3_l1tp_bwd_args* a, v
     K.raw = a->raw; K.gout = a->gout; K.gout_idx = a->gout_idx; K.tab = p->d_tab;
     const long long ntiles = (a->rows + p->L.TR - 1) / p->L.TR;
     const int grid = (int)std::min<long long>(ntiles, (long long)num_sms() * p->occ_bwd);
+    int red_blocks = grid;
+    bool tcw = false;
     if (want_gw) {
-        const size_t need = (size_t)grid * p->L.wtot;
+        const size_t need = (size_t)std::max(grid, num_sms()) * p->L.wtot;
         if (need > p->partial_cap) {
             if (p->d_partials) SE3_CUDA_TRY(cudaFree(p->d_partials));
             p->d_partials = nullptr; p->partial_cap = 0;
-            const size_t cap = (size_t)num_sms() * p->occ_bwd * p->L.wtot;
+            const size_t cap = (size_t)num_sms() * std::max(1, p->occ_bwd) * p->L.wtot;
             SE3_CUDA_TRY(cudaMalloc(&p->d_partials, sizeof(float) * cap));
             p->partial_cap = cap;
         }
-        K.partials = p->d_partials;
+        // weight gradients on the tensor cores (accumulators resident in TMEM) when eligible
+        int tc_grid = 0;
+        rc = se3_l1tp_tc_try_backward_w(p->n, p->m, p->t_in, p->t_out, p->L.ntab, p->d_tab, a, K.src, K.epi,
+                                        p->d_partials, p->L.wtot, p->w_off[0], p->w_off[3], num_sms(), st, &tc_grid, &tcw);
+        if (rc) return rc;
+        if (tcw) red_blocks = tc_grid;
+        else K.partials = p->d_partials;
     }
-    if (p->maxwj == 2) l1tp_bwd_kernel<2><<<grid, NT, p->L.smem_bwd, st>>>(p->L, K);
-    else l1tp_bwd_kernel<4><<<grid, NT, p->L.smem_bwd, st>>>(p->L, K);
-    SE3_LAUNCHED();
+    bool need_in = false;
+    for (int s = 0; s < a->nseg; ++s) need_in |= (K.gseg[s] != nullptr && K.gmode[s] != SE3_GRAD_NONE);
+    if (need_in || K.partials) {
+        if (p->maxwj == 2) l1tp_bwd_kernel<2><<<grid, NT, p->L.smem_bwd, st>>>(p->L, K);
+        else l1tp_bwd_kernel<4><<<grid, NT, p->L.smem_bwd, st>>>(p->L, K);
+        SE3_LAUNCHED();
+    }
     if (want_gw) {
         ReduceK Rk;
-        Rk.partials = p->d_partials; Rk.nblocks = grid; Rk.wtot = p->L.wtot;
+        Rk.partials = p->d_partials; Rk.nblocks = red_blocks; Rk.wtot = p->L.wtot;
         for (int s = 0; s < 4; ++s) { Rk.gw[s] = a->gw[s]; Rk.off[s] = p->w_off[s]; Rk.cnt[s] = p->w_cnt[s]; }
         l1tp_reduce_gw_kernel<<<(p->L.wtot + 255) / 256, 256, 0, st>>>(Rk);
         SE3_LAUNCHED();

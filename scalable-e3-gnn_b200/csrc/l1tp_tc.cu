@@ -22,7 +22,7 @@
 //   out0[m] = norm (Y0 P[m] + Q[m]),   out1[m][c] = norm (c3 Y1[c] P[N2+m] + Tc[m])
 #include <algorithm>
 
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace se3 {
 
@@ -34,7 +34,6 @@ static constexpr int SLOT_BYTES = 2 * SLOT_HALF;
 static constexpr int NBUILD_WARPS = 12;  // one 16-row x 2-K-chunk task per warp and chunk
 static constexpr int NEPI_WARPS = 8;
 static constexpr int BUILD_W0 = 4, EPI_W0 = 16;
-static constexpr float C3f = 0.57735026918962576451f;
 
 struct TcArgs {
     long long rows;
@@ -60,92 +59,6 @@ struct TcArgs {
     // shared memory byte offsets
     int o_b1, o_b2, o_b3, o_a, o_stage, o_out, o_post, o_tab, o_norm, o_sq, o_bar;
 };
-
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
-    const int sz = valid ? 16 : 0;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, bool valid) {
-    const int sz = valid ? 4 : 0;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n"
-        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
-        : "memory");
-}
-__device__ __forceinline__ void tc_ld8(uint32_t taddr, float (&v)[8]) {
-    uint32_t r[8];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr));
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, no-swizzle canonical layout: 8-row x 16-byte core matrices; LBO = 128 B between the two K-chunks
-// of one MMA, SBO = bytes between consecutive 8-row groups (cute/arch/mma_sm100_desc.hpp, version 1).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes) {
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((128u >> 4) & 0x3FFF) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
-}
-// instruction descriptor: D=f32, A=B=tf32, both K-major, M=64
-__device__ __forceinline__ uint32_t make_idesc(int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-}
-
-__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-    hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
-    lo = x - hi;
-}
-
-// sigmoid with two MUFU ops (ex2.approx, rcp.approx: ~1e-7 relative, far inside the 1e-5 parity budget)
-__device__ __forceinline__ float sigm(float x) {
-    float e, r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * x));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
-    return r;
-}
-
-// byte offset of element (row/col n, k) inside a canonical tile with KQ = K/4 sixteen-byte chunks per row
-__device__ __forceinline__ int canon_off(int n, int k, int KQ) { return (((n >> 3) * KQ + (k >> 2)) << 7) + ((n & 7) << 4) + ((k & 3) << 2); }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) l1tp_tc_fwd_kernel(const TcArgs A) {
     extern __shared__ __align__(1024) unsigned char smraw[];
@@ -633,13 +546,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) l1tp_tc_fwd_kernel(const TcArgs
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
     }
-}
-
-static int tc_stage_stride(int w) {
-    // >= w, multiple of 4 floats, == 4 (mod 32): conflict-free LDS.128 for 8 consecutive rows
-    int s = ((w + 3) & ~3);
-    while ((s & 31) != 4) s += 4;
-    return s;
 }
 
 }  // namespace se3

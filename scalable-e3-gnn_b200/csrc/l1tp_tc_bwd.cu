@@ -1,0 +1,596 @@
+// Tensor-core (tcgen05 / TMEM, 3xTF32) backward of the fused l<=1 tensor-product layer, SEGNN case
+// (inputs a x0e + b x1o, outputs c x0e + d x1o).  Two kernels share the producer and the H-tile builders:
+//
+//  (W) l1tp_tc_bwdw_kernel — weight gradients.  The reduction runs over rows, so rows are the MMA K dimension:
+//      feature tiles A[row][feature] and cotangent tiles H[row][channel] (both stored as 8-row x 16-byte core
+//      matrices) are used as MN-major operands, and the four accumulators
+//          gWZ_s += (S)^T (Y0 HZ)   gWV_s += S^T HG   gWZ_d += Dd^T HZ   gWV_v += sum_c AVc^T HVc
+//      stay resident in TMEM across ALL tiles of the CTA (128 columns); they are read once at the end and written
+//      as per-CTA partials that the deterministic reduction kernel of l1tp.cu sums.
+//  (I) l1tp_tc_bwdi_kernel — input gradients.  Per 64-row tile
+//          gS = [Y0 HZ | HG] . [WZ_s | WV_s]^T     gD = HZ . WZ_d^T     gTc = HVc . WV_v^T
+//      then g_s = gS, g_v[c] = c3 Y1[c] gD + c3 Y0 gTc, scattered per segment (store / red.v4 / run-length sorted).
+//
+// H tiles (gate VJP fused): HZ = norm * g_raw(l=0), HVc = norm * g_raw(l=1)[c], HG = c3 sum_c Y1[c] HVc.
+#include <algorithm>
+
+#include "tc_common.cuh"
+
+namespace se3 {
+
+static constexpr int TBW_THREADS = 512;  // warps: 0,2 producers | 1 MMA | 4-15 builders (4-7 also final epilogue)
+static constexpr int TMB = 32;           // rows per tile of the weight-gradient kernel (= 4 MMA K-steps)
+static constexpr int BW_BUILD_W0 = 4, BW_NBUILD = 12;
+
+struct TcBwdArgs {
+    long long rows;
+    RowSrc src;
+    const float* in2;
+    const float* wz;
+    const float* wv;
+    const float* nz;
+    const float* nv;
+    EpiL epi;
+    const float* raw;
+    const float* gout;
+    const int32_t* gout_idx;
+    float* gseg[SE3_MAX_SEG];
+    int gmode[SE3_MAX_SEG];
+    float* partials;
+    int wtot, gw_z_off, gw_v_off;
+    const int* tab;
+    int ntab;
+    int ns, nd, mz, mv, NSG, NDG, NSG8, NDG8, N2, N3, MS;  // MS: MMA M of the S operand (64 or 128)
+    int t_s, t_d, t_oz, t_ov, d_out, gwidth;
+    int sstride[SE3_MAX_SEG], soff[SE3_MAX_SEG], vec16[SE3_MAX_SEG], swidth[SE3_MAX_SEG];
+    int in2off, rawoff, rawstride, goff, gstride, slot_floats;
+    int graw_vec16, g_vec16, tmem_cols;
+    // shared memory byte offsets
+    int o_as, o_ad, o_av, o_t1, o_t2, o_t3, o_stage, o_tab, o_norm, o_tbl, o_bar;
+    int rg_s, rg_d, rg1, rg2, rg3;           // bytes per 8-row group of each tile
+    int sz_as, sz_ad, sz_t1, sz_t2, sz_t3;   // bytes of one (hi or lo) tile
+};
+
+// ---- cotangent (H) tiles for `nrows` rows of one stage slot: warp-task = 16 rows x 2 channel groups
+//   T1 = [Y0*HZ | HG]   T2 = HZ   T3[c] = HVc      element (r, ch) at (r>>3)*RG + (ch>>2)*128 + (r&7)*16 + (ch&3)*4
+__device__ __forceinline__ void put4(unsigned char* tile, int half, int off, const float (&v)[4]) {
+    float4 h, l;
+    split_tf32(v[0], h.x, l.x); split_tf32(v[1], h.y, l.y); split_tf32(v[2], h.z, l.z); split_tf32(v[3], h.w, l.w);
+    *reinterpret_cast<float4*>(tile + off) = h;
+    *reinterpret_cast<float4*>(tile + half + off) = l;
+}
+
+// cotangent of one l=0 output channel m (gate VJP fused), times its norm
+__device__ __forceinline__ float h_z(const TcBwdArgs& A, const float* rawr, const float* gr, const int* oz, const int* ov,
+                                     const float* nz, int m) {
+    if (m >= A.mz) return 0.0f;
+    const int rc = oz[m];
+    float h;
+    if (A.epi.mode != SE3_EPI_GATE) h = gr[rc];
+    else if (m < A.epi.ns_g) {
+        const float x = rawr[rc], s = sigm(x);
+        h = gr[m] * A.epi.cs * s * (1.0f + x * (1.0f - s));
+    } else {
+        const int v = m - A.epi.ns_g, vc = ov[v];
+        const float s = sigm(rawr[rc]);
+        const float* gg = gr + A.epi.ns_g + 3 * v;
+        h = A.epi.cg * s * (1.0f - s) * (gg[0] * rawr[vc] + gg[1] * rawr[vc + 1] + gg[2] * rawr[vc + 2]);
+    }
+    return h * nz[m];
+}
+// cotangent of the three components of l=1 output channel v
+__device__ __forceinline__ void h_v(const TcBwdArgs& A, const float* rawr, const float* gr, const int* oz, const int* ov,
+                                    const float* nv, int v, float& a, float& b, float& c) {
+    a = b = c = 0.0f;
+    if (v >= A.mv) return;
+    if (A.epi.mode != SE3_EPI_GATE) {
+        const float* gg = gr + ov[v];
+        a = gg[0]; b = gg[1]; c = gg[2];
+    } else {
+        const float s = A.epi.cg * sigm(rawr[oz[A.epi.ns_g + v]]);
+        const float* gg = gr + A.epi.ns_g + 3 * v;
+        a = s * gg[0]; b = s * gg[1]; c = s * gg[2];
+    }
+    a *= nv[3 * v]; b *= nv[3 * v + 1]; c *= nv[3 * v + 2];
+}
+
+__device__ __forceinline__ void build_h_task(const TcBwdArgs& A, unsigned char* smraw, const float* st, const int* tab,
+                                             const float* norm, int rb, int gp, int lane) {
+    const int row = rb * 16 + (lane & 15);
+    const int g = gp * 2 + (lane >> 4);
+    const int nzg = A.N2 >> 2, nvg = A.N3 >> 2;
+    const bool gate = A.epi.mode == SE3_EPI_GATE;
+    const int nsg = A.epi.ns_g;
+    const float* rawr = st + A.rawoff + row * A.rawstride;
+    const float* gr = st + A.goff + row * A.gstride;
+    const float4 y = *reinterpret_cast<const float4*>(st + A.in2off + row * 4);
+    const float* nz = norm;
+    const float* nv = norm + A.mz;
+    const int* oz = tab + A.t_oz;
+    const int* ov = tab + A.t_ov;
+    if (g < nzg) {
+        float hz[4], hy[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int m = 4 * g + j;
+            float h = 0.0f;
+            if (m < A.mz) {
+                const int rc = oz[m];
+                if (!gate) h = gr[rc];
+                else if (m < nsg) {
+                    const float x = rawr[rc], s = sigm(x);
+                    h = gr[m] * A.epi.cs * s * (1.0f + x * (1.0f - s));
+                } else {
+                    const int v = m - nsg, vc = ov[v];
+                    const float s = sigm(rawr[rc]);
+                    const float* gg = gr + nsg + 3 * v;
+                    h = A.epi.cg * s * (1.0f - s) * (gg[0] * rawr[vc] + gg[1] * rawr[vc + 1] + gg[2] * rawr[vc + 2]);
+                }
+                h *= nz[m];
+            }
+            hz[j] = h;
+            hy[j] = y.x * h;
+        }
+        const int off2 = (row >> 3) * A.rg2 + (g << 7) + ((row & 7) << 4);
+        const int off1 = (row >> 3) * A.rg1 + (g << 7) + ((row & 7) << 4);
+        put4(smraw + A.o_t2, A.sz_t2, off2, hz);
+        put4(smraw + A.o_t1, A.sz_t1, off1, hy);
+    } else if (g < nzg + nvg) {
+        const int gv = g - nzg;
+        float h0[4], h1[4], h2[4], hg[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int v = 4 * gv + j;
+            float a = 0.f, b = 0.f, c = 0.f;
+            if (v < A.mv) {
+                if (!gate) {
+                    const float* gg = gr + ov[v];
+                    a = gg[0]; b = gg[1]; c = gg[2];
+                } else {
+                    const float s = A.epi.cg * sigm(rawr[oz[nsg + v]]);
+                    const float* gg = gr + nsg + 3 * v;
+                    a = s * gg[0]; b = s * gg[1]; c = s * gg[2];
+                }
+                a *= nv[3 * v]; b *= nv[3 * v + 1]; c *= nv[3 * v + 2];
+            }
+            h0[j] = a; h1[j] = b; h2[j] = c;
+            hg[j] = C3f * (y.y * a + y.z * b + y.w * c);
+        }
+        const int off3 = (row >> 3) * A.rg3 + (gv << 7) + ((row & 7) << 4);
+        put4(smraw + A.o_t3, A.sz_t3, off3, h0);
+        put4(smraw + A.o_t3 + 2 * A.sz_t3, A.sz_t3, off3, h1);
+        put4(smraw + A.o_t3 + 4 * A.sz_t3, A.sz_t3, off3, h2);
+        const int off1 = (row >> 3) * A.rg1 + ((nzg + gv) << 7) + ((row & 7) << 4);
+        put4(smraw + A.o_t1, A.sz_t1, off1, hg);
+    }
+}
+
+// producer: one row per lane; segments (if with_x), in2, raw (gate) and the cotangent row
+template <int ROWS>
+__device__ __forceinline__ void producer_loop(const TcBwdArgs& A, unsigned char* smraw, uint32_t bar_full0,
+                                              uint32_t bar_empty0, int prow, bool with_x, long long ntiles) {
+    const long long R = A.rows;
+    long long cur[SE3_MAX_SEG];
+    long long curg;
+    {
+        const long long gr = (long long)blockIdx.x * ROWS + prow;
+#pragma unroll
+        for (int s = 0; s < SE3_MAX_SEG; ++s)
+            cur[s] = (with_x && s < A.src.nseg && gr < R) ? (A.src.idx[s] ? (long long)A.src.idx[s][gr] : gr) : 0;
+        curg = gr < R ? (A.gout_idx ? (long long)A.gout_idx[gr] : gr) : 0;
+    }
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int slot = it & 1, use = it >> 1;
+        const long long gr = tile * ROWS + prow;
+        const bool valid = gr < R;
+        mbar_wait(bar_empty0 + 8 * slot, (use & 1) ^ 1);
+        const uint32_t sbase = smem_u32(smraw) + A.o_stage + (uint32_t)slot * A.slot_floats * 4;
+        if (with_x) {
+#pragma unroll
+            for (int s = 0; s < SE3_MAX_SEG; ++s) {
+                if (s >= A.src.nseg) break;
+                const float* srcp = A.src.base[s] + (valid ? cur[s] * A.src.ld[s] : 0);
+                const uint32_t dst = sbase + (A.soff[s] + prow * A.sstride[s]) * 4;
+                const int w = A.swidth[s];
+                if (A.vec16[s]) for (int c = 0; c < w; c += 4) cp_async16(dst + c * 4, srcp + c, valid);
+                else for (int c = 0; c < w; ++c) cp_async4(dst + c * 4, srcp + c, valid);
+            }
+        }
+        cp_async16(sbase + (A.in2off + prow * 4) * 4, A.in2 + (valid ? gr * 4 : 0), valid);
+        if (A.epi.mode == SE3_EPI_GATE) {
+            const float* srcp = A.raw + (valid ? gr * A.d_out : 0);
+            const uint32_t dst = sbase + (A.rawoff + prow * A.rawstride) * 4;
+            if (A.graw_vec16) for (int c = 0; c < A.d_out; c += 4) cp_async16(dst + c * 4, srcp + c, valid);
+            else for (int c = 0; c < A.d_out; c += 2) {
+                const int sz = valid ? 8 : 0;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst + c * 4), "l"(srcp + c), "r"(sz) : "memory");
+            }
+        }
+        {
+            const float* srcp = A.gout + (valid ? curg * A.gwidth : 0);
+            const uint32_t dst = sbase + (A.goff + prow * A.gstride) * 4;
+            if (A.g_vec16) for (int c = 0; c < A.gwidth; c += 4) cp_async16(dst + c * 4, srcp + c, valid);
+            else for (int c = 0; c < A.gwidth; ++c) cp_async4(dst + c * 4, srcp + c, valid);
+        }
+        cp_async_mbar_arrive_noinc(bar_full0 + 8 * slot);
+        const long long grn = (tile + gridDim.x) * ROWS + prow;
+#pragma unroll
+        for (int s = 0; s < SE3_MAX_SEG; ++s)
+            cur[s] = (with_x && s < A.src.nseg && grn < R) ? (A.src.idx[s] ? (long long)A.src.idx[s][grn] : grn) : 0;
+        curg = grn < R ? (A.gout_idx ? (long long)A.gout_idx[grn] : grn) : 0;
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
+// tables shared by both kernels: plan tables, norms, packed (stride<<20 | offset) stage addresses of every scalar /
+// vector channel
+__device__ __forceinline__ void setup_tables(const TcBwdArgs& A, unsigned char* smraw, int nthreads) {
+    int* tab = reinterpret_cast<int*>(smraw + A.o_tab);
+    float* norm = reinterpret_cast<float*>(smraw + A.o_norm);
+    int* stab = reinterpret_cast<int*>(smraw + A.o_tbl);
+    int* vtab = stab + 8 * A.NSG8;
+    const int tid = threadIdx.x;
+    for (int t = tid; t < A.ntab; t += nthreads) tab[t] = A.tab[t];
+    for (int t = tid; t < A.mz; t += nthreads) norm[t] = A.nz ? A.nz[t] : 1.0f;
+    for (int t = tid; t < 3 * A.mv; t += nthreads) norm[A.mz + t] = A.nv ? A.nv[t] : 1.0f;
+    __syncthreads();
+    for (int k = tid; k < 8 * A.NSG8; k += nthreads) {
+        int e = -1;
+        if (k < A.ns) {
+            const int vc = tab[A.t_s + k];
+            int s = 0;
+            for (int q = 1; q < SE3_MAX_SEG; ++q)
+                if (q < A.src.nseg && vc >= A.src.cum[q]) s = q;
+            e = (A.sstride[s] << 20) | (A.soff[s] + vc - A.src.cum[s]);
+        }
+        stab[k] = e;
+    }
+    for (int k = tid; k < 8 * A.NDG8; k += nthreads) {
+        int e = -1;
+        if (k < A.nd) {
+            const int vc = tab[A.t_d + k];
+            int s = 0;
+            for (int q = 1; q < SE3_MAX_SEG; ++q)
+                if (q < A.src.nseg && vc >= A.src.cum[q]) s = q;
+            e = (A.sstride[s] << 20) | (A.soff[s] + vc - A.src.cum[s]);
+        }
+        vtab[k] = e;
+    }
+}
+
+// ===================================================================== (W) weight-gradient kernel
+__global__ void __launch_bounds__(TBW_THREADS, 1) l1tp_tc_bwdw_kernel(const TcBwdArgs A) {
+    extern __shared__ __align__(1024) unsigned char smraw[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float* smf = reinterpret_cast<float*>(smraw);
+    const int* tab = reinterpret_cast<const int*>(smraw + A.o_tab);
+    const float* norm = reinterpret_cast<const float*>(smraw + A.o_norm);
+    const int* stab = reinterpret_cast<const int*>(smraw + A.o_tbl);
+    const int* vtab = stab + 8 * A.NSG8;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + A.o_bar);
+    const uint32_t bar0 = smem_u32(bars);
+    // barriers: 0,1 stage full | 2,3 stage empty | 4 set full | 5 set empty | 6 acc full
+    auto BAR = [&](int i) { return bar0 + 8u * i; };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(BAR(i), TMB);  // one producer lane per row
+            mbar_init(BAR(2 + i), BW_NBUILD);
+        }
+        mbar_init(BAR(4), BW_NBUILD);
+        mbar_init(BAR(5), 1);
+        mbar_init(BAR(6), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    setup_tables(A, smraw, TBW_THREADS);
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(A.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const long long R = A.rows;
+    const long long ntiles = (R + TMB - 1) / TMB;
+    // TMEM columns
+    const int cD1 = 0, cD2 = A.N2, cD3 = A.N2 + A.N3, cD4 = 2 * A.N2 + A.N3;
+
+    if (warp == 0) {
+        producer_loop<TMB>(A, smraw, BAR(0), BAR(2), lane, true, ntiles);
+    } else if (warp == 1) {
+        // ---------------- MMA issuer: per tile 4 K-steps (8 rows each) x {S.HZY, S.HG, Dd.HZ, AVc.HVc} x 3xTF32.
+        // All operands are K-major with K = rows: transposed tiles [channel/feature][row], 8-channel groups of
+        // GS = (TMB/4)*128 bytes, the two 16-byte K-chunks of one MMA 128 bytes apart.
+        const uint32_t sb = smem_u32(smraw);
+        const uint32_t GS = (TMB / 4) * 128;
+        const uint32_t idS1 = make_idesc_ex(A.MS, A.N2, 0, 0), idS2 = make_idesc_ex(A.MS, A.N3, 0, 0);
+        const uint32_t idD = make_idesc_ex(64, A.N2, 0, 0), idV = make_idesc_ex(64, A.N3, 0, 0);
+        int it = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            mbar_wait(BAR(4), it & 1);
+            tc_fence_after();
+            if (lane == 0) {
+#pragma unroll 1
+                for (int ks = 0; ks < TMB / 8; ++ks) {
+                    const uint32_t acc0 = (it == 0 && ks == 0) ? 0u : 1u;
+                    const uint32_t ko = ks * 256;
+                    const uint32_t aS = sb + A.o_as + ko, aD = sb + A.o_ad + ko;
+                    const uint32_t b1 = sb + A.o_t1 + ko, b2 = sb + A.o_t2 + ko;
+                    const uint32_t bG = b1 + (A.N2 >> 3) * GS;
+#define SE3_MMA3(D, AH, ASZ, BH, BSZ, ID, FIRST)                                                         \
+    tc_mma_tf32(tmem_base + (D), make_desc((AH), GS), make_desc((BH), GS), (ID), (FIRST));                 \
+    tc_mma_tf32(tmem_base + (D), make_desc((AH), GS), make_desc((BH) + (BSZ), GS), (ID), 1u);              \
+    tc_mma_tf32(tmem_base + (D), make_desc((AH) + (ASZ), GS), make_desc((BH), GS), (ID), 1u);
+                    SE3_MMA3(cD1, aS, A.sz_as, b1, A.sz_t1, idS1, acc0)
+                    SE3_MMA3(cD2, aS, A.sz_as, bG, A.sz_t1, idS2, acc0)
+                    SE3_MMA3(cD3, aD, A.sz_ad, b2, A.sz_t2, idD, acc0)
+#pragma unroll 1
+                    for (int c = 0; c < 3; ++c) {
+                        const uint32_t aV = sb + A.o_av + c * 2 * A.sz_ad + ko;
+                        const uint32_t b3 = sb + A.o_t3 + c * 2 * A.sz_t3 + ko;
+                        SE3_MMA3(cD4, aV, A.sz_ad, b3, A.sz_t3, idV, (c == 0 ? acc0 : 1u))
+                    }
+#undef SE3_MMA3
+                }
+                tc_commit(BAR(5));
+            }
+            __syncwarp();
+        }
+        if (lane == 0) tc_commit(BAR(6));
+        __syncwarp();
+    } else if (warp >= BW_BUILD_W0) {
+        // ---------------- builders: transposed feature (S, Dd, AVc) and cotangent (T1, T2, T3c) tiles for 32 rows.
+        // warp-task = one 8-channel group x 16 rows: lane = (channel f8 = lane & 7, row quad q = lane >> 3); a thread
+        // gathers its channel for 4 consecutive rows and writes one 16-byte K-chunk (hi and lo).
+        const int bw = warp - BW_BUILD_W0;
+        const int f8 = lane & 7, q = lane >> 3;
+        const int nrb = TMB / 16;
+        const int nzg8 = A.N2 >> 3, nvg8 = A.N3 >> 3;
+        const int ntask = nrb * (A.NSG8 + A.NDG8 + nzg8 + nvg8);
+        const int GS = (TMB / 4) * 128;
+        const int* oz = tab + A.t_oz;
+        const int* ov = tab + A.t_ov;
+        const float* nz = norm;
+        const float* nv = norm + A.mz;
+        int it = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int slot = it & 1, use = it >> 1;
+            mbar_wait(BAR(slot), use & 1);                  // stage full
+            mbar_wait(BAR(5), (it & 1) ^ 1);                // tile set free (MMAs of the previous tile done)
+            const float* st = smf + (A.o_stage >> 2) + (size_t)slot * A.slot_floats;
+            for (int t = bw; t < ntask; t += BW_NBUILD) {
+                const int rb = t % nrb;
+                int g = t / nrb;
+                const int r0 = rb * 16 + q * 4;                       // first of this thread's 4 rows
+                const int off = g * GS + ((rb * 4 + q) << 7) + (f8 << 4);  // (group, K-chunk, channel) -- g rebased below
+                if (g < A.NSG8) {
+                    const int ee = stab[8 * g + f8];
+                    float v[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) v[i] = ee >= 0 ? st[(ee & 0xfffff) + (r0 + i) * (ee >> 20)] : 0.0f;
+                    put4(smraw + A.o_as, A.sz_as, off, v);
+                } else if (g < A.NSG8 + A.NDG8) {
+                    g -= A.NSG8;
+                    const int o2 = g * GS + ((rb * 4 + q) << 7) + (f8 << 4);
+                    const int ee = vtab[8 * g + f8];
+                    float d[4], a0[4], a1[4], a2[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 y = *reinterpret_cast<const float4*>(st + A.in2off + (r0 + i) * 4);
+                        float vx = 0.f, vy = 0.f, vz = 0.f;
+                        if (ee >= 0) {
+                            const float* p = st + (ee & 0xfffff) + (r0 + i) * (ee >> 20);
+                            vx = p[0]; vy = p[1]; vz = p[2];
+                        }
+                        const float sy0 = C3f * y.x;
+                        d[i] = C3f * (vx * y.y + vy * y.z + vz * y.w);
+                        a0[i] = sy0 * vx; a1[i] = sy0 * vy; a2[i] = sy0 * vz;
+                    }
+                    put4(smraw + A.o_ad, A.sz_ad, o2, d);
+                    put4(smraw + A.o_av, A.sz_ad, o2, a0);
+                    put4(smraw + A.o_av + 2 * A.sz_ad, A.sz_ad, o2, a1);
+                    put4(smraw + A.o_av + 4 * A.sz_ad, A.sz_ad, o2, a2);
+                } else if (g < A.NSG8 + A.NDG8 + nzg8) {
+                    g -= A.NSG8 + A.NDG8;
+                    const int o2 = g * GS + ((rb * 4 + q) << 7) + (f8 << 4);
+                    const int m = 8 * g + f8;
+                    float hz[4], hy[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int row = r0 + i;
+                        hz[i] = h_z(A, st + A.rawoff + row * A.rawstride, st + A.goff + row * A.gstride, oz, ov, nz, m);
+                        hy[i] = st[A.in2off + row * 4] * hz[i];
+                    }
+                    put4(smraw + A.o_t2, A.sz_t2, o2, hz);
+                    put4(smraw + A.o_t1, A.sz_t1, o2, hy);
+                } else {
+                    g -= A.NSG8 + A.NDG8 + nzg8;
+                    const int o2 = g * GS + ((rb * 4 + q) << 7) + (f8 << 4);
+                    const int v = 8 * g + f8;
+                    float h0[4], h1[4], h2[4], hg[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int row = r0 + i;
+                        const float4 y = *reinterpret_cast<const float4*>(st + A.in2off + row * 4);
+                        h_v(A, st + A.rawoff + row * A.rawstride, st + A.goff + row * A.gstride, oz, ov, nv, v, h0[i], h1[i], h2[i]);
+                        hg[i] = C3f * (y.y * h0[i] + y.z * h1[i] + y.w * h2[i]);
+                    }
+                    put4(smraw + A.o_t3, A.sz_t3, o2, h0);
+                    put4(smraw + A.o_t3 + 2 * A.sz_t3, A.sz_t3, o2, h1);
+                    put4(smraw + A.o_t3 + 4 * A.sz_t3, A.sz_t3, o2, h2);
+                    put4(smraw + A.o_t1, A.sz_t1, (nzg8 + g) * GS + ((rb * 4 + q) << 7) + (f8 << 4), hg);
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(BAR(4));
+                mbar_arrive(BAR(2 + slot));
+            }
+        }
+        // ---------------- final epilogue (warps 4-7): TMEM accumulators -> per-CTA partials
+        if (bw < 4) {
+            const int e = warp & 3;
+            mbar_wait(BAR(6), 0);
+            tc_fence_after();
+            float* part = A.partials + (long long)blockIdx.x * A.wtot;
+            const uint32_t tq = tmem_base + ((uint32_t)(32 * e) << 16);
+            // rows of the S operand
+            const int ks = A.MS == 128 ? 32 * e + lane : 16 * e + (lane & 15);
+            const bool ks_ok = (A.MS == 128 || lane < 16) && ks < A.ns;
+            const int kd = 16 * e + (lane & 15);
+            const bool kd_ok = lane < 16 && kd < A.nd;
+            for (int m0 = 0; m0 < A.N2; m0 += 8) {
+                float a[8], b[8];
+                tc_ld8(tq + cD1 + m0, a);
+                tc_ld8(tq + cD3 + m0, b);
+                tc_wait_ld();
+#ifdef SE3_TC_DEBUG
+                if (blockIdx.x == 0 && m0 == 0 && (lane < 3 || lane == 16))
+                    printf("dbg e=%d lane=%d D1: %g %g %g %g | D3: %g %g %g %g | A_S[0..3]=%g %g %g %g T1=%g %g T2=%g %g\n", e, lane, a[0], a[1], a[2],
+                           a[3], b[0], b[1], b[2], b[3], ((float*)(smraw + A.o_as))[0], ((float*)(smraw + A.o_as))[1],
+                           ((float*)(smraw + A.o_as))[4], ((float*)(smraw + A.o_as))[5], ((float*)(smraw + A.o_t1))[0],
+                           ((float*)(smraw + A.o_t1))[1], ((float*)(smraw + A.o_t2))[0], ((float*)(smraw + A.o_t2))[1]);
+#endif
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int m = m0 + j;
+                    if (m < A.mz) {
+                        if (ks_ok) part[A.gw_z_off + (long long)ks * A.mz + m] = a[j];
+                        if (kd_ok) part[A.gw_z_off + (long long)(A.ns + kd) * A.mz + m] = b[j];
+                    }
+                }
+            }
+            for (int m0 = 0; m0 < A.N3; m0 += 8) {
+                float a[8], b[8];
+                tc_ld8(tq + cD2 + m0, a);
+                tc_ld8(tq + cD4 + m0, b);
+                tc_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int m = m0 + j;
+                    if (m < A.mv) {
+                        if (ks_ok) part[A.gw_v_off + (long long)ks * A.mv + m] = a[j];
+                        if (kd_ok) part[A.gw_v_off + (long long)(A.ns + kd) * A.mv + m] = b[j];
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(A.tmem_cols) : "memory");
+    }
+}
+
+}  // namespace se3
+
+using namespace se3;
+
+static int fill_common(TcBwdArgs& A, const int n[4], const int m[4], const int t_in[4], const int t_out[4], int ntab,
+                       const int* d_tab, const se3_l1tp_bwd_args* a, const RowSrc& src, const EpiL& epi, int rows_per_tile,
+                       bool with_x) {
+    if (n[1] || n[2] || m[1] || m[2]) return 1;
+    const int ns = n[0], nd = n[3], mz = m[0], mv = m[3];
+    if (ns < 1 || nd < 1 || mz < 1 || mv < 1) return 1;
+    memset(&A, 0, sizeof(A));
+    A.ns = ns; A.nd = nd; A.mz = mz; A.mv = mv;
+    A.NSG = (ns + 3) >> 2; A.NDG = (nd + 3) >> 2;
+    A.NSG8 = (ns + 7) >> 3; A.NDG8 = (nd + 7) >> 3;
+    A.N2 = (mz + 7) & ~7; A.N3 = (mv + 7) & ~7;
+    if (A.NSG8 > 16 || A.NDG8 > 8 || A.N2 + A.N3 > 256) return 1;
+    A.MS = A.NSG8 > 8 ? 128 : 64;
+    A.rows = a->rows; A.src = src; A.in2 = a->in2; A.wz = a->w[0]; A.wv = a->w[3]; A.nz = a->norm[0]; A.nv = a->norm[3];
+    A.epi = epi; A.raw = a->raw; A.gout = a->gout; A.gout_idx = a->gout_idx; A.tab = d_tab; A.ntab = ntab;
+    A.t_s = t_in[0]; A.t_d = t_in[3]; A.t_oz = t_out[0]; A.t_ov = t_out[3];
+    A.d_out = mz + 3 * mv;
+    A.gwidth = epi.d_post;
+    if (((uintptr_t)a->in2 & 15) != 0) return 1;
+    int off = 0;
+    for (int s = 0; s < src.nseg; ++s) {
+        const int w = src.cum[s + 1] - src.cum[s];
+        A.swidth[s] = w;
+        A.sstride[s] = tc_stage_stride(w);
+        A.vec16[s] = ((w & 3) == 0 && (src.ld[s] & 3) == 0 && ((uintptr_t)src.base[s] & 15) == 0) ? 1 : 0;
+        if (with_x) {
+            if (!A.vec16[s] && w > 16) return 1;
+            A.soff[s] = off;
+            off += rows_per_tile * A.sstride[s];
+        }
+    }
+    A.in2off = off; off += rows_per_tile * 4;
+    A.rawstride = tc_stage_stride(A.d_out);
+    A.rawoff = off;
+    if (epi.mode == SE3_EPI_GATE) {
+        if ((A.d_out & 1) || ((uintptr_t)a->raw & 7)) return 1;
+        A.graw_vec16 = ((A.d_out & 3) == 0 && ((uintptr_t)a->raw & 15) == 0) ? 1 : 0;
+        off += rows_per_tile * A.rawstride;
+    }
+    A.gstride = tc_stage_stride(A.gwidth);
+    A.goff = off; off += rows_per_tile * A.gstride;
+    A.g_vec16 = ((A.gwidth & 3) == 0 && ((uintptr_t)a->gout & 15) == 0) ? 1 : 0;
+    if (!A.g_vec16 && A.gwidth > 16) return 1;
+    A.slot_floats = off;
+    return 0;
+}
+
+// weight gradients on the tensor cores; returns launched=false when the configuration is not eligible
+int se3_l1tp_tc_try_backward_w(const int n[4], const int m[4], const int t_in[4], const int t_out[4], int ntab,
+                               const int* d_tab, const se3_l1tp_bwd_args* a, const RowSrc& src, const EpiL& epi,
+                               float* partials, int wtot, int gw_z_off, int gw_v_off, int max_grid, cudaStream_t st,
+                               int* grid_out, bool* launched) {
+    *launched = false;
+    static int disabled = -1;
+    if (disabled < 0) {
+        const char* e = getenv("SE3_DISABLE_TC");
+        disabled = (e && (e[0] == '1' || e[0] == '2')) ? 1 : 0;
+    }
+    if (disabled) return SE3_OK;
+    TcBwdArgs A;
+    if (fill_common(A, n, m, t_in, t_out, ntab, d_tab, a, src, epi, TMB, true)) return SE3_OK;
+    A.partials = partials; A.wtot = wtot; A.gw_z_off = gw_z_off; A.gw_v_off = gw_v_off;
+    A.tmem_cols = 32;
+    while (A.tmem_cols < 2 * A.N2 + 2 * A.N3) A.tmem_cols <<= 1;
+    if (A.tmem_cols > 512) return SE3_OK;
+    auto al = [](int x, int q) { return (x + q - 1) / q * q; };
+    const int GS = (TMB / 4) * 128;  // bytes of one 8-channel group of a transposed tile
+    A.sz_as = A.NSG8 * GS; A.sz_ad = A.NDG8 * GS;
+    A.sz_t1 = ((A.N2 + A.N3) >> 3) * GS; A.sz_t2 = (A.N2 >> 3) * GS; A.sz_t3 = (A.N3 >> 3) * GS;
+    int o = 0;
+    A.o_as = o; o += 2 * A.sz_as;
+    A.o_ad = o; o += 2 * A.sz_ad;
+    A.o_av = o; o += 6 * A.sz_ad;
+    A.o_t1 = o; o += 2 * A.sz_t1;
+    A.o_t2 = o; o += 2 * A.sz_t2;
+    A.o_t3 = o; o += 6 * A.sz_t3;
+    o += 16 * GS;  // slack: M=64/128 operand reads run past the last real 8-channel group (those D rows are ignored)
+    o = al(o, 128);
+    A.o_stage = o; o += 2 * A.slot_floats * 4;
+    A.o_tab = o; o += al(ntab * 4, 16);
+    A.o_norm = o; o += al((A.mz + 3 * A.mv) * 4, 16);
+    A.o_tbl = o; o += al((8 * A.NSG8 + 8 * A.NDG8) * 4, 16);
+    A.o_bar = o; o += 8 * 8 + 16;
+    int dev = 0, maxsm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (o > maxsm) return SE3_OK;
+    const int smem = std::max(o, 120 * 1024);
+    static bool attr_set = false;
+    if (!attr_set) {
+        SE3_CUDA_TRY(cudaFuncSetAttribute(l1tp_tc_bwdw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
+        attr_set = true;
+    }
+    const long long ntiles = (a->rows + TMB - 1) / TMB;
+    const int grid = (int)std::min<long long>(ntiles, std::min(num_sms(), max_grid));
+    if (getenv("SE3_DEBUG_NANFILL")) cudaMemsetAsync(partials, 0xFF, sizeof(float) * (size_t)grid * wtot, st);
+    l1tp_tc_bwdw_kernel<<<grid, TBW_THREADS, smem, st>>>(A);
+    SE3_LAUNCHED();
+    g_tc_launches.fetch_add(1, std::memory_order_relaxed);
+    *grid_out = grid;
+    *launched = true;
+    return SE3_OK;
+}

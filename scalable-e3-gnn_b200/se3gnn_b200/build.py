@@ -52,7 +52,8 @@ def build(verbose: bool = False, force: bool = False) -> str:
         obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
         if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hm):
-            jobs.append([nvcc, *NVCC_FLAGS, "-c", src, "-o", obj] + (["-Xptxas", "-v"] if verbose else []))
+            extra = os.environ.get("SE3_NVCC_EXTRA", "").split()
+            jobs.append([nvcc, *NVCC_FLAGS, *extra, "-c", src, "-o", obj] + (["-Xptxas", "-v"] if verbose else []))
 
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -46,7 +46,8 @@ struct TcBwdArgs {
     int in2off, rawoff, rawstride, goff, gstride, slot_floats;
     int graw_vec16, g_vec16, tmem_cols;
     // shared memory byte offsets
-    int o_as, o_ad, o_av, o_t1, o_t2, o_t3, o_stage, o_tab, o_norm, o_tbl, o_bar;
+    int o_as, o_ad, o_av, o_t1, o_t2, o_t3, o_stage, o_tab, o_norm, o_tbl, o_bar, o_b1, o_b2, o_b3, o_gt;
+    int NS8, ND8, gts;
     int rg_s, rg_d, rg1, rg2, rg3;           // bytes per 8-row group of each tile
     int sz_as, sz_ad, sz_t1, sz_t2, sz_t3;   // bytes of one (hi or lo) tile
 };
@@ -487,6 +488,261 @@ __global__ void __launch_bounds__(TBW_THREADS, 1) l1tp_tc_bwdw_kernel(const TcBw
     }
 }
 
+
+// ===================================================================== (I) input-gradient kernel
+static constexpr int TBI_THREADS = 768;  // warps: 0,2 producers | 1 MMA | 4-15 builders | 16-23 epilogue
+static constexpr int TMI = 64;
+static constexpr int BI_BUILD_W0 = 4, BI_NBUILD = 12, BI_EPI_W0 = 16, BI_NEPI = 8;
+
+__global__ void __launch_bounds__(TBI_THREADS, 1) l1tp_tc_bwdi_kernel(const TcBwdArgs A) {
+    extern __shared__ __align__(1024) unsigned char smraw[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float* smf = reinterpret_cast<float*>(smraw);
+    const int* tab = reinterpret_cast<const int*>(smraw + A.o_tab);
+    const float* norm = reinterpret_cast<const float*>(smraw + A.o_norm);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + A.o_bar);
+    const uint32_t bar0 = smem_u32(bars);
+    // barriers: 0,1 stage full | 2,3 stage empty | 4 H full | 5 H empty | 6 acc full
+    auto BAR = [&](int i) { return bar0 + 8u * i; };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(BAR(i), TMI);
+            mbar_init(BAR(2 + i), BI_NBUILD);
+        }
+        mbar_init(BAR(4), BI_NBUILD);
+        mbar_init(BAR(5), BI_NEPI);
+        mbar_init(BAR(6), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    setup_tables(A, smraw, TBI_THREADS);
+    // W^T tiles (B operands, K-major with K = output channels), hi | lo
+    {
+        const int K1 = A.N2 + A.N3, NS = A.NS8 * 8, ND = A.ND8 * 8;
+        unsigned char* b1 = smraw + A.o_b1;
+        const int half1 = NS * K1 * 4;
+        for (int t = tid; t < NS * K1; t += TBI_THREADS) {
+            const int n = t / K1, ch = t - n * K1;
+            float x = 0.0f;
+            if (n < A.ns) {
+                if (ch < A.mz) x = __ldg(A.wz + (long long)n * A.mz + ch);
+                else if (ch >= A.N2 && ch - A.N2 < A.mv) x = __ldg(A.wv + (long long)n * A.mv + (ch - A.N2));
+            }
+            float hi, lo;
+            split_tf32(x, hi, lo);
+            const int o = canon_off(n, ch, K1 >> 2);
+            *reinterpret_cast<float*>(b1 + o) = hi;
+            *reinterpret_cast<float*>(b1 + half1 + o) = lo;
+        }
+        unsigned char* b2 = smraw + A.o_b2;
+        const int half2 = ND * A.N2 * 4;
+        for (int t = tid; t < ND * A.N2; t += TBI_THREADS) {
+            const int n = t / A.N2, ch = t - n * A.N2;
+            float x = 0.0f;
+            if (n < A.nd && ch < A.mz) x = __ldg(A.wz + (long long)(A.ns + n) * A.mz + ch);
+            float hi, lo;
+            split_tf32(x, hi, lo);
+            const int o = canon_off(n, ch, A.N2 >> 2);
+            *reinterpret_cast<float*>(b2 + o) = hi;
+            *reinterpret_cast<float*>(b2 + half2 + o) = lo;
+        }
+        unsigned char* b3 = smraw + A.o_b3;
+        const int half3 = ND * A.N3 * 4;
+        for (int t = tid; t < ND * A.N3; t += TBI_THREADS) {
+            const int n = t / A.N3, ch = t - n * A.N3;
+            float x = 0.0f;
+            if (n < A.nd && ch < A.mv) x = __ldg(A.wv + (long long)(A.ns + n) * A.mv + ch);
+            float hi, lo;
+            split_tf32(x, hi, lo);
+            const int o = canon_off(n, ch, A.N3 >> 2);
+            *reinterpret_cast<float*>(b3 + o) = hi;
+            *reinterpret_cast<float*>(b3 + half3 + o) = lo;
+        }
+    }
+    fence_proxy_async();
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(A.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const long long R = A.rows;
+    const long long ntiles = (R + TMI - 1) / TMI;
+    const int NS = A.NS8 * 8, ND = A.ND8 * 8;
+    const int cS = 0, cD = NS, cT = NS + ND;  // TMEM columns: gS | gD | gT0 gT1 gT2
+
+    if (warp == 0 || warp == 2) {
+        producer_loop<TMI>(A, smraw, BAR(0), BAR(2), (warp == 0 ? 0 : 32) + lane, false, ntiles);
+    } else if (warp == 1) {
+        const uint32_t sb = smem_u32(smraw);
+        const uint32_t id1 = make_idesc(NS), id2 = make_idesc(ND);
+        const uint32_t K1 = A.N2 + A.N3;
+        const uint32_t sbo_b1 = (K1 >> 2) * 128, sbo_b2 = (A.N2 >> 2) * 128, sbo_b3 = (A.N3 >> 2) * 128;
+        const uint32_t hb1 = NS * K1 * 4, hb2 = ND * A.N2 * 4, hb3 = ND * A.N3 * 4;
+        int it = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            mbar_wait(BAR(4), it & 1);
+            tc_fence_after();
+            if (lane == 0) {
+#define SE3_MMA3K(D, AH, ASZ, ASBO, BH, BSZ, BSBO, ID, FIRST)                                               \
+    tc_mma_tf32(tmem_base + (D), make_desc((AH), (ASBO)), make_desc((BH), (BSBO)), (ID), (FIRST));          \
+    tc_mma_tf32(tmem_base + (D), make_desc((AH), (ASBO)), make_desc((BH) + (BSZ), (BSBO)), (ID), 1u);       \
+    tc_mma_tf32(tmem_base + (D), make_desc((AH) + (ASZ), (ASBO)), make_desc((BH), (BSBO)), (ID), 1u);
+                for (uint32_t j = 0; j < K1 / 8; ++j) {
+                    SE3_MMA3K(cS, sb + A.o_t1 + j * 256, A.sz_t1, A.rg1, sb + A.o_b1 + j * 256, hb1, sbo_b1, id1, j ? 1u : 0u)
+                }
+                for (uint32_t j = 0; j < (uint32_t)A.N2 / 8; ++j) {
+                    SE3_MMA3K(cD, sb + A.o_t2 + j * 256, A.sz_t2, A.rg2, sb + A.o_b2 + j * 256, hb2, sbo_b2, id2, j ? 1u : 0u)
+                }
+                for (uint32_t c = 0; c < 3; ++c)
+                    for (uint32_t j = 0; j < (uint32_t)A.N3 / 8; ++j) {
+                        SE3_MMA3K(cT + c * ND, sb + A.o_t3 + c * 2 * A.sz_t3 + j * 256, A.sz_t3, A.rg3, sb + A.o_b3 + j * 256, hb3,
+                                  sbo_b3, id2, j ? 1u : 0u)
+                    }
+#undef SE3_MMA3K
+                tc_commit(BAR(6));
+            }
+            __syncwarp();
+        }
+    } else if (warp >= BI_BUILD_W0 && warp < BI_BUILD_W0 + BI_NBUILD) {
+        const int bw = warp - BI_BUILD_W0;
+        const int ngp = ((A.N2 >> 2) + (A.N3 >> 2) + 1) >> 1;
+        const int ntask = (TMI / 16) * ngp;
+        int it = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int slot = it & 1, use = it >> 1;
+            mbar_wait(BAR(slot), use & 1);       // stage full
+            mbar_wait(BAR(5), (it & 1) ^ 1);     // H tiles / g tile free (finish of the previous tile done)
+            const float* st = smf + (A.o_stage >> 2) + (size_t)slot * A.slot_floats;
+            for (int t = bw; t < ntask; t += BI_NBUILD) build_h_task(A, smraw, st, tab, norm, t % (TMI / 16), t / (TMI / 16), lane);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(BAR(4));
+                mbar_arrive(BAR(2 + slot));
+            }
+        }
+    } else if (warp >= BI_EPI_W0) {
+        const int e = warp & 3, h = (warp - BI_EPI_W0) >> 2;
+        const int et = tid - BI_EPI_W0 * 32;
+        const bool rowlane = lane < 16;
+        const int row = 16 * e + (lane & 15);
+        float* gt = reinterpret_cast<float*>(smraw + A.o_gt);
+        const int gts = A.gts;
+        const int* scol = tab + A.t_s;
+        const int* vcol = tab + A.t_d;
+        int it = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const long long row0 = tile * TMI;
+            const int nvalid = (int)min((long long)TMI, R - row0);
+            const long long gr = row0 + row;
+            float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rowlane && gr < R) y = __ldg(reinterpret_cast<const float4*>(A.in2) + gr);
+            mbar_wait(BAR(6), it & 1);
+            tc_fence_after();
+            const uint32_t acc = tmem_base + ((uint32_t)(32 * e) << 16);
+            float* grow = gt + row * gts;
+            if (h == 0) {
+                for (int k0 = 0; k0 < NS; k0 += 8) {
+                    float v[8];
+                    tc_ld8(acc + cS + k0, v);
+                    tc_wait_ld();
+                    if (rowlane) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (k0 + j < A.ns) grow[scol[k0 + j]] = v[j];
+                    }
+                }
+            } else {
+                const float sy0 = C3f * y.x, s1 = C3f * y.y, s2 = C3f * y.z, s3 = C3f * y.w;
+                for (int k0 = 0; k0 < ND; k0 += 8) {
+                    float d[8], t0[8], t1[8], t2[8];
+                    tc_ld8(acc + cD + k0, d);
+                    tc_ld8(acc + cT + k0, t0);
+                    tc_ld8(acc + cT + ND + k0, t1);
+                    tc_ld8(acc + cT + 2 * ND + k0, t2);
+                    tc_wait_ld();
+                    if (rowlane) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (k0 + j < A.nd) {
+                                float* o = grow + vcol[k0 + j];
+                                o[0] = fmaf(s1, d[j], sy0 * t0[j]);
+                                o[1] = fmaf(s2, d[j], sy0 * t1[j]);
+                                o[2] = fmaf(s3, d[j], sy0 * t2[j]);
+                            }
+                    }
+                }
+            }
+            tc_fence_before();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            // ---- scatter the input-gradient tile per segment
+            for (int s = 0; s < A.src.nseg; ++s) {
+                float* gb = A.gseg[s];
+                const int mode = A.gmode[s];
+                if (!gb || mode == SE3_GRAD_NONE) continue;
+                const int w = A.src.cum[s + 1] - A.src.cum[s], c0 = A.src.cum[s], ld = A.src.ld[s];
+                const int32_t* idx = A.src.idx[s];
+                const bool v4 = (w & 3) == 0 && (ld & 3) == 0 && (c0 & 3) == 0 && ((uintptr_t)gb & 15) == 0;
+                if (mode == SE3_GRAD_STORE || mode == SE3_GRAD_ATOMIC) {
+                    if (v4) {
+                        const int w4 = w >> 2;
+                        for (int t = et; t < nvalid * w4; t += 256) {
+                            const int r = t / w4, c = (t - r * w4) << 2;
+                            const float4 v = *reinterpret_cast<const float4*>(gt + r * gts + c0 + c);
+                            const long long dr = idx ? (long long)__ldg(idx + row0 + r) : row0 + r;
+                            float* dst = gb + dr * ld + c;
+                            if (mode == SE3_GRAD_STORE) *reinterpret_cast<float4*>(dst) = v;
+                            else red_add_v4(dst, v.x, v.y, v.z, v.w);
+                        }
+                    } else {
+                        for (int t = et; t < nvalid * w; t += 256) {
+                            const int r = t / w, c = t - r * w;
+                            const float v = gt[r * gts + c0 + c];
+                            const long long dr = idx ? (long long)__ldg(idx + row0 + r) : row0 + r;
+                            if (mode == SE3_GRAD_STORE) gb[dr * ld + c] = v;
+                            else atomicAdd(gb + dr * ld + c, v);
+                        }
+                    }
+                } else {  // SORTED: run-length combine equal destinations, one red per run
+                    int parts = 256 / w;
+                    if (parts < 1) parts = 1;
+                    const int rpp = (TMI + parts - 1) / parts;
+                    for (int item = et; item < w * parts; item += 256) {
+                        const int c = item % w, qd = item / w;
+                        const int rbeg = qd * rpp;
+                        const int rend = min(rbeg + rpp, nvalid);
+                        if (rbeg >= rend) continue;
+                        int cur = __ldg(idx + row0 + rbeg);
+                        float accv = 0.0f;
+                        for (int r = rbeg; r < rend; ++r) {
+                            const int k = __ldg(idx + row0 + r);
+                            if (k != cur) {
+                                atomicAdd(gb + (long long)cur * ld + c, accv);
+                                cur = k;
+                                accv = 0.0f;
+                            }
+                            accv += gt[r * gts + c0 + c];
+                        }
+                        atomicAdd(gb + (long long)cur * ld + c, accv);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(5));
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(A.tmem_cols) : "memory");
+    }
+}
+
 }  // namespace se3
 
 using namespace se3;
@@ -501,6 +757,7 @@ static int fill_common(TcBwdArgs& A, const int n[4], const int m[4], const int t
     A.ns = ns; A.nd = nd; A.mz = mz; A.mv = mv;
     A.NSG = (ns + 3) >> 2; A.NDG = (nd + 3) >> 2;
     A.NSG8 = (ns + 7) >> 3; A.NDG8 = (nd + 7) >> 3;
+    A.NS8 = A.NSG8; A.ND8 = A.NDG8;
     A.N2 = (mz + 7) & ~7; A.N3 = (mv + 7) & ~7;
     if (A.NSG8 > 16 || A.NDG8 > 8 || A.N2 + A.N3 > 256) return 1;
     A.MS = A.NSG8 > 8 ? 128 : 64;
@@ -591,6 +848,68 @@ int se3_l1tp_tc_try_backward_w(const int n[4], const int m[4], const int t_in[4]
     SE3_LAUNCHED();
     g_tc_launches.fetch_add(1, std::memory_order_relaxed);
     *grid_out = grid;
+    *launched = true;
+    return SE3_OK;
+}
+
+// input gradients on the tensor cores; returns launched=false when the configuration is not eligible
+int se3_l1tp_tc_try_backward_in(const int n[4], const int m[4], const int t_in[4], const int t_out[4], int ntab,
+                                const int* d_tab, const se3_l1tp_bwd_args* a, const RowSrc& src, const EpiL& epi,
+                                float* const gseg[SE3_MAX_SEG], const int gmode[SE3_MAX_SEG], cudaStream_t st,
+                                bool* launched) {
+    *launched = false;
+    static int disabled = -1;
+    if (disabled < 0) {
+        const char* e = getenv("SE3_DISABLE_TC");
+        disabled = (e && (e[0] == '1' || e[0] == '3')) ? 1 : 0;
+    }
+    if (disabled) return SE3_OK;
+    TcBwdArgs A;
+    if (fill_common(A, n, m, t_in, t_out, ntab, d_tab, a, src, epi, TMI, false)) return SE3_OK;
+    for (int s = 0; s < SE3_MAX_SEG; ++s) { A.gseg[s] = gseg[s]; A.gmode[s] = gmode[s]; }
+    auto al = [](int x, int q) { return (x + q - 1) / q * q; };
+    const int NS = A.NS8 * 8, ND = A.ND8 * 8;
+    if (NS > 256 || ND > 256) return SE3_OK;
+    A.tmem_cols = 32;
+    while (A.tmem_cols < NS + 4 * ND) A.tmem_cols <<= 1;
+    if (A.tmem_cols > 512) return SE3_OK;
+    const int nrg = TMI / 8;
+    A.rg1 = ((A.N2 + A.N3) >> 2) * 128; A.rg2 = (A.N2 >> 2) * 128; A.rg3 = (A.N3 >> 2) * 128;
+    A.sz_t1 = nrg * A.rg1; A.sz_t2 = nrg * A.rg2; A.sz_t3 = nrg * A.rg3;
+    A.gts = (src.cum[src.nseg] + 3) & ~3;
+    if ((A.gts & 31) == 0) A.gts += 4;
+    int o = 0;
+    A.o_t1 = o; o += 2 * A.sz_t1;
+    A.o_t2 = o; o += 2 * A.sz_t2;
+    A.o_t3 = o; o += 6 * A.sz_t3;
+    A.o_b1 = o; o += 2 * NS * (A.N2 + A.N3) * 4;
+    A.o_b2 = o; o += 2 * ND * A.N2 * 4;
+    A.o_b3 = o; o += 2 * ND * A.N3 * 4;
+    o = al(o, 128);
+    // the input-gradient tile aliases the H tiles: it is written only after the MMAs of the tile have completed
+    // (acc-full barrier) and the builders wait for the H-empty barrier (arrived after the scatter) before refilling
+    if (TMI * A.gts * 4 <= 2 * A.sz_t1 + 2 * A.sz_t2 + 6 * A.sz_t3) A.o_gt = A.o_t1;
+    else { A.o_gt = o; o += al(TMI * A.gts * 4, 16); }
+    A.o_stage = o; o += 2 * A.slot_floats * 4;
+    A.o_tab = o; o += al(ntab * 4, 16);
+    A.o_norm = o; o += al((A.mz + 3 * A.mv) * 4, 16);
+    A.o_tbl = o; o += al((8 * A.NSG8 + 8 * A.NDG8) * 4, 16);
+    A.o_bar = o; o += 8 * 8 + 16;
+    int dev = 0, maxsm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (o > maxsm) return SE3_OK;
+    const int smem = std::max(o, 120 * 1024);
+    static bool attr_set = false;
+    if (!attr_set) {
+        SE3_CUDA_TRY(cudaFuncSetAttribute(l1tp_tc_bwdi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
+        attr_set = true;
+    }
+    const long long ntiles = (a->rows + TMI - 1) / TMI;
+    const int grid = (int)std::min<long long>(ntiles, num_sms());
+    l1tp_tc_bwdi_kernel<<<grid, TBI_THREADS, smem, st>>>(A);
+    SE3_LAUNCHED();
+    g_tc_launches.fetch_add(1, std::memory_order_relaxed);
     *launched = true;
     return SE3_OK;
 }

@@ -40,6 +40,9 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=10_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dump", default=None, help="write the per-kernel table (JSON) here")
+    ap.add_argument("--parallel", default="dd", choices=["dd", "dp"],
+                    help="N>1: dd = Morton-range domain decomposition of ONE cloud of N x particles (default); "
+                         "dp = one independent cloud per GPU")
     return ap.parse_args()
 
 
@@ -169,15 +172,25 @@ def run_b200(a):
 
     torch.manual_seed(0)
     model = SEGNN(num_layers=a.layers).to(dev)
-    ts = TrainStep(model, leaf_size=a.leaf, distributed=world > 1)
+    dd = world > 1 and a.parallel == "dd"
+    ts = TrainStep(model, leaf_size=a.leaf, distributed=world > 1 and not dd, decompose=dd)
     n = a.particles
-    pos, vel, mass, target = (torch.from_numpy(x) for x in synthetic_cloud(n, a.kind, seed=1 + rank))
-    host = [t.pin_memory() for t in (pos, vel, mass, target)]
-    devt = [t.to(dev) for t in host]
+    if dd:
+        # ONE cloud of world x n particles; the device-resident arm holds it on every rank (the tree is replicated),
+        # the end-to-end arm starts from each rank's n-particle chunk in pinned host memory
+        cloud = [torch.from_numpy(x) for x in synthetic_cloud(n * world, a.kind, seed=1)]
+        host = [t[rank * n:(rank + 1) * n].contiguous().pin_memory() for t in cloud]
+        devt = [t.to(dev) for t in cloud]
+        step_dev, step_host = ts.step_device_dd, ts.step_host_dd
+    else:
+        pos, vel, mass, target = (torch.from_numpy(x) for x in synthetic_cloud(n, a.kind, seed=1 + rank))
+        host = [t.pin_memory() for t in (pos, vel, mass, target)]
+        devt = [t.to(dev) for t in host]
+        step_dev, step_host = ts.step_device, ts.step_host
     K, W = max(1, a.steps), max(3, a.warmup)
 
     for _ in range(W):
-        loss = ts.step_device(*devt)
+        loss = step_dev(*devt)
     barrier()
     g = ts.last_graph
     edges, cells = g.e, g.m
@@ -189,7 +202,7 @@ def run_b200(a):
     barrier()
     e0.record()
     for _ in range(K):
-        loss = ts.step_device(*devt)
+        loss = step_dev(*devt)
     e1.record()
     barrier()
     ms = allmax(e0.elapsed_time(e1))
@@ -198,21 +211,22 @@ def run_b200(a):
     value = n * world * K / (ms * 1e-3)
 
     # ---- end to end through the public host-buffer API (H2D of the step's inputs + D2H of the loss each step)
-    ts.step_host(*host)
+    step_host(*host)
     barrier()
     t0 = time.perf_counter()
     for _ in range(K):
-        lossf = ts.step_host(*host)
+        lossf = step_host(*host)
     torch.cuda.synchronize()
     dt = allmax(time.perf_counter() - t0)
     barrier()
-    e2e = {"value": n * world * K / dt, "unit": UNIT, "h2d_bytes_per_step": int(sum(t.numel() * 4 for t in host)),
-           "d2h_bytes_per_step": 4 + 16, "ms_per_step": dt * 1e3 / K}
+    e2e = {"value": n * world * K / dt, "unit": UNIT,
+           "h2d_bytes_per_step": int(sum(t.numel() * 4 for t in host)) * world,
+           "d2h_bytes_per_step": (4 + 16) * world, "ms_per_step": dt * 1e3 / K}
 
     # ---- per-kernel table (CUDA events on the launching stream around every library call), 2 more steps
     capi.profile_begin()
     for _ in range(2):
-        ts.step_device(*devt)
+        step_dev(*devt)
     prof = capi.profile_end()
     agg = {}
     for tag, t_ms, nb, fl in prof:
@@ -262,16 +276,28 @@ def run_b200(a):
     cb = None
     if world == 1 and not a.no_cpu_baseline:
         cb, _ = cpu_arm(a, steps=2, warmup=1, budget_s=40.0)
+    if dd:
+        from se3gnn_b200 import domain
+        lg = ts.last_local
+        par = (f"dd{world}: Morton-range domain decomposition of ONE {n * world}-particle cloud (replicated octree build, "
+               f"each rank keeps the CSR rows of the nodes it owns), NCCL all-to-all-v halo exchange per layer "
+               f"(rank 0: {lg.n_halo} halo nodes, {domain.halo_bytes(lg, 64, a.layers) / 1e6:.2f} MB/step), all-reduce of "
+               f"weight gradients")
+    elif world > 1:
+        par = f"dp{world} (one independent cloud per GPU, NCCL all-reduce of weight gradients)"
+    else:
+        par = "single GPU"
     cfg = workload(a)
-    cfg.update({"edges_per_gpu": edges, "cells_per_gpu": cells,
-                "parallelism": f"dp{world} (one independent cloud per GPU, NCCL all-reduce of weight gradients)",
+    tot_edges = edges if dd else edges * world      # dd: g is the global graph
+    cfg.update({"edges_total": tot_edges, "cells_total": cells if dd else cells * world,
+                "parallelism": par,
                 "l2": "no flush: per-step working set (per-edge activations, ~%.1f GB) exceeds the 126 MB L2"
-                      % (edges * 4 * (74 + 64 + 74 + 64 + 8) * a.layers / 1e9),
+                      % (tot_edges / world * 4 * (74 + 64 + 74 + 64 + 8) * a.layers / 1e9),
                 "optimizer": "Adam (torch fused) inside the timed step"})
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": cfg, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cb, "edges_per_s": edges * world * K / (ms * 1e-3),
+            "roofline": roofline, "cpu_baseline": cb, "edges_per_s": tot_edges * K / (ms * 1e-3),
             "loss": float(loss.item()), "kernels": table}
     print(json.dumps(line), flush=True)
     if world > 1:

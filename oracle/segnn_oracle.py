@@ -81,11 +81,13 @@ class SEGNNOracle(torch.nn.Module):
         return torch.cat([SILU_CST * torch.nn.functional.silu(s),
                           (SIGMOID_CST * torch.sigmoid(g)[:, :, None] * v).reshape(len(raw), -1)], 1)
 
-    def forward(self, x_in, node_attr, edge_attr, edge_extra, dst, src):
+    def forward(self, x_in, node_attr, edge_attr, edge_extra, dst, src, halo=None):
+        """``halo`` (domain-decomposition tests): callable appending the halo rows to the owned rows of x."""
         dst, src = dst.long(), src.long()
         x = self.embed(x_in, node_attr)
         for l in range(self.num_layers):
-            m = self.gate(self.msg1[l](torch.cat([x[dst], x[src], edge_extra], 1), edge_attr))
+            xe = x if halo is None else halo(x)
+            m = self.gate(self.msg1[l](torch.cat([xe[dst], xe[src], edge_extra], 1), edge_attr))
             m = self.gate(self.msg2[l](m, edge_attr))
             agg = torch.zeros_like(x).index_add(0, dst, m)
             u = self.gate(self.upd1[l](torch.cat([x, agg], 1), node_attr))

@@ -79,9 +79,13 @@ class SEGNN(nn.Module):
         return TPConfig(plan=plan, widths=widths, **kw)
 
     # -------------------------------------------------------------- forward
-    def forward(self, x_in, node_attr, edge_attr, edge_extra, dst, src):
+    def forward(self, x_in, node_attr, edge_attr, edge_extra, dst, src, halo=None):
         """x_in [Nn,8], node_attr [Nn,4], edge_attr [E,4], edge_extra [E,2], dst/src [E] int32 (sorted by dst).
-        Returns the per-node output [Nn, out_dim]."""
+        Returns the per-node output [Nn, out_dim].
+
+        Domain-decomposed run (``se3gnn_b200.domain``): the node arrays hold the rank's OWNED nodes, ``dst`` are owned
+        local ids, ``src`` may point past Nn into the halo, and ``halo(x) -> [Nn + n_halo, d]`` appends the halo rows
+        fetched from their owners (one NCCL all-to-all-v per layer, differentiable)."""
         if not x_in.is_cuda:
             raise RuntimeError("se3gnn_b200.SEGNN runs on CUDA (sm_100a) only; there is no CPU fallback")
         nn_, e, d = x_in.shape[0], edge_attr.shape[0], self.d
@@ -91,7 +95,8 @@ class SEGNN(nn.Module):
             ws, ns = self._wn(self.msg1[l])
             cfg = self._cfg(self.msg1[l], (d, d, edge_extra.shape[1]), True, "msg1",
                             grad_modes=(capi.GRAD_SORTED, capi.GRAD_ATOMIC, capi.GRAD_NONE), share_grad={1: 0})
-            m1 = tp_layer(cfg, e, [x, x, edge_extra], [dst, src, None], edge_attr, ws, ns)
+            xe = x if halo is None else halo(x)
+            m1 = tp_layer(cfg, e, [xe, xe, edge_extra], [dst, src, None], edge_attr, ws, ns)
             ws, ns = self._wn(self.msg2[l])
             cfg = self._cfg(self.msg2[l], (d,), True, "msg2", num_segments=nn_)
             agg = tp_layer(cfg, e, [m1], [None], edge_attr, ws, ns, seg_idx=dst)

@@ -1,0 +1,178 @@
+"""Morton-range domain decomposition of ONE particle cloud over the ranks of a box (north star).
+
+Scheme ("replicated tree, partitioned graph"):
+  * every rank holds the whole cloud (the bench all-gathers the slabs; 12 B/particle over NVLink) and builds the same
+    octree — integer work, bit-identical on every rank — so ownership, halo sets and the canonical edge order need
+    no negotiation;
+  * particles are split by Morton rank into `world` contiguous, equal-count slabs whose boundaries are snapped down to
+    a leaf start, so a leaf and all of its particles have one owner; a cell is owned by the owner of its first
+    particle;
+  * a rank keeps the edges whose *destination* it owns (CSR rows of its nodes), in the global (dst, src) order;
+  * sources it does not own are its halo (cells across the boundary: 26-neighbours, parents, children).  Before every
+    message layer the halo rows of the node features are fetched from their owners with one all-to-all-v (NCCL over
+    NVLink / NVSwitch: every peer at full bandwidth, so a single grouped exchange, no ring ordering); backward sends
+    the halo gradients the opposite way and adds them into the owners' rows;
+  * weight gradients are summed over ranks with one all-reduce of the flat gradient buffer.
+
+Everything here is index bookkeeping on torch tensors of whatever device the graph lives on (CUDA in the product,
+CPU in the world-2 gloo tests, which run the same code on the oracle's numpy graph).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def slab_bounds(n: int, world: int, leaf_of_rank: torch.Tensor, cell_start: torch.Tensor) -> torch.Tensor:
+    """[world+1] int64 particle-rank boundaries: equal counts (remainder to the first ranks), each interior boundary
+    snapped DOWN to the first rank of the leaf that contains it.  Monotone; slabs may be empty for tiny clouds."""
+    base, rem = divmod(n, world)
+    raw = [0]
+    for r in range(world):
+        raw.append(raw[-1] + base + (1 if r < rem else 0))
+    b = torch.tensor(raw, dtype=torch.int64, device=leaf_of_rank.device)
+    inner = b[1:-1]
+    if inner.numel():
+        ok = inner < n
+        leaf = leaf_of_rank[inner.clamp(max=max(n - 1, 0))].long()
+        snapped = torch.where(ok, cell_start[leaf].long(), inner)
+        b[1:-1] = snapped
+    return b
+
+
+@dataclass
+class LocalGraph:
+    """What one rank keeps of the global octree graph.  Local node ids: owned particles (global rank order), owned
+    cells (global cell order), then halo nodes (ascending global id)."""
+    rank: int
+    world: int
+    n_global: int                  # particles of the whole cloud
+    nn_global: int
+    n_part: int                    # owned particles
+    n_own: int                     # owned nodes (particles + cells)
+    n_halo: int
+    part_lo: int                   # global rank of the first owned particle
+    own_ids: torch.Tensor          # [n_own]  global node ids
+    halo_ids: torch.Tensor         # [n_halo] global node ids, ascending
+    dst: torch.Tensor              # [e_loc] int32 local (owned) destination, ascending
+    src: torch.Tensor              # [e_loc] int32 local source (owned or halo)
+    edge_ids: torch.Tensor         # [e_loc] int64 positions in the global edge arrays
+    recv_counts: List[int] = field(default_factory=list)   # halo rows received from each rank (halo order)
+    send_counts: List[int] = field(default_factory=list)   # rows sent to each rank
+    send_idx: Optional[torch.Tensor] = None                # [sum(send_counts)] int64 local owned ids, grouped by rank
+
+    @property
+    def e(self) -> int:
+        return int(self.dst.numel())
+
+
+def node_owner(bounds: torch.Tensor, n: int, cell_start: torch.Tensor) -> torch.Tensor:
+    """[n+m] int64 owner rank of every global node."""
+    dev = cell_start.device
+    first = torch.cat([torch.arange(n, device=dev, dtype=torch.int64), cell_start.long()])
+    # owner = last slab whose lower bound <= first particle (empty slabs never own anything)
+    own = torch.searchsorted(bounds[1:].contiguous(), first, right=True)
+    return own.clamp(max=bounds.numel() - 2)
+
+
+def local_graph(rank: int, world: int, n: int, cell_start: torch.Tensor, leaf_of_rank: torch.Tensor,
+                g_dst: torch.Tensor, g_src: torch.Tensor, bounds: Optional[torch.Tensor] = None) -> LocalGraph:
+    """Rank `rank`'s part of the global graph (no communication: the global graph is replicated)."""
+    dev = g_dst.device
+    m = int(cell_start.numel())
+    nn = n + m
+    if bounds is None:
+        bounds = slab_bounds(n, world, leaf_of_rank, cell_start)
+    owner = node_owner(bounds, n, cell_start)
+    mine = owner == rank
+    own_ids = torch.nonzero(mine).flatten()
+    n_own = int(own_ids.numel())
+    n_part = int((own_ids < n).sum())
+    e_ids = torch.nonzero(mine[g_dst.long()]).flatten()
+    sg = g_src[e_ids].long()
+    dg = g_dst[e_ids].long()
+    halo_ids = torch.unique(sg[~mine[sg]])          # sorted ascending
+    n_halo = int(halo_ids.numel())
+    g2l = torch.full((nn,), -1, device=dev, dtype=torch.int64)
+    g2l[own_ids] = torch.arange(n_own, device=dev, dtype=torch.int64)
+    g2l[halo_ids] = n_own + torch.arange(n_halo, device=dev, dtype=torch.int64)
+    howner = owner[halo_ids]
+    recv_counts = torch.bincount(howner, minlength=world).tolist() if n_halo else [0] * world
+    # halo_ids ascending is NOT grouped by owner in general (cells of several levels interleave owners): regroup
+    if n_halo:
+        perm = torch.argsort(howner, stable=True)
+        halo_ids = halo_ids[perm]
+        g2l[halo_ids] = n_own + torch.arange(n_halo, device=dev, dtype=torch.int64)
+    lo = int(bounds[rank])
+    return LocalGraph(rank=rank, world=world, n_global=n, nn_global=nn, n_part=n_part, n_own=n_own, n_halo=n_halo,
+                      part_lo=lo, own_ids=own_ids, halo_ids=halo_ids, dst=g2l[dg].to(torch.int32),
+                      src=g2l[sg].to(torch.int32), edge_ids=e_ids, recv_counts=[int(c) for c in recv_counts])
+
+
+def _a2a(out: torch.Tensor, inp: torch.Tensor, out_split: Sequence[int], in_split: Sequence[int], group=None):
+    """all-to-all-v of rows.  NCCL: on the device.  gloo (CPU tests, single-GPU emulation): staged through the host."""
+    if dist.get_backend(group) == "nccl" or not inp.is_cuda:
+        dist.all_to_all_single(out, inp.contiguous(), output_split_sizes=list(out_split), input_split_sizes=list(in_split),
+                               group=group)
+        return out
+    o = torch.empty(out.shape, dtype=out.dtype)
+    dist.all_to_all_single(o, inp.contiguous().cpu(), output_split_sizes=list(out_split), input_split_sizes=list(in_split),
+                           group=group)
+    out.copy_(o)
+    return out
+
+
+def exchange_halo_lists(lg: LocalGraph, group=None) -> LocalGraph:
+    """Tell every owner which of its nodes this rank needs; fills send_counts / send_idx.  One small all-to-all of
+    counts and one of global ids, once per graph build."""
+    dev = lg.own_ids.device
+    world = lg.world
+    rc = torch.tensor(lg.recv_counts, dtype=torch.int64, device=dev)
+    sc = torch.empty(world, dtype=torch.int64, device=dev)
+    _a2a(sc, rc, [1] * world, [1] * world, group)
+    lg.send_counts = [int(c) for c in sc.tolist()]
+    want = torch.empty(sum(lg.send_counts), dtype=torch.int64, device=dev)
+    _a2a(want, lg.halo_ids, lg.send_counts, lg.recv_counts, group)
+    g2l = torch.full((lg.nn_global,), -1, device=dev, dtype=torch.int64)
+    g2l[lg.own_ids] = torch.arange(lg.n_own, device=dev, dtype=torch.int64)
+    lg.send_idx = g2l[want]
+    if lg.send_idx.numel() and int(lg.send_idx.min()) < 0:
+        raise RuntimeError("domain decomposition: a peer asked for a node this rank does not own")
+    return lg
+
+
+class _HaloFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x_own: torch.Tensor, lg: LocalGraph, group):
+        ctx.lg, ctx.group = lg, group
+        d = x_own.shape[1]
+        send = x_own.index_select(0, lg.send_idx)
+        recv = torch.empty((lg.n_halo, d), device=x_own.device, dtype=x_own.dtype)
+        _a2a(recv, send, lg.recv_counts, lg.send_counts, group)
+        return torch.cat([x_own, recv], 0)
+
+    @staticmethod
+    def backward(ctx, g_ext: torch.Tensor):
+        lg = ctx.lg
+        g_own = g_ext[:lg.n_own].clone()
+        g_halo = g_ext[lg.n_own:].contiguous()
+        back = torch.empty((int(lg.send_idx.numel()), g_ext.shape[1]), device=g_ext.device, dtype=g_ext.dtype)
+        _a2a(back, g_halo, lg.send_counts, lg.recv_counts, ctx.group)
+        g_own.index_add_(0, lg.send_idx, back)
+        return g_own, None, None
+
+
+def halo_exchange(x_own: torch.Tensor, lg: LocalGraph, group=None) -> torch.Tensor:
+    """[n_own, D] -> [n_own + n_halo, D]: owned rows followed by the halo rows fetched from their owners
+    (differentiable: backward returns the halo gradients to the owners and adds them)."""
+    if lg.world == 1:
+        return x_own
+    return _HaloFn.apply(x_own, lg, group)
+
+
+def halo_bytes(lg: LocalGraph, d: int, layers: int) -> int:
+    """NVLink bytes this rank sends per training step (forward rows + backward gradients), fp32."""
+    return 4 * d * layers * (sum(lg.send_counts) + sum(lg.recv_counts))

@@ -11,6 +11,9 @@ from typing import Optional
 import numpy as np
 import torch
 
+import torch.distributed as dist
+
+from . import domain
 from .dist import allreduce_mean_, flatten_grads
 from .octree import build_octree_graph
 
@@ -52,10 +55,18 @@ class TrainStep:
     """One training step of the hot path.  ``world`` > 1: gradients are summed across ranks with one
     NCCL all-reduce of a flat buffer (each rank owns an independent cloud)."""
 
-    def __init__(self, model, leaf_size: int = 32, lr: float = 1e-3, distributed: bool = False):
+    def __init__(self, model, leaf_size: int = 32, lr: float = 1e-3, distributed: bool = False,
+                 decompose: bool = False, group=None):
+        """``distributed``: data parallel, every rank owns an independent cloud (mean of the weight gradients).
+        ``decompose``: Morton-range domain decomposition of ONE cloud over the ranks (``se3gnn_b200.domain``): every
+        rank is handed the whole cloud, builds the same octree, keeps the rows of the nodes it owns, exchanges halo
+        rows once per layer and the weight gradients are summed."""
         self.model = model
         self.leaf_size = leaf_size
         self.distributed = distributed
+        self.decompose = decompose
+        self.group = group
+        self.last_local = None
         params = [p for p in model.parameters()]
         self.flat_grad = flatten_grads(params)
         self.opt = torch.optim.Adam(params, lr=lr, fused=True)
@@ -76,6 +87,53 @@ class TrainStep:
             allreduce_mean_(self.flat_grad)
         self.opt.step()
         return loss.detach()
+
+    # ------------------------------------------------------------------ domain-decomposed step
+    def step_device_dd(self, pos, vel, mass, target) -> torch.Tensor:
+        """pos/vel/mass/target: the WHOLE cloud (identical on every rank).  Returns the global loss."""
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        rank = dist.get_rank(self.group) if dist.is_initialized() else 0
+        n = pos.shape[0]
+        self.flat_grad.zero_()
+        g = build_octree_graph(pos, vel, mass, leaf_size=self.leaf_size)
+        self.last_graph = g
+        lg = domain.local_graph(rank, world, g.n, g.cell_start, g.leaf_of_rank, g.dst, g.col)
+        if world > 1:
+            domain.exchange_halo_lists(lg, self.group)
+        self.last_local = lg
+        halo = (lambda x: domain.halo_exchange(x, lg, self.group)) if world > 1 else None
+        out = self.model(g.x_in.index_select(0, lg.own_ids), g.node_attr.index_select(0, lg.own_ids),
+                         g.edge_attr.index_select(0, lg.edge_ids), g.edge_extra.index_select(0, lg.edge_ids),
+                         lg.dst, lg.src, halo=halo)
+        own_part = g.order[lg.part_lo:lg.part_lo + lg.n_part].long()
+        tgt = target.index_select(0, own_part)
+        loss = (out[:lg.n_part] - tgt).square().sum() / (3.0 * n)
+        loss.backward()
+        lossd = loss.detach().clone()
+        if world > 1:
+            dist.all_reduce(self.flat_grad, group=self.group)
+            dist.all_reduce(lossd, group=self.group)
+        self.opt.step()
+        return lossd
+
+    def step_host_dd(self, pos_h, vel_h, mass_h, target_h) -> float:
+        """Each rank passes ITS CHUNK of the cloud (pinned CPU tensors, equal sizes); the chunks are copied to the
+        device and all-gathered over NCCL, then the decomposed step runs.  Returns the global loss (D2H read)."""
+        dev = self.flat_grad.device
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        loc = torch.empty((pos_h.shape[0], 10), device=dev, dtype=torch.float32)
+        loc[:, 0:3].copy_(pos_h, non_blocking=True)
+        loc[:, 3:6].copy_(vel_h, non_blocking=True)
+        loc[:, 6].copy_(mass_h, non_blocking=True)
+        loc[:, 7:10].copy_(target_h, non_blocking=True)
+        if world > 1:
+            allp = torch.empty((world * loc.shape[0], loc.shape[1]), device=dev, dtype=loc.dtype)
+            dist.all_gather_into_tensor(allp, loc, group=self.group)
+        else:
+            allp = loc
+        pos, vel, mass, target = (allp[:, 0:3].contiguous(), allp[:, 3:6].contiguous(), allp[:, 6].contiguous(),
+                                  allp[:, 7:10].contiguous())
+        return float(self.step_device_dd(pos, vel, mass, target).item())
 
     def step_host(self, pos_h, vel_h, mass_h, target_h) -> float:
         """pos/vel/mass/target: pinned CPU tensors.  Returns the loss as a Python float (D2H read)."""

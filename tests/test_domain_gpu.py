@@ -1,0 +1,64 @@
+"""Morton-range domain decomposition on the GPU path: two ranks (two processes sharing cuda:0, gloo rendezvous with
+host-staged halo exchange — NCCL refuses two ranks on one device; the multi-GPU NCCL run is tools/check_dd.py)
+run TrainStep.step_device_dd on one cloud and must reproduce the single-rank loss and weight gradients."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(n, layers):
+    from models.segnn.segnn import SEGNN
+    from se3gnn_b200.pipeline import TrainStep, synthetic_cloud
+    torch.manual_seed(0)
+    model = SEGNN(num_layers=layers).cuda()
+    data = [torch.from_numpy(a).cuda() for a in synthetic_cloud(n, "plummer", seed=5)]
+    return model, data, TrainStep
+
+
+def _worker(rank, world, port, n, layers, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.cuda.set_device(0)
+    from se3gnn_b200 import capi
+    model, data, TrainStep = _setup(n, layers)
+    ts = TrainStep(model, decompose=True)
+    l0 = capi.launch_count()
+    loss = ts.step_device_dd(*data)
+    torch.cuda.synchronize()
+    lg = ts.last_local
+    q.put((rank, float(loss), ts.flat_grad.cpu().numpy(), lg.n_part, lg.n_halo, lg.e, capi.launch_count() - l0))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n,layers", [(20000, 2)])
+def test_two_rank_decomposition_matches_single_rank(n, layers):
+    from conftest import PKG, ROOT
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    os.environ["PYTHONPATH"] = os.pathsep.join([PKG, ROOT, os.path.join(ROOT, "tests"), os.environ.get("PYTHONPATH", "")])
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, layers, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=600) for _ in procs], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+    model, data, TrainStep = _setup(n, layers)
+    ts = TrainStep(model)
+    loss = float(ts.step_device(*data))
+    torch.cuda.synchronize()
+    ref = ts.flat_grad.cpu().numpy()
+    g = ts.last_graph
+    assert res[0][3] + res[1][3] == n and res[0][5] + res[1][5] == g.e
+    assert res[0][4] > 0 and res[1][4] > 0 and all(r[6] > 20 for r in res)   # halos exist, CUDA kernels ran
+    scale = np.abs(ref).max()
+    for r in res:
+        assert abs(r[1] - loss) <= 2e-5 * abs(loss)
+        assert np.abs(r[2] - ref).max() <= 1e-4 * scale

@@ -1087,8 +1087,12 @@ struct se3_l1tp_plan {
     int w_off[4], w_cnt[4];
     int n[4], m[4];
     int t_in[4], t_out[4];
+    std::vector<int> h_tab;   // host copy of the column tables (slot assignment of the tcgen05 kernels)
 };
 
+int se3_l1tp_tc2_try_forward(const int n[4], const int m[4], const int t_in[4], const int t_out[4], int ntab,
+                             const int* h_tab, const int* d_tab, const se3_l1tp_fwd_args* a, const se3::RowSrc& src,
+                             const se3::EpiL& epi, cudaStream_t st, bool* launched);
 int se3_l1tp_tc_try_backward_w(const int n[4], const int m[4], const int t_in[4], const int t_out[4], int ntab,
                                const int* d_tab, const se3_l1tp_bwd_args* a, const se3::RowSrc& src, const se3::EpiL& epi,
                                float* partials, int wtot, int gw_z_off, int gw_v_off, int max_grid, cudaStream_t st,
@@ -1130,6 +1134,7 @@ extern "C" int se3_l1tp_plan_create(const se3_l1tp_desc* d, se3_l1tp_plan** out)
     }
     for (int s = 0; s < 4; ++s) { p->n[s] = d->n[s]; p->m[s] = d->m[s]; p->t_in[s] = t_in[s]; p->t_out[s] = t_out[s]; }
     L.ntab = (int)tab.size();
+    p->h_tab = tab;
     // families: E = (s 0e, dot 1o, cross 1e -> Z 0e, V 1o), O = (s 0o, dot 1e, cross 1o -> Z 0o, V 1e)
     const int fs[2] = {0, 1}, fd[2] = {3, 2}, fx[2] = {2, 3}, fz[2] = {0, 1}, fv[2] = {3, 2};
     int wtot = 0, njw = 0, nrm = 0;
@@ -1305,6 +1310,10 @@ extern "C" int se3_l1tp_forward(se3_l1tp_plan* p, const se3_l1tp_fwd_args* a, vo
     K.seg_idx = a->seg_idx; K.out_seg = a->out_seg; K.tab = p->d_tab;
     {   // tensor-core (tcgen05) path when the configuration is eligible
         bool launched = false;
+        rc = se3_l1tp_tc2_try_forward(p->n, p->m, p->t_in, p->t_out, p->L.ntab, p->h_tab.data(), p->d_tab, a, K.src, K.epi,
+                                      (cudaStream_t)stream, &launched);
+        if (rc) return rc;
+        if (launched) return SE3_OK;
         rc = se3_l1tp_tc_try_forward(p->n, p->m, p->t_in, p->t_out, p->L.ntab, p->d_tab, a, K.src, K.epi,
                                      (cudaStream_t)stream, &launched);
         if (rc) return rc;

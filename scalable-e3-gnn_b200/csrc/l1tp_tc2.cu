@@ -1,0 +1,648 @@
+// Second-generation tensor-core (tcgen05 / TMEM, 3xTF32) forward of the fused l<=1 tensor-product layer, SEGNN
+// case (inputs a x0e + b x1o in up to four gathered segments, outputs c x0e + d x1o).
+//
+// What changed against l1tp_tc.cu (profiles/r01_v8_*: the MMA-issuing warp and the per-chunk hand-offs were the
+// bottleneck, 11.5k cycles per 64-row tile against a tensor-pipe floor of 1.3k):
+//   * no staging copy and no role pipeline: 16 homogeneous worker warps gather the rows of tile t+1 from global
+//     memory straight into registers (issued a whole tile ahead), split them into tf32 hi/lo and store them ONCE, in
+//     their final UMMA operand form; one barrier per TILE hands the operand set to the MMA warp;
+//   * the operand set holds only raw data: scalars S[64 x K1] and the de-interleaved vector components
+//     Vx, Vy, Vz [64 x K2].  Nothing in it depends on the spherical harmonics, which enter in the epilogue:
+//         P  = S  . [WZ_s | WV_s]           (N1 columns)
+//         Uc = Vc . [WZ_d | WV_v]  c=x,y,z  (3 x N1 columns)
+//         out0[m]    = norm (Y0 P[m] + c3 sum_c Y1[c] Uc[m])
+//         out1[m][c] = norm c3 (Y1[c] P[N2+m] + Y0 Uc[N2+m])
+//     so the dot-product / Y0-scaled feature tiles of the first kernel (and their builders) are gone;
+//   * operand sets and TMEM accumulators are double buffered per tile: the MMAs of tile t run while the workers
+//     build tile t+1 and finish tile t-1 (TMEM -> registers -> smem tile -> coalesced stores / gate / segment sum);
+//   * all ring arithmetic is 32-bit and additive; the MMA warp only adds constants to precomputed descriptors.
+#include <algorithm>
+#include <vector>
+
+#include "tc_common.cuh"
+
+namespace se3 {
+
+static constexpr int W2 = 16;                 // worker warps
+static constexpr int T2_THREADS = (W2 + 1) * 32;
+static constexpr int WT = W2 * 32;            // worker threads
+static constexpr int TM2 = 64;
+static constexpr int MAXT = 6;                // warp tasks per warp and tile
+static constexpr int MAXCOL = 192;
+static constexpr int MAXK1 = 128;
+
+struct TaskE {                                // one warp task: 8 rows x 4 sixteen-byte pieces, or 32 four-byte pieces
+    const float* base;
+    const int32_t* idx;
+    int ld;
+    int info;                                 // wide: 1 | rb << 4 | cb << 8 | nchunk << 16   narrow: 0 | w << 4 | t << 12
+    int cum;                                  // first concatenated column of the segment
+    unsigned fast4;                           // wide: byte q = K-chunk + 1 of piece 4 cb + q if it is 4 aligned scalars
+};
+
+struct Tc2Args {
+    long long rows;
+    const float* in2;
+    const float* wz;
+    const float* wv;
+    const float* nz;
+    const float* nv;
+    EpiL epi;
+    float* out_raw;
+    float* out_post;
+    const float* resid;
+    const int32_t* seg_idx;
+    float* out_seg;
+    const int* tab;
+    int ntab, t_oz, t_ov;
+    int ns, nd, mz, mv, d_out;
+    int K1, K2, N1, N2;
+    int ntask;
+    int dop, dpp;
+    int o_b1, o_b2, o_a, a_bytes, o_out, o_post, o_tab, o_norm, o_task, o_ccode, o_pcol, o_bar;
+    int halfS, halfV, oV;                     // bytes: lo offset of S / V tiles, first V tile inside an operand set
+    TaskE task[W2 * MAXT];
+    unsigned short ccode[MAXCOL];             // per concatenated column: type << 13 | index (1: scalar slot, 2..4: x/y/z kd)
+    short sl2ch[MAXK1];                       // scalar slot -> scalar channel (-1: padding)
+};
+
+__device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+__global__ void __launch_bounds__(T2_THREADS, 1) l1tp_tc2_fwd_kernel(const __grid_constant__ Tc2Args A) {
+    extern __shared__ __align__(1024) unsigned char smraw[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int* tab = reinterpret_cast<int*>(smraw + A.o_tab);
+    float* norm = reinterpret_cast<float*>(smraw + A.o_norm);
+    TaskE* task = reinterpret_cast<TaskE*>(smraw + A.o_task);
+    unsigned short* ccode = reinterpret_cast<unsigned short*>(smraw + A.o_ccode);
+    int* pcol = reinterpret_cast<int*>(smraw + A.o_pcol);
+    int* gcol = pcol + A.epi.d_post;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + A.o_bar);
+    const uint32_t bar0 = smem_u32(bars);
+    // barriers: 0,1 operand set full | 2,3 accumulator full | 4,5 accumulator empty
+    auto BAR = [&](int i) { return bar0 + 8u * i; };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+    // ---------------- one-time setup
+    for (int t = tid; t < A.ntab; t += T2_THREADS) tab[t] = A.tab[t];
+    for (int t = tid; t < A.mz; t += T2_THREADS) norm[t] = A.nz ? A.nz[t] : 1.0f;
+    for (int t = tid; t < 3 * A.mv; t += T2_THREADS) norm[A.mz + t] = A.nv ? A.nv[t] : 1.0f;
+    for (int t = tid; t < A.ntask; t += T2_THREADS) task[t] = A.task[t];
+    for (int t = tid; t < MAXCOL; t += T2_THREADS) ccode[t] = A.ccode[t];
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(BAR(i), W2);
+            mbar_init(BAR(2 + i), 1);
+            mbar_init(BAR(4 + i), W2);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    {   // zero both operand sets (padding slots are never written again)
+        float4* z = reinterpret_cast<float4*>(smraw + A.o_a);
+        const int n16 = (2 * A.a_bytes) >> 4;
+        for (int t = tid; t < n16; t += T2_THREADS) z[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    if (A.epi.mode == SE3_EPI_GATE) {
+        for (int pp = tid; pp < A.epi.d_post; pp += T2_THREADS) {
+            if (pp < A.epi.ns_g) {
+                pcol[pp] = tab[A.t_oz + pp];
+                gcol[pp] = -1;
+            } else {
+                const int qv = pp - A.epi.ns_g, v = qv / 3, c = qv - 3 * v;
+                pcol[pp] = tab[A.t_ov + v] + c;
+                gcol[pp] = tab[A.t_oz + A.epi.ns_g + v];
+            }
+        }
+    }
+    {   // weights -> canonical K-major B tiles (hi | lo)
+        const int KQ1 = A.K1 >> 2, KQ2 = A.K2 >> 2;
+        unsigned char* b1 = smraw + A.o_b1;
+        const int half1 = A.N1 * A.K1 * 4;
+        for (int t = tid; t < A.N1 * A.K1; t += T2_THREADS) {
+            const int n = t / A.K1, k = t - n * A.K1;
+            const int ch = A.sl2ch[k];
+            float x = 0.0f;
+            if (ch >= 0) {
+                if (n < A.mz) x = __ldg(A.wz + (long long)ch * A.mz + n);
+                else if (n >= A.N2 && n - A.N2 < A.mv) x = __ldg(A.wv + (long long)ch * A.mv + (n - A.N2));
+            }
+            float hi, lo;
+            split_tf32(x, hi, lo);
+            const int o = canon_off(n, k, KQ1);
+            *reinterpret_cast<float*>(b1 + o) = hi;
+            *reinterpret_cast<float*>(b1 + half1 + o) = lo;
+        }
+        unsigned char* b2 = smraw + A.o_b2;
+        const int half2 = A.N1 * A.K2 * 4;
+        for (int t = tid; t < A.N1 * A.K2; t += T2_THREADS) {
+            const int n = t / A.K2, k = t - n * A.K2;
+            float x = 0.0f;
+            if (k < A.nd) {
+                if (n < A.mz) x = __ldg(A.wz + (long long)(A.ns + k) * A.mz + n);
+                else if (n >= A.N2 && n - A.N2 < A.mv) x = __ldg(A.wv + (long long)(A.ns + k) * A.mv + (n - A.N2));
+            }
+            float hi, lo;
+            split_tf32(x, hi, lo);
+            const int o = canon_off(n, k, KQ2);
+            *reinterpret_cast<float*>(b2 + o) = hi;
+            *reinterpret_cast<float*>(b2 + half2 + o) = lo;
+        }
+    }
+    fence_proxy_async();
+    if (warp == W2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const long long R = A.rows;
+    const long long ntiles = (R + TM2 - 1) / TM2;
+    const int nt = (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);   // tiles of this CTA
+    const uint32_t ACC = 4u * A.N1;                                            // TMEM columns per accumulator set
+
+    if (warp == W2) {
+        // ================= MMA issuer
+        const uint32_t sb = smem_u32(smraw);
+        const uint32_t idesc = make_idesc(A.N1);
+        const uint32_t sboS = (A.K1 >> 2) * 128, sboV = (A.K2 >> 2) * 128;
+        const uint64_t dB1h = make_desc(sb + A.o_b1, sboS), dB1l = make_desc(sb + A.o_b1 + A.N1 * A.K1 * 4, sboS);
+        const uint64_t dB2h = make_desc(sb + A.o_b2, sboV), dB2l = make_desc(sb + A.o_b2 + A.N1 * A.K2 * 4, sboV);
+        const int nk1 = A.K1 >> 3, nk2 = A.K2 >> 3;
+        const uint32_t vstep = (2u * A.halfV) >> 4;   // descriptor units between consecutive V tiles
+        for (int it = 0; it < nt; ++it) {
+            const int b = it & 1;
+            const uint32_t ph = (it >> 1) & 1;
+            mbar_wait(BAR(b), ph);
+            mbar_wait(BAR(4 + b), ph ^ 1);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t acc = tmem_base + (uint32_t)b * ACC;
+                const uint32_t aS = sb + A.o_a + (uint32_t)b * A.a_bytes;
+                const uint64_t dSh = make_desc(aS, sboS), dSl = make_desc(aS + A.halfS, sboS);
+                for (int j = 0; j < nk1; ++j) {
+                    const uint64_t o = (uint64_t)(j * 16);   // 256 bytes per K-step, in 16-byte units
+                    tc_mma_tf32(acc, dSh + o, dB1h + o, idesc, j ? 1u : 0u);
+                    tc_mma_tf32(acc, dSh + o, dB1l + o, idesc, 1u);
+                    tc_mma_tf32(acc, dSl + o, dB1h + o, idesc, 1u);
+                }
+                const uint64_t dVh = make_desc(aS + A.oV, sboV), dVl = make_desc(aS + A.oV + A.halfV, sboV);
+                for (int c = 0; c < 3; ++c) {
+                    const uint32_t accc = acc + (uint32_t)(c + 1) * A.N1;
+                    const uint64_t co = (uint64_t)c * vstep;
+                    for (int j = 0; j < nk2; ++j) {
+                        const uint64_t o = (uint64_t)(j * 16);
+                        tc_mma_tf32(accc, dVh + co + o, dB2h + o, idesc, j ? 1u : 0u);
+                        tc_mma_tf32(accc, dVh + co + o, dB2l + o, idesc, 1u);
+                        tc_mma_tf32(accc, dVl + co + o, dB2h + o, idesc, 1u);
+                    }
+                }
+                tc_commit(BAR(2 + b));
+            }
+            __syncwarp();
+        }
+    } else {
+        // ================= workers
+        const int KQ1 = A.K1 >> 2, KQ2 = A.K2 >> 2;
+        const int r8 = lane & 7, cq = lane >> 3;
+        float4 R4[MAXT];
+        int nidx[MAXT];
+        // per task constants of this thread
+        auto task_row = [&](const TaskE& T, int& row, int& lc, bool& act) {
+            if (T.info & 1) {
+                const int rb = (T.info >> 4) & 15, cb = (T.info >> 8) & 255, nch = T.info >> 16;
+                const int ch = cb * 4 + cq;
+                row = rb * 8 + r8;
+                lc = ch * 4;
+                act = ch < nch;
+            } else {
+                const int w = (T.info >> 4) & 255, tt = T.info >> 12;
+                const int p = tt * 32 + lane;
+                row = p / w;
+                lc = p - row * w;
+                act = row < TM2;
+            }
+        };
+        auto load_idx = [&](int it) {   // index values of tile `it` of this CTA
+            const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * TM2;
+#pragma unroll
+            for (int i = 0; i < MAXT; ++i) {
+                const int t = warp + i * W2;
+                nidx[i] = 0;
+                if (t < A.ntask) {
+                    const TaskE T = task[t];
+                    int row, lc; bool act;
+                    task_row(T, row, lc, act);
+                    long long gr = row0 + row;
+                    if (gr > R - 1) gr = R - 1;
+                    if (act) nidx[i] = T.idx ? __ldg(T.idx + gr) : (int)gr;   // identity rows: |rows| < 2^31 checked on host
+                }
+            }
+        };
+        auto load_rows = [&]() {        // gather with the index values in nidx
+#pragma unroll
+            for (int i = 0; i < MAXT; ++i) {
+                const int t = warp + i * W2;
+                R4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (t < A.ntask) {
+                    const TaskE T = task[t];
+                    int row, lc; bool act;
+                    task_row(T, row, lc, act);
+                    if (act) {
+                        const float* p = T.base + (long long)nidx[i] * T.ld + lc;
+                        if (T.info & 1) R4[i] = __ldg(reinterpret_cast<const float4*>(p));
+                        else R4[i].x = __ldg(p);
+                    }
+                }
+            }
+        };
+        auto put_col = [&](unsigned char* aset, int code, int row, float x) {
+            const int ty = code >> 13, ix = code & 0x1fff;
+            if (ty == 0) return;
+            float hi, lo;
+            split_tf32(x, hi, lo);
+            if (ty == 1) {
+                const int o = (((row >> 3) * KQ1 + (ix >> 2)) << 7) + ((row & 7) << 4) + ((ix & 3) << 2);
+                *reinterpret_cast<float*>(aset + o) = hi;
+                *reinterpret_cast<float*>(aset + A.halfS + o) = lo;
+            } else {
+                const int o = A.oV + (ty - 2) * 2 * A.halfV + (((row >> 3) * KQ2 + (ix >> 2)) << 7) + ((row & 7) << 4) + ((ix & 3) << 2);
+                *reinterpret_cast<float*>(aset + o) = hi;
+                *reinterpret_cast<float*>(aset + A.halfV + o) = lo;
+            }
+        };
+        auto build = [&](int b) {
+            unsigned char* aset = smraw + A.o_a + b * A.a_bytes;
+#pragma unroll
+            for (int i = 0; i < MAXT; ++i) {
+                const int t = warp + i * W2;
+                if (t < A.ntask) {
+                    const TaskE T = task[t];
+                    int row, lc; bool act;
+                    task_row(T, row, lc, act);
+                    if (!act) continue;
+                    const float4 v = R4[i];
+                    if (T.info & 1) {
+                        const int kc = (int)((T.fast4 >> (8 * cq)) & 255u);
+                        if (kc) {
+                            float4 h, l;
+                            split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+                            const int o = (((row >> 3) * KQ1 + (kc - 1)) << 7) + ((row & 7) << 4);
+                            *reinterpret_cast<float4*>(aset + o) = h;
+                            *reinterpret_cast<float4*>(aset + A.halfS + o) = l;
+                        } else {
+                            const int c0 = T.cum + lc;
+                            put_col(aset, ccode[c0], row, v.x);
+                            put_col(aset, ccode[c0 + 1], row, v.y);
+                            put_col(aset, ccode[c0 + 2], row, v.z);
+                            put_col(aset, ccode[c0 + 3], row, v.w);
+                        }
+                    } else {
+                        put_col(aset, ccode[T.cum + lc], row, v.x);
+                    }
+                }
+            }
+        };
+        // epilogue part 1: TMEM accumulators of tile `it` -> raw tile in shared memory
+        const int e = warp & 3, jq = warp >> 2;
+        float* otile = reinterpret_cast<float*>(smraw + A.o_out);
+        float* ptile = reinterpret_cast<float*>(smraw + A.o_post);
+        const bool gate = A.epi.mode == SE3_EPI_GATE;
+        const int dout = A.d_out, dpost = A.epi.d_post;
+        const float* nzs = norm;
+        const float* nvs = norm + A.mz;
+        const int* oz = tab + A.t_oz;
+        const int* ov = tab + A.t_ov;
+        auto drain = [&](int it) {
+            const int b = it & 1;
+            const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * TM2;
+            const int row = 16 * e + (lane & 15);
+            const bool rowlane = lane < 16;
+            const long long gr = row0 + row;
+            float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rowlane && gr < R) y = __ldg(reinterpret_cast<const float4*>(A.in2) + gr);
+            const float y1 = C3f * y.y, y2 = C3f * y.z, y3 = C3f * y.w, y0c = C3f * y.x;
+            mbar_wait(BAR(2 + b), (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t acc = tmem_base + (uint32_t)b * ACC + ((uint32_t)(32 * e) << 16);
+            float* orow = otile + row * A.dop;
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                const int cb = 16 * jq + 8 * h;
+                if (cb >= A.N1) break;
+                float p[8], ux[8], uy[8], uz[8];
+                tc_ld8(acc + cb, p);
+                tc_ld8(acc + A.N1 + cb, ux);
+                tc_ld8(acc + 2 * A.N1 + cb, uy);
+                tc_ld8(acc + 3 * A.N1 + cb, uz);
+                tc_wait_ld();
+                if (!rowlane) continue;
+                if (cb < A.N2) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int m = cb + j;
+                        if (m < A.mz) orow[oz[m]] = nzs[m] * fmaf(y.x, p[j], fmaf(y1, ux[j], fmaf(y2, uy[j], y3 * uz[j])));
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int m = cb - A.N2 + j;
+                        if (m < A.mv) {
+                            float* o = orow + ov[m];
+                            o[0] = nvs[3 * m] * fmaf(y1, p[j], y0c * ux[j]);
+                            o[1] = nvs[3 * m + 1] * fmaf(y2, p[j], y0c * uy[j]);
+                            o[2] = nvs[3 * m + 2] * fmaf(y3, p[j], y0c * uz[j]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(4 + b));
+        };
+        // epilogue part 2 (all worker threads): raw tile -> global (+residual); gate -> post rows / segment sum
+        auto finish = [&](int it) {
+            const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * TM2;
+            const int nvalid = (int)min((long long)TM2, R - row0);
+            const int et = tid;
+            const bool to_ptile = gate && A.seg_idx;
+            if (A.out_raw) {
+                float* dst = A.out_raw + row0 * dout;
+                const float* res = A.resid ? A.resid + row0 * dout : nullptr;
+                const int total = nvalid * dout;
+                if (A.dop == dout) {
+                    const int n4 = total >> 2;
+                    for (int t = et; t < n4; t += WT) {
+                        float4 v = reinterpret_cast<const float4*>(otile)[t];
+                        if (res) {
+                            const float4 q = __ldg(reinterpret_cast<const float4*>(res) + t);
+                            v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+                        }
+                        reinterpret_cast<float4*>(dst)[t] = v;
+                    }
+                    for (int t = (n4 << 2) + et; t < total; t += WT) dst[t] = otile[t] + (res ? __ldg(res + t) : 0.0f);
+                } else {
+                    for (int r = warp; r < nvalid; r += W2) {
+                        const float* orow2 = otile + r * A.dop;
+                        for (int c = lane; c < dout; c += 32) {
+                            float v = orow2[c];
+                            if (res) v += __ldg(res + r * dout + c);
+                            dst[r * dout + c] = v;
+                        }
+                    }
+                }
+            }
+            if (gate) {
+                float* dstp = A.out_post ? A.out_post + row0 * dpost : nullptr;
+                if ((dpost & 3) == 0) {
+                    const int q4 = dpost >> 2;
+                    const int total4 = nvalid * q4;
+                    for (int t = et; t < total4; t += WT) {
+                        const int r = t / q4, c0 = (t - r * q4) << 2;
+                        const float* orow2 = otile + r * A.dop;
+                        float v[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float x = orow2[pcol[c0 + j]];
+                            const int gc = gcol[c0 + j];
+                            const float gx = gc < 0 ? x : orow2[gc];
+                            v[j] = (gc < 0 ? A.epi.cs : A.epi.cg) * sigm(gx) * x;
+                        }
+                        const float4 o4 = make_float4(v[0], v[1], v[2], v[3]);
+                        if (dstp) reinterpret_cast<float4*>(dstp)[t] = o4;
+                        if (to_ptile) *reinterpret_cast<float4*>(ptile + r * A.dpp + c0) = o4;
+                    }
+                } else {
+                    for (int r = warp; r < nvalid; r += W2) {
+                        const float* orow2 = otile + r * A.dop;
+                        for (int c = lane; c < dpost; c += 32) {
+                            const float x = orow2[pcol[c]];
+                            const int gc = gcol[c];
+                            const float v = gc < 0 ? A.epi.cs * x * sigm(x) : A.epi.cg * sigm(orow2[gc]) * x;
+                            if (dstp) dstp[r * dpost + c] = v;
+                            if (to_ptile) ptile[r * A.dpp + c] = v;
+                        }
+                    }
+                }
+            }
+            if (A.seg_idx) {
+                if (to_ptile) named_bar(1, WT);
+                const float* stile = gate ? ptile : otile;
+                const int sstr = gate ? A.dpp : A.dop, swid = gate ? dpost : dout;
+                int parts = WT / swid;
+                if (parts < 1) parts = 1;
+                if (parts > TM2) parts = TM2;
+                const int rpp = (TM2 + parts - 1) / parts;
+                for (int item = et; item < swid * parts; item += WT) {
+                    const int c = item % swid, qd = item / swid;
+                    const int rbeg = qd * rpp;
+                    const int rend = min(rbeg + rpp, nvalid);
+                    if (rbeg >= rend) continue;
+                    int cur = __ldg(A.seg_idx + row0 + rbeg);
+                    float accv = 0.0f;
+                    for (int r = rbeg; r < rend; ++r) {
+                        const int k = __ldg(A.seg_idx + row0 + r);
+                        if (k != cur) {
+                            atomicAdd(A.out_seg + (long long)cur * swid + c, accv);
+                            cur = k;
+                            accv = 0.0f;
+                        }
+                        accv += stile[r * sstr + c];
+                    }
+                    atomicAdd(A.out_seg + (long long)cur * swid + c, accv);
+                }
+            }
+        };
+
+        // ---- software pipeline: loads of tile it+1 are in flight while tile it is built and tile it-1 is finished
+        if (nt > 0) {
+            load_idx(0);
+            load_rows();
+            if (nt > 1) load_idx(1);
+        }
+        for (int it = 0; it < nt; ++it) {
+            build(it & 1);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(it & 1));
+            if (it + 1 < nt) {
+                load_rows();
+                if (it + 2 < nt) load_idx(it + 2);
+            }
+            if (it >= 1) {
+                named_bar(2, WT);          // every worker is done reading the smem tile of tile it-2
+                drain(it - 1);
+                named_bar(1, WT);
+                finish(it - 1);
+            }
+        }
+        if (nt > 0) {
+            named_bar(2, WT);
+            drain(nt - 1);
+            named_bar(1, WT);
+            finish(nt - 1);
+        }
+    }
+    // ---------------- teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == W2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+}  // namespace se3
+
+using namespace se3;
+
+// Launches the second-generation forward when the configuration is eligible (launched=false otherwise: the caller
+// falls through to the first-generation tcgen05 kernel or the generic fp32 kernel).
+int se3_l1tp_tc2_try_forward(const int n[4], const int m[4], const int t_in[4], const int t_out[4], int ntab,
+                             const int* h_tab, const int* d_tab, const se3_l1tp_fwd_args* a, const RowSrc& src,
+                             const EpiL& epi, cudaStream_t st, bool* launched) {
+    *launched = false;
+    static int disabled = -1;
+    if (disabled < 0) {
+        const char* e = getenv("SE3_DISABLE_TC2");
+        const char* e1 = getenv("SE3_DISABLE_TC");
+        disabled = ((e && e[0] == '1') || (e1 && e1[0] == '1')) ? 1 : 0;
+    }
+    if (disabled) return SE3_OK;
+    if (n[1] || n[2] || m[1] || m[2]) return SE3_OK;
+    const int ns = n[0], nd = n[3], mz = m[0], mv = m[3];
+    if (ns < 1 || nd < 1 || mz < 1 || mv < 1) return SE3_OK;
+    if (a->rows >= (1ll << 31) - TM2) return SE3_OK;
+    if (((uintptr_t)a->in2 & 15) != 0) return SE3_OK;
+    const int dtot = src.cum[src.nseg];
+    if (dtot > MAXCOL - 4) return SE3_OK;
+    static Tc2Args A;   // large: keep off the stack; launches are serialised by the caller's stream use
+    memset(&A, 0, sizeof(A));
+    A.ns = ns; A.nd = nd; A.mz = mz; A.mv = mv;
+    A.N2 = (mz + 7) & ~7;
+    A.N1 = A.N2 + ((mv + 7) & ~7);
+    if (A.N1 > 64) return SE3_OK;   // 2 x 4 N1 TMEM columns
+    // ---- column kinds of the concatenated row
+    std::vector<int> kind(dtot, 0), chan(dtot, -1);   // 1 scalar, 2..4 vector x/y/z
+    for (int k = 0; k < ns; ++k) { const int c = h_tab[t_in[0] + k]; kind[c] = 1; chan[c] = k; }
+    for (int k = 0; k < nd; ++k) {
+        const int c = h_tab[t_in[3] + k];
+        for (int q = 0; q < 3; ++q) { kind[c + q] = 2 + q; chan[c + q] = k; }
+    }
+    // ---- scalar K slots: wide segments keep their 16-byte chunking, narrow segments fill the padding
+    std::vector<int> slot(dtot, -1);
+    std::vector<int> freeslots;
+    int wide[SE3_MAX_SEG];
+    int K1 = 0;
+    for (int s = 0; s < src.nseg; ++s) {
+        const int w = src.cum[s + 1] - src.cum[s];
+        wide[s] = ((w & 3) == 0 && (src.ld[s] & 3) == 0 && ((uintptr_t)src.base[s] & 15) == 0) ? 1 : 0;
+        if (!wide[s]) {
+            if (w > 16) return SE3_OK;
+            continue;
+        }
+        int first = -1, last = -1;
+        for (int c = 0; c < w; ++c)
+            if (kind[src.cum[s] + c] == 1) { if (first < 0) first = c; last = c; }
+        if (first < 0) continue;
+        const int lc0 = first & ~3, span = ((last + 4) & ~3) - lc0;
+        for (int c = lc0; c < lc0 + span; ++c) {
+            if (c < w && kind[src.cum[s] + c] == 1) slot[src.cum[s] + c] = K1 + c - lc0;
+            else freeslots.push_back(K1 + c - lc0);
+        }
+        K1 += span;
+    }
+    size_t fp = 0;
+    for (int s = 0; s < src.nseg; ++s) {
+        if (wide[s]) continue;
+        const int w = src.cum[s + 1] - src.cum[s];
+        for (int c = 0; c < w; ++c)
+            if (kind[src.cum[s] + c] == 1) slot[src.cum[s] + c] = fp < freeslots.size() ? freeslots[fp++] : K1++;
+    }
+    K1 = (K1 + 7) & ~7;
+    const int K2 = (nd + 7) & ~7;
+    if (K1 > MAXK1 || K1 < 8) return SE3_OK;
+    A.K1 = K1; A.K2 = K2;
+    for (int k = 0; k < MAXK1; ++k) A.sl2ch[k] = -1;
+    for (int c = 0; c < dtot; ++c) {
+        if (kind[c] == 1) { A.ccode[c] = (unsigned short)((1 << 13) | slot[c]); A.sl2ch[slot[c]] = (short)chan[c]; }
+        else if (kind[c] >= 2) A.ccode[c] = (unsigned short)((kind[c] << 13) | chan[c]);
+    }
+    // ---- warp tasks
+    int ntask = 0;
+    for (int s = 0; s < src.nseg; ++s) {
+        const int w = src.cum[s + 1] - src.cum[s];
+        if (wide[s]) {
+            const int nch = w >> 2, ncb = (nch + 3) >> 2;
+            for (int cb = 0; cb < ncb; ++cb)
+                for (int rb = 0; rb < TM2 / 8; ++rb) {
+                    if (ntask >= W2 * MAXT) return SE3_OK;
+                    TaskE& T = A.task[ntask++];
+                    T.base = src.base[s]; T.idx = src.idx[s]; T.ld = src.ld[s]; T.cum = src.cum[s];
+                    T.info = 1 | (rb << 4) | (cb << 8) | (nch << 16);
+                    T.fast4 = 0;
+                    for (int q = 0; q < 4; ++q) {
+                        const int ch = cb * 4 + q;
+                        if (ch >= nch) continue;
+                        const int c0 = src.cum[s] + 4 * ch;
+                        const bool f = kind[c0] == 1 && kind[c0 + 1] == 1 && kind[c0 + 2] == 1 && kind[c0 + 3] == 1 &&
+                                       (slot[c0] & 3) == 0 && slot[c0 + 1] == slot[c0] + 1 && slot[c0 + 2] == slot[c0] + 2 &&
+                                       slot[c0 + 3] == slot[c0] + 3;
+                        if (f) T.fast4 |= (unsigned)((slot[c0] >> 2) + 1) << (8 * q);
+                    }
+                }
+        } else {
+            const int nt_ = (TM2 * w + 31) / 32;
+            for (int t = 0; t < nt_; ++t) {
+                if (ntask >= W2 * MAXT) return SE3_OK;
+                TaskE& T = A.task[ntask++];
+                T.base = src.base[s]; T.idx = src.idx[s]; T.ld = src.ld[s]; T.cum = src.cum[s];
+                T.info = 0 | (w << 4) | (t << 12);
+                T.fast4 = 0;
+            }
+        }
+    }
+    A.ntask = ntask;
+    A.rows = a->rows; A.in2 = a->in2; A.wz = a->w[0]; A.wv = a->w[3]; A.nz = a->norm[0]; A.nv = a->norm[3];
+    A.epi = epi; A.out_raw = a->out_raw; A.out_post = a->out_post; A.resid = a->resid; A.seg_idx = a->seg_idx;
+    A.out_seg = a->out_seg; A.tab = d_tab; A.ntab = ntab; A.t_oz = t_out[0]; A.t_ov = t_out[3];
+    A.d_out = mz + 3 * mv;
+    A.dop = ((A.d_out & 1) || (A.d_out & 3) == 2) ? A.d_out : A.d_out + 2;
+    A.dpp = (epi.d_post & 3) == 0 ? tc_stage_stride(epi.d_post) : (epi.d_post | 1);
+    auto al = [](int x, int q) { return (x + q - 1) / q * q; };
+    A.halfS = TM2 * K1 * 4; A.halfV = TM2 * K2 * 4; A.oV = 2 * A.halfS;
+    A.a_bytes = 2 * A.halfS + 6 * A.halfV;
+    int o = 0;
+    A.o_b1 = o; o += 2 * A.N1 * K1 * 4;
+    A.o_b2 = o; o += 2 * A.N1 * K2 * 4;
+    o = al(o, 1024);
+    A.o_a = o; o += 2 * A.a_bytes;
+    A.o_out = o; o += al(TM2 * A.dop * 4, 16);
+    A.o_post = o; o += (epi.mode == SE3_EPI_GATE && a->seg_idx) ? al(TM2 * A.dpp * 4, 16) : 0;
+    A.o_tab = o; o += al(ntab * 4, 16);
+    A.o_norm = o; o += al((mz + 3 * mv) * 4, 16);
+    A.o_task = o; o += al(ntask * (int)sizeof(TaskE), 16);
+    A.o_ccode = o; o += al(MAXCOL * 2, 16);
+    A.o_pcol = o; o += al(2 * epi.d_post * 4 + 16, 16);
+    A.o_bar = o; o += 8 * 8 + 16;
+    int dev = 0, maxsm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (o > maxsm) return SE3_OK;
+    const int smem = std::max(o, 120 * 1024);   // > half an SM: one CTA per SM owns all 512 TMEM columns
+    static bool attr_set = false;
+    if (!attr_set) {
+        SE3_CUDA_TRY(cudaFuncSetAttribute(l1tp_tc2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
+        attr_set = true;
+    }
+    const long long ntiles = (a->rows + TM2 - 1) / TM2;
+    const int grid = (int)std::min<long long>(ntiles, num_sms());
+    l1tp_tc2_fwd_kernel<<<grid, T2_THREADS, smem, st>>>(A);
+    SE3_LAUNCHED();
+    g_tc_launches.fetch_add(1, std::memory_order_relaxed);
+    *launched = true;
+    return SE3_OK;
+}

@@ -295,45 +295,51 @@ __global__ void __launch_bounds__(TBW_THREADS, 1) l1tp_tc_bwdw_kernel(const TcBw
     const uint32_t tmem_base = *tmem_slot;
     const long long R = A.rows;
     const long long ntiles = (R + TMB - 1) / TMB;
+    const int nt_cta = (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
     // TMEM columns
     const int cD1 = 0, cD2 = A.N2, cD3 = A.N2 + A.N3, cD4 = 2 * A.N2 + A.N3;
 
     if (warp == 0) {
         producer_loop<TMB>(A, smraw, BAR(0), BAR(2), lane, true, ntiles);
     } else if (warp == 1) {
-        // ---------------- MMA issuer: per tile 4 K-steps (8 rows each) x {S.HZY, S.HG, Dd.HZ, AVc.HVc} x 3xTF32.
+        // ---------------- MMA issuer: per tile 4 K-steps (8 rows each) x {S.[HZY|HG], Dd.HZ, AVc.HVc} x 3xTF32.
         // All operands are K-major with K = rows: transposed tiles [channel/feature][row], 8-channel groups of
-        // GS = (TMB/4)*128 bytes, the two 16-byte K-chunks of one MMA 128 bytes apart.
+        // GS = (TMB/4)*128 bytes, the two 16-byte K-chunks of one MMA 128 bytes apart.  The tile set is single
+        // buffered, so every descriptor is tile-invariant: they are built once and the loop only adds constants
+        // (profiles/r01_v8: descriptor arithmetic made the issue loop 85 cycles per MMA, 3x the tensor-pipe floor).
         const uint32_t sb = smem_u32(smraw);
         const uint32_t GS = (TMB / 4) * 128;
-        const uint32_t idS1 = make_idesc_ex(A.MS, A.N2, 0, 0), idS2 = make_idesc_ex(A.MS, A.N3, 0, 0);
+        // S.[Y0 HZ | HG] is one MMA: the HG groups follow the HZ groups in the T1 tile and cD2 = cD1 + N2
+        const uint32_t idS = make_idesc_ex(A.MS, A.N2 + A.N3, 0, 0);
         const uint32_t idD = make_idesc_ex(64, A.N2, 0, 0), idV = make_idesc_ex(64, A.N3, 0, 0);
-        int it = 0;
-        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const uint64_t dSh = make_desc(sb + A.o_as, GS), dSl = make_desc(sb + A.o_as + A.sz_as, GS);
+        const uint64_t dDh = make_desc(sb + A.o_ad, GS), dDl = make_desc(sb + A.o_ad + A.sz_ad, GS);
+        const uint64_t dVh = make_desc(sb + A.o_av, GS), dVl = make_desc(sb + A.o_av + A.sz_ad, GS);
+        const uint64_t d1h = make_desc(sb + A.o_t1, GS), d1l = make_desc(sb + A.o_t1 + A.sz_t1, GS);
+        const uint64_t d2h = make_desc(sb + A.o_t2, GS), d2l = make_desc(sb + A.o_t2 + A.sz_t2, GS);
+        const uint64_t d3h = make_desc(sb + A.o_t3, GS), d3l = make_desc(sb + A.o_t3 + A.sz_t3, GS);
+        const uint64_t vA = (uint64_t)((2u * A.sz_ad) >> 4), vB = (uint64_t)((2u * A.sz_t3) >> 4);
+        for (int it = 0; it < nt_cta; ++it) {
             mbar_wait(BAR(4), it & 1);
             tc_fence_after();
             if (lane == 0) {
-#pragma unroll 1
+#pragma unroll
                 for (int ks = 0; ks < TMB / 8; ++ks) {
                     const uint32_t acc0 = (it == 0 && ks == 0) ? 0u : 1u;
-                    const uint32_t ko = ks * 256;
-                    const uint32_t aS = sb + A.o_as + ko, aD = sb + A.o_ad + ko;
-                    const uint32_t b1 = sb + A.o_t1 + ko, b2 = sb + A.o_t2 + ko;
-                    const uint32_t bG = b1 + (A.N2 >> 3) * GS;
-#define SE3_MMA3(D, AH, ASZ, BH, BSZ, ID, FIRST)                                                         \
-    tc_mma_tf32(tmem_base + (D), make_desc((AH), GS), make_desc((BH), GS), (ID), (FIRST));                 \
-    tc_mma_tf32(tmem_base + (D), make_desc((AH), GS), make_desc((BH) + (BSZ), GS), (ID), 1u);              \
-    tc_mma_tf32(tmem_base + (D), make_desc((AH) + (ASZ), GS), make_desc((BH), GS), (ID), 1u);
-                    SE3_MMA3(cD1, aS, A.sz_as, b1, A.sz_t1, idS1, acc0)
-                    SE3_MMA3(cD2, aS, A.sz_as, bG, A.sz_t1, idS2, acc0)
-                    SE3_MMA3(cD3, aD, A.sz_ad, b2, A.sz_t2, idD, acc0)
-#pragma unroll 1
+                    const uint64_t ko = (uint64_t)(ks * 16);   // 256 bytes per K-step in 16-byte units
+                    tc_mma_tf32(tmem_base + cD1, dSh + ko, d1h + ko, idS, acc0);
+                    tc_mma_tf32(tmem_base + cD1, dSh + ko, d1l + ko, idS, 1u);
+                    tc_mma_tf32(tmem_base + cD1, dSl + ko, d1h + ko, idS, 1u);
+                    tc_mma_tf32(tmem_base + cD3, dDh + ko, d2h + ko, idD, acc0);
+                    tc_mma_tf32(tmem_base + cD3, dDh + ko, d2l + ko, idD, 1u);
+                    tc_mma_tf32(tmem_base + cD3, dDl + ko, d2h + ko, idD, 1u);
+#pragma unroll
                     for (int c = 0; c < 3; ++c) {
-                        const uint32_t aV = sb + A.o_av + c * 2 * A.sz_ad + ko;
-                        const uint32_t b3 = sb + A.o_t3 + c * 2 * A.sz_t3 + ko;
-                        SE3_MMA3(cD4, aV, A.sz_ad, b3, A.sz_t3, idV, (c == 0 ? acc0 : 1u))
+                        const uint64_t oa = ko + (uint64_t)c * vA, ob = ko + (uint64_t)c * vB;
+                        tc_mma_tf32(tmem_base + cD4, dVh + oa, d3h + ob, idV, c == 0 ? acc0 : 1u);
+                        tc_mma_tf32(tmem_base + cD4, dVh + oa, d3l + ob, idV, 1u);
+                        tc_mma_tf32(tmem_base + cD4, dVl + oa, d3h + ob, idV, 1u);
                     }
-#undef SE3_MMA3
                 }
                 tc_commit(BAR(5));
             }
@@ -576,32 +582,44 @@ __global__ void __launch_bounds__(TBI_THREADS, 1) l1tp_tc_bwdi_kernel(const TcBw
     if (warp == 0 || warp == 2) {
         producer_loop<TMI>(A, smraw, BAR(0), BAR(2), (warp == 0 ? 0 : 32) + lane, false, ntiles);
     } else if (warp == 1) {
+        // descriptors are tile-invariant (single-buffered H tiles): build them once, add constants in the loop
         const uint32_t sb = smem_u32(smraw);
         const uint32_t id1 = make_idesc(NS), id2 = make_idesc(ND);
         const uint32_t K1 = A.N2 + A.N3;
         const uint32_t sbo_b1 = (K1 >> 2) * 128, sbo_b2 = (A.N2 >> 2) * 128, sbo_b3 = (A.N3 >> 2) * 128;
         const uint32_t hb1 = NS * K1 * 4, hb2 = ND * A.N2 * 4, hb3 = ND * A.N3 * 4;
-        int it = 0;
-        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const uint64_t a1h = make_desc(sb + A.o_t1, A.rg1), a1l = make_desc(sb + A.o_t1 + A.sz_t1, A.rg1);
+        const uint64_t a2h = make_desc(sb + A.o_t2, A.rg2), a2l = make_desc(sb + A.o_t2 + A.sz_t2, A.rg2);
+        const uint64_t a3h = make_desc(sb + A.o_t3, A.rg3), a3l = make_desc(sb + A.o_t3 + A.sz_t3, A.rg3);
+        const uint64_t b1h = make_desc(sb + A.o_b1, sbo_b1), b1l = make_desc(sb + A.o_b1 + hb1, sbo_b1);
+        const uint64_t b2h = make_desc(sb + A.o_b2, sbo_b2), b2l = make_desc(sb + A.o_b2 + hb2, sbo_b2);
+        const uint64_t b3h = make_desc(sb + A.o_b3, sbo_b3), b3l = make_desc(sb + A.o_b3 + hb3, sbo_b3);
+        const uint64_t v3 = (uint64_t)((2u * A.sz_t3) >> 4);
+        const int n1 = (int)(K1 >> 3), n2 = A.N2 >> 3, n3 = A.N3 >> 3;
+        const int nt_cta = (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+        for (int it = 0; it < nt_cta; ++it) {
             mbar_wait(BAR(4), it & 1);
             tc_fence_after();
             if (lane == 0) {
-#define SE3_MMA3K(D, AH, ASZ, ASBO, BH, BSZ, BSBO, ID, FIRST)                                               \
-    tc_mma_tf32(tmem_base + (D), make_desc((AH), (ASBO)), make_desc((BH), (BSBO)), (ID), (FIRST));          \
-    tc_mma_tf32(tmem_base + (D), make_desc((AH), (ASBO)), make_desc((BH) + (BSZ), (BSBO)), (ID), 1u);       \
-    tc_mma_tf32(tmem_base + (D), make_desc((AH) + (ASZ), (ASBO)), make_desc((BH), (BSBO)), (ID), 1u);
-                for (uint32_t j = 0; j < K1 / 8; ++j) {
-                    SE3_MMA3K(cS, sb + A.o_t1 + j * 256, A.sz_t1, A.rg1, sb + A.o_b1 + j * 256, hb1, sbo_b1, id1, j ? 1u : 0u)
+                for (int j = 0; j < n1; ++j) {
+                    const uint64_t o = (uint64_t)(j * 16);
+                    tc_mma_tf32(tmem_base + cS, a1h + o, b1h + o, id1, j ? 1u : 0u);
+                    tc_mma_tf32(tmem_base + cS, a1h + o, b1l + o, id1, 1u);
+                    tc_mma_tf32(tmem_base + cS, a1l + o, b1h + o, id1, 1u);
                 }
-                for (uint32_t j = 0; j < (uint32_t)A.N2 / 8; ++j) {
-                    SE3_MMA3K(cD, sb + A.o_t2 + j * 256, A.sz_t2, A.rg2, sb + A.o_b2 + j * 256, hb2, sbo_b2, id2, j ? 1u : 0u)
+                for (int j = 0; j < n2; ++j) {
+                    const uint64_t o = (uint64_t)(j * 16);
+                    tc_mma_tf32(tmem_base + cD, a2h + o, b2h + o, id2, j ? 1u : 0u);
+                    tc_mma_tf32(tmem_base + cD, a2h + o, b2l + o, id2, 1u);
+                    tc_mma_tf32(tmem_base + cD, a2l + o, b2h + o, id2, 1u);
                 }
-                for (uint32_t c = 0; c < 3; ++c)
-                    for (uint32_t j = 0; j < (uint32_t)A.N3 / 8; ++j) {
-                        SE3_MMA3K(cT + c * ND, sb + A.o_t3 + c * 2 * A.sz_t3 + j * 256, A.sz_t3, A.rg3, sb + A.o_b3 + j * 256, hb3,
-                                  sbo_b3, id2, j ? 1u : 0u)
+                for (int c = 0; c < 3; ++c)
+                    for (int j = 0; j < n3; ++j) {
+                        const uint64_t o = (uint64_t)(j * 16), oa = o + (uint64_t)c * v3;
+                        tc_mma_tf32(tmem_base + cT + c * ND, a3h + oa, b3h + o, id2, j ? 1u : 0u);
+                        tc_mma_tf32(tmem_base + cT + c * ND, a3h + oa, b3l + o, id2, 1u);
+                        tc_mma_tf32(tmem_base + cT + c * ND, a3l + oa, b3h + o, id2, 1u);
                     }
-#undef SE3_MMA3K
                 tc_commit(BAR(6));
             }
             __syncwarp();
@@ -761,6 +779,7 @@ static int fill_common(TcBwdArgs& A, const int n[4], const int m[4], const int t
     A.N2 = (mz + 7) & ~7; A.N3 = (mv + 7) & ~7;
     if (A.NSG8 > 16 || A.NDG8 > 8 || A.N2 + A.N3 > 256) return 1;
     A.MS = A.NSG8 > 8 ? 128 : 64;
+    if (A.MS == 128 && ((A.N2 + A.N3) & 15)) return 1;   // M=128 needs N % 16 == 0 (S.[HZY|HG] is one MMA)
     A.rows = a->rows; A.src = src; A.in2 = a->in2; A.wz = a->w[0]; A.wv = a->w[3]; A.nz = a->norm[0]; A.nv = a->norm[3];
     A.epi = epi; A.raw = a->raw; A.gout = a->gout; A.gout_idx = a->gout_idx; A.tab = d_tab; A.ntab = ntab;
     A.t_s = t_in[0]; A.t_d = t_in[3]; A.t_oz = t_out[0]; A.t_ov = t_out[3];

@@ -27,17 +27,25 @@ static constexpr int W2 = 16;                 // worker warps
 static constexpr int T2_THREADS = (W2 + 1) * 32;
 static constexpr int WT = W2 * 32;            // worker threads
 static constexpr int TM2 = 64;
-static constexpr int MAXT = 6;                // warp tasks per warp and tile
 static constexpr int MAXCOL = 192;
 static constexpr int MAXK1 = 128;
 
-struct TaskE {                                // one warp task: 8 rows x 4 sixteen-byte pieces, or 32 four-byte pieces
+static constexpr int MAXB = 4;                // wide blocks per warp and tile (8 per tile)
+
+struct BlockE {                               // one wide block: 64 rows x 4 consecutive 16-byte pieces of a segment
     const float* base;
     const int32_t* idx;
     int ld;
-    int info;                                 // wide: 1 | rb << 4 | cb << 8 | nchunk << 16   narrow: 0 | w << 4 | t << 12
     int cum;                                  // first concatenated column of the segment
-    unsigned fast4;                           // wide: byte q = K-chunk + 1 of piece 4 cb + q if it is 4 aligned scalars
+    int nch;                                  // 16-byte pieces per row of the segment
+    int cb;                                   // pieces 4 cb .. 4 cb + 3
+    unsigned fast4;                           // byte q = K-chunk + 1 of piece 4 cb + q if it is 4 aligned scalars
+    int pad;
+};
+struct NarrowE {                              // 32 four-byte pieces of a narrow segment (row-major over 64 rows x w)
+    const float* base;
+    const int32_t* idx;
+    int ld, cum, w, t;
 };
 
 struct Tc2Args {
@@ -53,15 +61,16 @@ struct Tc2Args {
     const float* resid;
     const int32_t* seg_idx;
     float* out_seg;
-    const int* tab;
-    int ntab, t_oz, t_ov;
     int ns, nd, mz, mv, d_out;
+    int oz0, ov0;                             // affine output layout: z channel m at oz0 + m, v channel m at ov0 + 3 m
     int K1, K2, N1, N2;
-    int ntask;
+    int nblk, nnar;
     int dop, dpp;
-    int o_b1, o_b2, o_a, a_bytes, o_out, o_post, o_tab, o_norm, o_task, o_ccode, o_pcol, o_bar;
+    unsigned mg_ns, mg_mv, mg_h;              // ceil(2^32 / d) for d = gate_ns, mv, d_out / 2
+    int o_b1, o_b2, o_a, a_bytes, o_out, o_post, o_norm, o_blk, o_ccode, o_bar;
     int halfS, halfV, oV;                     // bytes: lo offset of S / V tiles, first V tile inside an operand set
-    TaskE task[W2 * MAXT];
+    BlockE blk[2 * MAXB];
+    NarrowE nar[W2];
     unsigned short ccode[MAXCOL];             // per concatenated column: type << 13 | index (1: scalar slot, 2..4: x/y/z kd)
     short sl2ch[MAXK1];                       // scalar slot -> scalar channel (-1: padding)
 };
@@ -71,12 +80,9 @@ __device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.syn
 __global__ void __launch_bounds__(T2_THREADS, 1) l1tp_tc2_fwd_kernel(const __grid_constant__ Tc2Args A) {
     extern __shared__ __align__(1024) unsigned char smraw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    int* tab = reinterpret_cast<int*>(smraw + A.o_tab);
     float* norm = reinterpret_cast<float*>(smraw + A.o_norm);
-    TaskE* task = reinterpret_cast<TaskE*>(smraw + A.o_task);
+    BlockE* blks = reinterpret_cast<BlockE*>(smraw + A.o_blk);
     unsigned short* ccode = reinterpret_cast<unsigned short*>(smraw + A.o_ccode);
-    int* pcol = reinterpret_cast<int*>(smraw + A.o_pcol);
-    int* gcol = pcol + A.epi.d_post;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + A.o_bar);
     const uint32_t bar0 = smem_u32(bars);
     // barriers: 0,1 operand set full | 2,3 accumulator full | 4,5 accumulator empty
@@ -84,10 +90,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) l1tp_tc2_fwd_kernel(const __gri
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
     // ---------------- one-time setup
-    for (int t = tid; t < A.ntab; t += T2_THREADS) tab[t] = A.tab[t];
-    for (int t = tid; t < A.mz; t += T2_THREADS) norm[t] = A.nz ? A.nz[t] : 1.0f;
-    for (int t = tid; t < 3 * A.mv; t += T2_THREADS) norm[A.mz + t] = A.nv ? A.nv[t] : 1.0f;
-    for (int t = tid; t < A.ntask; t += T2_THREADS) task[t] = A.task[t];
+    for (int t = tid; t < 3 * A.mv; t += T2_THREADS) norm[t] = A.nv ? A.nv[t] : 1.0f;
+    for (int t = tid; t < A.nblk; t += T2_THREADS) blks[t] = A.blk[t];
     for (int t = tid; t < MAXCOL; t += T2_THREADS) ccode[t] = A.ccode[t];
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
@@ -103,18 +107,6 @@ __global__ void __launch_bounds__(T2_THREADS, 1) l1tp_tc2_fwd_kernel(const __gri
         for (int t = tid; t < n16; t += T2_THREADS) z[t] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
-    if (A.epi.mode == SE3_EPI_GATE) {
-        for (int pp = tid; pp < A.epi.d_post; pp += T2_THREADS) {
-            if (pp < A.epi.ns_g) {
-                pcol[pp] = tab[A.t_oz + pp];
-                gcol[pp] = -1;
-            } else {
-                const int qv = pp - A.epi.ns_g, v = qv / 3, c = qv - 3 * v;
-                pcol[pp] = tab[A.t_ov + v] + c;
-                gcol[pp] = tab[A.t_oz + A.epi.ns_g + v];
-            }
-        }
-    }
     {   // weights -> canonical K-major B tiles (hi | lo)
         const int KQ1 = A.K1 >> 2, KQ2 = A.K2 >> 2;
         unsigned char* b1 = smraw + A.o_b1;
@@ -124,7 +116,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) l1tp_tc2_fwd_kernel(const __gri
             const int ch = A.sl2ch[k];
             float x = 0.0f;
             if (ch >= 0) {
-                if (n < A.mz) x = __ldg(A.wz + (long long)ch * A.mz + n);
+                if (n < A.mz) x = __ldg(A.wz + (long long)ch * A.mz + n) * (A.nz ? __ldg(A.nz + n) : 1.0f);
                 else if (n >= A.N2 && n - A.N2 < A.mv) x = __ldg(A.wv + (long long)ch * A.mv + (n - A.N2));
             }
             float hi, lo;
@@ -139,7 +131,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) l1tp_tc2_fwd_kernel(const __gri
             const int n = t / A.K2, k = t - n * A.K2;
             float x = 0.0f;
             if (k < A.nd) {
-                if (n < A.mz) x = __ldg(A.wz + (long long)(A.ns + k) * A.mz + n);
+                if (n < A.mz) x = __ldg(A.wz + (long long)(A.ns + k) * A.mz + n) * (A.nz ? __ldg(A.nz + n) : 1.0f);
                 else if (n >= A.N2 && n - A.N2 < A.mv) x = __ldg(A.wv + (long long)(A.ns + k) * A.mv + (n - A.N2));
             }
             float hi, lo;
@@ -206,155 +198,165 @@ __global__ void __launch_bounds__(T2_THREADS, 1) l1tp_tc2_fwd_kernel(const __gri
         }
     } else {
         // ================= workers
+        // Everything about WHERE a thread's pieces come from and go to is tile-invariant and lives in registers:
+        // warp w owns row group rb = w & 7 (rows 8 rb + (lane & 7)) of the wide blocks (w >> 3) + 2 i.
         const int KQ1 = A.K1 >> 2, KQ2 = A.K2 >> 2;
         const int r8 = lane & 7, cq = lane >> 3;
-        float4 R4[MAXT];
-        int nidx[MAXT];
-        // per task constants of this thread
-        auto task_row = [&](const TaskE& T, int& row, int& lc, bool& act) {
-            if (T.info & 1) {
-                const int rb = (T.info >> 4) & 15, cb = (T.info >> 8) & 255, nch = T.info >> 16;
-                const int ch = cb * 4 + cq;
-                row = rb * 8 + r8;
-                lc = ch * 4;
-                act = ch < nch;
-            } else {
-                const int w = (T.info >> 4) & 255, tt = T.info >> 12;
-                const int p = tt * 32 + lane;
-                row = p / w;
-                lc = p - row * w;
-                act = row < TM2;
-            }
+        const int wrow = (warp & 7) * 8 + r8;
+        const int rowpartS = (((wrow >> 3) * KQ1) << 7) + ((wrow & 7) << 4);
+        const int rowpartV = (((wrow >> 3) * KQ2) << 7) + ((wrow & 7) << 4);
+        auto enc = [&](int code, int rpS, int rpV) -> int {   // destination of one column: -1 none, bit 30 = V tile
+            const int ty = code >> 13, ix = code & 0x1fff;
+            if (ty == 0) return -1;
+            if (ty == 1) return rpS + ((ix >> 2) << 7) + ((ix & 3) << 2);
+            return (1 << 30) | (A.oV + (ty - 2) * 2 * A.halfV + rpV + ((ix >> 2) << 7) + ((ix & 3) << 2));
         };
-        auto load_idx = [&](int it) {   // index values of tile `it` of this CTA
-            const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * TM2;
+        int gofs[MAXB], dd[MAXB][4];
+        bool act[MAXB], fast[MAXB];
 #pragma unroll
-            for (int i = 0; i < MAXT; ++i) {
-                const int t = warp + i * W2;
-                nidx[i] = 0;
-                if (t < A.ntask) {
-                    const TaskE T = task[t];
-                    int row, lc; bool act;
-                    task_row(T, row, lc, act);
-                    long long gr = row0 + row;
-                    if (gr > R - 1) gr = R - 1;
-                    if (act) nidx[i] = T.idx ? __ldg(T.idx + gr) : (int)gr;   // identity rows: |rows| < 2^31 checked on host
+        for (int i = 0; i < MAXB; ++i) {
+            const int g = (warp >> 3) + 2 * i;
+            act[i] = false; fast[i] = false; gofs[i] = 0;
+            dd[i][0] = dd[i][1] = dd[i][2] = dd[i][3] = -1;
+            if (g < A.nblk) {
+                const BlockE B = blks[g];
+                const int ch = B.cb * 4 + cq;
+                if (ch < B.nch) {
+                    act[i] = true;
+                    gofs[i] = 4 * ch;
+                    const int kc = (int)((B.fast4 >> (8 * cq)) & 255u);
+                    if (kc) {
+                        fast[i] = true;
+                        dd[i][0] = rowpartS + ((kc - 1) << 7);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) dd[i][j] = enc(ccode[B.cum + 4 * ch + j], rowpartS, rowpartV);
+                    }
                 }
+            }
+        }
+        // narrow pieces: at most one task (32 four-byte pieces) per warp
+        bool nact = false;
+        int nrow = 0, ngofs = 0, ndd = -1;
+        if (warp < A.nnar) {
+            const NarrowE N = A.nar[warp];
+            const int p = N.t * 32 + lane;
+            nrow = p / N.w;
+            ngofs = p - nrow * N.w;
+            nact = nrow < TM2;
+            if (nact)
+                ndd = enc(ccode[N.cum + ngofs], (((nrow >> 3) * KQ1) << 7) + ((nrow & 7) << 4),
+                          (((nrow >> 3) * KQ2) << 7) + ((nrow & 7) << 4));
+        }
+        float4 R4[MAXB];
+        float RN = 0.0f;
+        int nidx[MAXB], nnidx = 0;
+        auto load_idx = [&](int it) {   // index values of tile `it` of this CTA (identity rows: |rows| < 2^31, host-checked)
+            const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * TM2;
+            long long gr = row0 + wrow;
+            if (gr > R - 1) gr = R - 1;
+#pragma unroll
+            for (int i = 0; i < MAXB; ++i) {
+                nidx[i] = (int)gr;
+                if (act[i]) {
+                    const int32_t* ip = blks[(warp >> 3) + 2 * i].idx;
+                    if (ip) nidx[i] = __ldg(ip + gr);
+                }
+            }
+            if (nact) {
+                long long g2 = row0 + nrow;
+                if (g2 > R - 1) g2 = R - 1;
+                const int32_t* ip = A.nar[warp].idx;
+                nnidx = ip ? __ldg(ip + g2) : (int)g2;
             }
         };
         auto load_rows = [&]() {        // gather with the index values in nidx
 #pragma unroll
-            for (int i = 0; i < MAXT; ++i) {
-                const int t = warp + i * W2;
-                R4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (t < A.ntask) {
-                    const TaskE T = task[t];
-                    int row, lc; bool act;
-                    task_row(T, row, lc, act);
-                    if (act) {
-                        const float* p = T.base + (long long)nidx[i] * T.ld + lc;
-                        if (T.info & 1) R4[i] = __ldg(reinterpret_cast<const float4*>(p));
-                        else R4[i].x = __ldg(p);
-                    }
+            for (int i = 0; i < MAXB; ++i) {
+                if (act[i]) {
+                    const BlockE& B = blks[(warp >> 3) + 2 * i];
+                    R4[i] = __ldg(reinterpret_cast<const float4*>(B.base + (long long)nidx[i] * B.ld + gofs[i]));
                 }
             }
+            if (nact) RN = __ldg(A.nar[warp].base + (long long)nnidx * A.nar[warp].ld + ngofs);
         };
-        auto put_col = [&](unsigned char* aset, int code, int row, float x) {
-            const int ty = code >> 13, ix = code & 0x1fff;
-            if (ty == 0) return;
+        auto put = [&](unsigned char* aset, int d, float x) {
+            if (d < 0) return;
             float hi, lo;
             split_tf32(x, hi, lo);
-            if (ty == 1) {
-                const int o = (((row >> 3) * KQ1 + (ix >> 2)) << 7) + ((row & 7) << 4) + ((ix & 3) << 2);
-                *reinterpret_cast<float*>(aset + o) = hi;
-                *reinterpret_cast<float*>(aset + A.halfS + o) = lo;
-            } else {
-                const int o = A.oV + (ty - 2) * 2 * A.halfV + (((row >> 3) * KQ2 + (ix >> 2)) << 7) + ((row & 7) << 4) + ((ix & 3) << 2);
-                *reinterpret_cast<float*>(aset + o) = hi;
-                *reinterpret_cast<float*>(aset + A.halfV + o) = lo;
-            }
+            const int o = d & 0x3fffffff;
+            *reinterpret_cast<float*>(aset + o) = hi;
+            *reinterpret_cast<float*>(aset + o + ((d >> 30) ? A.halfV : A.halfS)) = lo;
         };
         auto build = [&](int b) {
             unsigned char* aset = smraw + A.o_a + b * A.a_bytes;
 #pragma unroll
-            for (int i = 0; i < MAXT; ++i) {
-                const int t = warp + i * W2;
-                if (t < A.ntask) {
-                    const TaskE T = task[t];
-                    int row, lc; bool act;
-                    task_row(T, row, lc, act);
-                    if (!act) continue;
-                    const float4 v = R4[i];
-                    if (T.info & 1) {
-                        const int kc = (int)((T.fast4 >> (8 * cq)) & 255u);
-                        if (kc) {
-                            float4 h, l;
-                            split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-                            const int o = (((row >> 3) * KQ1 + (kc - 1)) << 7) + ((row & 7) << 4);
-                            *reinterpret_cast<float4*>(aset + o) = h;
-                            *reinterpret_cast<float4*>(aset + A.halfS + o) = l;
-                        } else {
-                            const int c0 = T.cum + lc;
-                            put_col(aset, ccode[c0], row, v.x);
-                            put_col(aset, ccode[c0 + 1], row, v.y);
-                            put_col(aset, ccode[c0 + 2], row, v.z);
-                            put_col(aset, ccode[c0 + 3], row, v.w);
-                        }
-                    } else {
-                        put_col(aset, ccode[T.cum + lc], row, v.x);
-                    }
+            for (int i = 0; i < MAXB; ++i) {
+                if (!act[i]) continue;
+                const float4 v = R4[i];
+                if (fast[i]) {
+                    float4 h, l;
+                    split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+                    *reinterpret_cast<float4*>(aset + dd[i][0]) = h;
+                    *reinterpret_cast<float4*>(aset + dd[i][0] + A.halfS) = l;
+                } else {
+                    put(aset, dd[i][0], v.x);
+                    put(aset, dd[i][1], v.y);
+                    put(aset, dd[i][2], v.z);
+                    put(aset, dd[i][3], v.w);
                 }
             }
+            if (nact) put(aset, ndd, RN);
         };
-        // epilogue part 1: TMEM accumulators of tile `it` -> raw tile in shared memory
+        // epilogue part 1: TMEM accumulators of tile `it` -> raw tile in shared memory (affine output layout; the l=0
+        // norms are folded into the weights)
         const int e = warp & 3, jq = warp >> 2;
         float* otile = reinterpret_cast<float*>(smraw + A.o_out);
         float* ptile = reinterpret_cast<float*>(smraw + A.o_post);
         const bool gate = A.epi.mode == SE3_EPI_GATE;
         const int dout = A.d_out, dpost = A.epi.d_post;
-        const float* nzs = norm;
-        const float* nvs = norm + A.mz;
-        const int* oz = tab + A.t_oz;
-        const int* ov = tab + A.t_ov;
+        const int drow = 16 * e + (lane & 15);
+        const bool rowlane = lane < 16;
         auto drain = [&](int it) {
             const int b = it & 1;
             const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * TM2;
-            const int row = 16 * e + (lane & 15);
-            const bool rowlane = lane < 16;
-            const long long gr = row0 + row;
+            const long long gr = row0 + drow;
             float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
             if (rowlane && gr < R) y = __ldg(reinterpret_cast<const float4*>(A.in2) + gr);
             const float y1 = C3f * y.y, y2 = C3f * y.z, y3 = C3f * y.w, y0c = C3f * y.x;
             mbar_wait(BAR(2 + b), (it >> 1) & 1);
             tc_fence_after();
             const uint32_t acc = tmem_base + (uint32_t)b * ACC + ((uint32_t)(32 * e) << 16);
-            float* orow = otile + row * A.dop;
-#pragma unroll 1
+            float* orow = otile + drow * A.dop;
+#pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int cb = 16 * jq + 8 * h;
-                if (cb >= A.N1) break;
-                float p[8], ux[8], uy[8], uz[8];
-                tc_ld8(acc + cb, p);
-                tc_ld8(acc + A.N1 + cb, ux);
-                tc_ld8(acc + 2 * A.N1 + cb, uy);
-                tc_ld8(acc + 3 * A.N1 + cb, uz);
-                tc_wait_ld();
-                if (!rowlane) continue;
-                if (cb < A.N2) {
+                if (cb < A.N1) {
+                    float p[8], ux[8], uy[8], uz[8];
+                    tc_ld8(acc + cb, p);
+                    tc_ld8(acc + A.N1 + cb, ux);
+                    tc_ld8(acc + 2 * A.N1 + cb, uy);
+                    tc_ld8(acc + 3 * A.N1 + cb, uz);
+                    tc_wait_ld();
+                    if (rowlane) {
+                        if (cb < A.N2) {
+                            float* o = orow + A.oz0 + cb;
+                            const int lim = A.mz - cb;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int m = cb + j;
-                        if (m < A.mz) orow[oz[m]] = nzs[m] * fmaf(y.x, p[j], fmaf(y1, ux[j], fmaf(y2, uy[j], y3 * uz[j])));
-                    }
-                } else {
+                            for (int j = 0; j < 8; ++j)
+                                if (j < lim) o[j] = fmaf(y.x, p[j], fmaf(y1, ux[j], fmaf(y2, uy[j], y3 * uz[j])));
+                        } else {
+                            const int m0 = cb - A.N2;
+                            float* o = orow + A.ov0 + 3 * m0;
+                            const float* nv3 = norm + 3 * m0;
+                            const int lim = A.mv - m0;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int m = cb - A.N2 + j;
-                        if (m < A.mv) {
-                            float* o = orow + ov[m];
-                            o[0] = nvs[3 * m] * fmaf(y1, p[j], y0c * ux[j]);
-                            o[1] = nvs[3 * m + 1] * fmaf(y2, p[j], y0c * uy[j]);
-                            o[2] = nvs[3 * m + 2] * fmaf(y3, p[j], y0c * uz[j]);
+                            for (int j = 0; j < 8; ++j)
+                                if (j < lim) {
+                                    o[3 * j] = nv3[3 * j] * fmaf(y1, p[j], y0c * ux[j]);
+                                    o[3 * j + 1] = nv3[3 * j + 1] * fmaf(y2, p[j], y0c * uy[j]);
+                                    o[3 * j + 2] = nv3[3 * j + 2] * fmaf(y3, p[j], y0c * uz[j]);
+                                }
                         }
                     }
                 }
@@ -367,15 +369,14 @@ __global__ void __launch_bounds__(T2_THREADS, 1) l1tp_tc2_fwd_kernel(const __gri
         auto finish = [&](int it) {
             const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * TM2;
             const int nvalid = (int)min((long long)TM2, R - row0);
-            const int et = tid;
             const bool to_ptile = gate && A.seg_idx;
             if (A.out_raw) {
                 float* dst = A.out_raw + row0 * dout;
                 const float* res = A.resid ? A.resid + row0 * dout : nullptr;
                 const int total = nvalid * dout;
-                if (A.dop == dout) {
+                if (A.dop == dout) {   // the tile is the exact image of the global rows: linear 16-byte copy
                     const int n4 = total >> 2;
-                    for (int t = et; t < n4; t += WT) {
+                    for (int t = tid; t < n4; t += WT) {
                         float4 v = reinterpret_cast<const float4*>(otile)[t];
                         if (res) {
                             const float4 q = __ldg(reinterpret_cast<const float4*>(res) + t);
@@ -383,7 +384,18 @@ __global__ void __launch_bounds__(T2_THREADS, 1) l1tp_tc2_fwd_kernel(const __gri
                         }
                         reinterpret_cast<float4*>(dst)[t] = v;
                     }
-                    for (int t = (n4 << 2) + et; t < total; t += WT) dst[t] = otile[t] + (res ? __ldg(res + t) : 0.0f);
+                    for (int t = (n4 << 2) + tid; t < total; t += WT) dst[t] = otile[t] + (res ? __ldg(res + t) : 0.0f);
+                } else if ((dout & 1) == 0) {   // 8-byte pairs, rows at stride dop (even)
+                    const int hw = dout >> 1, n2 = nvalid * hw;
+                    for (int t = tid; t < n2; t += WT) {
+                        const int r = (int)__umulhi((unsigned)t, A.mg_h), c2 = t - r * hw;
+                        float2 v = *reinterpret_cast<const float2*>(otile + r * A.dop + 2 * c2);
+                        if (res) {
+                            const float2 q = __ldg(reinterpret_cast<const float2*>(res) + t);
+                            v.x += q.x; v.y += q.y;
+                        }
+                        reinterpret_cast<float2*>(dst)[t] = v;
+                    }
                 } else {
                     for (int r = warp; r < nvalid; r += W2) {
                         const float* orow2 = otile + r * A.dop;
@@ -397,34 +409,29 @@ __global__ void __launch_bounds__(T2_THREADS, 1) l1tp_tc2_fwd_kernel(const __gri
             }
             if (gate) {
                 float* dstp = A.out_post ? A.out_post + row0 * dpost : nullptr;
-                if ((dpost & 3) == 0) {
-                    const int q4 = dpost >> 2;
-                    const int total4 = nvalid * q4;
-                    for (int t = et; t < total4; t += WT) {
-                        const int r = t / q4, c0 = (t - r * q4) << 2;
-                        const float* orow2 = otile + r * A.dop;
-                        float v[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float x = orow2[pcol[c0 + j]];
-                            const int gc = gcol[c0 + j];
-                            const float gx = gc < 0 ? x : orow2[gc];
-                            v[j] = (gc < 0 ? A.epi.cs : A.epi.cg) * sigm(gx) * x;
-                        }
-                        const float4 o4 = make_float4(v[0], v[1], v[2], v[3]);
-                        if (dstp) reinterpret_cast<float4*>(dstp)[t] = o4;
-                        if (to_ptile) *reinterpret_cast<float4*>(ptile + r * A.dpp + c0) = o4;
+                const int nsg = A.epi.ns_g;
+                const int ns_tot = nvalid * nsg;
+                for (int t = tid; t < ns_tot; t += WT) {          // swish on the scalars
+                    const int r = (int)__umulhi((unsigned)t, A.mg_ns), c = t - r * nsg;
+                    const float x = otile[r * A.dop + A.oz0 + c];
+                    const float v = A.epi.cs * x * sigm(x);
+                    if (dstp) dstp[r * dpost + c] = v;
+                    if (to_ptile) ptile[r * A.dpp + c] = v;
+                }
+                const int nv_tot = nvalid * A.mv;
+                for (int t = tid; t < nv_tot; t += WT) {          // sigmoid gate on the vectors, one channel per thread
+                    const int r = (int)__umulhi((unsigned)t, A.mg_mv), v = t - r * A.mv;
+                    const float* orow2 = otile + r * A.dop;
+                    const float s = A.epi.cg * sigm(orow2[A.oz0 + nsg + v]);
+                    const float* xv = orow2 + A.ov0 + 3 * v;
+                    const float a0 = s * xv[0], a1 = s * xv[1], a2 = s * xv[2];
+                    if (dstp) {
+                        float* d = dstp + r * dpost + nsg + 3 * v;
+                        d[0] = a0; d[1] = a1; d[2] = a2;
                     }
-                } else {
-                    for (int r = warp; r < nvalid; r += W2) {
-                        const float* orow2 = otile + r * A.dop;
-                        for (int c = lane; c < dpost; c += 32) {
-                            const float x = orow2[pcol[c]];
-                            const int gc = gcol[c];
-                            const float v = gc < 0 ? A.epi.cs * x * sigm(x) : A.epi.cg * sigm(orow2[gc]) * x;
-                            if (dstp) dstp[r * dpost + c] = v;
-                            if (to_ptile) ptile[r * A.dpp + c] = v;
-                        }
+                    if (to_ptile) {
+                        float* d = ptile + r * A.dpp + nsg + 3 * v;
+                        d[0] = a0; d[1] = a1; d[2] = a2;
                     }
                 }
             }
@@ -436,7 +443,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) l1tp_tc2_fwd_kernel(const __gri
                 if (parts < 1) parts = 1;
                 if (parts > TM2) parts = TM2;
                 const int rpp = (TM2 + parts - 1) / parts;
-                for (int item = et; item < swid * parts; item += WT) {
+                for (int item = tid; item < swid * parts; item += WT) {
                     const int c = item % swid, qd = item / swid;
                     const int rbeg = qd * rpp;
                     const int rend = min(rbeg + rpp, nvalid);
@@ -571,47 +578,52 @@ int se3_l1tp_tc2_try_forward(const int n[4], const int m[4], const int t_in[4], 
         if (kind[c] == 1) { A.ccode[c] = (unsigned short)((1 << 13) | slot[c]); A.sl2ch[slot[c]] = (short)chan[c]; }
         else if (kind[c] >= 2) A.ccode[c] = (unsigned short)((kind[c] << 13) | chan[c]);
     }
-    // ---- warp tasks
-    int ntask = 0;
+    // ---- affine output layout (every irreps string of the form  c x0e + d x1o  in one block each)
+    A.oz0 = h_tab[t_out[0]]; A.ov0 = h_tab[t_out[3]];
+    for (int k = 0; k < mz; ++k) if (h_tab[t_out[0] + k] != A.oz0 + k) return SE3_OK;
+    for (int k = 0; k < mv; ++k) if (h_tab[t_out[3] + k] != A.ov0 + 3 * k) return SE3_OK;
+    if (epi.mode == SE3_EPI_GATE && (epi.ns_g < 1 || epi.ns_g + mv != mz)) return SE3_OK;
+    // ---- wide blocks (warp w: row group w & 7, blocks (w >> 3) + 2 i) and narrow tasks (one per warp at most)
+    int nblk = 0, nnar = 0;
     for (int s = 0; s < src.nseg; ++s) {
         const int w = src.cum[s + 1] - src.cum[s];
         if (wide[s]) {
             const int nch = w >> 2, ncb = (nch + 3) >> 2;
-            for (int cb = 0; cb < ncb; ++cb)
-                for (int rb = 0; rb < TM2 / 8; ++rb) {
-                    if (ntask >= W2 * MAXT) return SE3_OK;
-                    TaskE& T = A.task[ntask++];
-                    T.base = src.base[s]; T.idx = src.idx[s]; T.ld = src.ld[s]; T.cum = src.cum[s];
-                    T.info = 1 | (rb << 4) | (cb << 8) | (nch << 16);
-                    T.fast4 = 0;
-                    for (int q = 0; q < 4; ++q) {
-                        const int ch = cb * 4 + q;
-                        if (ch >= nch) continue;
-                        const int c0 = src.cum[s] + 4 * ch;
-                        const bool f = kind[c0] == 1 && kind[c0 + 1] == 1 && kind[c0 + 2] == 1 && kind[c0 + 3] == 1 &&
-                                       (slot[c0] & 3) == 0 && slot[c0 + 1] == slot[c0] + 1 && slot[c0 + 2] == slot[c0] + 2 &&
-                                       slot[c0 + 3] == slot[c0] + 3;
-                        if (f) T.fast4 |= (unsigned)((slot[c0] >> 2) + 1) << (8 * q);
-                    }
+            for (int cb = 0; cb < ncb; ++cb) {
+                if (nblk >= 2 * MAXB) return SE3_OK;
+                BlockE& B = A.blk[nblk++];
+                B.base = src.base[s]; B.idx = src.idx[s]; B.ld = src.ld[s]; B.cum = src.cum[s]; B.nch = nch; B.cb = cb;
+                B.fast4 = 0; B.pad = 0;
+                for (int q = 0; q < 4; ++q) {
+                    const int ch = cb * 4 + q;
+                    if (ch >= nch) continue;
+                    const int c0 = src.cum[s] + 4 * ch;
+                    const bool f = kind[c0] == 1 && kind[c0 + 1] == 1 && kind[c0 + 2] == 1 && kind[c0 + 3] == 1 &&
+                                   (slot[c0] & 3) == 0 && slot[c0 + 1] == slot[c0] + 1 && slot[c0 + 2] == slot[c0] + 2 &&
+                                   slot[c0 + 3] == slot[c0] + 3;
+                    if (f) B.fast4 |= (unsigned)((slot[c0] >> 2) + 1) << (8 * q);
                 }
+            }
         } else {
             const int nt_ = (TM2 * w + 31) / 32;
             for (int t = 0; t < nt_; ++t) {
-                if (ntask >= W2 * MAXT) return SE3_OK;
-                TaskE& T = A.task[ntask++];
-                T.base = src.base[s]; T.idx = src.idx[s]; T.ld = src.ld[s]; T.cum = src.cum[s];
-                T.info = 0 | (w << 4) | (t << 12);
-                T.fast4 = 0;
+                if (nnar >= W2) return SE3_OK;
+                NarrowE& N = A.nar[nnar++];
+                N.base = src.base[s]; N.idx = src.idx[s]; N.ld = src.ld[s]; N.cum = src.cum[s]; N.w = w; N.t = t;
             }
         }
     }
-    A.ntask = ntask;
+    A.nblk = nblk; A.nnar = nnar;
     A.rows = a->rows; A.in2 = a->in2; A.wz = a->w[0]; A.wv = a->w[3]; A.nz = a->norm[0]; A.nv = a->norm[3];
     A.epi = epi; A.out_raw = a->out_raw; A.out_post = a->out_post; A.resid = a->resid; A.seg_idx = a->seg_idx;
-    A.out_seg = a->out_seg; A.tab = d_tab; A.ntab = ntab; A.t_oz = t_out[0]; A.t_ov = t_out[3];
+    A.out_seg = a->out_seg;
     A.d_out = mz + 3 * mv;
     A.dop = ((A.d_out & 1) || (A.d_out & 3) == 2) ? A.d_out : A.d_out + 2;
     A.dpp = (epi.d_post & 3) == 0 ? tc_stage_stride(epi.d_post) : (epi.d_post | 1);
+    auto magic = [](int d) { return d > 1 ? (unsigned)((0x100000000ull + (unsigned)d - 1) / (unsigned)d) : 0u; };
+    if (epi.mode == SE3_EPI_GATE && (epi.ns_g < 2 || mv < 2)) return SE3_OK;   // magic division needs d >= 2
+    A.mg_ns = magic(epi.ns_g); A.mg_mv = magic(mv); A.mg_h = magic(std::max(2, A.d_out >> 1));
+    if ((A.d_out >> 1) < 2) return SE3_OK;
     auto al = [](int x, int q) { return (x + q - 1) / q * q; };
     A.halfS = TM2 * K1 * 4; A.halfV = TM2 * K2 * 4; A.oV = 2 * A.halfS;
     A.a_bytes = 2 * A.halfS + 6 * A.halfV;
@@ -622,11 +634,9 @@ int se3_l1tp_tc2_try_forward(const int n[4], const int m[4], const int t_in[4], 
     A.o_a = o; o += 2 * A.a_bytes;
     A.o_out = o; o += al(TM2 * A.dop * 4, 16);
     A.o_post = o; o += (epi.mode == SE3_EPI_GATE && a->seg_idx) ? al(TM2 * A.dpp * 4, 16) : 0;
-    A.o_tab = o; o += al(ntab * 4, 16);
-    A.o_norm = o; o += al((mz + 3 * mv) * 4, 16);
-    A.o_task = o; o += al(ntask * (int)sizeof(TaskE), 16);
+    A.o_norm = o; o += al((3 * mv) * 4, 16);
+    A.o_blk = o; o += al(2 * MAXB * (int)sizeof(BlockE), 16);
     A.o_ccode = o; o += al(MAXCOL * 2, 16);
-    A.o_pcol = o; o += al(2 * epi.d_post * 4 + 16, 16);
     A.o_bar = o; o += 8 * 8 + 16;
     int dev = 0, maxsm = 0;
     cudaGetDevice(&dev);

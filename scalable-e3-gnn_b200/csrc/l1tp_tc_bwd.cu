@@ -271,9 +271,11 @@ __global__ void __launch_bounds__(TBW_THREADS, 1) l1tp_tc_bwdw_kernel(const TcBw
     const int* vtab = stab + 8 * A.NSG8;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + A.o_bar);
     const uint32_t bar0 = smem_u32(bars);
-    // barriers: 0,1 stage full | 2,3 stage empty | 4 set full | 5 set empty | 6 acc full
+    // barriers: 0,1 stage full | 2,3 stage empty | 4,7 half-set full | 5,8 half-set empty | 6 acc full.
+    // The 32-row tile set is handed over in two 16-row halves (2 K-steps each), so the builders fill one half while the
+    // tensor pipe consumes the other (profiles/r01_v8: 65 % of the builders' time was spent waiting for whole-set MMAs).
     auto BAR = [&](int i) { return bar0 + 8u * i; };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(BAR(i), TMB);  // one producer lane per row
@@ -282,6 +284,8 @@ __global__ void __launch_bounds__(TBW_THREADS, 1) l1tp_tc_bwdw_kernel(const TcBw
         mbar_init(BAR(4), BW_NBUILD);
         mbar_init(BAR(5), 1);
         mbar_init(BAR(6), 1);
+        mbar_init(BAR(7), BW_NBUILD);
+        mbar_init(BAR(8), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     setup_tables(A, smraw, TBW_THREADS);
@@ -319,13 +323,15 @@ __global__ void __launch_bounds__(TBW_THREADS, 1) l1tp_tc_bwdw_kernel(const TcBw
         const uint64_t d2h = make_desc(sb + A.o_t2, GS), d2l = make_desc(sb + A.o_t2 + A.sz_t2, GS);
         const uint64_t d3h = make_desc(sb + A.o_t3, GS), d3l = make_desc(sb + A.o_t3 + A.sz_t3, GS);
         const uint64_t vA = (uint64_t)((2u * A.sz_ad) >> 4), vB = (uint64_t)((2u * A.sz_t3) >> 4);
-        for (int it = 0; it < nt_cta; ++it) {
-            mbar_wait(BAR(4), it & 1);
+        for (int it = 0; it < 2 * nt_cta; ++it) {
+            const int hf = it & 1, tl = it >> 1;
+            mbar_wait(BAR(hf ? 7 : 4), tl & 1);
             tc_fence_after();
             if (lane == 0) {
 #pragma unroll
-                for (int ks = 0; ks < TMB / 8; ++ks) {
-                    const uint32_t acc0 = (it == 0 && ks == 0) ? 0u : 1u;
+                for (int k2 = 0; k2 < TMB / 16; ++k2) {
+                    const int ks = hf * (TMB / 16) + k2;
+                    const uint32_t acc0 = (it == 0 && k2 == 0) ? 0u : 1u;
                     const uint64_t ko = (uint64_t)(ks * 16);   // 256 bytes per K-step in 16-byte units
                     tc_mma_tf32(tmem_base + cD1, dSh + ko, d1h + ko, idS, acc0);
                     tc_mma_tf32(tmem_base + cD1, dSh + ko, d1l + ko, idS, 1u);
@@ -341,7 +347,7 @@ __global__ void __launch_bounds__(TBW_THREADS, 1) l1tp_tc_bwdw_kernel(const TcBw
                         tc_mma_tf32(tmem_base + cD4, dVl + oa, d3h + ob, idV, 1u);
                     }
                 }
-                tc_commit(BAR(5));
+                tc_commit(BAR(hf ? 8 : 5));
             }
             __syncwarp();
         }
@@ -365,11 +371,11 @@ __global__ void __launch_bounds__(TBW_THREADS, 1) l1tp_tc_bwdw_kernel(const TcBw
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int slot = it & 1, use = it >> 1;
             mbar_wait(BAR(slot), use & 1);                  // stage full
-            mbar_wait(BAR(5), (it & 1) ^ 1);                // tile set free (MMAs of the previous tile done)
             const float* st = smf + (A.o_stage >> 2) + (size_t)slot * A.slot_floats;
-            for (int t = bw; t < ntask; t += BW_NBUILD) {
-                const int rb = t % nrb;
-                int g = t / nrb;
+            for (int rb = 0; rb < nrb; ++rb) {
+            mbar_wait(BAR(rb ? 8 : 5), (it & 1) ^ 1);       // half-set free (its MMAs of the previous tile are done)
+            for (int t = bw; t < ntask / nrb; t += BW_NBUILD) {
+                int g = t;
                 const int r0 = rb * 16 + q * 4;                       // first of this thread's 4 rows
                 const int off = g * GS + ((rb * 4 + q) << 7) + (f8 << 4);  // (group, K-chunk, channel) -- g rebased below
                 if (g < A.NSG8) {
@@ -432,10 +438,10 @@ __global__ void __launch_bounds__(TBW_THREADS, 1) l1tp_tc_bwdw_kernel(const TcBw
             }
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(BAR(4));
-                mbar_arrive(BAR(2 + slot));
+            if (lane == 0) mbar_arrive(BAR(rb ? 7 : 4));
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(2 + slot));
         }
         // ---------------- final epilogue (warps 4-7): TMEM accumulators -> per-CTA partials
         if (bw < 4) {
@@ -849,7 +855,7 @@ int se3_l1tp_tc_try_backward_w(const int n[4], const int m[4], const int t_in[4]
     A.o_tab = o; o += al(ntab * 4, 16);
     A.o_norm = o; o += al((A.mz + 3 * A.mv) * 4, 16);
     A.o_tbl = o; o += al((8 * A.NSG8 + 8 * A.NDG8) * 4, 16);
-    A.o_bar = o; o += 8 * 8 + 16;
+    A.o_bar = o; o += 12 * 8 + 16;
     int dev = 0, maxsm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);

@@ -1093,6 +1093,10 @@ struct se3_l1tp_plan {
 int se3_l1tp_tc2_try_forward(const int n[4], const int m[4], const int t_in[4], const int t_out[4], int ntab,
                              const int* h_tab, const int* d_tab, const se3_l1tp_fwd_args* a, const se3::RowSrc& src,
                              const se3::EpiL& epi, cudaStream_t st, bool* launched);
+int se3_l1tp_tc2_try_backward_in(const int n[4], const int m[4], const int t_in[4], const int t_out[4], int ntab,
+                                 const int* h_tab, const int* d_tab, const se3_l1tp_bwd_args* a, const se3::RowSrc& src,
+                                 const se3::EpiL& epi, float* const gseg[SE3_MAX_SEG], const int gmode[SE3_MAX_SEG],
+                                 cudaStream_t st, bool* launched);
 int se3_l1tp_tc_try_backward_w(const int n[4], const int m[4], const int t_in[4], const int t_out[4], int ntab,
                                const int* d_tab, const se3_l1tp_bwd_args* a, const se3::RowSrc& src, const se3::EpiL& epi,
                                float* partials, int wtot, int gw_z_off, int gw_v_off, int max_grid, cudaStream_t st,
@@ -1383,6 +1387,10 @@ extern "C" int se3_l1tp_backward(se3_l1tp_plan* p, const se3_l1tp_bwd_args* a, v
     for (int s = 0; s < a->nseg; ++s) need_in |= (K.gseg[s] != nullptr && K.gmode[s] != SE3_GRAD_NONE);
     if (need_in) {   // input gradients on the tensor cores when eligible
         bool tci = false;
+        rc = se3_l1tp_tc2_try_backward_in(p->n, p->m, p->t_in, p->t_out, p->L.ntab, p->h_tab.data(), p->d_tab, a, K.src,
+                                          K.epi, K.gseg, K.gmode, st, &tci);
+        if (rc) return rc;
+        if (!tci)
         rc = se3_l1tp_tc_try_backward_in(p->n, p->m, p->t_in, p->t_out, p->L.ntab, p->d_tab, a, K.src, K.epi, K.gseg,
                                          K.gmode, st, &tci);
         if (rc) return rc;

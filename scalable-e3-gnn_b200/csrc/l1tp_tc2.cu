@@ -75,8 +75,6 @@ struct Tc2Args {
     short sl2ch[MAXK1];                       // scalar slot -> scalar channel (-1: padding)
 };
 
-__device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-
 __global__ void __launch_bounds__(T2_THREADS, 1) l1tp_tc2_fwd_kernel(const __grid_constant__ Tc2Args A) {
     extern __shared__ __align__(1024) unsigned char smraw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;

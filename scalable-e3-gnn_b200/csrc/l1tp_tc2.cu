@@ -258,14 +258,14 @@ __global__ void __launch_bounds__(T2_THREADS, 1) l1tp_tc2_fwd_kernel(const __gri
                 nidx[i] = (int)gr;
                 if (act[i]) {
                     const int32_t* ip = blks[(warp >> 3) + 2 * i].idx;
-                    if (ip) nidx[i] = __ldg(ip + gr);
+                    if (ip) nidx[i] = ldgi_v(ip + gr);
                 }
             }
             if (nact) {
                 long long g2 = row0 + nrow;
                 if (g2 > R - 1) g2 = R - 1;
                 const int32_t* ip = A.nar[warp].idx;
-                nnidx = ip ? __ldg(ip + g2) : (int)g2;
+                nnidx = ip ? ldgi_v(ip + g2) : (int)g2;
             }
         };
         auto load_rows = [&]() {        // gather with the index values in nidx
@@ -273,10 +273,10 @@ __global__ void __launch_bounds__(T2_THREADS, 1) l1tp_tc2_fwd_kernel(const __gri
             for (int i = 0; i < MAXB; ++i) {
                 if (act[i]) {
                     const BlockE& B = blks[(warp >> 3) + 2 * i];
-                    R4[i] = __ldg(reinterpret_cast<const float4*>(B.base + (long long)nidx[i] * B.ld + gofs[i]));
+                    R4[i] = ldg4_v(B.base + (long long)nidx[i] * B.ld + gofs[i]);
                 }
             }
-            if (nact) RN = __ldg(A.nar[warp].base + (long long)nnidx * A.nar[warp].ld + ngofs);
+            if (nact) RN = ldg1_v(A.nar[warp].base + (long long)nnidx * A.nar[warp].ld + ngofs);
         };
         auto put = [&](unsigned char* aset, int d, float x) {
             if (d < 0) return;
@@ -315,12 +315,16 @@ __global__ void __launch_bounds__(T2_THREADS, 1) l1tp_tc2_fwd_kernel(const __gri
         const int dout = A.d_out, dpost = A.epi.d_post;
         const int drow = 16 * e + (lane & 15);
         const bool rowlane = lane < 16;
+        float4 ypre = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto prefetch_y = [&](int it) {   // in2 row of this thread's epilogue row of tile `it`, consumed by drain(it)
+            const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * TM2;
+            long long gr = row0 + drow;
+            if (gr > R - 1) gr = R - 1;
+            if (rowlane) ypre = ldg4_v(A.in2 + gr * 4);
+        };
         auto drain = [&](int it) {
             const int b = it & 1;
-            const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * TM2;
-            const long long gr = row0 + drow;
-            float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (rowlane && gr < R) y = __ldg(reinterpret_cast<const float4*>(A.in2) + gr);
+            const float4 y = ypre;
             const float y1 = C3f * y.y, y2 = C3f * y.z, y3 = C3f * y.w, y0c = C3f * y.x;
             mbar_wait(BAR(2 + b), (it >> 1) & 1);
             tc_fence_after();
@@ -483,6 +487,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) l1tp_tc2_fwd_kernel(const __gri
                 named_bar(1, WT);
                 finish(it - 1);
             }
+            prefetch_y(it);
         }
         if (nt > 0) {
             named_bar(2, WT);

@@ -45,12 +45,12 @@ struct Tc2BwdArgs {
     int NSP, NDP;
     int nSI, nVI;
     int gts;
-    int o_bs1, o_bs2, o_bd, o_bt, o_t, t_bytes, o_gt, o_norm, o_tab, o_bar;
+    int o_bs1, o_bs2, o_bd, o_bt, o_t, t_bytes, o_gt, o_norm, o_tab, o_bar, o_sidx;
     int halfT1, halfT3, oT3;
 };
 
-__device__ __forceinline__ float2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
-__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float2 ldg2(const float* p) { return ldg2_v(p); }
+__device__ __forceinline__ float4 ldg4(const float* p) { return ldg4_v(p); }
 
 __global__ void __launch_bounds__(B2_THREADS, 1) l1tp_tc2_bwdi_kernel(const __grid_constant__ Tc2BwdArgs A) {
     extern __shared__ __align__(1024) unsigned char smraw[];
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(B2_THREADS, 1) l1tp_tc2_bwdi_kernel(const __gr
             long long gr = row0 + wrow;
             if (gr > R - 1) gr = R - 1;
             growi_n = gr;
-            gidx_n = A.gout_idx ? (long long)__ldg(A.gout_idx + gr) : gr;
+            gidx_n = A.gout_idx ? (long long)ldgi_v(A.gout_idx + gr) : gr;
         };
         auto load_s = [&](int j, float4& r4, float4& g4) {
             const int c = 4 * j;
@@ -316,12 +316,24 @@ __global__ void __launch_bounds__(B2_THREADS, 1) l1tp_tc2_bwdi_kernel(const __gr
         const bool rowlane = lane < 16;
         const int* scol = tab + A.t_s;
         const int* vcol = tab + A.t_d;
+        int* sidx = reinterpret_cast<int*>(smraw + A.o_sidx);   // [SE3_MAX_SEG][64] destination rows of the tile being scattered
+        int pidx[SE3_MAX_SEG];
+        float4 ypre = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto prefetch_sidx = [&](int it) {   // issued early in the iteration; consumed by drain(it)
+            const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * TMB2;
+            long long gr = row0 + drow;
+            if (gr > R - 1) gr = R - 1;
+            if (rowlane) ypre = ldg4_v(A.in2 + gr * 4);
+#pragma unroll
+            for (int s = 0; s < SE3_MAX_SEG; ++s) {
+                pidx[s] = (int)gr;
+                if (cgq == 0 && rowlane && s < A.src.nseg && A.src.idx[s]) pidx[s] = ldgi_v(A.src.idx[s] + gr);
+            }
+        };
         auto drain = [&](int it) {
             const int b = it & 1;
             const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * TMB2;
-            const long long gr = row0 + drow;
-            float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (rowlane && gr < R) y = __ldg(reinterpret_cast<const float4*>(A.in2) + gr);
+            const float4 y = ypre;
             const float sy0 = C3f * y.x, s1 = C3f * y.y, s2 = C3f * y.z, s3 = C3f * y.w;
             mbar_wait(BAR(2 + b), (it >> 1) & 1);
             tc_fence_after();
@@ -356,6 +368,10 @@ __global__ void __launch_bounds__(B2_THREADS, 1) l1tp_tc2_bwdi_kernel(const __gr
                         }
                 }
             }
+            if (cgq == 0 && rowlane) {
+#pragma unroll
+                for (int s = 0; s < SE3_MAX_SEG; ++s) sidx[s * TMB2 + drow] = pidx[s];
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(4 + b));
@@ -369,7 +385,7 @@ __global__ void __launch_bounds__(B2_THREADS, 1) l1tp_tc2_bwdi_kernel(const __gr
                 const int mode = A.gmode[s];
                 if (!gb || mode == SE3_GRAD_NONE) continue;
                 const int w = A.src.cum[s + 1] - A.src.cum[s], c0 = A.src.cum[s], ld = A.src.ld[s];
-                const int32_t* idx = A.src.idx[s];
+                const int* idx = sidx + s * TMB2;   // destination row of every tile row (identity rows included)
                 const bool v4 = (w & 3) == 0 && (ld & 3) == 0 && (c0 & 3) == 0 && ((uintptr_t)gb & 15) == 0;
                 if (mode == SE3_GRAD_STORE || mode == SE3_GRAD_ATOMIC) {
                     if (v4) {
@@ -377,7 +393,7 @@ __global__ void __launch_bounds__(B2_THREADS, 1) l1tp_tc2_bwdi_kernel(const __gr
                         for (int t = tid; t < nvalid * w4; t += BWT) {
                             const int r = t / w4, c = (t - r * w4) << 2;
                             const float4 v = *reinterpret_cast<const float4*>(gt + r * gts + c0 + c);
-                            const long long dr = idx ? (long long)__ldg(idx + row0 + r) : row0 + r;
+                            const long long dr = idx[r];
                             float* dst = gb + dr * ld + c;
                             if (mode == SE3_GRAD_STORE) *reinterpret_cast<float4*>(dst) = v;
                             else red_add_v4(dst, v.x, v.y, v.z, v.w);
@@ -386,7 +402,7 @@ __global__ void __launch_bounds__(B2_THREADS, 1) l1tp_tc2_bwdi_kernel(const __gr
                         for (int t = tid; t < nvalid * w; t += BWT) {
                             const int r = t / w, c = t - r * w;
                             const float v = gt[r * gts + c0 + c];
-                            const long long dr = idx ? (long long)__ldg(idx + row0 + r) : row0 + r;
+                            const long long dr = idx[r];
                             if (mode == SE3_GRAD_STORE) gb[dr * ld + c] = v;
                             else atomicAdd(gb + dr * ld + c, v);
                         }
@@ -401,10 +417,10 @@ __global__ void __launch_bounds__(B2_THREADS, 1) l1tp_tc2_bwdi_kernel(const __gr
                         const int rbeg = qd * rpp;
                         const int rend = min(rbeg + rpp, nvalid);
                         if (rbeg >= rend) continue;
-                        int cur = __ldg(idx + row0 + rbeg);
+                        int cur = idx[rbeg];
                         float accv = 0.0f;
                         for (int r = rbeg; r < rend; ++r) {
-                            const int k = __ldg(idx + row0 + r);
+                            const int k = idx[r];
                             if (k != cur) {
                                 atomicAdd(gb + (long long)cur * ld + c, accv);
                                 cur = k;
@@ -440,6 +456,7 @@ __global__ void __launch_bounds__(B2_THREADS, 1) l1tp_tc2_bwdi_kernel(const __gr
                 named_bar(1, BWT);
                 scatter(it - 1);
             }
+            prefetch_sidx(it);
         }
         if (nt > 0) {
             named_bar(2, BWT);
@@ -519,6 +536,7 @@ int se3_l1tp_tc2_try_backward_in(const int n[4], const int m[4], const int t_in[
     A.o_norm = o; o += al((mz + 3 * mv) * 4, 16);
     A.o_tab = o; o += al(ntab * 4, 16);
     A.o_bar = o; o += 8 * 8 + 16;
+    A.o_sidx = o; o += SE3_MAX_SEG * TMB2 * 4;
     int dev = 0, maxsm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);

@@ -47,7 +47,7 @@ struct TcBwdArgs {
     int graw_vec16, g_vec16, tmem_cols;
     // shared memory byte offsets
     int o_as, o_ad, o_av, o_t1, o_t2, o_t3, o_stage, o_tab, o_norm, o_tbl, o_bar, o_b1, o_b2, o_b3, o_gt;
-    int NS8, ND8, gts;
+    int NS8, ND8, gts, o_sidx;
     int rg_s, rg_d, rg1, rg2, rg3;           // bytes per 8-row group of each tile
     int sz_as, sz_ad, sz_t1, sz_t2, sz_t3;   // bytes of one (hi or lo) tile
 };
@@ -169,7 +169,8 @@ __device__ __forceinline__ void build_h_task(const TcBwdArgs& A, unsigned char* 
 // producer: one row per lane; segments (if with_x), in2, raw (gate) and the cotangent row
 template <int ROWS>
 __device__ __forceinline__ void producer_loop(const TcBwdArgs& A, unsigned char* smraw, uint32_t bar_full0,
-                                              uint32_t bar_empty0, int prow, bool with_x, long long ntiles) {
+                                              uint32_t bar_empty0, int prow, bool with_x, long long ntiles,
+                                              int part = 0, int nparts = 1) {
     const long long R = A.rows;
     long long cur[SE3_MAX_SEG];
     long long curg;
@@ -194,16 +195,16 @@ __device__ __forceinline__ void producer_loop(const TcBwdArgs& A, unsigned char*
                 const float* srcp = A.src.base[s] + (valid ? cur[s] * A.src.ld[s] : 0);
                 const uint32_t dst = sbase + (A.soff[s] + prow * A.sstride[s]) * 4;
                 const int w = A.swidth[s];
-                if (A.vec16[s]) for (int c = 0; c < w; c += 4) cp_async16(dst + c * 4, srcp + c, valid);
-                else for (int c = 0; c < w; ++c) cp_async4(dst + c * 4, srcp + c, valid);
+                if (A.vec16[s]) for (int c = 4 * part; c < w; c += 4 * nparts) cp_async16(dst + c * 4, srcp + c, valid);
+                else for (int c = part; c < w; c += nparts) cp_async4(dst + c * 4, srcp + c, valid);
             }
         }
-        cp_async16(sbase + (A.in2off + prow * 4) * 4, A.in2 + (valid ? gr * 4 : 0), valid);
+        if (part == 0) cp_async16(sbase + (A.in2off + prow * 4) * 4, A.in2 + (valid ? gr * 4 : 0), valid);
         if (A.epi.mode == SE3_EPI_GATE) {
             const float* srcp = A.raw + (valid ? gr * A.d_out : 0);
             const uint32_t dst = sbase + (A.rawoff + prow * A.rawstride) * 4;
-            if (A.graw_vec16) for (int c = 0; c < A.d_out; c += 4) cp_async16(dst + c * 4, srcp + c, valid);
-            else for (int c = 0; c < A.d_out; c += 2) {
+            if (A.graw_vec16) for (int c = 4 * part; c < A.d_out; c += 4 * nparts) cp_async16(dst + c * 4, srcp + c, valid);
+            else for (int c = 2 * part; c < A.d_out; c += 2 * nparts) {
                 const int sz = valid ? 8 : 0;
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst + c * 4), "l"(srcp + c), "r"(sz) : "memory");
             }
@@ -211,8 +212,8 @@ __device__ __forceinline__ void producer_loop(const TcBwdArgs& A, unsigned char*
         {
             const float* srcp = A.gout + (valid ? curg * A.gwidth : 0);
             const uint32_t dst = sbase + (A.goff + prow * A.gstride) * 4;
-            if (A.g_vec16) for (int c = 0; c < A.gwidth; c += 4) cp_async16(dst + c * 4, srcp + c, valid);
-            else for (int c = 0; c < A.gwidth; ++c) cp_async4(dst + c * 4, srcp + c, valid);
+            if (A.g_vec16) for (int c = 4 * part; c < A.gwidth; c += 4 * nparts) cp_async16(dst + c * 4, srcp + c, valid);
+            else for (int c = part; c < A.gwidth; c += nparts) cp_async4(dst + c * 4, srcp + c, valid);
         }
         cp_async_mbar_arrive_noinc(bar_full0 + 8 * slot);
         const long long grn = (tile + gridDim.x) * ROWS + prow;
@@ -220,6 +221,96 @@ __device__ __forceinline__ void producer_loop(const TcBwdArgs& A, unsigned char*
         for (int s = 0; s < SE3_MAX_SEG; ++s)
             cur[s] = (with_x && s < A.src.nseg && grn < R) ? (A.src.idx[s] ? (long long)A.src.idx[s][grn] : grn) : 0;
         curg = grn < R ? (A.gout_idx ? (long long)A.gout_idx[grn] : grn) : 0;
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
+// Coalesced producer (weight-gradient kernel): NP producer lanes walk the 16/8/4-byte pieces of the tile row-major
+// (consecutive lanes = consecutive pieces of one row), so one cp.async instruction touches a few 128-byte lines instead
+// of 32 (profiles/r01_v13_bwdw: with one row per lane the single producer warp was the bottleneck, builders waited
+// 27 % of the time for "stage full").  Row indices of the tile are staged in shared memory first.
+template <int ROWS, int NP>
+__device__ __forceinline__ void producer_loop_coalesced(const TcBwdArgs& A, unsigned char* smraw, uint32_t bar_full0,
+                                                        uint32_t bar_empty0, int pl, long long ntiles) {
+    const long long R = A.rows;
+    int* sidx = reinterpret_cast<int*>(smraw + A.o_sidx);   // [2][SE3_MAX_SEG + 1][ROWS]
+    const bool idxlane = pl < ROWS;
+    long long cur[SE3_MAX_SEG], curg = 0;
+    auto fetch_idx = [&](long long tile) {
+        const long long gr = tile * ROWS + pl;
+#pragma unroll
+        for (int s = 0; s < SE3_MAX_SEG; ++s)
+            cur[s] = (idxlane && s < A.src.nseg && gr < R) ? (A.src.idx[s] ? (long long)A.src.idx[s][gr] : gr) : 0;
+        curg = (idxlane && gr < R) ? (A.gout_idx ? (long long)A.gout_idx[gr] : gr) : 0;
+    };
+    fetch_idx(blockIdx.x);
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int slot = it & 1, use = it >> 1;
+        mbar_wait(bar_empty0 + 8 * slot, (use & 1) ^ 1);
+        int* si = sidx + slot * (SE3_MAX_SEG + 1) * ROWS;
+        if (idxlane) {
+#pragma unroll
+            for (int s = 0; s < SE3_MAX_SEG; ++s) si[s * ROWS + pl] = (int)cur[s];
+            si[SE3_MAX_SEG * ROWS + pl] = (int)curg;
+        }
+        named_bar(3, NP);
+        const uint32_t sbase = smem_u32(smraw) + A.o_stage + (uint32_t)slot * A.slot_floats * 4;
+        const long long row0 = tile * ROWS;
+        // one source: `ppr` pieces of PB bytes per row
+        auto copy_src = [&](const float* base, const int* ix, int ld, int ppr, int pb_floats, int soff, int sstride) {
+            int row = 0, c = pl;
+            while (c >= ppr) { c -= ppr; ++row; }
+            while (row < ROWS) {
+                const bool valid = row0 + row < R;
+                const float* srcp = base + (valid ? (long long)ix[row] * ld : 0) + c * pb_floats;
+                const uint32_t dst = sbase + (soff + row * sstride + c * pb_floats) * 4;
+                if (pb_floats == 4) cp_async16(dst, srcp, valid);
+                else if (pb_floats == 2) {
+                    const int sz = valid ? 8 : 0;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(srcp), "r"(sz) : "memory");
+                } else cp_async4(dst, srcp, valid);
+                c += NP;
+                while (c >= ppr) { c -= ppr; ++row; }
+            }
+        };
+#pragma unroll
+        for (int s = 0; s < SE3_MAX_SEG; ++s) {
+            if (s >= A.src.nseg) break;
+            const int w = A.swidth[s];
+            if (A.vec16[s]) copy_src(A.src.base[s], si + s * ROWS, A.src.ld[s], w >> 2, 4, A.soff[s], A.sstride[s]);
+            else copy_src(A.src.base[s], si + s * ROWS, A.src.ld[s], w, 1, A.soff[s], A.sstride[s]);
+        }
+        {   // in2: identity rows
+            int row = pl;
+            while (row < ROWS) {
+                const bool valid = row0 + row < R;
+                cp_async16(sbase + (A.in2off + row * 4) * 4, A.in2 + (valid ? (row0 + row) * 4 : 0), valid);
+                row += NP;
+            }
+        }
+        if (A.epi.mode == SE3_EPI_GATE) {
+            // identity rows of the saved pre-activation: index = row0 + row, via a tiny identity trick (ix = nullptr)
+            int row = 0, c = pl;
+            const int ppr = A.graw_vec16 ? (A.d_out >> 2) : (A.d_out >> 1), pbf = A.graw_vec16 ? 4 : 2;
+            while (c >= ppr) { c -= ppr; ++row; }
+            while (row < ROWS) {
+                const bool valid = row0 + row < R;
+                const float* srcp = A.raw + (valid ? (row0 + row) * A.d_out : 0) + c * pbf;
+                const uint32_t dst = sbase + (A.rawoff + row * A.rawstride + c * pbf) * 4;
+                if (pbf == 4) cp_async16(dst, srcp, valid);
+                else {
+                    const int sz = valid ? 8 : 0;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(srcp), "r"(sz) : "memory");
+                }
+                c += NP;
+                while (c >= ppr) { c -= ppr; ++row; }
+            }
+        }
+        if (A.g_vec16) copy_src(A.gout, si + SE3_MAX_SEG * ROWS, A.gwidth, A.gwidth >> 2, 4, A.goff, A.gstride);
+        else copy_src(A.gout, si + SE3_MAX_SEG * ROWS, A.gwidth, A.gwidth, 1, A.goff, A.gstride);
+        cp_async_mbar_arrive_noinc(bar_full0 + 8 * slot);
+        fetch_idx(tile + gridDim.x);
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
 }
@@ -278,7 +369,7 @@ __global__ void __launch_bounds__(TBW_THREADS, 1) l1tp_tc_bwdw_kernel(const TcBw
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
-            mbar_init(BAR(i), TMB);  // one producer lane per row
+            mbar_init(BAR(i), 64);  // 64 producer lanes (warps 0 and 2)
             mbar_init(BAR(2 + i), BW_NBUILD);
         }
         mbar_init(BAR(4), BW_NBUILD);
@@ -303,8 +394,8 @@ __global__ void __launch_bounds__(TBW_THREADS, 1) l1tp_tc_bwdw_kernel(const TcBw
     // TMEM columns
     const int cD1 = 0, cD2 = A.N2, cD3 = A.N2 + A.N3, cD4 = 2 * A.N2 + A.N3;
 
-    if (warp == 0) {
-        producer_loop<TMB>(A, smraw, BAR(0), BAR(2), lane, true, ntiles);
+    if (warp == 0 || warp == 2) {
+        producer_loop<TMB>(A, smraw, BAR(0), BAR(2), lane, true, ntiles, warp == 0 ? 0 : 1, 2);
     } else if (warp == 1) {
         // ---------------- MMA issuer: per tile 4 K-steps (8 rows each) x {S.[HZY|HG], Dd.HZ, AVc.HVc} x 3xTF32.
         // All operands are K-major with K = rows: transposed tiles [channel/feature][row], 8-channel groups of
@@ -856,6 +947,7 @@ int se3_l1tp_tc_try_backward_w(const int n[4], const int m[4], const int t_in[4]
     A.o_norm = o; o += al((A.mz + 3 * A.mv) * 4, 16);
     A.o_tbl = o; o += al((8 * A.NSG8 + 8 * A.NDG8) * 4, 16);
     A.o_bar = o; o += 12 * 8 + 16;
+    A.o_sidx = o; o += 2 * (SE3_MAX_SEG + 1) * TMB * 4;
     int dev = 0, maxsm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);

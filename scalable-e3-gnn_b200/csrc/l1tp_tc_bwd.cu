@@ -18,9 +18,9 @@
 
 namespace se3 {
 
-static constexpr int TBW_THREADS = 512;  // warps: 0,2 producers | 1 MMA | 4-15 builders (4-7 also final epilogue)
+static constexpr int TBW_THREADS = 768;  // warps: 0,2 producers | 1 MMA | 4-15 builders (4-7 also final epilogue)
 static constexpr int TMB = 32;           // rows per tile of the weight-gradient kernel (= 4 MMA K-steps)
-static constexpr int BW_BUILD_W0 = 4, BW_NBUILD = 12;
+static constexpr int BW_BUILD_W0 = 4, BW_NBUILD = 20, BW_NSLOT = 3;
 
 struct TcBwdArgs {
     long long rows;
@@ -47,7 +47,7 @@ struct TcBwdArgs {
     int graw_vec16, g_vec16, tmem_cols;
     // shared memory byte offsets
     int o_as, o_ad, o_av, o_t1, o_t2, o_t3, o_stage, o_tab, o_norm, o_tbl, o_bar, o_b1, o_b2, o_b3, o_gt;
-    int NS8, ND8, gts, o_sidx;
+    int NS8, ND8, gts;
     int rg_s, rg_d, rg1, rg2, rg3;           // bytes per 8-row group of each tile
     int sz_as, sz_ad, sz_t1, sz_t2, sz_t3;   // bytes of one (hi or lo) tile
 };
@@ -167,23 +167,27 @@ __device__ __forceinline__ void build_h_task(const TcBwdArgs& A, unsigned char* 
 }
 
 // producer: one row per lane; segments (if with_x), in2, raw (gate) and the cotangent row
-template <int ROWS>
+template <int ROWS, int NSLOT = 2>
 __device__ __forceinline__ void producer_loop(const TcBwdArgs& A, unsigned char* smraw, uint32_t bar_full0,
                                               uint32_t bar_empty0, int prow, bool with_x, long long ntiles,
                                               int part = 0, int nparts = 1) {
     const long long R = A.rows;
-    long long cur[SE3_MAX_SEG];
-    long long curg;
-    {
-        const long long gr = (long long)blockIdx.x * ROWS + prow;
+    // row indices are fetched TWO tiles ahead (cur: next tile to load, nxt: the one after): with an almost always
+    // empty stage the one-ahead prefetch was consumed immediately and its latency serialised with the row loads
+    // (profiles/r01_v16_bwdw: the producers spent 75 % of their time waiting for index values)
+    long long cur[SE3_MAX_SEG], nxt[SE3_MAX_SEG];
+    long long curg, nxtg;
+    auto fetch = [&](long long tile, long long (&c)[SE3_MAX_SEG], long long& cg) {
+        const long long gr = tile * ROWS + prow;
 #pragma unroll
         for (int s = 0; s < SE3_MAX_SEG; ++s)
-            cur[s] = (with_x && s < A.src.nseg && gr < R) ? (A.src.idx[s] ? (long long)A.src.idx[s][gr] : gr) : 0;
-        curg = gr < R ? (A.gout_idx ? (long long)A.gout_idx[gr] : gr) : 0;
-    }
-    int it = 0;
+            c[s] = (with_x && s < A.src.nseg && gr < R) ? (A.src.idx[s] ? (long long)A.src.idx[s][gr] : gr) : 0;
+        cg = gr < R ? (A.gout_idx ? (long long)A.gout_idx[gr] : gr) : 0;
+    };
+    fetch(blockIdx.x, cur, curg);
+    fetch((long long)blockIdx.x + gridDim.x, nxt, nxtg);
+    int it = 0, slot = 0, use = 0;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        const int slot = it & 1, use = it >> 1;
         const long long gr = tile * ROWS + prow;
         const bool valid = gr < R;
         mbar_wait(bar_empty0 + 8 * slot, (use & 1) ^ 1);
@@ -216,101 +220,11 @@ __device__ __forceinline__ void producer_loop(const TcBwdArgs& A, unsigned char*
             else for (int c = part; c < A.gwidth; c += nparts) cp_async4(dst + c * 4, srcp + c, valid);
         }
         cp_async_mbar_arrive_noinc(bar_full0 + 8 * slot);
-        const long long grn = (tile + gridDim.x) * ROWS + prow;
 #pragma unroll
-        for (int s = 0; s < SE3_MAX_SEG; ++s)
-            cur[s] = (with_x && s < A.src.nseg && grn < R) ? (A.src.idx[s] ? (long long)A.src.idx[s][grn] : grn) : 0;
-        curg = grn < R ? (A.gout_idx ? (long long)A.gout_idx[grn] : grn) : 0;
-    }
-    asm volatile("cp.async.wait_all;" ::: "memory");
-}
-
-// Coalesced producer (weight-gradient kernel): NP producer lanes walk the 16/8/4-byte pieces of the tile row-major
-// (consecutive lanes = consecutive pieces of one row), so one cp.async instruction touches a few 128-byte lines instead
-// of 32 (profiles/r01_v13_bwdw: with one row per lane the single producer warp was the bottleneck, builders waited
-// 27 % of the time for "stage full").  Row indices of the tile are staged in shared memory first.
-template <int ROWS, int NP>
-__device__ __forceinline__ void producer_loop_coalesced(const TcBwdArgs& A, unsigned char* smraw, uint32_t bar_full0,
-                                                        uint32_t bar_empty0, int pl, long long ntiles) {
-    const long long R = A.rows;
-    int* sidx = reinterpret_cast<int*>(smraw + A.o_sidx);   // [2][SE3_MAX_SEG + 1][ROWS]
-    const bool idxlane = pl < ROWS;
-    long long cur[SE3_MAX_SEG], curg = 0;
-    auto fetch_idx = [&](long long tile) {
-        const long long gr = tile * ROWS + pl;
-#pragma unroll
-        for (int s = 0; s < SE3_MAX_SEG; ++s)
-            cur[s] = (idxlane && s < A.src.nseg && gr < R) ? (A.src.idx[s] ? (long long)A.src.idx[s][gr] : gr) : 0;
-        curg = (idxlane && gr < R) ? (A.gout_idx ? (long long)A.gout_idx[gr] : gr) : 0;
-    };
-    fetch_idx(blockIdx.x);
-    int it = 0;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        const int slot = it & 1, use = it >> 1;
-        mbar_wait(bar_empty0 + 8 * slot, (use & 1) ^ 1);
-        int* si = sidx + slot * (SE3_MAX_SEG + 1) * ROWS;
-        if (idxlane) {
-#pragma unroll
-            for (int s = 0; s < SE3_MAX_SEG; ++s) si[s * ROWS + pl] = (int)cur[s];
-            si[SE3_MAX_SEG * ROWS + pl] = (int)curg;
-        }
-        named_bar(3, NP);
-        const uint32_t sbase = smem_u32(smraw) + A.o_stage + (uint32_t)slot * A.slot_floats * 4;
-        const long long row0 = tile * ROWS;
-        // one source: `ppr` pieces of PB bytes per row
-        auto copy_src = [&](const float* base, const int* ix, int ld, int ppr, int pb_floats, int soff, int sstride) {
-            int row = 0, c = pl;
-            while (c >= ppr) { c -= ppr; ++row; }
-            while (row < ROWS) {
-                const bool valid = row0 + row < R;
-                const float* srcp = base + (valid ? (long long)ix[row] * ld : 0) + c * pb_floats;
-                const uint32_t dst = sbase + (soff + row * sstride + c * pb_floats) * 4;
-                if (pb_floats == 4) cp_async16(dst, srcp, valid);
-                else if (pb_floats == 2) {
-                    const int sz = valid ? 8 : 0;
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(srcp), "r"(sz) : "memory");
-                } else cp_async4(dst, srcp, valid);
-                c += NP;
-                while (c >= ppr) { c -= ppr; ++row; }
-            }
-        };
-#pragma unroll
-        for (int s = 0; s < SE3_MAX_SEG; ++s) {
-            if (s >= A.src.nseg) break;
-            const int w = A.swidth[s];
-            if (A.vec16[s]) copy_src(A.src.base[s], si + s * ROWS, A.src.ld[s], w >> 2, 4, A.soff[s], A.sstride[s]);
-            else copy_src(A.src.base[s], si + s * ROWS, A.src.ld[s], w, 1, A.soff[s], A.sstride[s]);
-        }
-        {   // in2: identity rows
-            int row = pl;
-            while (row < ROWS) {
-                const bool valid = row0 + row < R;
-                cp_async16(sbase + (A.in2off + row * 4) * 4, A.in2 + (valid ? (row0 + row) * 4 : 0), valid);
-                row += NP;
-            }
-        }
-        if (A.epi.mode == SE3_EPI_GATE) {
-            // identity rows of the saved pre-activation: index = row0 + row, via a tiny identity trick (ix = nullptr)
-            int row = 0, c = pl;
-            const int ppr = A.graw_vec16 ? (A.d_out >> 2) : (A.d_out >> 1), pbf = A.graw_vec16 ? 4 : 2;
-            while (c >= ppr) { c -= ppr; ++row; }
-            while (row < ROWS) {
-                const bool valid = row0 + row < R;
-                const float* srcp = A.raw + (valid ? (row0 + row) * A.d_out : 0) + c * pbf;
-                const uint32_t dst = sbase + (A.rawoff + row * A.rawstride + c * pbf) * 4;
-                if (pbf == 4) cp_async16(dst, srcp, valid);
-                else {
-                    const int sz = valid ? 8 : 0;
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(srcp), "r"(sz) : "memory");
-                }
-                c += NP;
-                while (c >= ppr) { c -= ppr; ++row; }
-            }
-        }
-        if (A.g_vec16) copy_src(A.gout, si + SE3_MAX_SEG * ROWS, A.gwidth, A.gwidth >> 2, 4, A.goff, A.gstride);
-        else copy_src(A.gout, si + SE3_MAX_SEG * ROWS, A.gwidth, A.gwidth, 1, A.goff, A.gstride);
-        cp_async_mbar_arrive_noinc(bar_full0 + 8 * slot);
-        fetch_idx(tile + gridDim.x);
+        for (int s = 0; s < SE3_MAX_SEG; ++s) cur[s] = nxt[s];
+        curg = nxtg;
+        fetch(tile + 2ll * gridDim.x, nxt, nxtg);
+        if (++slot == NSLOT) { slot = 0; ++use; }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
 }
@@ -362,15 +276,15 @@ __global__ void __launch_bounds__(TBW_THREADS, 1) l1tp_tc_bwdw_kernel(const TcBw
     const int* vtab = stab + 8 * A.NSG8;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + A.o_bar);
     const uint32_t bar0 = smem_u32(bars);
-    // barriers: 0,1 stage full | 2,3 stage empty | 4,7 half-set full | 5,8 half-set empty | 6 acc full.
+    // barriers: 9..11 stage full | 12..14 stage empty (3-slot stage ring) | 4,7 half-set full | 5,8 half-set empty | 6 acc full.
     // The 32-row tile set is handed over in two 16-row halves (2 K-steps each), so the builders fill one half while the
     // tensor pipe consumes the other (profiles/r01_v8: 65 % of the builders' time was spent waiting for whole-set MMAs).
     auto BAR = [&](int i) { return bar0 + 8u * i; };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(BAR(i), 64);  // 64 producer lanes (warps 0 and 2)
-            mbar_init(BAR(2 + i), BW_NBUILD);
+        for (int i = 0; i < BW_NSLOT; ++i) {
+            mbar_init(BAR(9 + i), 64);  // 64 producer lanes (warps 0 and 2)
+            mbar_init(BAR(12 + i), BW_NBUILD);
         }
         mbar_init(BAR(4), BW_NBUILD);
         mbar_init(BAR(5), 1);
@@ -395,7 +309,7 @@ __global__ void __launch_bounds__(TBW_THREADS, 1) l1tp_tc_bwdw_kernel(const TcBw
     const int cD1 = 0, cD2 = A.N2, cD3 = A.N2 + A.N3, cD4 = 2 * A.N2 + A.N3;
 
     if (warp == 0 || warp == 2) {
-        producer_loop<TMB>(A, smraw, BAR(0), BAR(2), lane, true, ntiles, warp == 0 ? 0 : 1, 2);
+        producer_loop<TMB, BW_NSLOT>(A, smraw, BAR(9), BAR(12), lane, true, ntiles, warp == 0 ? 0 : 1, 2);
     } else if (warp == 1) {
         // ---------------- MMA issuer: per tile 4 K-steps (8 rows each) x {S.[HZY|HG], Dd.HZ, AVc.HVc} x 3xTF32.
         // All operands are K-major with K = rows: transposed tiles [channel/feature][row], 8-channel groups of
@@ -460,8 +374,8 @@ __global__ void __launch_bounds__(TBW_THREADS, 1) l1tp_tc_bwdw_kernel(const TcBw
         const float* nv = norm + A.mz;
         int it = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-            const int slot = it & 1, use = it >> 1;
-            mbar_wait(BAR(slot), use & 1);                  // stage full
+            const int slot = it % BW_NSLOT, use = it / BW_NSLOT;
+            mbar_wait(BAR(9 + slot), use & 1);              // stage full
             const float* st = smf + (A.o_stage >> 2) + (size_t)slot * A.slot_floats;
             for (int rb = 0; rb < nrb; ++rb) {
             mbar_wait(BAR(rb ? 8 : 5), (it & 1) ^ 1);       // half-set free (its MMAs of the previous tile are done)
@@ -532,7 +446,7 @@ __global__ void __launch_bounds__(TBW_THREADS, 1) l1tp_tc_bwdw_kernel(const TcBw
             if (lane == 0) mbar_arrive(BAR(rb ? 7 : 4));
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(2 + slot));
+            if (lane == 0) mbar_arrive(BAR(12 + slot));
         }
         // ---------------- final epilogue (warps 4-7): TMEM accumulators -> per-CTA partials
         if (bw < 4) {
@@ -942,12 +856,11 @@ int se3_l1tp_tc_try_backward_w(const int n[4], const int m[4], const int t_in[4]
     A.o_t3 = o; o += 6 * A.sz_t3;
     o += 16 * GS;  // slack: M=64/128 operand reads run past the last real 8-channel group (those D rows are ignored)
     o = al(o, 128);
-    A.o_stage = o; o += 2 * A.slot_floats * 4;
+    A.o_stage = o; o += BW_NSLOT * A.slot_floats * 4;
     A.o_tab = o; o += al(ntab * 4, 16);
     A.o_norm = o; o += al((A.mz + 3 * A.mv) * 4, 16);
     A.o_tbl = o; o += al((8 * A.NSG8 + 8 * A.NDG8) * 4, 16);
-    A.o_bar = o; o += 12 * 8 + 16;
-    A.o_sidx = o; o += 2 * (SE3_MAX_SEG + 1) * TMB * 4;
+    A.o_bar = o; o += 16 * 8 + 16;
     int dev = 0, maxsm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);

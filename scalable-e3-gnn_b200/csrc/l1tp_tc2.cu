@@ -23,14 +23,15 @@
 
 namespace se3 {
 
-static constexpr int W2 = 16;                 // worker warps
+static constexpr int W2 = 16;                 // worker warps (multiple of 8: row groups; of 4: TMEM lane quarters)
 static constexpr int T2_THREADS = (W2 + 1) * 32;
 static constexpr int WT = W2 * 32;            // worker threads
 static constexpr int TM2 = 64;
 static constexpr int MAXCOL = 192;
 static constexpr int MAXK1 = 128;
 
-static constexpr int MAXB = 4;                // wide blocks per warp and tile (8 per tile)
+static constexpr int NG = W2 / 8;              // warps per row group
+static constexpr int MAXB = 4;                // wide blocks per warp and tile (NG * MAXB per tile)
 
 struct BlockE {                               // one wide block: 64 rows x 4 consecutive 16-byte pieces of a segment
     const float* base;
@@ -69,7 +70,7 @@ struct Tc2Args {
     unsigned mg_ns, mg_mv, mg_h;              // ceil(2^32 / d) for d = gate_ns, mv, d_out / 2
     int o_b1, o_b2, o_a, a_bytes, o_out, o_post, o_norm, o_blk, o_ccode, o_bar;
     int halfS, halfV, oV;                     // bytes: lo offset of S / V tiles, first V tile inside an operand set
-    BlockE blk[2 * MAXB];
+    BlockE blk[NG * MAXB];
     NarrowE nar[W2];
     unsigned short ccode[MAXCOL];             // per concatenated column: type << 13 | index (1: scalar slot, 2..4: x/y/z kd)
     short sl2ch[MAXK1];                       // scalar slot -> scalar channel (-1: padding)
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) l1tp_tc2_fwd_kernel(const __gri
     } else {
         // ================= workers
         // Everything about WHERE a thread's pieces come from and go to is tile-invariant and lives in registers:
-        // warp w owns row group rb = w & 7 (rows 8 rb + (lane & 7)) of the wide blocks (w >> 3) + 2 i.
+        // warp w owns row group rb = w & 7 (rows 8 rb + (lane & 7)) of the wide blocks (w >> 3) + NG i.
         const int KQ1 = A.K1 >> 2, KQ2 = A.K2 >> 2;
         const int r8 = lane & 7, cq = lane >> 3;
         const int wrow = (warp & 7) * 8 + r8;
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) l1tp_tc2_fwd_kernel(const __gri
         bool act[MAXB], fast[MAXB];
 #pragma unroll
         for (int i = 0; i < MAXB; ++i) {
-            const int g = (warp >> 3) + 2 * i;
+            const int g = (warp >> 3) + NG * i;
             act[i] = false; fast[i] = false; gofs[i] = 0;
             dd[i][0] = dd[i][1] = dd[i][2] = dd[i][3] = -1;
             if (g < A.nblk) {
@@ -257,7 +258,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) l1tp_tc2_fwd_kernel(const __gri
             for (int i = 0; i < MAXB; ++i) {
                 nidx[i] = (int)gr;
                 if (act[i]) {
-                    const int32_t* ip = blks[(warp >> 3) + 2 * i].idx;
+                    const int32_t* ip = blks[(warp >> 3) + NG * i].idx;
                     if (ip) nidx[i] = ldgi_v(ip + gr);
                 }
             }
@@ -272,7 +273,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) l1tp_tc2_fwd_kernel(const __gri
 #pragma unroll
             for (int i = 0; i < MAXB; ++i) {
                 if (act[i]) {
-                    const BlockE& B = blks[(warp >> 3) + 2 * i];
+                    const BlockE& B = blks[(warp >> 3) + NG * i];
                     R4[i] = ldg4_v(B.base + (long long)nidx[i] * B.ld + gofs[i]);
                 }
             }
@@ -332,32 +333,50 @@ __global__ void __launch_bounds__(T2_THREADS, 1) l1tp_tc2_fwd_kernel(const __gri
             float* orow = otile + drow * A.dop;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const int cb = 16 * jq + 8 * h;
+                const int cb = 8 * (jq + (W2 / 4) * h);   // 8-column blocks jq, jq + W2/4 (N1 <= 64: at most 8 blocks)
                 if (cb < A.N1) {
-                    float p[8], ux[8], uy[8], uz[8];
+                    // two accumulators at a time (16 live registers, not 32: the prefetched rows of the next tile stay
+                    // in registers across the whole epilogue)
+                    float p[8], u[8];
                     tc_ld8(acc + cb, p);
-                    tc_ld8(acc + A.N1 + cb, ux);
-                    tc_ld8(acc + 2 * A.N1 + cb, uy);
-                    tc_ld8(acc + 3 * A.N1 + cb, uz);
+                    tc_ld8(acc + A.N1 + cb, u);
                     tc_wait_ld();
-                    if (rowlane) {
-                        if (cb < A.N2) {
+                    if (cb < A.N2) {
+                        float sacc[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) sacc[j] = fmaf(y.x, p[j], y1 * u[j]);
+                        tc_ld8(acc + 2 * A.N1 + cb, p);
+                        tc_ld8(acc + 3 * A.N1 + cb, u);
+                        tc_wait_ld();
+                        if (rowlane) {
                             float* o = orow + A.oz0 + cb;
                             const int lim = A.mz - cb;
 #pragma unroll
                             for (int j = 0; j < 8; ++j)
-                                if (j < lim) o[j] = fmaf(y.x, p[j], fmaf(y1, ux[j], fmaf(y2, uy[j], y3 * uz[j])));
-                        } else {
-                            const int m0 = cb - A.N2;
-                            float* o = orow + A.ov0 + 3 * m0;
-                            const float* nv3 = norm + 3 * m0;
-                            const int lim = A.mv - m0;
+                                if (j < lim) o[j] = fmaf(y2, p[j], fmaf(y3, u[j], sacc[j]));
+                        }
+                    } else {
+                        const int m0 = cb - A.N2;
+                        float* o = orow + A.ov0 + 3 * m0;
+                        const float* nv3 = norm + 3 * m0;
+                        const int lim = A.mv - m0;
+                        float pk[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) pk[j] = p[j];
+                        if (rowlane) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                if (j < lim) o[3 * j] = nv3[3 * j] * fmaf(y1, pk[j], y0c * u[j]);
+                        }
+                        tc_ld8(acc + 2 * A.N1 + cb, p);
+                        tc_ld8(acc + 3 * A.N1 + cb, u);
+                        tc_wait_ld();
+                        if (rowlane) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j)
                                 if (j < lim) {
-                                    o[3 * j] = nv3[3 * j] * fmaf(y1, p[j], y0c * ux[j]);
-                                    o[3 * j + 1] = nv3[3 * j + 1] * fmaf(y2, p[j], y0c * uy[j]);
-                                    o[3 * j + 2] = nv3[3 * j + 2] * fmaf(y3, p[j], y0c * uz[j]);
+                                    o[3 * j + 1] = nv3[3 * j + 1] * fmaf(y2, pk[j], y0c * p[j]);
+                                    o[3 * j + 2] = nv3[3 * j + 2] * fmaf(y3, pk[j], y0c * u[j]);
                                 }
                         }
                     }
@@ -586,14 +605,14 @@ int se3_l1tp_tc2_try_forward(const int n[4], const int m[4], const int t_in[4], 
     for (int k = 0; k < mz; ++k) if (h_tab[t_out[0] + k] != A.oz0 + k) return SE3_OK;
     for (int k = 0; k < mv; ++k) if (h_tab[t_out[3] + k] != A.ov0 + 3 * k) return SE3_OK;
     if (epi.mode == SE3_EPI_GATE && (epi.ns_g < 1 || epi.ns_g + mv != mz)) return SE3_OK;
-    // ---- wide blocks (warp w: row group w & 7, blocks (w >> 3) + 2 i) and narrow tasks (one per warp at most)
+    // ---- wide blocks (warp w: row group w & 7, blocks (w >> 3) + NG i) and narrow tasks (one per warp at most)
     int nblk = 0, nnar = 0;
     for (int s = 0; s < src.nseg; ++s) {
         const int w = src.cum[s + 1] - src.cum[s];
         if (wide[s]) {
             const int nch = w >> 2, ncb = (nch + 3) >> 2;
             for (int cb = 0; cb < ncb; ++cb) {
-                if (nblk >= 2 * MAXB) return SE3_OK;
+                if (nblk >= NG * MAXB) return SE3_OK;
                 BlockE& B = A.blk[nblk++];
                 B.base = src.base[s]; B.idx = src.idx[s]; B.ld = src.ld[s]; B.cum = src.cum[s]; B.nch = nch; B.cb = cb;
                 B.fast4 = 0; B.pad = 0;
@@ -638,7 +657,7 @@ int se3_l1tp_tc2_try_forward(const int n[4], const int m[4], const int t_in[4], 
     A.o_out = o; o += al(TM2 * A.dop * 4, 16);
     A.o_post = o; o += (epi.mode == SE3_EPI_GATE && a->seg_idx) ? al(TM2 * A.dpp * 4, 16) : 0;
     A.o_norm = o; o += al((3 * mv) * 4, 16);
-    A.o_blk = o; o += al(2 * MAXB * (int)sizeof(BlockE), 16);
+    A.o_blk = o; o += al(NG * MAXB * (int)sizeof(BlockE), 16);
     A.o_ccode = o; o += al(MAXCOL * 2, 16);
     A.o_bar = o; o += 8 * 8 + 16;
     int dev = 0, maxsm = 0;

@@ -266,7 +266,8 @@ def run_b200(a):
                 "share_of_step": tr["ms"] / tot_ms,
                 "fp32_tflops": tr["flops"] / (tr["ms"] * 1e-3) / 1e12,
                 "fp32_peak_tflops_at_clock": fp32_peak,
-                "note": "fp32 CUDA-core contraction (1e-5 parity target): FMA-pipe-bound, see DESIGN.md"}
+                "note": "tcgen05 3xTF32 kernel (fp32 parity 1e-5); bound by SIMT issue of the operand build / epilogue around "
+                        "the MMAs, not by HBM or the tensor pipe: see DESIGN.md section 4 and profiles/"}
     table = {k: {"ms_per_step": v["ms"] / 2, "GBps": v["bytes"] / max(v["ms"], 1e-9) / 1e6,
                  "TFLOPs": v["flops"] / max(v["ms"], 1e-9) / 1e9, "launches_per_step": v["launches"] // 2}
              for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}

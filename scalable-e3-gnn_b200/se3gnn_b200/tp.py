@@ -83,11 +83,15 @@ class TPConfig:
         return 2 * (fe + fo)
 
     def algo_bytes(self, rows: int, segs, idxs, backward: bool, nseg_out: int = 0, has_resid: bool = False,
-                   grads=None) -> float:
+                   grads=None, part: Optional[str] = None) -> float:
         """Algorithmic HBM bytes of one launch: every operand once; a segment gathered through a
-        *sorted* index is charged once per distinct row (segment-cached), an unsorted gather once per row."""
+        *sorted* index is charged once per distinct row (segment-cached), an unsorted gather once per row.
+        ``part`` (backward only): "w" = weight-gradient kernel alone (reads the in1 segments, writes only the weight
+        gradients), "i" = input-gradient kernel alone (does not read the in1 segments)."""
         b = rows * 4 * 4  # in2
         for i, s in enumerate(segs):
+            if backward and part == "i":
+                break
             w = self.widths[i]
             if idxs[i] is None:
                 b += rows * w * 4
@@ -110,6 +114,8 @@ class TPConfig:
                 b += rows * d_out * 4
             b += (nseg_out if nseg_out else rows) * d_post * 4 + (rows * 4 if nseg_out else 0)
             for i, s in enumerate(segs):
+                if part == "w":
+                    break
                 if grads is not None and grads[i]:
                     w = self.widths[i]
                     srt = idxs[i] is not None and i < len(self.grad_modes) and self.grad_modes[i] == capi.GRAD_SORTED
@@ -259,11 +265,33 @@ class TPLayerFn(torch.autograd.Function):
         if nig[2] and cfg.need_gin2:
             gin2 = torch.empty_like(in2)
             a.gin2 = gin2.data_ptr()
-        with capi.mark(cfg.tag + ".bwd",
-                       cfg.algo_bytes(ctx.rows, segs, ctx.idxs, True, cfg.num_segments if ctx.seg_idx is not None else 0,
-                                      False, seg_need) if capi._prof is not None else 0.0,
-                       2.0 * cfg.flops_fwd_per_row() * ctx.rows):
+        nso = cfg.num_segments if ctx.seg_idx is not None else 0
+        if capi._prof is None:
             capi.check(lib.se3_l1tp_backward(cfg.plan.handle, C.byref(a), capi.current_stream_ptr()), "se3_l1tp_backward")
+        else:
+            # per-kernel table of bench.py: the C ABI runs the weight-gradient and the input-gradient kernels of one call
+            # back to back; time them separately by asking for one output group per call (same kernels, same results)
+            want_w, want_i = any(g is not None for g in gws), any(g is not None for g in gsegs)
+            keep_w, keep_i = [a.gw[i] for i in range(4)], [a.gseg[i] for i in range(capi.MAX_SEG)]
+            if want_w:
+                keep_gin2 = a.gin2
+                a.gin2 = None
+                for i in range(capi.MAX_SEG):
+                    a.gseg[i] = None
+                with capi.mark(cfg.tag + ".bwdw", cfg.algo_bytes(ctx.rows, segs, ctx.idxs, True, nso, False, seg_need, "w"),
+                               float(cfg.flops_fwd_per_row()) * ctx.rows):
+                    capi.check(lib.se3_l1tp_backward(cfg.plan.handle, C.byref(a), capi.current_stream_ptr()), "se3_l1tp_backward")
+                for i in range(capi.MAX_SEG):
+                    a.gseg[i] = keep_i[i]
+                a.gin2 = keep_gin2
+            if want_i or gin2 is not None:
+                for i in range(4):
+                    a.gw[i] = None
+                with capi.mark(cfg.tag + ".bwdi", cfg.algo_bytes(ctx.rows, segs, ctx.idxs, True, nso, False, seg_need, "i"),
+                               float(cfg.flops_fwd_per_row()) * ctx.rows):
+                    capi.check(lib.se3_l1tp_backward(cfg.plan.handle, C.byref(a), capi.current_stream_ptr()), "se3_l1tp_backward")
+                for i in range(4):
+                    a.gw[i] = keep_w[i]
         gresid = gout if (ctx.has_resid and nig[3]) else None
         out_gsegs = []
         for i in range(nseg):

@@ -71,6 +71,11 @@ def _to_lists(w, nrm, dev):
     ("4x0e+3x0o+2x1e+5x1o", "3x0e+2x0o+2x1e+3x1o", 3001),
     ("34x0e+10x1o", "1x1o", 1),
     ("96x0e+32x1o", "80x0e+24x1o", 513),
+    # tile tails of the tcgen05 kernels (64-row tiles; 32-row tiles in the weight-gradient kernel)
+    ("34x0e+10x1o+34x0e+10x1o+2x0e", "44x0e+10x1o", 65),
+    ("34x0e+10x1o", "34x0e+10x1o", 63),
+    ("34x0e+10x1o", "44x0e+10x1o", 1),
+    ("2x1o+2x0e", "34x0e+10x1o", 130),
 ])
 def test_plain_vs_oracle_large(in1, out, rows):
     from se3gnn_b200 import capi
@@ -90,8 +95,12 @@ def test_plain_vs_oracle_large(in1, out, rows):
     xt = torch.from_numpy(x).to(dev).requires_grad_(True)
     yt = torch.from_numpy(y).to(dev).requires_grad_(True)
     cfg = TPConfig(plan=get_plan(Irreps(in1), Irreps(out)), widths=(din,), need_gin2=True)
+    tc0 = capi.tc_launch_count()
     o = tp_layer(cfg, rows, [xt], [None], yt, ws, ns)
     o.backward(torch.from_numpy(go).to(dev))
+    if "0o" not in in1 and "1e" not in in1 and out != "1x1o" and "96x0e" not in in1 and din % 4 == 0:
+        # a x0e + b x1o -> c x0e + d x1o: forward, weight-gradient and input-gradient all run on the tensor cores
+        assert capi.tc_launch_count() - tc0 == 3, "tcgen05 kernels did not launch"
     w64 = {k: v.astype(np.float64) for k, v in w.items()}
     ref = O.forward(x.astype(np.float64), y.astype(np.float64), w64, nrm, in1, out)
     gx, gy, gw = O.backward(x.astype(np.float64), y.astype(np.float64), go.astype(np.float64), w64, nrm, in1, out)

@@ -1377,8 +1377,12 @@ extern "C" int se3_l1tp_backward(se3_l1tp_plan* p, const se3_l1tp_bwd_args* a, v
         }
         // weight gradients on the tensor cores (accumulators resident in TMEM) when eligible
         int tc_grid = 0;
+        // SE3_BWDW_GRID (diagnostics): fewer CTAs = a different partition of the rows over the fp32 accumulators
+        static int grid_cap = -1;
+        if (grid_cap < 0) { const char* e = getenv("SE3_BWDW_GRID"); grid_cap = e ? std::max(1, atoi(e)) : 0; }
         rc = se3_l1tp_tc_try_backward_w(p->n, p->m, p->t_in, p->t_out, p->L.ntab, p->d_tab, a, K.src, K.epi,
-                                        p->d_partials, p->L.wtot, p->w_off[0], p->w_off[3], num_sms(), st, &tc_grid, &tcw);
+                                        p->d_partials, p->L.wtot, p->w_off[0], p->w_off[3],
+                                        grid_cap ? std::min(grid_cap, num_sms()) : num_sms(), st, &tc_grid, &tcw);
         if (rc) return rc;
         if (tcw) red_blocks = tc_grid;
         else K.partials = p->d_partials;

@@ -68,7 +68,7 @@ struct Tc2Args {
     int nblk, nnar;
     int dop, dpp;
     unsigned mg_ns, mg_mv, mg_h;              // ceil(2^32 / d) for d = gate_ns, mv, d_out / 2
-    int o_b1, o_b2, o_a, a_bytes, o_out, o_post, o_norm, o_blk, o_ccode, o_bar;
+    int o_b1, o_b2, o_a, a_bytes, o_out, o_post, o_norm, o_blk, o_ccode, o_bar, o_sseg, o_hs;
     int halfS, halfV, oV;                     // bytes: lo offset of S / V tiles, first V tile inside an operand set
     BlockE blk[NG * MAXB];
     NarrowE nar[W2];
@@ -76,6 +76,9 @@ struct Tc2Args {
     short sl2ch[MAXK1];                       // scalar slot -> scalar channel (-1: padding)
 };
 
+// SEG: the launch ends in the sorted-segment sum (kept out of the other instantiation: its prefetch registers and
+// barriers cost the plain launches 7 % through register pressure)
+template <bool SEG>
 __global__ void __launch_bounds__(T2_THREADS, 1) l1tp_tc2_fwd_kernel(const __grid_constant__ Tc2Args A) {
     extern __shared__ __align__(1024) unsigned char smraw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -317,11 +320,19 @@ __global__ void __launch_bounds__(T2_THREADS, 1) l1tp_tc2_fwd_kernel(const __gri
         const int drow = 16 * e + (lane & 15);
         const bool rowlane = lane < 16;
         float4 ypre = make_float4(0.f, 0.f, 0.f, 0.f);
-        auto prefetch_y = [&](int it) {   // in2 row of this thread's epilogue row of tile `it`, consumed by drain(it)
+        int segpre = -1;
+        int* sseg = reinterpret_cast<int*>(smraw + A.o_sseg);
+        float4* hsm = reinterpret_cast<float4*>(smraw + A.o_hs);
+        auto prefetch_y = [&](int it) {   // in2 row (and segment id) of this thread's epilogue row of tile `it`, consumed by drain(it)
             const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * TM2;
             long long gr = row0 + drow;
             if (gr > R - 1) gr = R - 1;
             if (rowlane) ypre = ldg4_v(A.in2 + gr * 4);
+            if (SEG && jq == 0) {
+                if (rowlane) segpre = ldgi_v(A.seg_idx + gr);
+                else if (e == 0 && lane == 16) segpre = row0 > 0 ? ldgi_v(A.seg_idx + row0 - 1) : -1;
+                else if (e == 0 && lane == 17) segpre = row0 + TM2 < R ? ldgi_v(A.seg_idx + row0 + TM2) : -1;
+            }
         };
         auto drain = [&](int it) {
             const int b = it & 1;
@@ -382,6 +393,11 @@ __global__ void __launch_bounds__(T2_THREADS, 1) l1tp_tc2_fwd_kernel(const __gri
                     }
                 }
             }
+            if (SEG && jq == 0) {
+                if (rowlane) sseg[1 + drow] = segpre;
+                else if (e == 0 && lane == 16) sseg[0] = segpre;
+                else if (e == 0 && lane == 17) sseg[65] = segpre;
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(4 + b));
@@ -390,7 +406,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) l1tp_tc2_fwd_kernel(const __gri
         auto finish = [&](int it) {
             const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * TM2;
             const int nvalid = (int)min((long long)TM2, R - row0);
-            const bool to_ptile = gate && A.seg_idx;
+            const bool to_ptile = SEG && gate;
             if (A.out_raw) {
                 float* dst = A.out_raw + row0 * dout;
                 const float* res = A.resid ? A.resid + row0 * dout : nullptr;
@@ -456,32 +472,11 @@ __global__ void __launch_bounds__(T2_THREADS, 1) l1tp_tc2_fwd_kernel(const __gri
                     }
                 }
             }
-            if (A.seg_idx) {
+            if (SEG) {
                 if (to_ptile) named_bar(1, WT);
                 const float* stile = gate ? ptile : otile;
                 const int sstr = gate ? A.dpp : A.dop, swid = gate ? dpost : dout;
-                int parts = WT / swid;
-                if (parts < 1) parts = 1;
-                if (parts > TM2) parts = TM2;
-                const int rpp = (TM2 + parts - 1) / parts;
-                for (int item = tid; item < swid * parts; item += WT) {
-                    const int c = item % swid, qd = item / swid;
-                    const int rbeg = qd * rpp;
-                    const int rend = min(rbeg + rpp, nvalid);
-                    if (rbeg >= rend) continue;
-                    int cur = __ldg(A.seg_idx + row0 + rbeg);
-                    float accv = 0.0f;
-                    for (int r = rbeg; r < rend; ++r) {
-                        const int k = __ldg(A.seg_idx + row0 + r);
-                        if (k != cur) {
-                            atomicAdd(A.out_seg + (long long)cur * swid + c, accv);
-                            cur = k;
-                            accv = 0.0f;
-                        }
-                        accv += stile[r * sstr + c];
-                    }
-                    atomicAdd(A.out_seg + (long long)cur * swid + c, accv);
-                }
+                sorted_segment_sum_tile<WT>(stile, sstr, swid, nvalid, sseg, A.out_seg, swid, hsm, tid, 3);
             }
         };
 
@@ -660,6 +655,8 @@ int se3_l1tp_tc2_try_forward(const int n[4], const int m[4], const int t_in[4], 
     A.o_blk = o; o += al(NG * MAXB * (int)sizeof(BlockE), 16);
     A.o_ccode = o; o += al(MAXCOL * 2, 16);
     A.o_bar = o; o += 8 * 8 + 16;
+    A.o_sseg = o; o += a->seg_idx ? 68 * 4 : 0;
+    A.o_hs = o; o += a->seg_idx ? 8 * std::max(epi.d_post, A.d_out) * 16 : 0;
     int dev = 0, maxsm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
@@ -667,12 +664,14 @@ int se3_l1tp_tc2_try_forward(const int n[4], const int m[4], const int t_in[4], 
     const int smem = std::max(o, 120 * 1024);   // > half an SM: one CTA per SM owns all 512 TMEM columns
     static bool attr_set = false;
     if (!attr_set) {
-        SE3_CUDA_TRY(cudaFuncSetAttribute(l1tp_tc2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
+        SE3_CUDA_TRY(cudaFuncSetAttribute(l1tp_tc2_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
+        SE3_CUDA_TRY(cudaFuncSetAttribute(l1tp_tc2_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
         attr_set = true;
     }
     const long long ntiles = (a->rows + TM2 - 1) / TM2;
     const int grid = (int)std::min<long long>(ntiles, num_sms());
-    l1tp_tc2_fwd_kernel<<<grid, T2_THREADS, smem, st>>>(A);
+    if (a->seg_idx) l1tp_tc2_fwd_kernel<true><<<grid, T2_THREADS, smem, st>>>(A);
+    else l1tp_tc2_fwd_kernel<false><<<grid, T2_THREADS, smem, st>>>(A);
     SE3_LAUNCHED();
     g_tc_launches.fetch_add(1, std::memory_order_relaxed);
     *launched = true;

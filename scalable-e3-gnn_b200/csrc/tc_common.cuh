@@ -88,6 +88,67 @@ __device__ __forceinline__ int ldgi_v(const int* p) {
 __device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// Sorted-segment sum of one 64-row tile (rows sorted by segment id): out[seg * ld + c] += sum of the tile rows of seg.
+// Segments that lie strictly inside the tile have exactly one writer and are written with a plain store (the
+// destination is zero-initialised); only the (at most two) segments shared with the neighbouring tiles use `red`.
+//   pass A (all NT threads): thread = (column, 8-row part); complete runs inside a part -> store; the part's head and
+//                            tail runs go to shared memory;
+//   pass B (one thread per column): merge heads/tails across the parts in row order; store or red as above.
+// sseg[0] = segment of the row before the tile (-1: none), sseg[1..64] = rows, sseg[65] = segment of the row after.
+template <int NT>
+__device__ __forceinline__ void sorted_segment_sum_tile(const float* tile, int tstride, int width, int nvalid, const int* sseg,
+                                                        float* out, int ld, float4* hs, int tid, int barid) {
+    int parts = NT / width;
+    if (parts < 1) parts = 1;
+    if (parts > 8) parts = 8;
+    const int rpp = (64 + parts - 1) / parts;
+    for (int item = tid; item < width * parts; item += NT) {
+        const int c = item % width, qd = item / width;
+        const int rbeg = qd * rpp, rend = min(rbeg + rpp, nvalid);
+        float4 h = make_float4(__int_as_float(-1), 0.0f, __int_as_float(-1), 0.0f);
+        if (rbeg < rend) {
+            int cur = sseg[1 + rbeg];
+            float acc = 0.0f, sum_h = 0.0f;
+            const int seg_h = cur;
+            bool first = true;
+            for (int r = rbeg; r < rend; ++r) {
+                const int k = sseg[1 + r];
+                if (k != cur) {
+                    if (first) { sum_h = acc; first = false; }
+                    else out[(long long)cur * ld + c] = acc;
+                    cur = k;
+                    acc = 0.0f;
+                }
+                acc += tile[r * tstride + c];
+            }
+            if (first) h = make_float4(__int_as_float(seg_h), acc, __int_as_float(-1), 0.0f);
+            else h = make_float4(__int_as_float(seg_h), sum_h, __int_as_float(cur), acc);
+        }
+        hs[qd * width + c] = h;
+    }
+    named_bar(barid, NT);
+    for (int c = tid; c < width; c += NT) {
+        const int prevseg = sseg[0], nextseg = sseg[65];
+        int cur = -1;
+        float acc = 0.0f;
+        auto emit = [&](int seg, float v) {
+            if (seg < 0) return;
+            float* p = out + (long long)seg * ld + c;
+            if (seg == prevseg || seg == nextseg) atomicAdd(p, v);
+            else *p = v;
+        };
+        for (int q = 0; q < parts; ++q) {
+            const float4 h = hs[q * width + c];
+            const int sh = __float_as_int(h.x), st = __float_as_int(h.z);
+            if (sh < 0) continue;
+            if (sh == cur) acc += h.y;
+            else { emit(cur, acc); cur = sh; acc = h.y; }
+            if (st >= 0) { emit(cur, acc); cur = st; acc = h.w; }
+        }
+        emit(cur, acc);
+    }
+}
+
 // K-major, no-swizzle canonical layout: 8-row x 16-byte core matrices; LBO = 128 B between the two K-chunks
 // of one MMA, SBO = bytes between consecutive 8-row groups (cute/arch/mma_sm100_desc.hpp, version 1).
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes) {

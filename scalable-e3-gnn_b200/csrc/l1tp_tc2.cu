@@ -319,7 +319,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) l1tp_tc2_fwd_kernel(const __gri
         const int dout = A.d_out, dpost = A.epi.d_post;
         const int drow = 16 * e + (lane & 15);
         const bool rowlane = lane < 16;
-        float4 ypre = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 ypre = make_float4(0.f, 0.f, 0.f, 0.f), ypre2 = ypre;   // in2 of this thread's two epilogue rows
+        const int fg = lane >> 2, fq = lane & 3;                        // 16x256b fragment: rows fg, fg + 8; columns 2 fq, 2 fq + 1
         int segpre = -1;
         int* sseg = reinterpret_cast<int*>(smraw + A.o_sseg);
         float4* hsm = reinterpret_cast<float4*>(smraw + A.o_hs);
@@ -327,7 +328,13 @@ __global__ void __launch_bounds__(T2_THREADS, 1) l1tp_tc2_fwd_kernel(const __gri
             const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * TM2;
             long long gr = row0 + drow;
             if (gr > R - 1) gr = R - 1;
-            if (rowlane) ypre = ldg4_v(A.in2 + gr * 4);
+            {
+                long long ga = row0 + 16 * e + fg, gb = ga + 8;
+                if (ga > R - 1) ga = R - 1;
+                if (gb > R - 1) gb = R - 1;
+                ypre = ldg4_v(A.in2 + ga * 4);
+                ypre2 = ldg4_v(A.in2 + gb * 4);
+            }
             if (SEG && jq == 0) {
                 if (rowlane) segpre = ldgi_v(A.seg_idx + gr);
                 else if (e == 0 && lane == 16) segpre = row0 > 0 ? ldgi_v(A.seg_idx + row0 - 1) : -1;
@@ -336,59 +343,53 @@ __global__ void __launch_bounds__(T2_THREADS, 1) l1tp_tc2_fwd_kernel(const __gri
         };
         auto drain = [&](int it) {
             const int b = it & 1;
-            const float4 y = ypre;
-            const float y1 = C3f * y.y, y2 = C3f * y.z, y3 = C3f * y.w, y0c = C3f * y.x;
+            // per row: Y0, c3 Y1x, c3 Y1y, c3 Y1z, c3 Y0
+            const float ya[5] = {ypre.x, C3f * ypre.y, C3f * ypre.z, C3f * ypre.w, C3f * ypre.x};
+            const float yb[5] = {ypre2.x, C3f * ypre2.y, C3f * ypre2.z, C3f * ypre2.w, C3f * ypre2.x};
             mbar_wait(BAR(2 + b), (it >> 1) & 1);
             tc_fence_after();
             const uint32_t acc = tmem_base + (uint32_t)b * ACC + ((uint32_t)(32 * e) << 16);
-            float* orow = otile + drow * A.dop;
+            float* rowa = otile + (16 * e + fg) * A.dop;
+            float* rowb = rowa + 8 * A.dop;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int cb = 8 * (jq + (W2 / 4) * h);   // 8-column blocks jq, jq + W2/4 (N1 <= 64: at most 8 blocks)
                 if (cb < A.N1) {
-                    // two accumulators at a time (16 live registers, not 32: the prefetched rows of the next tile stay
-                    // in registers across the whole epilogue)
-                    float p[8], u[8];
-                    tc_ld8(acc + cb, p);
-                    tc_ld8(acc + A.N1 + cb, u);
+                    float p[4], ux[4], uy[4], uz[4];
+                    tc_ld_16x256(acc + cb, p);
+                    tc_ld_16x256(acc + A.N1 + cb, ux);
+                    tc_ld_16x256(acc + 2 * A.N1 + cb, uy);
+                    tc_ld_16x256(acc + 3 * A.N1 + cb, uz);
                     tc_wait_ld();
                     if (cb < A.N2) {
-                        float sacc[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) sacc[j] = fmaf(y.x, p[j], y1 * u[j]);
-                        tc_ld8(acc + 2 * A.N1 + cb, p);
-                        tc_ld8(acc + 3 * A.N1 + cb, u);
-                        tc_wait_ld();
-                        if (rowlane) {
-                            float* o = orow + A.oz0 + cb;
-                            const int lim = A.mz - cb;
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                if (j < lim) o[j] = fmaf(y2, p[j], fmaf(y3, u[j], sacc[j]));
+                        const int m = cb + 2 * fq;              // z channels m, m + 1
+                        float2 oa, ob;
+                        oa.x = fmaf(ya[0], p[0], fmaf(ya[1], ux[0], fmaf(ya[2], uy[0], ya[3] * uz[0])));
+                        oa.y = fmaf(ya[0], p[1], fmaf(ya[1], ux[1], fmaf(ya[2], uy[1], ya[3] * uz[1])));
+                        ob.x = fmaf(yb[0], p[2], fmaf(yb[1], ux[2], fmaf(yb[2], uy[2], yb[3] * uz[2])));
+                        ob.y = fmaf(yb[0], p[3], fmaf(yb[1], ux[3], fmaf(yb[2], uy[3], yb[3] * uz[3])));
+                        if (m + 1 < A.mz) {
+                            *reinterpret_cast<float2*>(rowa + A.oz0 + m) = oa;
+                            *reinterpret_cast<float2*>(rowb + A.oz0 + m) = ob;
+                        } else if (m < A.mz) {
+                            rowa[A.oz0 + m] = oa.x;
+                            rowb[A.oz0 + m] = ob.x;
                         }
                     } else {
-                        const int m0 = cb - A.N2;
-                        float* o = orow + A.ov0 + 3 * m0;
-                        const float* nv3 = norm + 3 * m0;
-                        const int lim = A.mv - m0;
-                        float pk[8];
+                        const int m = cb - A.N2 + 2 * fq;       // v channels m, m + 1
+                        const float* nv3 = norm + 3 * m;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) pk[j] = p[j];
-                        if (rowlane) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                if (j < lim) o[3 * j] = nv3[3 * j] * fmaf(y1, pk[j], y0c * u[j]);
-                        }
-                        tc_ld8(acc + 2 * A.N1 + cb, p);
-                        tc_ld8(acc + 3 * A.N1 + cb, u);
-                        tc_wait_ld();
-                        if (rowlane) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                if (j < lim) {
-                                    o[3 * j + 1] = nv3[3 * j + 1] * fmaf(y2, pk[j], y0c * p[j]);
-                                    o[3 * j + 2] = nv3[3 * j + 2] * fmaf(y3, pk[j], y0c * u[j]);
-                                }
+                        for (int u = 0; u < 2; ++u) {
+                            if (m + u < A.mv) {
+                                float* oa = rowa + A.ov0 + 3 * (m + u);
+                                float* ob = rowb + A.ov0 + 3 * (m + u);
+                                oa[0] = nv3[3 * u] * fmaf(ya[1], p[u], ya[4] * ux[u]);
+                                oa[1] = nv3[3 * u + 1] * fmaf(ya[2], p[u], ya[4] * uy[u]);
+                                oa[2] = nv3[3 * u + 2] * fmaf(ya[3], p[u], ya[4] * uz[u]);
+                                ob[0] = nv3[3 * u] * fmaf(yb[1], p[2 + u], yb[4] * ux[2 + u]);
+                                ob[1] = nv3[3 * u + 1] * fmaf(yb[2], p[2 + u], yb[4] * uy[2 + u]);
+                                ob[2] = nv3[3 * u + 2] * fmaf(yb[3], p[2 + u], yb[4] * uz[2 + u]);
+                            }
                         }
                     }
                 }
@@ -637,6 +638,7 @@ int se3_l1tp_tc2_try_forward(const int n[4], const int m[4], const int t_in[4], 
     A.d_out = mz + 3 * mv;
     A.dop = ((A.d_out & 1) || (A.d_out & 3) == 2) ? A.d_out : A.d_out + 2;
     A.dpp = (epi.d_post & 3) == 0 ? tc_stage_stride(epi.d_post) : (epi.d_post | 1);
+    if ((A.dop & 1) || (A.oz0 & 1)) return SE3_OK;   // the epilogue stores z outputs in 8-byte pairs
     auto magic = [](int d) { return d > 1 ? (unsigned)((0x100000000ull + (unsigned)d - 1) / (unsigned)d) : 0u; };
     if (epi.mode == SE3_EPI_GATE && (epi.ns_g < 2 || mv < 2)) return SE3_OK;   // magic division needs d >= 2
     A.mg_ns = magic(epi.ns_g); A.mg_mv = magic(mv); A.mg_h = magic(std::max(2, A.d_out >> 1));

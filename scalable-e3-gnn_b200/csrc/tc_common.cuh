@@ -86,6 +86,19 @@ __device__ __forceinline__ int ldgi_v(const int* p) {
     return v;
 }
 __device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+// 16 TMEM lanes x 8 columns per warp instruction, every lane gets data (mma.m16n8 accumulator fragment):
+//   v[0], v[1] = (lane row g = laneid >> 2,     columns 2 (laneid & 3) + {0, 1})
+//   v[2], v[3] = (lane row g + 8,               same columns)
+// Used to drain M = 64 accumulators, whose rows occupy TMEM lanes 0..15 of every 32-lane quarter: the 32x32b shape
+// leaves half of the warp without data.
+__device__ __forceinline__ void tc_ld_16x256(uint32_t taddr, float (&v)[4]) {
+    uint32_t r[4];
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Sorted-segment sum of one 64-row tile (rows sorted by segment id): out[seg * ld + c] += sum of the tile rows of seg.

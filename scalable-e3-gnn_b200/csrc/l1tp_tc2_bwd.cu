@@ -318,55 +318,70 @@ __global__ void __launch_bounds__(B2_THREADS, 1) l1tp_tc2_bwdi_kernel(const __gr
         const int* vcol = tab + A.t_d;
         int* sidx = reinterpret_cast<int*>(smraw + A.o_sidx);   // [SE3_MAX_SEG][64] destination rows of the tile being scattered
         int pidx[SE3_MAX_SEG];
-        float4 ypre = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 ypre = make_float4(0.f, 0.f, 0.f, 0.f), ypre2 = ypre;   // in2 of this thread's two epilogue rows
         auto prefetch_sidx = [&](int it) {   // issued early in the iteration; consumed by drain(it)
             const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * TMB2;
             long long gr = row0 + drow;
             if (gr > R - 1) gr = R - 1;
-            if (rowlane) ypre = ldg4_v(A.in2 + gr * 4);
+            {
+                long long ga = row0 + 16 * e + (lane >> 2), gb = ga + 8;
+                if (ga > R - 1) ga = R - 1;
+                if (gb > R - 1) gb = R - 1;
+                ypre = ldg4_v(A.in2 + ga * 4);
+                ypre2 = ldg4_v(A.in2 + gb * 4);
+            }
 #pragma unroll
             for (int s = 0; s < SE3_MAX_SEG; ++s) {
                 pidx[s] = (int)gr;
                 if (cgq == 0 && rowlane && s < A.src.nseg && A.src.idx[s]) pidx[s] = ldgi_v(A.src.idx[s] + gr);
             }
         };
+        const int fg = lane >> 2, fq = lane & 3;   // 16x256b fragment: rows fg, fg + 8 of the quarter; columns 2 fq, 2 fq + 1
         auto drain = [&](int it) {
             const int b = it & 1;
-            const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * TMB2;
-            const float4 y = ypre;
-            const float sy0 = C3f * y.x, s1 = C3f * y.y, s2 = C3f * y.z, s3 = C3f * y.w;
+            const float4 y = ypre, y2 = ypre2;
+            const float ya[4] = {C3f * y.x, C3f * y.y, C3f * y.z, C3f * y.w};
+            const float yb[4] = {C3f * y2.x, C3f * y2.y, C3f * y2.z, C3f * y2.w};
             mbar_wait(BAR(2 + b), (it >> 1) & 1);
             tc_fence_after();
             const uint32_t acc = tmem_base + (uint32_t)b * ACC + ((uint32_t)(32 * e) << 16);
-            float* grow = gt + drow * gts;
-            for (int k0 = 8 * cgq; k0 < A.NSP; k0 += 32) {
-                float a[8], c[8];
-                tc_ld8(acc + cS1 + k0, a);
-                tc_ld8(acc + cS2 + k0, c);
+            float* rowa = gt + (16 * e + fg) * gts;
+            float* rowb = rowa + 8 * gts;
+            for (int k0 = 8 * cgq; k0 < A.NSP; k0 += 8 * (BW2 / 4)) {
+                float a[4], c[4];
+                tc_ld_16x256(acc + cS1 + k0, a);
+                tc_ld_16x256(acc + cS2 + k0, c);
                 tc_wait_ld();
-                if (rowlane) {
+                const int n = k0 + 2 * fq;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (k0 + j < A.ns) grow[scol[k0 + j]] = fmaf(y.x, a[j], c[j]);
-                }
+                for (int u = 0; u < 2; ++u)
+                    if (n + u < A.ns) {
+                        const int col = scol[n + u];
+                        rowa[col] = fmaf(y.x, a[u], c[u]);
+                        rowb[col] = fmaf(y2.x, a[2 + u], c[2 + u]);
+                    }
             }
-            for (int k0 = 8 * cgq; k0 < A.NDP; k0 += 32) {
-                float d[8], t0[8], t1[8], t2[8];
-                tc_ld8(acc + cD + k0, d);
-                tc_ld8(acc + cT + k0, t0);
-                tc_ld8(acc + cT + A.NDP + k0, t1);
-                tc_ld8(acc + cT + 2 * A.NDP + k0, t2);
+            for (int k0 = 8 * cgq; k0 < A.NDP; k0 += 8 * (BW2 / 4)) {
+                float d[4], t0[4], t1[4], t2[4];
+                tc_ld_16x256(acc + cD + k0, d);
+                tc_ld_16x256(acc + cT + k0, t0);
+                tc_ld_16x256(acc + cT + A.NDP + k0, t1);
+                tc_ld_16x256(acc + cT + 2 * A.NDP + k0, t2);
                 tc_wait_ld();
-                if (rowlane) {
+                const int ch = k0 + 2 * fq;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (k0 + j < A.nd) {
-                            float* o = grow + vcol[k0 + j];
-                            o[0] = fmaf(s1, d[j], sy0 * t0[j]);
-                            o[1] = fmaf(s2, d[j], sy0 * t1[j]);
-                            o[2] = fmaf(s3, d[j], sy0 * t2[j]);
-                        }
-                }
+                for (int u = 0; u < 2; ++u)
+                    if (ch + u < A.nd) {
+                        const int col = vcol[ch + u];
+                        float* oa = rowa + col;
+                        float* ob = rowb + col;
+                        oa[0] = fmaf(ya[1], d[u], ya[0] * t0[u]);
+                        oa[1] = fmaf(ya[2], d[u], ya[0] * t1[u]);
+                        oa[2] = fmaf(ya[3], d[u], ya[0] * t2[u]);
+                        ob[0] = fmaf(yb[1], d[2 + u], yb[0] * t0[2 + u]);
+                        ob[1] = fmaf(yb[2], d[2 + u], yb[0] * t1[2 + u]);
+                        ob[2] = fmaf(yb[3], d[2 + u], yb[0] * t2[2 + u]);
+                    }
             }
             if (cgq == 0 && rowlane) {
 #pragma unroll

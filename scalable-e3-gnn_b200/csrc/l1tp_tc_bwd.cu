@@ -44,7 +44,7 @@ struct TcBwdArgs {
     int t_s, t_d, t_oz, t_ov, d_out, gwidth;
     int sstride[SE3_MAX_SEG], soff[SE3_MAX_SEG], vec16[SE3_MAX_SEG], swidth[SE3_MAX_SEG];
     int in2off, rawoff, rawstride, goff, gstride, slot_floats;
-    int graw_vec16, g_vec16, tmem_cols;
+    int graw_vec16, g_vec16, tmem_cols, use_tma;
     // shared memory byte offsets
     int o_as, o_ad, o_av, o_t1, o_t2, o_t3, o_stage, o_tab, o_norm, o_tbl, o_bar, o_b1, o_b2, o_b3, o_gt;
     int NS8, ND8, gts;
@@ -229,6 +229,97 @@ __device__ __forceinline__ void producer_loop(const TcBwdArgs& A, unsigned char*
     asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
+// TMA producer (weight-gradient kernel): the stage is filled by cp.async.bulk copies that complete on the slot's
+// mbarrier (complete_tx): one 256-byte copy per gathered row and segment, one contiguous copy per tile for in2, the
+// saved pre-activation and narrow identity segments.  The LDGSTS producer above needs ~90 warp instructions and ~1100
+// 32-byte sector requests per 32-row tile and was bound by outstanding requests, not by HBM (profiles/r01_final_*bwdw*).
+// part 0: in1 segments; part 1: in2, pre-activation, cotangent.  The last, partial tile is copied by hand (zero fill).
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(bar), "r"(bytes) : "memory");
+}
+template <int ROWS, int NSLOT>
+__device__ __forceinline__ void producer_loop_tma(const TcBwdArgs& A, unsigned char* smraw, uint32_t bar_full0,
+                                                  uint32_t bar_empty0, int lane, long long ntiles, int part) {
+    const long long R = A.rows;
+    const bool gate = A.epi.mode == SE3_EPI_GATE;
+    long long cur[SE3_MAX_SEG], nxt[SE3_MAX_SEG];
+    long long curg, nxtg;
+    auto fetch = [&](long long tile, long long (&c)[SE3_MAX_SEG], long long& cg) {
+        long long gr = tile * ROWS + lane;
+        if (gr > R - 1) gr = R - 1;
+        if (gr < 0) gr = 0;
+#pragma unroll
+        for (int s = 0; s < SE3_MAX_SEG; ++s)
+            c[s] = (part == 0 && s < A.src.nseg && tile < ntiles) ? (A.src.idx[s] ? (long long)A.src.idx[s][gr] : gr) : 0;
+        cg = (part == 1 && tile < ntiles) ? (A.gout_idx ? (long long)A.gout_idx[gr] : gr) : 0;
+    };
+    fetch(blockIdx.x, cur, curg);
+    fetch((long long)blockIdx.x + gridDim.x, nxt, nxtg);
+    uint32_t bytes = 0;
+    if (part == 0) {
+        for (int s = 0; s < A.src.nseg; ++s) bytes += (uint32_t)(ROWS * A.swidth[s] * 4);
+    } else {
+        bytes = (uint32_t)(ROWS * 16 + (gate ? ROWS * A.d_out * 4 : 0) + ROWS * A.gwidth * 4);
+    }
+    int slot = 0, use = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        mbar_wait(bar_empty0 + 8 * slot, (use & 1) ^ 1);
+        const uint32_t bar = bar_full0 + 8 * slot;
+        unsigned char* sptr = smraw + A.o_stage + (size_t)slot * A.slot_floats * 4;
+        const uint32_t sbase = smem_u32(sptr);
+        const long long row0 = tile * ROWS;
+        if (row0 + ROWS <= R) {
+            if (lane == 0) mbar_arrive_tx(bar, bytes);
+            __syncwarp();
+            if (part == 0) {
+#pragma unroll
+                for (int s = 0; s < SE3_MAX_SEG; ++s) {
+                    if (s >= A.src.nseg) break;
+                    const int w = A.swidth[s];
+                    if (A.vec16[s])
+                        bulk_g2s(sbase + (A.soff[s] + lane * A.sstride[s]) * 4, A.src.base[s] + cur[s] * A.src.ld[s], (uint32_t)(w * 4), bar);
+                    else if (lane == 0)
+                        bulk_g2s(sbase + A.soff[s] * 4, A.src.base[s] + row0 * w, (uint32_t)(ROWS * w * 4), bar);
+                }
+            } else {
+                if (lane == 0) bulk_g2s(sbase + A.in2off * 4, A.in2 + row0 * 4, (uint32_t)(ROWS * 16), bar);
+                if (lane == 1 && gate) bulk_g2s(sbase + A.rawoff * 4, A.raw + row0 * A.d_out, (uint32_t)(ROWS * A.d_out * 4), bar);
+                bulk_g2s(sbase + (A.goff + lane * A.gstride) * 4, A.gout + curg * A.gwidth, (uint32_t)(A.gwidth * 4), bar);
+            }
+        } else {
+            // partial tile: plain loads / stores, zero rows past the end
+            float* sf = reinterpret_cast<float*>(sptr);
+            const bool valid = row0 + lane < R;
+            if (part == 0) {
+                for (int s = 0; s < A.src.nseg; ++s) {
+                    const int w = A.swidth[s];
+                    const float* srcp = A.src.base[s] + (valid ? cur[s] * A.src.ld[s] : 0);
+                    float* d = sf + A.soff[s] + lane * A.sstride[s];
+                    for (int c = 0; c < w; ++c) d[c] = valid ? __ldg(srcp + c) : 0.0f;
+                }
+            } else {
+                const long long gr = row0 + lane;
+                for (int c = 0; c < 4; ++c) sf[A.in2off + lane * 4 + c] = valid ? __ldg(A.in2 + gr * 4 + c) : 0.0f;
+                if (gate)
+                    for (int c = 0; c < A.d_out; ++c) sf[A.rawoff + lane * A.rawstride + c] = valid ? __ldg(A.raw + gr * A.d_out + c) : 0.0f;
+                for (int c = 0; c < A.gwidth; ++c) sf[A.goff + lane * A.gstride + c] = valid ? __ldg(A.gout + curg * A.gwidth + c) : 0.0f;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar);
+        }
+#pragma unroll
+        for (int s = 0; s < SE3_MAX_SEG; ++s) cur[s] = nxt[s];
+        curg = nxtg;
+        fetch(tile + 2ll * gridDim.x, nxt, nxtg);
+        if (++slot == NSLOT) { slot = 0; ++use; }
+    }
+}
+
 // tables shared by both kernels: plan tables, norms, packed (stride<<20 | offset) stage addresses of every scalar /
 // vector channel
 __device__ __forceinline__ void setup_tables(const TcBwdArgs& A, unsigned char* smraw, int nthreads) {
@@ -283,7 +374,7 @@ __global__ void __launch_bounds__(TBW_THREADS, 1) l1tp_tc_bwdw_kernel(const TcBw
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
     if (tid == 0) {
         for (int i = 0; i < BW_NSLOT; ++i) {
-            mbar_init(BAR(9 + i), 64);  // 64 producer lanes (warps 0 and 2)
+            mbar_init(BAR(9 + i), A.use_tma ? 2 : 64);  // TMA: one expect_tx arrival per producer warp; else 64 producer lanes
             mbar_init(BAR(12 + i), BW_NBUILD);
         }
         mbar_init(BAR(4), BW_NBUILD);
@@ -309,7 +400,8 @@ __global__ void __launch_bounds__(TBW_THREADS, 1) l1tp_tc_bwdw_kernel(const TcBw
     const int cD1 = 0, cD2 = A.N2, cD3 = A.N2 + A.N3, cD4 = 2 * A.N2 + A.N3;
 
     if (warp == 0 || warp == 2) {
-        producer_loop<TMB, BW_NSLOT>(A, smraw, BAR(9), BAR(12), lane, true, ntiles, warp == 0 ? 0 : 1, 2);
+        if (A.use_tma) producer_loop_tma<TMB, BW_NSLOT>(A, smraw, BAR(9), BAR(12), lane, ntiles, warp == 0 ? 0 : 1);
+        else producer_loop<TMB, BW_NSLOT>(A, smraw, BAR(9), BAR(12), lane, true, ntiles, warp == 0 ? 0 : 1, 2);
     } else if (warp == 1) {
         // ---------------- MMA issuer: per tile 4 K-steps (8 rows each) x {S.[HZY|HG], Dd.HZ, AVc.HVc} x 3xTF32.
         // All operands are K-major with K = rows: transposed tiles [channel/feature][row], 8-channel groups of
@@ -778,7 +870,7 @@ using namespace se3;
 
 static int fill_common(TcBwdArgs& A, const int n[4], const int m[4], const int t_in[4], const int t_out[4], int ntab,
                        const int* d_tab, const se3_l1tp_bwd_args* a, const RowSrc& src, const EpiL& epi, int rows_per_tile,
-                       bool with_x) {
+                       bool with_x, bool want_tma = false) {
     if (n[1] || n[2] || m[1] || m[2]) return 1;
     const int ns = n[0], nd = n[3], mz = m[0], mv = m[3];
     if (ns < 1 || nd < 1 || mz < 1 || mv < 1) return 1;
@@ -797,20 +889,36 @@ static int fill_common(TcBwdArgs& A, const int n[4], const int m[4], const int t
     A.d_out = mz + 3 * mv;
     A.gwidth = epi.d_post;
     if (((uintptr_t)a->in2 & 15) != 0) return 1;
+    // TMA (cp.async.bulk) staging: wide segments and the cotangent go row by row (256-byte rows), narrow identity
+    // segments / in2 / the saved pre-activation as ONE contiguous copy per tile (their stage layout is then dense)
+    bool tma = want_tma && with_x && ((epi.d_post & 3) == 0) && (((uintptr_t)a->gout & 15) == 0);
+    if (tma && epi.mode == SE3_EPI_GATE && (((rows_per_tile * (mz + 3 * mv) * 4) & 15) || ((uintptr_t)a->raw & 15))) tma = false;
+    for (int s = 0; s < src.nseg && tma; ++s) {
+        const int w = src.cum[s + 1] - src.cum[s];
+        const bool wide = (w & 3) == 0 && (src.ld[s] & 3) == 0 && ((uintptr_t)src.base[s] & 15) == 0;
+        if (!wide && (src.idx[s] || src.ld[s] != w || ((rows_per_tile * w * 4) & 15) || ((uintptr_t)src.base[s] & 15))) tma = false;
+    }
+    {   // measured: with two or more GATHERED wide segments (msg1: x[dst], x[src]) the 256-byte per-row bulk copies are no
+        // faster than the LDGSTS producer (1.25 vs 1.20 ms), with at most one they are (msg2: 0.93 vs 1.08 ms)
+        int gathered = 0;
+        for (int s = 0; s < src.nseg; ++s) gathered += (src.idx[s] != nullptr) ? 1 : 0;
+        if (gathered >= 2) tma = false;
+    }
+    A.use_tma = tma ? 1 : 0;
     int off = 0;
     for (int s = 0; s < src.nseg; ++s) {
         const int w = src.cum[s + 1] - src.cum[s];
         A.swidth[s] = w;
-        A.sstride[s] = tc_stage_stride(w);
         A.vec16[s] = ((w & 3) == 0 && (src.ld[s] & 3) == 0 && ((uintptr_t)src.base[s] & 15) == 0) ? 1 : 0;
+        A.sstride[s] = (tma && !A.vec16[s]) ? w : tc_stage_stride(w);
         if (with_x) {
             if (!A.vec16[s] && w > 16) return 1;
             A.soff[s] = off;
-            off += rows_per_tile * A.sstride[s];
+            off += (rows_per_tile * A.sstride[s] + 3) & ~3;
         }
     }
     A.in2off = off; off += rows_per_tile * 4;
-    A.rawstride = tc_stage_stride(A.d_out);
+    A.rawstride = tma ? A.d_out : tc_stage_stride(A.d_out);
     A.rawoff = off;
     if (epi.mode == SE3_EPI_GATE) {
         if ((A.d_out & 1) || ((uintptr_t)a->raw & 7)) return 1;
@@ -838,7 +946,9 @@ int se3_l1tp_tc_try_backward_w(const int n[4], const int m[4], const int t_in[4]
     }
     if (disabled) return SE3_OK;
     TcBwdArgs A;
-    if (fill_common(A, n, m, t_in, t_out, ntab, d_tab, a, src, epi, TMB, true)) return SE3_OK;
+    static int no_tma = -1;
+    if (no_tma < 0) { const char* e = getenv("SE3_DISABLE_TMA"); no_tma = (e && e[0] == '1') ? 1 : 0; }
+    if (fill_common(A, n, m, t_in, t_out, ntab, d_tab, a, src, epi, TMB, true, !no_tma)) return SE3_OK;
     A.partials = partials; A.wtot = wtot; A.gw_z_off = gw_z_off; A.gw_v_off = gw_v_off;
     A.tmem_cols = 32;
     while (A.tmem_cols < 2 * A.N2 + 2 * A.N3) A.tmem_cols <<= 1;

@@ -255,7 +255,8 @@ def run_b200(a):
     ach = tr["bytes"] / (tr["ms"] * 1e-3) / 1e9
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(top[0])
+        if a.particles == 100_000 and a.layers == 4 and a.kind == "plummer":   # the workload the ncu capture was taken on
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(top[0])
     except Exception:
         pass
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0

@@ -1097,6 +1097,10 @@ int se3_l1tp_tc2_try_backward_in(const int n[4], const int m[4], const int t_in[
                                  const int* h_tab, const int* d_tab, const se3_l1tp_bwd_args* a, const se3::RowSrc& src,
                                  const se3::EpiL& epi, float* const gseg[SE3_MAX_SEG], const int gmode[SE3_MAX_SEG],
                                  cudaStream_t st, bool* launched);
+int se3_l1tp_tc2_try_backward_w(const int n[4], const int m[4], const int t_in[4], const int t_out[4], int ntab,
+                                const int* h_tab, const se3_l1tp_bwd_args* a, const se3::RowSrc& src, const se3::EpiL& epi,
+                                float* partials, int wtot, int gw_z_off, int gw_v_off, int max_grid, cudaStream_t st,
+                                int* grid_out, bool* launched);
 int se3_l1tp_tc_try_backward_w(const int n[4], const int m[4], const int t_in[4], const int t_out[4], int ntab,
                                const int* d_tab, const se3_l1tp_bwd_args* a, const se3::RowSrc& src, const se3::EpiL& epi,
                                float* partials, int wtot, int gw_z_off, int gw_v_off, int max_grid, cudaStream_t st,
@@ -1380,6 +1384,11 @@ extern "C" int se3_l1tp_backward(se3_l1tp_plan* p, const se3_l1tp_bwd_args* a, v
         // SE3_BWDW_GRID (diagnostics): fewer CTAs = a different partition of the rows over the fp32 accumulators
         static int grid_cap = -1;
         if (grid_cap < 0) { const char* e = getenv("SE3_BWDW_GRID"); grid_cap = e ? std::max(1, atoi(e)) : 0; }
+        rc = se3_l1tp_tc2_try_backward_w(p->n, p->m, p->t_in, p->t_out, p->L.ntab, p->h_tab.data(), a, K.src, K.epi,
+                                         p->d_partials, p->L.wtot, p->w_off[0], p->w_off[3],
+                                         grid_cap ? std::min(grid_cap, num_sms()) : num_sms(), st, &tc_grid, &tcw);
+        if (rc) return rc;
+        if (!tcw)
         rc = se3_l1tp_tc_try_backward_w(p->n, p->m, p->t_in, p->t_out, p->L.ntab, p->d_tab, a, K.src, K.epi,
                                         p->d_partials, p->L.wtot, p->w_off[0], p->w_off[3],
                                         grid_cap ? std::min(grid_cap, num_sms()) : num_sms(), st, &tc_grid, &tcw);

@@ -160,6 +160,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) l1tp_tc2_bwdw_kernel(const __gr
         float2 hR[2], hvRg, hvRv[3], hvGv[3];                         // HS raw; HX raw gates / raw vectors / cotangent vectors
         float4 hG = xsR, hY = xsR;
         long long xs_i = 0, xv_i = 0, xs_in = 0, xv_in = 0, hg_i = 0, hg_in = 0;
+        const SegW xsS = A.seg[T.xs_seg >= 0 ? T.xs_seg : 0], xvS = A.seg[T.xv_seg >= 0 ? T.xv_seg : 0];
         const int xs_row = T.xs_q * 4 + r4, xv_row = T.xv_q * 4 + r4;
         const int h_q = T.hs_q >= 0 ? T.hs_q : T.hx_q;
         const int h_row = h_q * 4 + r4;
@@ -168,12 +169,12 @@ __global__ void __launch_bounds__(T3_THREADS, 1) l1tp_tc2_bwdw_kernel(const __gr
             const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * TW;
             if (T.xs_seg >= 0) {
                 const long long gr = clampr(row0 + xs_row);
-                const int32_t* ip = A.seg[T.xs_seg].idx;
+                const int32_t* ip = xsS.idx;
                 xs_in = ip ? (long long)ldgi_v(ip + gr) : gr;
             }
             if (T.xv_seg >= 0) {
                 const long long gr = clampr(row0 + xv_row);
-                const int32_t* ip = A.seg[T.xv_seg].idx;
+                const int32_t* ip = xvS.idx;
                 xv_in = ip ? (long long)ldgi_v(ip + gr) : gr;
             }
             if (h_q >= 0) {
@@ -184,11 +185,11 @@ __global__ void __launch_bounds__(T3_THREADS, 1) l1tp_tc2_bwdw_kernel(const __gr
         auto load_rows = [&](int it) {
             const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * TW;
             if (T.xs_seg >= 0) {
-                const SegW& S = A.seg[T.xs_seg];
+                const SegW& S = xsS;
                 if (4 * pc + 3 < S.nss) xsR = ldg4_v(S.base + xs_i * S.ld + 4 * pc);
             }
             if (T.xv_seg >= 0) {
-                const SegW& S = A.seg[T.xv_seg];
+                const SegW& S = xvS;
                 const float* rp = S.base + xv_i * S.ld;
                 if (pc < (S.nvs >> 1)) {
 #pragma unroll
@@ -269,11 +270,11 @@ __global__ void __launch_bounds__(T3_THREADS, 1) l1tp_tc2_bwdw_kernel(const __gr
             unsigned char* set = smraw + A.o_set + b * SETB;
             const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * TW;
             if (T.xs_seg >= 0) {
-                const SegW& S = A.seg[T.xs_seg];
+                const SegW& S = xsS;
                 if (4 * pc + 3 < S.nss) st4(set, tw_off(cS, xs_row, S.koff + 4 * pc), xsR.x, xsR.y, xsR.z, xsR.w);
             }
             if (T.xv_seg >= 0) {
-                const SegW& S = A.seg[T.xv_seg];
+                const SegW& S = xvS;
                 if (pc < (S.nvs >> 1)) {
                     const float v[6] = {xvR[0].x, xvR[0].y, xvR[1].x, xvR[1].y, xvR[2].x, xvR[2].y};
                     const float y1 = C3f * xvY.y, y2 = C3f * xvY.z, y3 = C3f * xvY.w, y0 = C3f * xvY.x;

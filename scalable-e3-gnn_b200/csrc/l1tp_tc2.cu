@@ -240,8 +240,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) l1tp_tc2_fwd_kernel(const __gri
         // narrow pieces: at most one task (32 four-byte pieces) per warp
         bool nact = false;
         int nrow = 0, ngofs = 0, ndd = -1;
+        const NarrowE NW = A.nar[warp < A.nnar ? warp : 0];   // hoisted: no dynamic parameter indexing in the tile loop
         if (warp < A.nnar) {
-            const NarrowE N = A.nar[warp];
+            const NarrowE N = NW;
             const int p = N.t * 32 + lane;
             nrow = p / N.w;
             ngofs = p - nrow * N.w;
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) l1tp_tc2_fwd_kernel(const __gri
             if (nact) {
                 long long g2 = row0 + nrow;
                 if (g2 > R - 1) g2 = R - 1;
-                const int32_t* ip = A.nar[warp].idx;
+                const int32_t* ip = NW.idx;
                 nnidx = ip ? ldgi_v(ip + g2) : (int)g2;
             }
         };
@@ -280,7 +281,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) l1tp_tc2_fwd_kernel(const __gri
                     R4[i] = ldg4_v(B.base + (long long)nidx[i] * B.ld + gofs[i]);
                 }
             }
-            if (nact) RN = ldg1_v(A.nar[warp].base + (long long)nnidx * A.nar[warp].ld + ngofs);
+            if (nact) RN = ldg1_v(NW.base + (long long)nnidx * NW.ld + ngofs);
         };
         auto put = [&](unsigned char* aset, int d, float x) {
             if (d < 0) return;

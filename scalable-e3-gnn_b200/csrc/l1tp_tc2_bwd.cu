@@ -395,7 +395,9 @@ __global__ void __launch_bounds__(B2_THREADS, 1) l1tp_tc2_bwdi_kernel(const __gr
         auto scatter = [&](int it) {
             const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * TMB2;
             const int nvalid = (int)min((long long)TMB2, R - row0);
-            for (int s = 0; s < A.src.nseg; ++s) {
+#pragma unroll
+            for (int s = 0; s < SE3_MAX_SEG; ++s) {   // unrolled: no dynamic indexing of the kernel parameters in the tile loop
+                if (s >= A.src.nseg) break;
                 float* gb = A.gseg[s];
                 const int mode = A.gmode[s];
                 if (!gb || mode == SE3_GRAD_NONE) continue;

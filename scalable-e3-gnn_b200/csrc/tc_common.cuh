@@ -145,25 +145,46 @@ __device__ __forceinline__ void sorted_segment_sum_tile(const float* tile, int t
         hs[qd * width + c] = h;
     }
     named_bar(barid, NT);
-    for (int c = tid; c < width; c += NT) {
-        const int prevseg = sseg[0], nextseg = sseg[65];
-        int cur = -1;
-        float acc = 0.0f;
+    // pass B, spread over all threads: a run is owned by the thread of the part it STARTS in (as that part's head, if the
+    // previous non-empty part does not end with the same segment, or as its tail); the owner adds the heads of the
+    // following parts that continue the run and emits it.
+    const int prevseg = sseg[0], nextseg = sseg[65];
+    for (int item = tid; item < width * parts; item += NT) {
+        const int c = item % width, qd = item / width;
+        const float4 h = hs[qd * width + c];
+        const int sh = __float_as_int(h.x), st = __float_as_int(h.z);
+        if (sh < 0) continue;
         auto emit = [&](int seg, float v) {
-            if (seg < 0) return;
             float* p = out + (long long)seg * ld + c;
             if (seg == prevseg || seg == nextseg) atomicAdd(p, v);
             else *p = v;
         };
-        for (int q = 0; q < parts; ++q) {
-            const float4 h = hs[q * width + c];
-            const int sh = __float_as_int(h.x), st = __float_as_int(h.z);
-            if (sh < 0) continue;
-            if (sh == cur) acc += h.y;
-            else { emit(cur, acc); cur = sh; acc = h.y; }
-            if (st >= 0) { emit(cur, acc); cur = st; acc = h.w; }
+        auto extend = [&](int seg, float acc) {   // add the heads of the following parts while they continue `seg`
+            for (int q2 = qd + 1; q2 < parts; ++q2) {
+                const float4 g = hs[q2 * width + c];
+                const int s2 = __float_as_int(g.x);
+                if (s2 < 0) continue;
+                if (s2 != seg) break;
+                acc += g.y;
+                if (__float_as_int(g.z) >= 0) break;   // that part goes on with another segment: the run ended there
+            }
+            emit(seg, acc);
+        };
+        bool head_owned = true;
+        for (int q0 = qd - 1; q0 >= 0; --q0) {
+            const float4 g = hs[q0 * width + c];
+            const int s0 = __float_as_int(g.x);
+            if (s0 < 0) continue;
+            const int last = __float_as_int(g.z) >= 0 ? __float_as_int(g.z) : s0;
+            head_owned = last != sh;
+            break;
         }
-        emit(cur, acc);
+        if (st >= 0) {
+            if (head_owned) emit(sh, h.y);   // the head run ends inside this part
+            extend(st, h.w);                 // the tail run starts here
+        } else if (head_owned) {
+            extend(sh, h.y);
+        }
     }
 }
 

@@ -78,7 +78,7 @@ struct Tc2Args {
 
 // SEG: the launch ends in the sorted-segment sum (kept out of the other instantiation: its prefetch registers and
 // barriers cost the plain launches 7 % through register pressure)
-template <bool SEG>
+template <bool SEG, bool GATE>
 __global__ void __launch_bounds__(T2_THREADS, 1) l1tp_tc2_fwd_kernel(const __grid_constant__ Tc2Args A) {
     extern __shared__ __align__(1024) unsigned char smraw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) l1tp_tc2_fwd_kernel(const __gri
         const int e = warp & 3, jq = warp >> 2;
         float* otile = reinterpret_cast<float*>(smraw + A.o_out);
         float* ptile = reinterpret_cast<float*>(smraw + A.o_post);
-        const bool gate = A.epi.mode == SE3_EPI_GATE;
+        constexpr bool gate = GATE;
         const int dout = A.d_out, dpost = A.epi.d_post;
         const int drow = 16 * e + (lane & 15);
         const bool rowlane = lane < 16;
@@ -667,14 +667,17 @@ int se3_l1tp_tc2_try_forward(const int n[4], const int m[4], const int t_in[4], 
     const int smem = std::max(o, 120 * 1024);   // > half an SM: one CTA per SM owns all 512 TMEM columns
     static bool attr_set = false;
     if (!attr_set) {
-        SE3_CUDA_TRY(cudaFuncSetAttribute(l1tp_tc2_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
-        SE3_CUDA_TRY(cudaFuncSetAttribute(l1tp_tc2_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
+        SE3_CUDA_TRY(cudaFuncSetAttribute(l1tp_tc2_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
+        SE3_CUDA_TRY(cudaFuncSetAttribute(l1tp_tc2_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
+        SE3_CUDA_TRY(cudaFuncSetAttribute(l1tp_tc2_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
+        SE3_CUDA_TRY(cudaFuncSetAttribute(l1tp_tc2_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
         attr_set = true;
     }
     const long long ntiles = (a->rows + TM2 - 1) / TM2;
     const int grid = (int)std::min<long long>(ntiles, num_sms());
-    if (a->seg_idx) l1tp_tc2_fwd_kernel<true><<<grid, T2_THREADS, smem, st>>>(A);
-    else l1tp_tc2_fwd_kernel<false><<<grid, T2_THREADS, smem, st>>>(A);
+    const bool g = epi.mode == SE3_EPI_GATE;
+    if (a->seg_idx) { if (g) l1tp_tc2_fwd_kernel<true, true><<<grid, T2_THREADS, smem, st>>>(A); else l1tp_tc2_fwd_kernel<true, false><<<grid, T2_THREADS, smem, st>>>(A); }
+    else { if (g) l1tp_tc2_fwd_kernel<false, true><<<grid, T2_THREADS, smem, st>>>(A); else l1tp_tc2_fwd_kernel<false, false><<<grid, T2_THREADS, smem, st>>>(A); }
     SE3_LAUNCHED();
     g_tc_launches.fetch_add(1, std::memory_order_relaxed);
     *launched = true;

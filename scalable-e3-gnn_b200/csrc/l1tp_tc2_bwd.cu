@@ -52,6 +52,7 @@ struct Tc2BwdArgs {
 __device__ __forceinline__ float2 ldg2(const float* p) { return ldg2_v(p); }
 __device__ __forceinline__ float4 ldg4(const float* p) { return ldg4_v(p); }
 
+template <bool GATE>
 __global__ void __launch_bounds__(B2_THREADS, 1) l1tp_tc2_bwdi_kernel(const __grid_constant__ Tc2BwdArgs A) {
     extern __shared__ __align__(1024) unsigned char smraw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -62,7 +63,7 @@ __global__ void __launch_bounds__(B2_THREADS, 1) l1tp_tc2_bwdi_kernel(const __gr
     // barriers: 0,1 operand set full | 2,3 accumulator full | 4,5 accumulator empty
     auto BAR = [&](int i) { return bar0 + 8u * i; };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-    const bool gate = A.epi.mode == SE3_EPI_GATE;
+    constexpr bool gate = GATE;
 
     for (int t = tid; t < A.ntab; t += B2_THREADS) tab[t] = A.tab[t];
     for (int t = tid; t < A.mz; t += B2_THREADS) norm[t] = A.nz ? A.nz[t] : 1.0f;
@@ -561,12 +562,14 @@ int se3_l1tp_tc2_try_backward_in(const int n[4], const int m[4], const int t_in[
     const int smem = std::max(o, 120 * 1024);
     static bool attr_set = false;
     if (!attr_set) {
-        SE3_CUDA_TRY(cudaFuncSetAttribute(l1tp_tc2_bwdi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
+        SE3_CUDA_TRY(cudaFuncSetAttribute(l1tp_tc2_bwdi_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
+        SE3_CUDA_TRY(cudaFuncSetAttribute(l1tp_tc2_bwdi_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
         attr_set = true;
     }
     const long long ntiles = (a->rows + TMB2 - 1) / TMB2;
     const int grid = (int)std::min<long long>(ntiles, num_sms());
-    l1tp_tc2_bwdi_kernel<<<grid, B2_THREADS, smem, st>>>(A);
+    if (gate) l1tp_tc2_bwdi_kernel<true><<<grid, B2_THREADS, smem, st>>>(A);
+    else l1tp_tc2_bwdi_kernel<false><<<grid, B2_THREADS, smem, st>>>(A);
     SE3_LAUNCHED();
     g_tc_launches.fetch_add(1, std::memory_order_relaxed);
     *launched = true;

@@ -68,6 +68,7 @@ __device__ __forceinline__ uint64_t mk_desc_mn(uint32_t saddr) {        // MN-ma
            (1ull << 46) | (1ull << 61);
 }
 
+template <bool GATE>
 __global__ void __launch_bounds__(T3_THREADS, 1) l1tp_tc2_bwdw_kernel(const __grid_constant__ Tc3Args A) {
     extern __shared__ __align__(1024) unsigned char smraw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) l1tp_tc2_bwdw_kernel(const __gr
     // barriers: 0,1 set full | 2,3 set empty | 4 accumulators final
     auto BAR = [&](int i) { return bar0 + 8u * i; };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
-    const bool gate = A.epi.mode == SE3_EPI_GATE;
+    constexpr bool gate = GATE;
 
     for (int t = tid; t < A.mz; t += T3_THREADS) norm[t] = A.nz ? A.nz[t] : 1.0f;
     for (int t = tid; t < 3 * A.mv; t += T3_THREADS) norm[A.mz + t] = A.nv ? A.nv[t] : 1.0f;
@@ -567,12 +568,14 @@ int se3_l1tp_tc2_try_backward_w(const int n[4], const int m[4], const int t_in[4
     if (o > maxsm) return SE3_OK;
     static bool attr_set = false;
     if (!attr_set) {
-        SE3_CUDA_TRY(cudaFuncSetAttribute(l1tp_tc2_bwdw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
+        SE3_CUDA_TRY(cudaFuncSetAttribute(l1tp_tc2_bwdw_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
+        SE3_CUDA_TRY(cudaFuncSetAttribute(l1tp_tc2_bwdw_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
         attr_set = true;
     }
     const long long ntiles = (a->rows + TW - 1) / TW;
     const int grid = (int)std::min<long long>(ntiles, std::min(num_sms(), max_grid));
-    l1tp_tc2_bwdw_kernel<<<grid, T3_THREADS, o, st>>>(A);
+    if (gate) l1tp_tc2_bwdw_kernel<true><<<grid, T3_THREADS, o, st>>>(A);
+    else l1tp_tc2_bwdw_kernel<false><<<grid, T3_THREADS, o, st>>>(A);
     SE3_LAUNCHED();
     g_tc_launches.fetch_add(1, std::memory_order_relaxed);
     *grid_out = grid;

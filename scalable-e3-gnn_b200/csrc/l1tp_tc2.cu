@@ -69,7 +69,7 @@ struct Tc2Args {
     int dop, dpp;
     unsigned mg_ns, mg_mv, mg_h;              // ceil(2^32 / d) for d = gate_ns, mv, d_out / 2
     int o_b1, o_b2, o_a, a_bytes, o_out, o_post, o_norm, o_blk, o_ccode, o_bar, o_sseg, o_hs;
-    int halfS, halfV, oV;                     // bytes: lo offset of S / V tiles, first V tile inside an operand set
+    int halfS, halfV, oV, HALF;               // bytes of one S / V tile (hi), first V tile, lo offset of every tile (= all hi tiles)
     BlockE blk[NG * MAXB];
     NarrowE nar[W2];
     unsigned short ccode[MAXCOL];             // per concatenated column: type << 13 | index (1: scalar slot, 2..4: x/y/z kd)
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) l1tp_tc2_fwd_kernel(const __gri
         const uint64_t dB1h = make_desc(sb + A.o_b1, sboS), dB1l = make_desc(sb + A.o_b1 + A.N1 * A.K1 * 4, sboS);
         const uint64_t dB2h = make_desc(sb + A.o_b2, sboV), dB2l = make_desc(sb + A.o_b2 + A.N1 * A.K2 * 4, sboV);
         const int nk1 = A.K1 >> 3, nk2 = A.K2 >> 3;
-        const uint32_t vstep = (2u * A.halfV) >> 4;   // descriptor units between consecutive V tiles
+        const uint32_t vstep = ((uint32_t)A.halfV) >> 4;   // descriptor units between consecutive V tiles
         for (int it = 0; it < nt; ++it) {
             const int b = it & 1;
             const uint32_t ph = (it >> 1) & 1;
@@ -176,14 +176,14 @@ __global__ void __launch_bounds__(T2_THREADS, 1) l1tp_tc2_fwd_kernel(const __gri
             if (lane == 0) {
                 const uint32_t acc = tmem_base + (uint32_t)b * ACC;
                 const uint32_t aS = sb + A.o_a + (uint32_t)b * A.a_bytes;
-                const uint64_t dSh = make_desc(aS, sboS), dSl = make_desc(aS + A.halfS, sboS);
+                const uint64_t dSh = make_desc(aS, sboS), dSl = make_desc(aS + A.HALF, sboS);
                 for (int j = 0; j < nk1; ++j) {
                     const uint64_t o = (uint64_t)(j * 16);   // 256 bytes per K-step, in 16-byte units
                     tc_mma_tf32(acc, dSh + o, dB1h + o, idesc, j ? 1u : 0u);
                     tc_mma_tf32(acc, dSh + o, dB1l + o, idesc, 1u);
                     tc_mma_tf32(acc, dSl + o, dB1h + o, idesc, 1u);
                 }
-                const uint64_t dVh = make_desc(aS + A.oV, sboV), dVl = make_desc(aS + A.oV + A.halfV, sboV);
+                const uint64_t dVh = make_desc(aS + A.oV, sboV), dVl = make_desc(aS + A.oV + A.HALF, sboV);
                 for (int c = 0; c < 3; ++c) {
                     const uint32_t accc = acc + (uint32_t)(c + 1) * A.N1;
                     const uint64_t co = (uint64_t)c * vstep;
@@ -207,11 +207,11 @@ __global__ void __launch_bounds__(T2_THREADS, 1) l1tp_tc2_fwd_kernel(const __gri
         const int wrow = (warp & 7) * 8 + r8;
         const int rowpartS = (((wrow >> 3) * KQ1) << 7) + ((wrow & 7) << 4);
         const int rowpartV = (((wrow >> 3) * KQ2) << 7) + ((wrow & 7) << 4);
-        auto enc = [&](int code, int rpS, int rpV) -> int {   // destination of one column: -1 none, bit 30 = V tile
+        auto enc = [&](int code, int rpS, int rpV) -> int {   // destination of one column (hi tile byte offset): -1 none
             const int ty = code >> 13, ix = code & 0x1fff;
             if (ty == 0) return -1;
             if (ty == 1) return rpS + ((ix >> 2) << 7) + ((ix & 3) << 2);
-            return (1 << 30) | (A.oV + (ty - 2) * 2 * A.halfV + rpV + ((ix >> 2) << 7) + ((ix & 3) << 2));
+            return A.oV + (ty - 2) * A.halfV + rpV + ((ix >> 2) << 7) + ((ix & 3) << 2);
         };
         int gofs[MAXB], dd[MAXB][4];
         bool act[MAXB], fast[MAXB];
@@ -287,9 +287,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) l1tp_tc2_fwd_kernel(const __gri
             if (d < 0) return;
             float hi, lo;
             split_tf32(x, hi, lo);
-            const int o = d & 0x3fffffff;
-            *reinterpret_cast<float*>(aset + o) = hi;
-            *reinterpret_cast<float*>(aset + o + ((d >> 30) ? A.halfV : A.halfS)) = lo;
+            *reinterpret_cast<float*>(aset + d) = hi;
+            *reinterpret_cast<float*>(aset + d + A.HALF) = lo;
         };
         auto build = [&](int b) {
             unsigned char* aset = smraw + A.o_a + b * A.a_bytes;
@@ -301,7 +300,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) l1tp_tc2_fwd_kernel(const __gri
                     float4 h, l;
                     split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
                     *reinterpret_cast<float4*>(aset + dd[i][0]) = h;
-                    *reinterpret_cast<float4*>(aset + dd[i][0] + A.halfS) = l;
+                    *reinterpret_cast<float4*>(aset + dd[i][0] + A.HALF) = l;
                 } else {
                     put(aset, dd[i][0], v.x);
                     put(aset, dd[i][1], v.y);
@@ -645,8 +644,9 @@ int se3_l1tp_tc2_try_forward(const int n[4], const int m[4], const int t_in[4], 
     A.mg_ns = magic(epi.ns_g); A.mg_mv = magic(mv); A.mg_h = magic(std::max(2, A.d_out >> 1));
     if ((A.d_out >> 1) < 2) return SE3_OK;
     auto al = [](int x, int q) { return (x + q - 1) / q * q; };
-    A.halfS = TM2 * K1 * 4; A.halfV = TM2 * K2 * 4; A.oV = 2 * A.halfS;
-    A.a_bytes = 2 * A.halfS + 6 * A.halfV;
+    A.halfS = TM2 * K1 * 4; A.halfV = TM2 * K2 * 4; A.oV = A.halfS;
+    A.HALF = A.halfS + 3 * A.halfV;
+    A.a_bytes = 2 * A.HALF;
     int o = 0;
     A.o_b1 = o; o += 2 * A.N1 * K1 * 4;
     A.o_b2 = o; o += 2 * A.N1 * K2 * 4;

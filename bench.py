@@ -80,7 +80,7 @@ def run_reference(a):
             "dtype": "f32", "data": "synthetic", "config": workload(a), "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------- clocks
@@ -308,13 +308,22 @@ def run_b200(a):
             "data": "synthetic", "config": cfg, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cb, "edges_per_s": tot_edges * K / (ms * 1e-3),
             "loss": float(loss.item()), "kernels": table}
-    print(json.dumps(line), flush=True)
+    _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
+def _emit(line: str):
+    """The ONE JSON line goes to the real stdout; everything else libraries print to fd 1 (e.g. NCCL's version banner)
+    was redirected to stderr at start-up."""
+    os.write(_REAL_STDOUT, (line + "\n").encode())
+
+
 if __name__ == "__main__":
     args = parse()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -544,7 +544,7 @@ int se3_l1tp_tc2_try_forward(const int n[4], const int m[4], const int t_in[4], 
     if (((uintptr_t)a->in2 & 15) != 0) return SE3_OK;
     const int dtot = src.cum[src.nseg];
     if (dtot > MAXCOL - 4) return SE3_OK;
-    static Tc2Args A;   // large: keep off the stack; launches are serialised by the caller's stream use
+    static thread_local Tc2Args A;   // large: keep off the stack; one per host thread (autograd runs backward on its own threads)
     memset(&A, 0, sizeof(A));
     A.ns = ns; A.nd = nd; A.mz = mz; A.mv = mv;
     A.N2 = (mz + 7) & ~7;

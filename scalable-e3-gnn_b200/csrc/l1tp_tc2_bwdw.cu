@@ -447,7 +447,7 @@ int se3_l1tp_tc2_try_backward_w(const int n[4], const int m[4], const int t_in[4
     const int ns = n[0], nd = n[3], mz = m[0], mv = m[3];
     if (ns < 1 || nd < 1 || mz < 1 || mv < 1) return SE3_OK;
     if (a->rows >= (1ll << 31) - TW) return SE3_OK;
-    static Tc3Args A;
+    static thread_local Tc3Args A;
     memset(&A, 0, sizeof(A));
     const bool gate = epi.mode == SE3_EPI_GATE;
     A.ns = ns; A.nd = nd; A.mz = mz; A.mv = mv; A.d_out = mz + 3 * mv;

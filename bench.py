@@ -85,59 +85,47 @@ def run_reference(a):
 
 # ------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """SM clock / throttle reasons DURING the timed region, sampled through NVML in a thread (an `nvidia-smi -lms`
-    child process was measured to perturb the timed region)."""
+    """SM clock / throttle reasons while the GPU executes the timed region, read through NVML from the launching thread
+    once all timed work has been queued.  The first NVML query of a process costs ~28 ms and is taken in the
+    constructor."""
 
-    def __init__(self, gpu_index, period=0.05):
-        import threading
-        self.sm, self.mx, self.reasons, self.err = [], [], set(), None
-        self._stop = threading.Event()
+    def __init__(self, gpu_index):
+        self.sm, self.reasons, self.err = [], set(), None
         try:
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
             self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
-            # the first NVML query of a process was measured at ~28 ms (later ones ~1 us): take it here, outside the
-            # timed region, so that the sampler cannot stall the launching thread
-            pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM)
-            try:
-                pynvml.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-            except Exception:
-                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            self.names = {"hw_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                          "hw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                          "sw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                          "sw_power_cap": getattr(pynvml, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+            self.sample(record=False)
         except Exception as e:  # pragma: no cover
             self.nv, self.err = None, repr(e)
-            return
-        self.period = period
-        self.t = threading.Thread(target=self._run, daemon=True)
-        self.t.start()
 
-    def _run(self):
+    def sample(self, record=True):
+        if self.nv is None:
+            return
         nv = self.nv
-        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
-                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
-                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
-                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
-        while not self._stop.is_set():
+        try:
+            c = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
             try:
-                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                try:
-                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                except Exception:
-                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for k, bit in names.items():
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            if record:
+                self.sm.append(c)
+                for k, bit in self.names.items():
                     if r & bit:
                         self.reasons.add(k)
-            except Exception as e:  # pragma: no cover
-                self.err = repr(e)
-                break
-            self._stop.wait(self.period)
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
 
     def stop(self):
         if self.nv is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: %s" % self.err]}
-        self._stop.set()
-        self.t.join(timeout=2)
         med = statistics.median(self.sm) if self.sm else None
         return {"sm_mhz": med, "sm_max_mhz": self.max_sm, "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
@@ -196,8 +184,18 @@ def run_b200(a):
         step_dev, step_host = ts.step_device, ts.step_host
     K, W = max(1, a.steps), max(3, a.warmup)
 
-    for _ in range(max(W, 5)):   # a few more untimed steps than asked: the caching allocator settles after ~4 steps
+    # untimed warm-up: at least W steps AND ~1.5 s of wall time (in the first process on a fresh box the first half second
+    # of steps was measured 7-10 % slow: allocator growth, clock / power-state ramp, page-ins)
+    t_w = time.perf_counter()
+    for _ in range(W):
         loss = step_dev(*devt)
+    torch.cuda.synchronize()
+    per = (time.perf_counter() - t_w) / W
+    extra = int(allmax(float(max(0, int((1.5 - per * W) / max(per, 1e-4))))))   # same count on every rank (collectives inside)
+    for i in range(extra):
+        loss = step_dev(*devt)
+        if i % 4 == 3:
+            torch.cuda.synchronize()
     barrier()
     g = ts.last_graph
     edges, cells = g.e, g.m
@@ -208,9 +206,15 @@ def run_b200(a):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    for _ in range(K):
+    for i in range(K):
         loss = step_dev(*devt)
     e1.record()
+    if clk is not None:
+        # all timed work is queued and the GPU is still executing the last timed step(s): these samples see the clocks
+        # of the timed region and cannot delay it.  (NVML queries take ~1 us but sporadically 10-30 ms; issued between
+        # the steps, or from a sampler thread, they inflated the timed region by 10-35 % on some runs.)
+        for _ in range(3):
+            clk.sample()
     barrier()
     ms = allmax(e0.elapsed_time(e1))
     launches = (capi.launch_count() - l0) // K

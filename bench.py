@@ -184,14 +184,14 @@ def run_b200(a):
         step_dev, step_host = ts.step_device, ts.step_host
     K, W = max(1, a.steps), max(3, a.warmup)
 
-    # untimed warm-up: at least W steps AND ~1.5 s of wall time (in the first process on a fresh box the first half second
+    # untimed warm-up: at least W steps AND ~3 s of wall time (in the first process on a fresh box the first half second
     # of steps was measured 7-10 % slow: allocator growth, clock / power-state ramp, page-ins)
     t_w = time.perf_counter()
     for _ in range(W):
         loss = step_dev(*devt)
     torch.cuda.synchronize()
     per = (time.perf_counter() - t_w) / W
-    extra = int(allmax(float(max(0, int((1.5 - per * W) / max(per, 1e-4))))))   # same count on every rank (collectives inside)
+    extra = int(allmax(float(max(0, int((3.0 - per * W) / max(per, 1e-4))))))   # same count on every rank (collectives inside)
     for i in range(extra):
         loss = step_dev(*devt)
         if i % 4 == 3:

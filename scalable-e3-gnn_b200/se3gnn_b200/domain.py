@@ -63,6 +63,7 @@ class LocalGraph:
     recv_counts: List[int] = field(default_factory=list)   # halo rows received from each rank (halo order)
     send_counts: List[int] = field(default_factory=list)   # rows sent to each rank
     send_idx: Optional[torch.Tensor] = None                # [sum(send_counts)] int64 local owned ids, grouped by rank
+    edge_runs: Optional[list] = None                       # [(a, b)] ranges of the global edge arrays (CSR rows of owned nodes)
 
     @property
     def e(self) -> int:
@@ -78,9 +79,24 @@ def node_owner(bounds: torch.Tensor, n: int, cell_start: torch.Tensor) -> torch.
     return own.clamp(max=bounds.numel() - 2)
 
 
+def _runs(ids: torch.Tensor):
+    """Maximal runs of consecutive integers in a sorted 1-D tensor -> (starts, ends) python lists (ends exclusive)."""
+    if ids.numel() == 0:
+        return [], []
+    brk = torch.nonzero(ids[1:] != ids[:-1] + 1).flatten() + 1
+    starts = torch.cat([ids[:1], ids[brk]])
+    ends = torch.cat([ids[brk - 1], ids[-1:]]) + 1
+    return starts.tolist(), ends.tolist()
+
+
 def local_graph(rank: int, world: int, n: int, cell_start: torch.Tensor, leaf_of_rank: torch.Tensor,
-                g_dst: torch.Tensor, g_src: torch.Tensor, bounds: Optional[torch.Tensor] = None) -> LocalGraph:
-    """Rank `rank`'s part of the global graph (no communication: the global graph is replicated)."""
+                g_dst: torch.Tensor, g_src: torch.Tensor, bounds: Optional[torch.Tensor] = None,
+                rowptr: Optional[torch.Tensor] = None) -> LocalGraph:
+    """Rank `rank`'s part of the global graph (no communication: the global graph is replicated).
+
+    With `rowptr` (CSR by destination, as the builder returns it) the owned edges are taken as the CSR row ranges of
+    the owned nodes — one range for the particle slab and one per octree level — instead of a mask over all E global
+    edges; `LocalGraph.edge_runs` then lets callers slice per-edge arrays with a few contiguous copies."""
     dev = g_dst.device
     m = int(cell_start.numel())
     nn = n + m
@@ -91,9 +107,20 @@ def local_graph(rank: int, world: int, n: int, cell_start: torch.Tensor, leaf_of
     own_ids = torch.nonzero(mine).flatten()
     n_own = int(own_ids.numel())
     n_part = int((own_ids < n).sum())
-    e_ids = torch.nonzero(mine[g_dst.long()]).flatten()
-    sg = g_src[e_ids].long()
-    dg = g_dst[e_ids].long()
+    runs = None
+    if rowptr is not None and n_own > 0:
+        ns, ne = _runs(own_ids)                                   # node ranges: particle slab + one per level
+        idx = torch.tensor(ns + ne, device=dev, dtype=torch.int64)
+        rp = rowptr.index_select(0, idx).tolist()
+        runs = [(int(a), int(b)) for a, b in zip(rp[:len(ns)], rp[len(ns):]) if b > a]
+        e_ids = torch.cat([torch.arange(a, b, device=dev, dtype=torch.int64) for a, b in runs]) if runs else \
+            torch.empty(0, device=dev, dtype=torch.int64)
+        sg = torch.cat([g_src[a:b] for a, b in runs]).long() if runs else e_ids
+        dg = torch.cat([g_dst[a:b] for a, b in runs]).long() if runs else e_ids
+    else:
+        e_ids = torch.nonzero(mine[g_dst.long()]).flatten()
+        sg = g_src[e_ids].long()
+        dg = g_dst[e_ids].long()
     halo_ids = torch.unique(sg[~mine[sg]])          # sorted ascending
     n_halo = int(halo_ids.numel())
     g2l = torch.full((nn,), -1, device=dev, dtype=torch.int64)
@@ -107,9 +134,21 @@ def local_graph(rank: int, world: int, n: int, cell_start: torch.Tensor, leaf_of
         halo_ids = halo_ids[perm]
         g2l[halo_ids] = n_own + torch.arange(n_halo, device=dev, dtype=torch.int64)
     lo = int(bounds[rank])
-    return LocalGraph(rank=rank, world=world, n_global=n, nn_global=nn, n_part=n_part, n_own=n_own, n_halo=n_halo,
-                      part_lo=lo, own_ids=own_ids, halo_ids=halo_ids, dst=g2l[dg].to(torch.int32),
-                      src=g2l[sg].to(torch.int32), edge_ids=e_ids, recv_counts=[int(c) for c in recv_counts])
+    lg = LocalGraph(rank=rank, world=world, n_global=n, nn_global=nn, n_part=n_part, n_own=n_own, n_halo=n_halo,
+                    part_lo=lo, own_ids=own_ids, halo_ids=halo_ids, dst=g2l[dg].to(torch.int32),
+                    src=g2l[sg].to(torch.int32), edge_ids=e_ids, recv_counts=[int(c) for c in recv_counts])
+    lg.edge_runs = runs
+    return lg
+
+
+def take_edges(lg: LocalGraph, t: torch.Tensor) -> torch.Tensor:
+    """Rows of a per-edge array of the global graph that belong to this rank, in local edge order."""
+    runs = getattr(lg, "edge_runs", None)
+    if runs is None:
+        return t.index_select(0, lg.edge_ids)
+    if not runs:
+        return t[:0]
+    return torch.cat([t[a:b] for a, b in runs])
 
 
 def _a2a(out: torch.Tensor, inp: torch.Tensor, out_split: Sequence[int], in_split: Sequence[int], group=None):

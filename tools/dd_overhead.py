@@ -16,9 +16,9 @@ def tm(f, n=10):
     for _ in range(n): r = f()
     torch.cuda.synchronize(); return (time.perf_counter() - t) / n * 1e3, r
 t_b, g = tm(lambda: build_octree_graph(pos, vel, mass))
-t_l, lg = tm(lambda: domain.local_graph(0, world, g.n, g.cell_start, g.leaf_of_rank, g.dst, g.col))
+t_l, lg = tm(lambda: domain.local_graph(0, world, g.n, g.cell_start, g.leaf_of_rank, g.dst, g.col, rowptr=g.rowptr))
 t_s, _ = tm(lambda: (g.x_in.index_select(0, lg.own_ids), g.node_attr.index_select(0, lg.own_ids),
-                     g.edge_attr.index_select(0, lg.edge_ids), g.edge_extra.index_select(0, lg.edge_ids)))
+                     domain.take_edges(lg, g.edge_attr), domain.take_edges(lg, g.edge_extra)))
 pos1 = pos[:100_000].contiguous(); vel1 = vel[:100_000].contiguous(); m1 = mass[:100_000].contiguous()
 t_b1, _ = tm(lambda: build_octree_graph(pos1, vel1, m1))
 print(f"world {world}: global build {t_b:.2f} ms (single-GPU-size build {t_b1:.2f} ms), local_graph {t_l:.2f} ms, slicing {t_s:.2f} ms; "

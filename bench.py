@@ -184,6 +184,7 @@ def run_b200(a):
         step_dev, step_host = ts.step_device, ts.step_host
     K, W = max(1, a.steps), max(3, a.warmup)
 
+    clk = ClockSampler(local) if rank == 0 else None   # NVML initialised before the warm-up, well away from the timed region
     # untimed warm-up: at least W steps AND ~3 s of wall time (in the first process on a fresh box the first half second
     # of steps was measured 7-10 % slow: allocator growth, clock / power-state ramp, page-ins)
     t_w = time.perf_counter()
@@ -201,13 +202,22 @@ def run_b200(a):
     edges, cells = g.e, g.m
 
     # ---- timed region: K steps, inputs resident in HBM
-    clk = ClockSampler(local) if rank == 0 else None
     l0 = capi.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    import gc
+    gc.collect()
+    gc.disable()      # no collector pauses on the launching thread inside the timed regions
+    # one more untimed step right before the timed region: the host-side preparation above leaves the GPU idle for
+    # tens of ms, after which the first steps were sporadically slow (value 27-35 ms against a steady 23.3 ms)
+    step_dev(*devt)
     barrier()
     e0.record()
     for i in range(K):
         loss = step_dev(*devt)
+        # a training loop reads its loss every step (the e2e arm does); without this per-step synchronisation the host
+        # runs one step ahead and the device-timed region showed sporadic 10-50 % outliers (23.3 -> 27-35 ms) that the
+        # synchronised loop does not have; the synchronisation itself costs < 0.1 ms per step
+        torch.cuda.synchronize()
     e1.record()
     if clk is not None:
         # all timed work is queued and the GPU is still executing the last timed step(s): these samples see the clocks

@@ -187,16 +187,14 @@ def run_b200(a):
     clk = ClockSampler(local) if rank == 0 else None   # NVML initialised before the warm-up, well away from the timed region
     # untimed warm-up: at least W steps AND ~3 s of wall time (in the first process on a fresh box the first half second
     # of steps was measured 7-10 % slow: allocator growth, clock / power-state ramp, page-ins)
-    t_w = time.perf_counter()
-    for _ in range(W):
-        loss = step_dev(*devt)
-    torch.cuda.synchronize()
-    per = (time.perf_counter() - t_w) / W
-    extra = int(allmax(float(max(0, int((3.0 - per * W) / max(per, 1e-4))))))   # same count on every rank (collectives inside)
-    for i in range(extra):
-        loss = step_dev(*devt)
-        if i % 4 == 3:
-            torch.cuda.synchronize()
+    t_w, n_w = time.perf_counter(), 0
+    while True:
+        for _ in range(4):
+            loss = step_dev(*devt)
+        n_w += 4
+        torch.cuda.synchronize()
+        if n_w >= W and allmax(time.perf_counter() - t_w) >= 3.0:   # same decision on every rank (collectives inside the steps)
+            break
     barrier()
     g = ts.last_graph
     edges, cells = g.e, g.m

@@ -118,9 +118,9 @@ def local_graph(rank: int, world: int, n: int, cell_start: torch.Tensor, leaf_of
         sg = torch.cat([g_src[a:b] for a, b in runs]).long() if runs else e_ids
         dg = torch.cat([g_dst[a:b] for a, b in runs]).long() if runs else e_ids
     else:
-        e_ids = torch.nonzero(mine[g_dst.long()]).flatten()
-        sg = g_src[e_ids].long()
-        dg = g_dst[e_ids].long()
+        e_ids = torch.nonzero(mine.index_select(0, g_dst)).flatten()      # int32 indices: no E-sized int64 copy
+        sg = g_src.index_select(0, e_ids).long()
+        dg = g_dst.index_select(0, e_ids).long()
     halo_ids = torch.unique(sg[~mine[sg]])          # sorted ascending
     n_halo = int(halo_ids.numel())
     g2l = torch.full((nn,), -1, device=dev, dtype=torch.int64)
@@ -141,11 +141,21 @@ def local_graph(rank: int, world: int, n: int, cell_start: torch.Tensor, leaf_of
     return lg
 
 
+def gather_rows(t: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
+    """t[ids] for a contiguous [R, w] float32 tensor.  Rows of 8 / 16 bytes are gathered as ONE 1-D index_select of
+    8- / 16-byte elements (float64 / complex128 views): torch's row gather of narrow 2-D tensors was measured at
+    ~0.5 ms for 1.8M rows, the 1-D path runs at memory speed."""
+    if t.dim() == 2 and t.dtype == torch.float32 and t.is_contiguous() and t.shape[1] in (2, 4):
+        wide = torch.float64 if t.shape[1] == 2 else torch.complex128
+        return t.view(wide).reshape(-1).index_select(0, ids).view(torch.float32).reshape(-1, t.shape[1])
+    return t.index_select(0, ids)
+
+
 def take_edges(lg: LocalGraph, t: torch.Tensor) -> torch.Tensor:
     """Rows of a per-edge array of the global graph that belong to this rank, in local edge order."""
     runs = getattr(lg, "edge_runs", None)
     if runs is None:
-        return t.index_select(0, lg.edge_ids)
+        return gather_rows(t, lg.edge_ids)
     if not runs:
         return t[:0]
     return torch.cat([t[a:b] for a, b in runs])

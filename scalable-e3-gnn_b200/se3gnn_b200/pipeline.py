@@ -103,7 +103,7 @@ class TrainStep:
             domain.exchange_halo_lists(lg, self.group)
         self.last_local = lg
         halo = (lambda x: domain.halo_exchange(x, lg, self.group)) if world > 1 else None
-        out = self.model(g.x_in.index_select(0, lg.own_ids), g.node_attr.index_select(0, lg.own_ids),
+        out = self.model(g.x_in.index_select(0, lg.own_ids), domain.gather_rows(g.node_attr, lg.own_ids),
                          domain.take_edges(lg, g.edge_attr), domain.take_edges(lg, g.edge_extra),
                          lg.dst, lg.src, halo=halo)
         own_part = g.order[lg.part_lo:lg.part_lo + lg.n_part].long()

@@ -105,3 +105,29 @@ def test_slab_bounds_are_leaf_aligned():
         own = domain.node_owner(b, g["n"], G["cell_start"])
         # a leaf and all its particles have one owner
         assert bool((own[:g["n"]] == own[g["n"] + G["leaf_of_rank"]]).all())
+
+
+def test_gather_rows_and_runs():
+    from se3gnn_b200 import domain
+    torch.manual_seed(0)
+    for w in (2, 4, 8):
+        t = torch.randn(777, w)
+        ids = torch.randint(0, 777, (3000,))
+        assert torch.equal(domain.gather_rows(t, ids), t[ids])
+    ids = torch.tensor([3, 4, 5, 9, 10, 20])
+    assert domain._runs(ids) == ([3, 9, 20], [6, 11, 21])
+    assert domain._runs(torch.tensor([7])) == ([7], [8])
+    assert domain._runs(torch.empty(0, dtype=torch.int64)) == ([], [])
+
+
+def test_row_range_extraction_equals_mask_extraction():
+    from se3gnn_b200 import domain
+    g, G = _global(1200, 16)
+    rp = torch.from_numpy(g["rowptr"].astype(np.int64))
+    for world in (2, 5):
+        for r in range(world):
+            a = domain.local_graph(r, world, g["n"], G["cell_start"], G["leaf_of_rank"], G["dst"], G["src"])
+            b = domain.local_graph(r, world, g["n"], G["cell_start"], G["leaf_of_rank"], G["dst"], G["src"], rowptr=rp)
+            assert torch.equal(a.edge_ids, b.edge_ids) and torch.equal(a.dst, b.dst) and torch.equal(a.src, b.src)
+            assert torch.equal(a.halo_ids, b.halo_ids) and a.recv_counts == b.recv_counts
+            assert torch.equal(domain.take_edges(b, G["edge_attr"]), domain.take_edges(a, G["edge_attr"]))

@@ -121,6 +121,41 @@ typedef struct se3_l1tp_bwd_args {
 
 int se3_l1tp_backward(se3_l1tp_plan* plan, const se3_l1tp_bwd_args* args, void* stream);
 
+/* ---------------------------------------------------------------- o3tp ---- */
+/* Fully connected O(3) tensor product for 0 <= l <= 2 (BASELINE configs[2]): the generalisation of
+ * L1TensorProduct the reference excludes (L1TP:13-14 asserts lmax == 1), same conventions: paths enumerated
+ * (i_out, i_in2, i_in1) (L1TP:122-151), 'component' x 'element' normalisation (L1TP:124,145,169), unit-norm couplings
+ * that reduce to cg000/cg110/cg011/cg111 (L1TP:91-94) for l <= 1.  Specification: oracle/lmax2_oracle.py.
+ * in2 is a spherical-harmonics type input (multiplicity 1 per irrep).  Flat layouts are e3nn's: a `mul x l` block is
+ * [mul, 2l+1] row-major; l=1 components (x,y,z); l=2 components (xy, yz, 2zz-xx-yy, zx, xx-yy) (orthonormal).
+ * Weights: one flat fp32 buffer, path p owns a [mul_in1, mul_out] row-major block at weight_offset[p]. */
+#define SE3_O3_MAX_IRREPS 8
+typedef struct se3_o3tp_desc {
+    int32_t n_in1, n_in2, n_out;
+    int32_t in1_mul[SE3_O3_MAX_IRREPS], in1_l[SE3_O3_MAX_IRREPS], in1_p[SE3_O3_MAX_IRREPS]; /* p = +1 / -1 */
+    int32_t in2_l[3], in2_p[3];
+    int32_t out_mul[SE3_O3_MAX_IRREPS], out_l[SE3_O3_MAX_IRREPS], out_p[SE3_O3_MAX_IRREPS];
+} se3_o3tp_desc;
+
+typedef struct se3_o3tp_plan se3_o3tp_plan; /* opaque */
+
+int se3_o3tp_plan_create(const se3_o3tp_desc* desc, se3_o3tp_plan** plan);
+void se3_o3tp_plan_destroy(se3_o3tp_plan* plan);
+/* dims[0..7] = d_in1, d_in2, d_out, n_paths, weight_floats, rows per tile forward, rows per tile backward, reserved */
+int se3_o3tp_plan_info(const se3_o3tp_plan* plan, int32_t dims[8]);
+/* host arrays of n_paths entries each (any may be NULL); path_weight = the normalisation factor a_out */
+int se3_o3tp_plan_paths(const se3_o3tp_plan* plan, int32_t* i_in1, int32_t* i_in2, int32_t* i_out,
+                        int32_t* weight_offset, float* path_weight);
+/* host: the unit-norm coupling tensor of l1 x l2 -> l3 as [2l1+1][2l2+1][2l3+1] doubles; returns SE3_ERR_INVALID if
+ * the triangle rule excludes the triple */
+int se3_o3tp_coupling(int32_t l1, int32_t l2, int32_t l3, double* out);
+/* out[rows, d_out] = TP(in1[rows, d_in1], in2[rows, d_in2]; w) */
+int se3_o3tp_forward(se3_o3tp_plan* plan, int64_t rows, const float* in1, const float* in2, const float* w,
+                     float* out, void* stream);
+/* gin1[rows, d_in1] and gw[weight_floats] are overwritten; gin2[rows, d_in2] may be NULL (skipped) */
+int se3_o3tp_backward(se3_o3tp_plan* plan, int64_t rows, const float* in1, const float* in2, const float* w,
+                      const float* gout, float* gin1, float* gin2, float* gw, void* stream);
+
 /* -------------------------------------------------------------- octree ---- */
 /* Builder-defined API (the reference's numba graph builder is not in the mount; the
  * specification is oracle/octree_oracle.py).  All arrays are caller-allocated device memory. */

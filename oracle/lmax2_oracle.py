@@ -12,7 +12,7 @@ unmodified reference).  The l = 2 part is fixed by that convention plus SO(3)/O(
   l = 2 in the orthonormal basis Q_a of symmetric traceless 3x3 tensors listed in `Q2`;
 * the coupling tensor C(l1,l2,l3) is THE invariant tensor of D_l1 x D_l2 x D_l3 (one-dimensional for |l1-l2| <= l3 <=
   l1+l2), computed numerically as the null space of the invariance equations, with unit Frobenius norm (as the
-  reference's constants: 1, 1/sqrt3, 1/sqrt6) and the sign of the reference for l <= 1 / first non-zero entry positive
+  reference's constants: 1, 1/sqrt3, 1/sqrt6) and the sign of the reference for l <= 1 / of `_sign_convention`
   otherwise;
 * fully connected ("uvw") weights per path, output = a_out * sum_paths sum_u W[u,w] sum_ij C[i,j,k] x1[u,i] x2[j],
   a_out = sqrt((2 l_out + 1) / sum_paths mul1 mul2)  ('component' x 'element', `L1TP:124,145,169`).
@@ -86,8 +86,7 @@ def cg(l1: int, l2: int, l3: int) -> np.ndarray:
             c = c * np.sign((c * ref).sum())
             assert np.abs(c - ref).max() < 1e-10, f"l<=1 coupling {key} differs from the reference constants"
         else:
-            flat = c.reshape(-1)
-            c = c * np.sign(flat[np.nonzero(np.abs(flat) > 1e-9)[0][0]])
+            c = c * np.sign((c * _sign_convention(l1, l2, l3)).sum())
     _CG_CACHE[key] = c
     return c
 
@@ -112,6 +111,24 @@ def _reference_cg(l1, l2, l3):
         eps[0, 2, 1] = eps[2, 1, 0] = eps[1, 0, 2] = -1.0
         return c6 * eps          # out_k = (in1 x in2)_k / sqrt6, `L1TP:279,293`
     return None
+
+
+def _sign_convention(l1, l2, l3):
+    """The invariant is unique up to sign; the sign chosen for triples involving l = 2: +delta when one factor is a
+    scalar, otherwise trace(B1_i B2_j B3_k) with B the orthonormal 3x3 bases (l=1: antisymmetric eps_iab / sqrt2, l=2:
+    Q2).  For 1x1->1 this rule gives +epsilon, i.e. it continues the reference's choice."""
+    d1, d2, d3 = 2 * l1 + 1, 2 * l2 + 1, 2 * l3 + 1
+    if l1 == 0:
+        return np.eye(d3)[None, :, :]
+    if l2 == 0:
+        return np.eye(d3)[:, None, :]
+    if l3 == 0:
+        return np.eye(d1)[:, :, None]
+    eps = np.zeros((3, 3, 3))
+    eps[0, 1, 2] = eps[1, 2, 0] = eps[2, 0, 1] = 1.0
+    eps[0, 2, 1] = eps[2, 1, 0] = eps[1, 0, 2] = -1.0
+    B = {1: eps / math.sqrt(2.0), 2: Q2}
+    return np.einsum("iab,jbc,kca->ijk", B[l1], B[l2], B[l3])
 
 
 def spherical_harmonics(vec: np.ndarray, lmax: int) -> np.ndarray:

@@ -1,0 +1,234 @@
+// l <= 2 fully connected O(3) tensor product (se3_o3tp_*): first CUDA path for BASELINE configs[2] / SURVEY 8f-3.
+// One persistent CTA per resident slot walks row tiles; per tile and output irrep: coupling features into shared memory,
+// then the weight contraction as a register-blocked fp32 SIMT GEMM out of shared memory.  The tile
+// programs live in o3tp_body.inl (shared with the CPU emulation under tests/emu), the planning in o3tp_tables.h.
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "o3tp_tables.h"
+
+namespace {
+
+using se3::set_error;
+
+typedef float4 o3f4;
+#define O3_DEV __device__ __forceinline__
+#define O3_THREADS { const int tid = threadIdx.x; const int NT = blockDim.x;
+#define O3_END } __syncthreads();
+#define O3_ATOMIC_ADD(p, v) atomicAdd((p), (v))
+#define O3_I2F(i) __int_as_float(i)
+#define O3_NT_DECL
+#define O3_LD4(p) (*reinterpret_cast<const float4*>(p))
+#define O3_UNROLL _Pragma("unroll")
+#include "o3tp_body.inl"
+
+constexpr int O3_NT = 256;
+
+__device__ __forceinline__ const int32_t* load_table(const int32_t* __restrict__ tab_g, int32_t* sm) {
+    const int words = tab_g[o3::H_WORDS];
+    for (int i = threadIdx.x; i < words; i += blockDim.x) sm[i] = tab_g[i];
+    __syncthreads();
+    return sm;
+}
+
+__global__ void __launch_bounds__(O3_NT) o3tp_fwd_kernel(const int32_t* __restrict__ tab_g, const float* __restrict__ in1,
+                                                         const float* __restrict__ in2, const float* __restrict__ w,
+                                                         float* __restrict__ out, long long rows, int TE) {
+    extern __shared__ __align__(16) int32_t o3_sm[];
+    const int32_t* tab = load_table(tab_g, o3_sm);
+    float* fl = reinterpret_cast<float*>(o3_sm + tab[o3::H_WORDS]);
+    float* Ws = fl;
+    fl += tab[o3::H_NWP];
+    O3Fwd S;
+    S.tab = tab; S.Ws = Ws; S.TE = TE; S.Rp = (TE * tab[o3::H_DMAX]) | 1;
+    S.xs = fl; fl += TE * (tab[o3::H_D1] | 1);
+    S.ys = fl; fl += TE * (tab[o3::H_D2] | 1);
+    S.os = fl; fl += TE * (tab[o3::H_DOUT] | 1);
+    S.F = fl;
+    for (int io = 0; io < tab[o3::H_NIO]; ++io) {
+        const int32_t* IO = tab + tab[o3::H_IO] + io * o3::IO_W;
+        const int mul = IO[o3::IO_MUL], K = IO[o3::IO_K], mulp = (mul + 3) & ~3;
+        for (int idx = threadIdx.x; idx < K * mulp; idx += blockDim.x) {
+            const int kk = idx / mulp, c = idx - kk * mulp;
+            Ws[IO[o3::IO_WSOFF] + idx] = c < mul ? w[IO[o3::IO_WOFF] + kk * mul + c] : 0.f;
+        }
+    }
+    __syncthreads();
+    const long long ntiles = (rows + TE - 1) / TE;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long row0 = tile * TE;
+        const int nrow = (int)min((long long)TE, rows - row0);
+        o3_fwd_tile(S, in1, in2, out, row0, nrow);
+    }
+}
+
+__global__ void __launch_bounds__(O3_NT) o3tp_bwd_kernel(const int32_t* __restrict__ tab_g, const float* __restrict__ in1,
+                                                         const float* __restrict__ in2, const float* __restrict__ w,
+                                                         const float* __restrict__ gout, float* __restrict__ gin1,
+                                                         float* __restrict__ gin2, float* __restrict__ gw, long long rows,
+                                                         int TE) {
+    extern __shared__ __align__(16) int32_t o3_sm[];
+    const int32_t* tab = load_table(tab_g, o3_sm);
+    float* fl = reinterpret_cast<float*>(o3_sm + tab[o3::H_WORDS]);
+    float* WT = fl;
+    fl += tab[o3::H_NWT];
+    float* gWs = fl;
+    fl += tab[o3::H_NW];
+    const int D1p = tab[o3::H_D1] | 1, D2p = tab[o3::H_D2] | 1, DOp = tab[o3::H_DOUT] | 1;
+    O3Bwd S;
+    S.tab = tab; S.WT = WT; S.gWs = gWs; S.TE = TE; S.Rp = (TE * tab[o3::H_DMAX]) | 1;
+    S.xs = fl; fl += TE * D1p;
+    S.gxs = fl; fl += TE * D1p;
+    S.ys = fl; fl += TE * D2p;
+    S.gys = fl; fl += TE * D2p;
+    S.gs = fl; fl += TE * DOp;
+    S.F = fl; fl += (size_t)tab[o3::H_KPMAX] * S.Rp;
+    S.G = fl; fl += (size_t)tab[o3::H_KPMAX] * S.Rp;
+    S.GT = fl;
+    for (int io = 0; io < tab[o3::H_NIO]; ++io) {
+        const int32_t* IO = tab + tab[o3::H_IO] + io * o3::IO_W;
+        const int mul = IO[o3::IO_MUL], K = IO[o3::IO_K], Kp = (K + 3) & ~3;
+        for (int idx = threadIdx.x; idx < mul * Kp; idx += blockDim.x) {
+            const int wi = idx / Kp, kk = idx - wi * Kp;
+            WT[IO[o3::IO_WTOFF] + idx] = kk < K ? w[IO[o3::IO_WOFF] + kk * mul + wi] : 0.f;
+        }
+    }
+    for (int idx = threadIdx.x; idx < tab[o3::H_NW]; idx += blockDim.x) gWs[idx] = 0.f;
+    __syncthreads();
+    const long long ntiles = (rows + TE - 1) / TE;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long row0 = tile * TE;
+        const int nrow = (int)min((long long)TE, rows - row0);
+        o3_bwd_tile(S, in1, in2, gout, gin1, gin2, row0, nrow);
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < tab[o3::H_NW]; idx += blockDim.x) atomicAdd(gw + idx, gWs[idx]);
+}
+
+constexpr size_t SMEM_MAX = 227 * 1024;
+constexpr size_t SMEM_TWO = 110 * 1024;  // budget that lets two CTAs share an SM
+
+}  // namespace
+
+struct se3_o3tp_plan {
+    o3::Plan P;
+    int32_t* d_tab = nullptr;
+    int te_f = 0, te_b = 0;
+    size_t smem_f = 0, smem_b = 0;
+    int grid_f = 0, grid_b = 0;
+};
+
+static int pick_tile(const std::vector<int32_t>& blob, bool bwd, int* te, size_t* smem) {
+    const int cand[4] = {32, 16, 8, 4};
+    auto bytes = [&](int t) { return 4 * (blob.size() + (bwd ? o3::bwd_floats(blob, t) : o3::fwd_floats(blob, t))); };
+    for (int c : cand)
+        if (bytes(c) <= SMEM_TWO) { *te = c; *smem = bytes(c); return 0; }
+    for (int c : cand)
+        if (bytes(c) <= SMEM_MAX) { *te = c; *smem = bytes(c); return 0; }
+    return SE3_ERR_TOO_LARGE;
+}
+
+extern "C" int se3_o3tp_plan_create(const se3_o3tp_desc* d, se3_o3tp_plan** out) {
+    if (!d || !out) { set_error("null argument"); return SE3_ERR_INVALID; }
+    *out = nullptr;
+    if (d->n_in1 < 1 || d->n_in1 > SE3_O3_MAX_IRREPS || d->n_out < 1 || d->n_out > SE3_O3_MAX_IRREPS || d->n_in2 < 1 ||
+        d->n_in2 > 3) {
+        set_error("o3tp: irreps counts out of range (in1/out 1..%d, in2 1..3)", SE3_O3_MAX_IRREPS);
+        return SE3_ERR_INVALID;
+    }
+    se3_o3tp_plan* p = new se3_o3tp_plan();
+    for (int i = 0; i < d->n_in1; ++i) p->P.in1.push_back({d->in1_mul[i], d->in1_l[i], d->in1_p[i]});
+    for (int i = 0; i < d->n_in2; ++i) p->P.in2.push_back({1, d->in2_l[i], d->in2_p[i]});
+    for (int i = 0; i < d->n_out; ++i) p->P.out.push_back({d->out_mul[i], d->out_l[i], d->out_p[i]});
+    if (!o3::build_plan(p->P)) {
+        set_error("%s", p->P.err.c_str());
+        delete p;
+        return SE3_ERR_INVALID;
+    }
+    if (pick_tile(p->P.blob, false, &p->te_f, &p->smem_f) || pick_tile(p->P.blob, true, &p->te_b, &p->smem_b)) {
+        set_error("o3tp: irreps too large for the shared-memory tiling (%d weights, d_in1 %d)", p->P.nW, p->P.D1);
+        delete p;
+        return SE3_ERR_TOO_LARGE;
+    }
+    cudaError_t e = cudaMalloc(&p->d_tab, p->P.blob.size() * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(p->d_tab, p->P.blob.data(), p->P.blob.size() * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(o3tp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(o3tp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
+    int bf = 0, bb = 0;
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bf, o3tp_fwd_kernel, O3_NT, p->smem_f);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bb, o3tp_bwd_kernel, O3_NT, p->smem_b);
+    if (e != cudaSuccess || bf < 1 || bb < 1) {
+        set_error("o3tp: CUDA setup failed: %s", e != cudaSuccess ? cudaGetErrorString(e) : "kernel does not fit an SM");
+        if (p->d_tab) cudaFree(p->d_tab);
+        delete p;
+        return e != cudaSuccess ? (int)e : SE3_ERR_TOO_LARGE;
+    }
+    p->grid_f = bf * se3::num_sms();
+    p->grid_b = bb * se3::num_sms();
+    *out = p;
+    return SE3_OK;
+}
+
+extern "C" void se3_o3tp_plan_destroy(se3_o3tp_plan* p) {
+    if (!p) return;
+    if (p->d_tab) cudaFree(p->d_tab);
+    delete p;
+}
+
+extern "C" int se3_o3tp_plan_info(const se3_o3tp_plan* p, int32_t dims[8]) {
+    if (!p || !dims) { set_error("null argument"); return SE3_ERR_INVALID; }
+    dims[0] = p->P.D1; dims[1] = p->P.D2; dims[2] = p->P.Dout; dims[3] = (int32_t)p->P.paths.size();
+    dims[4] = p->P.nW; dims[5] = p->te_f; dims[6] = p->te_b; dims[7] = 0;
+    return SE3_OK;
+}
+
+extern "C" int se3_o3tp_plan_paths(const se3_o3tp_plan* p, int32_t* i1, int32_t* i2, int32_t* io, int32_t* woff,
+                                   float* pw) {
+    if (!p) { set_error("null argument"); return SE3_ERR_INVALID; }
+    for (size_t k = 0; k < p->P.paths.size(); ++k) {
+        const o3::PathH& h = p->P.paths[k];
+        if (i1) i1[k] = h.i1;
+        if (i2) i2[k] = h.i2;
+        if (io) io[k] = h.io;
+        if (woff) woff[k] = h.woff;
+        if (pw) pw[k] = p->P.a[h.io];
+    }
+    return SE3_OK;
+}
+
+extern "C" int se3_o3tp_coupling(int32_t l1, int32_t l2, int32_t l3, double* out) {
+    double C[5][5][5];
+    if (!out || !o3::cg(l1, l2, l3, C)) { set_error("o3tp: no coupling for (%d,%d,%d)", l1, l2, l3); return SE3_ERR_INVALID; }
+    for (int i = 0; i < 2 * l1 + 1; ++i)
+        for (int j = 0; j < 2 * l2 + 1; ++j)
+            for (int k = 0; k < 2 * l3 + 1; ++k) *out++ = C[i][j][k];
+    return SE3_OK;
+}
+
+extern "C" int se3_o3tp_forward(se3_o3tp_plan* p, int64_t rows, const float* in1, const float* in2, const float* w,
+                                float* out, void* stream) {
+    if (!p || rows < 0 || (rows > 0 && (!in1 || !in2 || !w || !out))) { set_error("o3tp forward: bad argument"); return SE3_ERR_INVALID; }
+    if (rows == 0) return SE3_OK;
+    const long long ntiles = (rows + p->te_f - 1) / p->te_f;
+    const int grid = (int)std::min<long long>(ntiles, p->grid_f);
+    o3tp_fwd_kernel<<<grid, O3_NT, p->smem_f, (cudaStream_t)stream>>>(p->d_tab, in1, in2, w, out, rows, p->te_f);
+    SE3_LAUNCHED();
+    return SE3_OK;
+}
+
+extern "C" int se3_o3tp_backward(se3_o3tp_plan* p, int64_t rows, const float* in1, const float* in2, const float* w,
+                                 const float* gout, float* gin1, float* gin2, float* gw, void* stream) {
+    if (!p || rows < 0 || !gw || (rows > 0 && (!in1 || !in2 || !w || !gout || !gin1))) {
+        set_error("o3tp backward: bad argument");
+        return SE3_ERR_INVALID;
+    }
+    SE3_CUDA_TRY(cudaMemsetAsync(gw, 0, sizeof(float) * p->P.nW, (cudaStream_t)stream));
+    if (rows == 0) return SE3_OK;
+    const long long ntiles = (rows + p->te_b - 1) / p->te_b;
+    const int grid = (int)std::min<long long>(ntiles, p->grid_b);
+    o3tp_bwd_kernel<<<grid, O3_NT, p->smem_b, (cudaStream_t)stream>>>(p->d_tab, in1, in2, w, gout, gin1, gin2, gw, rows,
+                                                                     p->te_b);
+    SE3_LAUNCHED();
+    return SE3_OK;
+}

@@ -1,0 +1,261 @@
+// Host-side planning of the l <= 2 tensor product (BASELINE configs[2]): coupling tensors, path list,
+// normalisation and the flat int32 table ("blob") the tile programs in o3tp_body.inl walk.  Pure C++ (no CUDA) so the
+// CPU emulation of the tile programs (tests/emu) shares it with the library.
+//
+// Specification: oracle/lmax2_oracle.py.  For l <= 1 the couplings and the normalisation are the reference's
+// (/root/reference/models/segnn/l1_tensor_prod.py:91-94 constants, :122-189 'component' x 'element'); the reference has
+// no l = 2 code (L1TP:13-14), so l = 2 follows the same convention: unit-norm invariant tensors, real bases
+// l=1 -> (x,y,z), l=2 -> Q_a below.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace o3 {
+
+enum { MAX_IRR = 8 };
+// blob header words
+enum { H_NIO = 0, H_D1, H_D2, H_DOUT, H_IO, H_PATH, H_GRP, H_ENT, H_WORDS, H_NW, H_KPMAX, H_DMAX, H_MULPMAX,
+       H_NPATH, H_NWP, H_NWT, HDR_W };
+// per output irrep
+enum { IO_MUL = 0, IO_D, IO_OFF, IO_K, IO_WOFF, IO_A, IO_PBEG, IO_PEND, IO_GBEG, IO_GEND, IO_WSOFF, IO_WTOFF, IO_W };
+// per path: entries (i, j, -, v) grouped by output component c: [P_EB0+c, P_EB0+c+1)
+enum { P_OFF1 = 0, P_D1, P_MUL1, P_OFF2, P_KOFF, P_EB0, PATH_W = P_EB0 + 7 };
+// per (output irrep, in1 irrep) group for the backward: entries grouped by in1 component i (a=jabs, b=koff, c, v)
+// and grouped by in2 column (a=i, b=koff, c, v)
+enum { G_OFF1 = 0, G_D1, G_MUL1, G_NJ, G_IB0, G_JABS = G_IB0 + 6, G_JB0 = G_JABS + 9, GRP_W = G_JB0 + 10 };
+enum { ENT_W = 4 };
+
+struct Irrep { int mul, l, p; };
+struct PathH { int i1, i2, io, woff, koff; };
+
+inline double eps3(int i, int j, int k) {
+    if (i == j || j == k || i == k) return 0.0;
+    return ((j - i + 3) % 3 == 1) ? 1.0 : -1.0;
+}
+
+// orthonormal (Frobenius) 3x3 bases: l=0 identity, l=1 antisymmetric, l=2 symmetric traceless Q_a in the order
+// (xy, yz, 2zz-xx-yy, zx, xx-yy)
+inline void basis(int l, double B[5][3][3]) {
+    std::memset(B, 0, sizeof(double) * 45);
+    const double s2 = 1.0 / std::sqrt(2.0), s3 = 1.0 / std::sqrt(3.0), s6 = 1.0 / std::sqrt(6.0);
+    if (l == 0) {
+        for (int a = 0; a < 3; ++a) B[0][a][a] = s3;
+    } else if (l == 1) {
+        for (int i = 0; i < 3; ++i)
+            for (int a = 0; a < 3; ++a)
+                for (int b = 0; b < 3; ++b) B[i][a][b] = eps3(i, a, b) * s2;
+    } else {
+        B[0][0][1] = B[0][1][0] = s2;
+        B[1][1][2] = B[1][2][1] = s2;
+        B[2][0][0] = B[2][1][1] = -s6; B[2][2][2] = 2 * s6;
+        B[3][0][2] = B[3][2][0] = s2;
+        B[4][0][0] = s2; B[4][1][1] = -s2;
+    }
+}
+
+// Unit-norm coupling tensor C[i][j][k] of l1 x l2 -> l3.  With a scalar factor it is +delta/sqrt(dim) (the reference's
+// cg000 / cg110 / cg011); otherwise trace(B1_i B2_j B3_k), which for 1x1->1 is +epsilon/sqrt6 (the reference's cg111 with
+// out = in1 x in2, L1TP:279).  Returns false if the triangle rule excludes the triple.
+inline bool cg(int l1, int l2, int l3, double C[5][5][5]) {
+    std::memset(C, 0, sizeof(double) * 125);
+    if (l1 < 0 || l2 < 0 || l3 < 0 || l1 > 2 || l2 > 2 || l3 > 2) return false;
+    if (l3 < std::abs(l1 - l2) || l3 > l1 + l2) return false;
+    if (l1 == 0) {
+        for (int k = 0; k < 2 * l3 + 1; ++k) C[0][k][k] = 1.0 / std::sqrt(2.0 * l3 + 1);
+        return true;
+    }
+    if (l2 == 0) {
+        for (int k = 0; k < 2 * l3 + 1; ++k) C[k][0][k] = 1.0 / std::sqrt(2.0 * l3 + 1);
+        return true;
+    }
+    if (l3 == 0) {
+        for (int k = 0; k < 2 * l1 + 1; ++k) C[k][k][0] = 1.0 / std::sqrt(2.0 * l1 + 1);
+        return true;
+    }
+    double B1[5][3][3], B2[5][3][3], B3[5][3][3];
+    basis(l1, B1); basis(l2, B2); basis(l3, B3);
+    double nrm = 0;
+    for (int i = 0; i < 2 * l1 + 1; ++i)
+        for (int j = 0; j < 2 * l2 + 1; ++j)
+            for (int k = 0; k < 2 * l3 + 1; ++k) {
+                double s = 0;
+                for (int a = 0; a < 3; ++a)
+                    for (int b = 0; b < 3; ++b)
+                        for (int c = 0; c < 3; ++c) s += B1[i][a][b] * B2[j][b][c] * B3[k][c][a];
+                if (std::fabs(s) < 1e-14) s = 0;
+                C[i][j][k] = s;
+                nrm += s * s;
+            }
+    nrm = std::sqrt(nrm);
+    for (int i = 0; i < 5; ++i)
+        for (int j = 0; j < 5; ++j)
+            for (int k = 0; k < 5; ++k) C[i][j][k] /= nrm;
+    return true;
+}
+
+struct Plan {
+    std::vector<Irrep> in1, in2, out;
+    std::vector<PathH> paths;
+    std::vector<float> a;  // per output irrep
+    std::vector<int32_t> blob;
+    int D1 = 0, D2 = 0, Dout = 0, nW = 0;
+    std::string err;
+};
+
+inline int32_t f2i(float f) { int32_t i; std::memcpy(&i, &f, 4); return i; }
+
+// paths in the reference's enumeration order (io, i2, i1) (L1TP:122-151), triangle + parity selection rules; weights of
+// path p are a [mul1, mul_out] row-major block at woff (blocks of one output irrep are adjacent: stacked [K, mul_out]).
+inline bool build_plan(Plan& P) {
+    if (P.in1.empty() || P.out.empty() || P.in2.empty() || (int)P.in1.size() > MAX_IRR || (int)P.out.size() > MAX_IRR ||
+        (int)P.in2.size() > 3) {
+        P.err = "o3tp: 1..8 in1/out irreps and 1..3 in2 irreps supported";
+        return false;
+    }
+    std::vector<int> off1, off2, offo;
+    auto offs = [&](const std::vector<Irrep>& v, std::vector<int>& o, bool mul1) {
+        int acc = 0;
+        for (auto& ir : v) {
+            if (ir.l < 0 || ir.l > 2 || (ir.p != 1 && ir.p != -1) || ir.mul < 1 || (mul1 && ir.mul != 1)) return -1;
+            o.push_back(acc);
+            acc += ir.mul * (2 * ir.l + 1);
+        }
+        return acc;
+    };
+    P.D1 = offs(P.in1, off1, false);
+    P.D2 = offs(P.in2, off2, true);
+    P.Dout = offs(P.out, offo, false);
+    if (P.D1 < 0 || P.D2 < 0 || P.Dout < 0) {
+        P.err = "o3tp: irreps need 0 <= l <= 2, parity +-1, mul >= 1 (in2: mul == 1)";
+        return false;
+    }
+    P.paths.clear();
+    P.a.assign(P.out.size(), 0.f);
+    std::vector<int32_t> io_w, path_w, grp_w, ent_w;
+    int woff = 0, kpmax = 4, dmax = 1, mulpmax = 4, wsoff = 0, wtoff = 0;
+    double C[5][5][5];
+    for (size_t io = 0; io < P.out.size(); ++io) {
+        const Irrep o = P.out[io];
+        const int d = 2 * o.l + 1;
+        const int pbeg = (int)P.paths.size(), gbeg = (int)(grp_w.size() / GRP_W);
+        int K = 0;
+        const int woff0 = woff;
+        for (size_t i2 = 0; i2 < P.in2.size(); ++i2)
+            for (size_t i1 = 0; i1 < P.in1.size(); ++i1) {
+                const Irrep a = P.in1[i1], b = P.in2[i2];
+                if (o.l < std::abs(a.l - b.l) || o.l > a.l + b.l || o.p != a.p * b.p) continue;
+                P.paths.push_back({(int)i1, (int)i2, (int)io, woff, K});
+                woff += a.mul * o.mul;
+                K += a.mul;
+            }
+        // paths were appended in (i2, i1) order; K offsets follow that order
+        const int pend = (int)P.paths.size();
+        P.a[io] = K > 0 ? (float)std::sqrt((double)d / (double)K) : 0.f;
+        for (int p = pbeg; p < pend; ++p) {
+            const PathH& ph = P.paths[p];
+            const Irrep a = P.in1[ph.i1], b = P.in2[ph.i2];
+            cg(a.l, b.l, o.l, C);
+            int32_t rec[PATH_W] = {0};
+            rec[P_OFF1] = off1[ph.i1]; rec[P_D1] = 2 * a.l + 1; rec[P_MUL1] = a.mul; rec[P_OFF2] = off2[ph.i2];
+            rec[P_KOFF] = ph.koff;
+            for (int c = 0; c < d; ++c) {
+                rec[P_EB0 + c] = (int32_t)(ent_w.size() / ENT_W);
+                for (int i = 0; i < 2 * a.l + 1; ++i)
+                    for (int j = 0; j < 2 * b.l + 1; ++j)
+                        if (C[i][j][c] != 0.0) {
+                            ent_w.push_back(i); ent_w.push_back(j); ent_w.push_back(c);
+                            ent_w.push_back(f2i((float)C[i][j][c]));
+                        }
+            }
+            for (int c = d; c < 7; ++c) rec[P_EB0 + c] = (int32_t)(ent_w.size() / ENT_W);
+            path_w.insert(path_w.end(), rec, rec + PATH_W);
+        }
+        // backward groups: one per in1 irrep that reaches this output
+        for (size_t i1 = 0; i1 < P.in1.size(); ++i1) {
+            std::vector<int> ps;
+            for (int p = pbeg; p < pend; ++p)
+                if (P.paths[p].i1 == (int)i1) ps.push_back(p);
+            if (ps.empty()) continue;
+            const Irrep a = P.in1[i1];
+            const int d1 = 2 * a.l + 1;
+            int32_t rec[GRP_W] = {0};
+            rec[G_OFF1] = off1[i1]; rec[G_D1] = d1; rec[G_MUL1] = a.mul;
+            for (int i = 0; i < d1; ++i) {
+                rec[G_IB0 + i] = (int32_t)(ent_w.size() / ENT_W);
+                for (int p : ps) {
+                    const Irrep b = P.in2[P.paths[p].i2];
+                    cg(a.l, b.l, o.l, C);
+                    for (int j = 0; j < 2 * b.l + 1; ++j)
+                        for (int c = 0; c < d; ++c)
+                            if (C[i][j][c] != 0.0) {
+                                ent_w.push_back(off2[P.paths[p].i2] + j); ent_w.push_back(P.paths[p].koff);
+                                ent_w.push_back(c); ent_w.push_back(f2i((float)C[i][j][c]));
+                            }
+                }
+            }
+            for (int i = d1; i < 6; ++i) rec[G_IB0 + i] = (int32_t)(ent_w.size() / ENT_W);
+            int nj = 0;
+            for (int p : ps) {
+                const Irrep b = P.in2[P.paths[p].i2];
+                cg(a.l, b.l, o.l, C);
+                for (int j = 0; j < 2 * b.l + 1; ++j) {
+                    rec[G_JABS + nj] = off2[P.paths[p].i2] + j;
+                    rec[G_JB0 + nj] = (int32_t)(ent_w.size() / ENT_W);
+                    for (int i = 0; i < d1; ++i)
+                        for (int c = 0; c < d; ++c)
+                            if (C[i][j][c] != 0.0) {
+                                ent_w.push_back(i); ent_w.push_back(P.paths[p].koff); ent_w.push_back(c);
+                                ent_w.push_back(f2i((float)C[i][j][c]));
+                            }
+                    ++nj;
+                }
+            }
+            rec[G_NJ] = nj;
+            for (int j = nj; j < 10; ++j) rec[G_JB0 + j] = (int32_t)(ent_w.size() / ENT_W);
+            grp_w.insert(grp_w.end(), rec, rec + GRP_W);
+        }
+        const int mulp = (o.mul + 3) & ~3, Kp = (K + 3) & ~3;
+        int32_t rec[IO_W] = {0};
+        rec[IO_MUL] = o.mul; rec[IO_D] = d; rec[IO_OFF] = offo[io]; rec[IO_K] = K; rec[IO_WOFF] = woff0;
+        rec[IO_A] = f2i(P.a[io]); rec[IO_PBEG] = pbeg; rec[IO_PEND] = pend; rec[IO_GBEG] = gbeg;
+        rec[IO_GEND] = (int32_t)(grp_w.size() / GRP_W); rec[IO_WSOFF] = wsoff; rec[IO_WTOFF] = wtoff;
+        io_w.insert(io_w.end(), rec, rec + IO_W);
+        wsoff += K * mulp;
+        wtoff += o.mul * Kp;
+        if (Kp > kpmax) kpmax = Kp;
+        if (d > dmax) dmax = d;
+        if (mulp > mulpmax) mulpmax = mulp;
+    }
+    P.nW = woff;
+    if (P.nW == 0) {
+        P.err = "o3tp: no path connects in1 x in2 to out";
+        return false;
+    }
+    std::vector<int32_t>& B = P.blob;
+    B.assign(HDR_W, 0);
+    B[H_NIO] = (int32_t)P.out.size(); B[H_D1] = P.D1; B[H_D2] = P.D2; B[H_DOUT] = P.Dout;
+    B[H_IO] = (int32_t)B.size(); B.insert(B.end(), io_w.begin(), io_w.end());
+    B[H_PATH] = (int32_t)B.size(); B.insert(B.end(), path_w.begin(), path_w.end());
+    B[H_GRP] = (int32_t)B.size(); B.insert(B.end(), grp_w.begin(), grp_w.end());
+    B[H_ENT] = (int32_t)B.size(); B.insert(B.end(), ent_w.begin(), ent_w.end());
+    while (B.size() % 4) B.push_back(0);
+    B[H_WORDS] = (int32_t)B.size(); B[H_NW] = P.nW; B[H_KPMAX] = kpmax; B[H_DMAX] = dmax; B[H_MULPMAX] = mulpmax;
+    B[H_NPATH] = (int32_t)P.paths.size(); B[H_NWP] = wsoff; B[H_NWT] = wtoff;
+    return true;
+}
+
+// shared-memory floats of the tile programs (excluding the table), for a tile of TE rows
+inline size_t fwd_floats(const std::vector<int32_t>& B, int TE) {
+    const size_t Rp = (size_t)(TE * B[H_DMAX]) | 1;
+    return (size_t)B[H_NWP] + (size_t)TE * ((B[H_D1] | 1) + (B[H_D2] | 1) + (B[H_DOUT] | 1)) + (size_t)B[H_KPMAX] * Rp + 8;
+}
+inline size_t bwd_floats(const std::vector<int32_t>& B, int TE) {
+    const size_t Rp = (size_t)(TE * B[H_DMAX]) | 1;
+    return (size_t)B[H_NWT] + (size_t)B[H_NW] + (size_t)TE * (2 * (B[H_D1] | 1) + 2 * (B[H_D2] | 1) + (B[H_DOUT] | 1)) +
+           (size_t)(2 * B[H_KPMAX] + B[H_MULPMAX]) * Rp + 8;
+}
+
+}  // namespace o3

@@ -65,6 +65,18 @@ class Octree(C.Structure):
     ]
 
 
+O3_MAX_IRREPS = 8
+
+
+class O3tpDesc(C.Structure):
+    _fields_ = [
+        ("n_in1", C.c_int32), ("n_in2", C.c_int32), ("n_out", C.c_int32),
+        ("in1_mul", C.c_int32 * O3_MAX_IRREPS), ("in1_l", C.c_int32 * O3_MAX_IRREPS), ("in1_p", C.c_int32 * O3_MAX_IRREPS),
+        ("in2_l", C.c_int32 * 3), ("in2_p", C.c_int32 * 3),
+        ("out_mul", C.c_int32 * O3_MAX_IRREPS), ("out_l", C.c_int32 * O3_MAX_IRREPS), ("out_p", C.c_int32 * O3_MAX_IRREPS),
+    ]
+
+
 EXPORTS = [
     # name, restype, argtypes  (must list every symbol include/se3gnn_b200.h declares)
     ("se3_last_error", C.c_char_p, []),
@@ -76,6 +88,14 @@ EXPORTS = [
     ("se3_l1tp_plan_info", C.c_int, [C.c_void_p, _i32p, _i32p, _i32p, _i32p]),
     ("se3_l1tp_forward", C.c_int, [C.c_void_p, C.POINTER(L1tpFwdArgs), C.c_void_p]),
     ("se3_l1tp_backward", C.c_int, [C.c_void_p, C.POINTER(L1tpBwdArgs), C.c_void_p]),
+    ("se3_o3tp_plan_create", C.c_int, [C.POINTER(O3tpDesc), C.POINTER(C.c_void_p)]),
+    ("se3_o3tp_plan_destroy", None, [C.c_void_p]),
+    ("se3_o3tp_plan_info", C.c_int, [C.c_void_p, _i32p]),
+    ("se3_o3tp_plan_paths", C.c_int, [C.c_void_p, _i32p, _i32p, _i32p, _i32p, C.POINTER(C.c_float)]),
+    ("se3_o3tp_coupling", C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double)]),
+    ("se3_o3tp_forward", C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("se3_o3tp_backward", C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     ("se3_octree_work_bytes", C.c_int, [C.c_int64, C.c_int64, C.POINTER(C.c_size_t)]),
     ("se3_octree_build", C.c_int, [C.c_void_p, C.POINTER(Octree), C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.c_void_p]),
     ("se3_graph_degrees", C.c_int, [C.POINTER(Octree), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -214,3 +234,48 @@ class L1tpPlan:
                 self.handle = None
         except Exception:
             pass
+
+
+class O3tpPlan:
+    """Owns a ``se3_o3tp_plan`` (l <= 2 tensor product: path list, coupling tables, tiling)."""
+
+    def __init__(self, in1, in2, out):
+        """in1/out: [(mul, l, p)], in2: [(l, p)] (multiplicity 1 each)."""
+        d = O3tpDesc()
+        if len(in1) > O3_MAX_IRREPS or len(out) > O3_MAX_IRREPS or len(in2) > 3:
+            raise Se3Error(f"o3tp supports up to {O3_MAX_IRREPS} in1/out irreps and 3 in2 irreps")
+        d.n_in1, d.n_in2, d.n_out = len(in1), len(in2), len(out)
+        for i, (mul, l, p) in enumerate(in1):
+            d.in1_mul[i], d.in1_l[i], d.in1_p[i] = int(mul), int(l), int(p)
+        for i, (l, p) in enumerate(in2):
+            d.in2_l[i], d.in2_p[i] = int(l), int(p)
+        for i, (mul, l, p) in enumerate(out):
+            d.out_mul[i], d.out_l[i], d.out_p[i] = int(mul), int(l), int(p)
+        h = C.c_void_p()
+        check(lib().se3_o3tp_plan_create(C.byref(d), C.byref(h)), "se3_o3tp_plan_create")
+        self.handle = h
+        dims = (C.c_int32 * 8)()
+        check(lib().se3_o3tp_plan_info(h, dims))
+        self.d_in1, self.d_in2, self.d_out, self.n_paths, self.weight_floats, self.tile_fwd, self.tile_bwd = list(dims)[:7]
+        n = max(1, self.n_paths)
+        arrs = [(C.c_int32 * n)() for _ in range(4)]
+        pw = (C.c_float * n)()
+        check(lib().se3_o3tp_plan_paths(h, *arrs, pw))
+        self.paths = [(arrs[0][k], arrs[1][k], arrs[2][k], arrs[3][k], float(pw[k])) for k in range(self.n_paths)]
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None) and _lib is not None:
+                _lib.se3_o3tp_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+def o3tp_coupling(l1: int, l2: int, l3: int):
+    """Nested list [2l1+1][2l2+1][2l3+1] of the library's unit-norm coupling tensor."""
+    n = (2 * l1 + 1) * (2 * l2 + 1) * (2 * l3 + 1)
+    buf = (C.c_double * n)()
+    check(lib().se3_o3tp_coupling(l1, l2, l3, buf), "se3_o3tp_coupling")
+    it = iter(buf)
+    return [[[next(it) for _ in range(2 * l3 + 1)] for _ in range(2 * l2 + 1)] for _ in range(2 * l1 + 1)]

@@ -1,0 +1,94 @@
+"""Fully connected O(3) tensor product for l <= 2 with a spherical-harmonics type second input: the generalisation of
+the reference's ``L1TensorProduct`` that BASELINE configs[2] (SEGNN l_max = 2) needs.  The reference excludes l = 2
+(``/root/reference/models/segnn/l1_tensor_prod.py:13-14``); this module keeps its conventions — constructor argument
+order, ``iri1/iri2/iro/in1_dim/in2_dim/instructions`` attributes (``L1TP:16-21,121,151``), path enumeration
+``(i_out, i_in2, i_in1)``, 'component' x 'element' normalisation (``L1TP:124,145,169``) — so that for l <= 1 irreps of
+SH type it computes exactly what ``L1TensorProduct`` does (weights laid out per path instead of stacked per species).
+
+All arithmetic runs in the CUDA library (``se3_o3tp_forward/backward``, csrc/o3tp.cu); there is no eager fallback.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import capi
+from .irreps import Instruction, Irreps, as_irreps
+
+__all__ = ["O3TensorProduct"]
+
+
+class _O3tpFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, in1, in2, weight, mod):
+        plan = mod._plan
+        rows = in1.shape[0]
+        out = torch.empty((rows, plan.d_out), device=in1.device, dtype=torch.float32)
+        with capi.mark("o3tp.fwd", mod.algo_bytes(rows, "fwd"), mod.flops(rows)):
+            capi.check(capi.lib().se3_o3tp_forward(plan.handle, rows, capi.ptr(in1), capi.ptr(in2), capi.ptr(weight),
+                                                   capi.ptr(out), capi.current_stream_ptr()), "se3_o3tp_forward")
+        ctx.save_for_backward(in1, in2, weight)
+        ctx.mod = mod
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        in1, in2, weight = ctx.saved_tensors
+        mod = ctx.mod
+        plan = mod._plan
+        rows = in1.shape[0]
+        gout = gout.contiguous()
+        gin1 = torch.empty_like(in1)
+        gin2 = torch.empty_like(in2) if ctx.needs_input_grad[1] else None
+        gw = torch.empty_like(weight)
+        with capi.mark("o3tp.bwd", mod.algo_bytes(rows, "bwd"), 2 * mod.flops(rows)):
+            capi.check(capi.lib().se3_o3tp_backward(plan.handle, rows, capi.ptr(in1), capi.ptr(in2), capi.ptr(weight),
+                                                    capi.ptr(gout), capi.ptr(gin1), capi.ptr(gin2), capi.ptr(gw),
+                                                    capi.current_stream_ptr()), "se3_o3tp_backward")
+        return gin1, gin2, gw, None
+
+
+class O3TensorProduct(torch.nn.Module):
+    def __init__(self, in1_irreps, out_irreps=None, in2_irreps=None):
+        super().__init__()
+        self.iri1 = as_irreps(in1_irreps)
+        self.iri2 = Irreps.spherical_harmonics(2) if in2_irreps is None else as_irreps(in2_irreps)
+        self.iro = self.iri1 if out_irreps is None else as_irreps(out_irreps)
+        assert max(self.iri1.lmax, self.iri2.lmax, self.iro.lmax) <= 2, "Maximal l supported by this tensor product is 2."
+        assert all(mi.mul == 1 for mi in self.iri2), "in2 must have multiplicity 1 per irrep (spherical harmonics type)"
+        self.in1_dim, self.in2_dim = self.iri1.dim, self.iri2.dim
+        self._plan = capi.O3tpPlan([(mi.mul, mi.ir.l, mi.ir.p) for mi in self.iri1],
+                                   [(mi.ir.l, mi.ir.p) for mi in self.iri2],
+                                   [(mi.mul, mi.ir.l, mi.ir.p) for mi in self.iro])
+        assert (self._plan.d_in1, self._plan.d_in2, self._plan.d_out) == (self.in1_dim, self.in2_dim, self.iro.dim)
+        self.instructions = [
+            Instruction(i1, i2, io, "uvw", True, a, (self.iri1[i1].mul, 1, self.iro[io].mul))
+            for i1, i2, io, _, a in self._plan.paths
+        ]
+        self.weight_offsets = [p[3] for p in self._plan.paths]
+        self.weight = torch.nn.Parameter(torch.randn(self._plan.weight_floats))
+
+    def weight_views(self):
+        """Per-path [mul_in1, mul_out] views of the flat weight, in `instructions` order."""
+        return [self.weight[o:o + ins.path_shape[0] * ins.path_shape[2]].view(ins.path_shape[0], ins.path_shape[2])
+                for o, ins in zip(self.weight_offsets, self.instructions)]
+
+    def flops(self, rows: int) -> float:
+        """Algorithmic flops of the weight contraction, forward (2 per multiply-add)."""
+        return float(rows) * sum(2.0 * ins.path_shape[0] * ins.path_shape[2] * self.iro[ins.i_out].ir.dim
+                                 for ins in self.instructions)
+
+    def algo_bytes(self, rows: int, part: str) -> float:
+        """Algorithmic HBM bytes (the TP-standalone formula): every operand once, fp32."""
+        d1, d2, do = self.in1_dim, self.in2_dim, self.iro.dim
+        per_row = (d1 + d2 + do) if part == "fwd" else (do + d1 + d2 + d1 + d2)
+        return 4.0 * (rows * per_row + self._plan.weight_floats)
+
+    def forward(self, in1: torch.Tensor, in2: torch.Tensor) -> torch.Tensor:
+        torch._assert(in1.dim() == 2 and in1.shape[-1] == self.in1_dim, "Incorrect last dimension for in1")
+        torch._assert(in2.dim() == 2 and in2.shape[-1] == self.in2_dim, "Incorrect last dimension for in2")
+        torch._assert(in1.shape[0] == in2.shape[0], "in1 and in2 need the same number of rows")
+        if not (in1.is_cuda and in2.is_cuda and self.weight.is_cuda):
+            raise capi.Se3Error("O3TensorProduct runs on CUDA tensors only (no CPU fallback)")
+        if in1.dtype != torch.float32 or in2.dtype != torch.float32:
+            raise capi.Se3Error("O3TensorProduct computes in fp32; cast the inputs")
+        return _O3tpFn.apply(in1.contiguous(), in2.contiguous(), self.weight, self)

@@ -1,0 +1,132 @@
+// TEST INFRASTRUCTURE ONLY.  CPU emulation of the o3tp CUDA tile programs: includes the very source the kernels are
+// built from (csrc/o3tp_body.inl + csrc/o3tp_tables.h) with the block's threads run one after another, phase by phase,
+// and mirrors the kernel wrappers' shared-memory carve-up and weight staging (csrc/o3tp.cu).  Lets the CPU test suite
+// check the table walking / indexing of the GPU code against the oracle; it is never used by the product path.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../scalable-e3-gnn_b200/csrc/o3tp_tables.h"
+
+namespace {
+struct o3f4 { float x, y, z, w; };
+inline float i2f(int32_t i) { float f; std::memcpy(&f, &i, 4); return f; }
+#define O3_DEV static inline
+#define O3_THREADS for (int tid = 0; tid < NT_; ++tid) { const int NT = NT_;
+#define O3_END }
+#define O3_ATOMIC_ADD(p, v) (*(p) += (v))
+#define O3_I2F(i) i2f(i)
+#define O3_NT_DECL , int NT_
+#define O3_LD4(p) (o3f4{(p)[0], (p)[1], (p)[2], (p)[3]})
+#define O3_UNROLL
+#define __restrict__
+#include "../../scalable-e3-gnn_b200/csrc/o3tp_body.inl"
+}  // namespace
+
+static bool make_plan(o3::Plan& P, int n1, const int* in1, int n2, const int* in2, int no, const int* out) {
+    for (int i = 0; i < n1; ++i) P.in1.push_back({in1[3 * i], in1[3 * i + 1], in1[3 * i + 2]});
+    for (int i = 0; i < n2; ++i) P.in2.push_back({1, in2[2 * i], in2[2 * i + 1]});
+    for (int i = 0; i < no; ++i) P.out.push_back({out[3 * i], out[3 * i + 1], out[3 * i + 2]});
+    return o3::build_plan(P);
+}
+
+extern "C" {
+
+// irreps as flat int triples (mul, l, p) / pairs (l, p); returns weight count or -1; dims = D1, D2, Dout, npaths
+int emu_plan(int n1, const int* in1, int n2, const int* in2, int no, const int* out, int* dims, int* path_io,
+             int* path_i1, int* path_i2, int* path_woff, float* path_a) {
+    o3::Plan P;
+    if (!make_plan(P, n1, in1, n2, in2, no, out)) return -1;
+    dims[0] = P.D1; dims[1] = P.D2; dims[2] = P.Dout; dims[3] = (int)P.paths.size();
+    for (size_t k = 0; k < P.paths.size(); ++k) {
+        path_io[k] = P.paths[k].io; path_i1[k] = P.paths[k].i1; path_i2[k] = P.paths[k].i2;
+        path_woff[k] = P.paths[k].woff; path_a[k] = P.a[P.paths[k].io];
+    }
+    return P.nW;
+}
+
+int emu_coupling(int l1, int l2, int l3, double* out) {
+    double C[5][5][5];
+    if (!o3::cg(l1, l2, l3, C)) return -1;
+    for (int i = 0; i < 2 * l1 + 1; ++i)
+        for (int j = 0; j < 2 * l2 + 1; ++j)
+            for (int k = 0; k < 2 * l3 + 1; ++k) *out++ = C[i][j][k];
+    return 0;
+}
+
+int emu_forward(int n1, const int* in1i, int n2, const int* in2i, int no, const int* outi, long long rows,
+                const float* in1, const float* in2, const float* w, float* out, int TE, int NT, int nblocks) {
+    o3::Plan P;
+    if (!make_plan(P, n1, in1i, n2, in2i, no, outi)) return -1;
+    const int32_t* tab = P.blob.data();
+    const long long ntiles = (rows + TE - 1) / TE;
+    for (int b = 0; b < nblocks; ++b) {
+        std::vector<float> sm(o3::fwd_floats(P.blob, TE), -1e30f);  // poison: unwritten reads show up
+        float* fl = sm.data();
+        float* Ws = fl; fl += tab[o3::H_NWP];
+        O3Fwd S;
+        S.tab = tab; S.Ws = Ws; S.TE = TE; S.Rp = (TE * tab[o3::H_DMAX]) | 1;
+        S.xs = fl; fl += TE * (tab[o3::H_D1] | 1);
+        S.ys = fl; fl += TE * (tab[o3::H_D2] | 1);
+        S.os = fl; fl += TE * (tab[o3::H_DOUT] | 1);
+        S.F = fl;
+        for (int io = 0; io < tab[o3::H_NIO]; ++io) {
+            const int32_t* IO = tab + tab[o3::H_IO] + io * o3::IO_W;
+            const int mul = IO[o3::IO_MUL], K = IO[o3::IO_K], mulp = (mul + 3) & ~3;
+            for (int idx = 0; idx < K * mulp; ++idx) {
+                const int kk = idx / mulp, c = idx - kk * mulp;
+                Ws[IO[o3::IO_WSOFF] + idx] = c < mul ? w[IO[o3::IO_WOFF] + kk * mul + c] : 0.f;
+            }
+        }
+        for (long long tile = b; tile < ntiles; tile += nblocks) {
+            const long long row0 = tile * TE;
+            o3_fwd_tile(S, in1, in2, out, row0, (int)std::min<long long>(TE, rows - row0), NT);
+        }
+    }
+    return 0;
+}
+
+int emu_backward(int n1, const int* in1i, int n2, const int* in2i, int no, const int* outi, long long rows,
+                 const float* in1, const float* in2, const float* w, const float* gout, float* gin1, float* gin2,
+                 float* gw, int TE, int NT, int nblocks) {
+    o3::Plan P;
+    if (!make_plan(P, n1, in1i, n2, in2i, no, outi)) return -1;
+    const int32_t* tab = P.blob.data();
+    const long long ntiles = (rows + TE - 1) / TE;
+    for (int i = 0; i < P.nW; ++i) gw[i] = 0.f;
+    for (int b = 0; b < nblocks; ++b) {
+        std::vector<float> sm(o3::bwd_floats(P.blob, TE), -1e30f);
+        float* fl = sm.data();
+        float* WT = fl; fl += tab[o3::H_NWT];
+        float* gWs = fl; fl += tab[o3::H_NW];
+        const int D1p = tab[o3::H_D1] | 1, D2p = tab[o3::H_D2] | 1, DOp = tab[o3::H_DOUT] | 1;
+        O3Bwd S;
+        S.tab = tab; S.WT = WT; S.gWs = gWs; S.TE = TE; S.Rp = (TE * tab[o3::H_DMAX]) | 1;
+        S.xs = fl; fl += TE * D1p;
+        S.gxs = fl; fl += TE * D1p;
+        S.ys = fl; fl += TE * D2p;
+        S.gys = fl; fl += TE * D2p;
+        S.gs = fl; fl += TE * DOp;
+        S.F = fl; fl += (size_t)tab[o3::H_KPMAX] * S.Rp;
+        S.G = fl; fl += (size_t)tab[o3::H_KPMAX] * S.Rp;
+        S.GT = fl;
+        for (int io = 0; io < tab[o3::H_NIO]; ++io) {
+            const int32_t* IO = tab + tab[o3::H_IO] + io * o3::IO_W;
+            const int mul = IO[o3::IO_MUL], K = IO[o3::IO_K], Kp = (K + 3) & ~3;
+            for (int idx = 0; idx < mul * Kp; ++idx) {
+                const int wi = idx / Kp, kk = idx - wi * Kp;
+                WT[IO[o3::IO_WTOFF] + idx] = kk < K ? w[IO[o3::IO_WOFF] + kk * mul + wi] : 0.f;
+            }
+        }
+        for (int idx = 0; idx < tab[o3::H_NW]; ++idx) gWs[idx] = 0.f;
+        for (long long tile = b; tile < ntiles; tile += nblocks) {
+            const long long row0 = tile * TE;
+            o3_bwd_tile(S, in1, in2, gout, gin1, gin2, row0, (int)std::min<long long>(TE, rows - row0), NT);
+        }
+        for (int idx = 0; idx < tab[o3::H_NW]; ++idx) gw[idx] += gWs[idx];
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,143 @@
+"""CPU emulation of the l <= 2 tensor-product CUDA tile programs (`tests/emu/o3tp_emu.cpp` compiles the kernels' own
+source, `csrc/o3tp_body.inl` + `csrc/o3tp_tables.h`, with the block's threads run sequentially) against the oracle.
+Checks the planning, the table walk and all shared-memory indexing without a GPU; the GPU parity test proper is
+`tests/test_o3tp_gpu.py`."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import lmax2_oracle as l2
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "emu", "o3tp_emu.cpp")
+DEPS = [SRC] + [os.path.join(HERE, "..", "scalable-e3-gnn_b200", "csrc", f) for f in ("o3tp_body.inl", "o3tp_tables.h")]
+LIB = os.path.join(HERE, "emu", "_build", "libo3tp_emu.so")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(d) for d in DEPS):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", SRC, "-o", LIB], check=True)
+    return C.CDLL(LIB)
+
+
+def _flat(irreps, pair=False):
+    v = []
+    for mul, l, p in irreps:
+        v += [l, p] if pair else [mul, l, p]
+    return (C.c_int * len(v))(*v)
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+CASES = {
+    "sh1": ([(8, 0, 1), (4, 1, -1)], 1, [(6, 0, 1), (5, 1, -1)]),
+    "balanced2": ([(23, 0, 1), (7, 1, -1), (4, 2, 1)], 2, [(23, 0, 1), (7, 1, -1), (4, 2, 1)]),
+    "message2": ([(23, 0, 1), (7, 1, -1), (4, 2, 1), (23, 0, 1), (7, 1, -1), (4, 2, 1), (2, 0, 1)], 2,
+                 [(34, 0, 1), (7, 1, -1), (4, 2, 1)]),
+    "mixed_parity": ([(3, 0, 1), (2, 1, -1), (2, 2, 1), (1, 1, 1), (1, 2, -1), (2, 0, -1)], 2,
+                     [(3, 0, 1), (2, 1, -1), (1, 2, 1), (2, 1, 1), (1, 2, -1), (5, 0, -1)]),
+    "dead_output": ([(4, 0, 1)], 1, [(3, 0, 1), (2, 1, 1), (2, 1, -1)]),       # 1e has no path: columns must be 0
+    "scalar_attr": ([(5, 0, 1), (3, 2, 1)], 0, [(4, 0, 1), (2, 2, 1)]),
+}
+
+
+def _oracle(in1, in2, out, x1, y, w, g):
+    ws, o = [], 0
+    for shp in l2.weight_shapes(in1, in2, out):
+        n = shp[0] * shp[1]
+        ws.append(torch.from_numpy(w[o:o + n].astype(np.float64).reshape(shp)).requires_grad_())
+        o += n
+    assert o == len(w)
+    x1t = torch.from_numpy(x1.astype(np.float64)).requires_grad_()
+    yt = torch.from_numpy(y.astype(np.float64)).requires_grad_()
+    res = l2.forward(x1t, yt, ws, in1, in2, out)
+    (res * torch.from_numpy(g.astype(np.float64))).sum().backward()
+    gw = np.concatenate([t.grad.numpy().reshape(-1) for t in ws])
+    return res.detach().numpy(), x1t.grad.numpy(), yt.grad.numpy(), gw
+
+
+def _close(got, want, tol=2e-5):
+    scale = max(1.0, float(np.abs(want).max()))
+    assert np.abs(got - want).max() <= tol * scale, float(np.abs(got - want).max() / scale)
+
+
+def test_couplings_match_oracle(emu):
+    for a in range(3):
+        for b in range(3):
+            for c in range(3):
+                buf = (C.c_double * 125)()
+                rc = emu.emu_coupling(a, b, c, buf)
+                want = l2.cg(a, b, c)
+                if not want.any():
+                    assert rc == -1
+                    continue
+                assert rc == 0
+                got = np.frombuffer(buf, dtype=np.float64)[:want.size].reshape(want.shape)
+                np.testing.assert_allclose(got, want, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_plan_matches_oracle(emu, name):
+    in1, lmax, out = CASES[name]
+    in2 = l2.sh_irreps(lmax)
+    dims = (C.c_int * 4)()
+    arr = [(C.c_int * 128)() for _ in range(4)]
+    pa = (C.c_float * 128)()
+    nw = emu.emu_plan(len(in1), _flat(in1), len(in2), _flat(in2, True), len(out), _flat(out), dims, *arr, pa)
+    ps = l2.paths(in1, in2, out)
+    assert dims[3] == len(ps)
+    assert [(arr[1][k], arr[2][k], arr[0][k]) for k in range(len(ps))] == ps
+    shapes = l2.weight_shapes(in1, in2, out)
+    assert nw == sum(a * b for a, b in shapes)
+    offs = np.cumsum([0] + [a * b for a, b in shapes])[:-1]
+    assert [arr[3][k] for k in range(len(ps))] == list(offs)
+    a = l2.norm_factors(in1, in2, out)
+    np.testing.assert_allclose([pa[k] for k in range(len(ps))], [a[p[2]] for p in ps], rtol=1e-6)
+
+
+@pytest.mark.parametrize("name,rows,TE,NT,nblocks", [
+    ("sh1", 37, 16, 64, 2), ("balanced2", 45, 16, 256, 1), ("balanced2", 33, 32, 96, 3), ("message2", 21, 8, 256, 2),
+    ("mixed_parity", 19, 4, 7, 1), ("dead_output", 9, 8, 32, 1), ("scalar_attr", 16, 16, 33, 1), ("message2", 1, 32, 256, 4),
+])
+def test_emulated_kernels_match_oracle(emu, name, rows, TE, NT, nblocks):
+    in1, lmax, out = CASES[name]
+    in2 = l2.sh_irreps(lmax)
+    rng = np.random.default_rng(hash(name) % 1000)
+    d1 = sum(m * (2 * l + 1) for m, l, _ in in1)
+    d2 = sum(2 * l + 1 for _, l, _ in in2)
+    do = sum(m * (2 * l + 1) for m, l, _ in out)
+    x1 = rng.standard_normal((rows, d1)).astype(np.float32)
+    y = rng.standard_normal((rows, d2)).astype(np.float32)
+    nw = sum(a * b for a, b in l2.weight_shapes(in1, in2, out))
+    w = rng.standard_normal(nw).astype(np.float32)
+    g = rng.standard_normal((rows, do)).astype(np.float32)
+    want_o, want_gx, want_gy, want_gw = _oracle(in1, in2, out, x1, y, w, g)
+
+    spec = (len(in1), _flat(in1), len(in2), _flat(in2, True), len(out), _flat(out))
+    got_o = np.full((rows, do), np.nan, np.float32)
+    assert emu.emu_forward(*spec, C.c_longlong(rows), _fp(x1), _fp(y), _fp(w), _fp(got_o), TE, NT, nblocks) == 0
+    _close(got_o, want_o)
+
+    gx = np.full((rows, d1), np.nan, np.float32)
+    gy = np.full((rows, d2), np.nan, np.float32)
+    gw = np.full(nw, np.nan, np.float32)
+    assert emu.emu_backward(*spec, C.c_longlong(rows), _fp(x1), _fp(y), _fp(w), _fp(g), _fp(gx), _fp(gy), _fp(gw),
+                            TE, NT, nblocks) == 0
+    _close(gx, want_gx)
+    _close(gy, want_gy)
+    _close(gw, want_gw)
+    # gin2 is optional
+    gx2 = np.full((rows, d1), np.nan, np.float32)
+    gw2 = np.full(nw, np.nan, np.float32)
+    assert emu.emu_backward(*spec, C.c_longlong(rows), _fp(x1), _fp(y), _fp(w), _fp(g), _fp(gx2), None, _fp(gw2),
+                            TE, NT, nblocks) == 0
+    np.testing.assert_array_equal(gx2, gx)
+    np.testing.assert_array_equal(gw2, gw)

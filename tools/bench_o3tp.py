@@ -36,7 +36,7 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    hbm = float(peaks.get("hbm_gbps_burst", peaks.get("hbm_gbps", 6550.0)))
+    hbm = float(peaks.get("hbm_gbs", 6550.0))
     for name, (i1, io) in CONFIGS.items():
         torch.manual_seed(0)
         tp = O3TensorProduct(Irreps(i1), Irreps(io)).cuda()

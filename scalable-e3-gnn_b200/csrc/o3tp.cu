@@ -21,9 +21,10 @@ typedef float4 o3f4;
 #define O3_NT_DECL
 #define O3_LD4(p) (*reinterpret_cast<const float4*>(p))
 #define O3_UNROLL _Pragma("unroll")
+#include "o3tp_cg_gen.inl"
 #include "o3tp_body.inl"
 
-constexpr int O3_NT = 256;
+constexpr int O3_NT = 32 * o3::NWARP;
 
 __device__ __forceinline__ const int32_t* load_table(const int32_t* __restrict__ tab_g, int32_t* sm) {
     const int words = tab_g[o3::H_WORDS];
@@ -41,14 +42,13 @@ __global__ void __launch_bounds__(O3_NT) o3tp_fwd_kernel(const int32_t* __restri
     float* Ws = fl;
     fl += tab[o3::H_NWP];
     O3Fwd S;
-    S.tab = tab; S.Ws = Ws; S.TE = TE; S.Rp = (TE * tab[o3::H_DMAX]) | 1;
+    S.tab = tab; S.Ws = Ws; S.TE = TE;
     S.xs = fl; fl += TE * (tab[o3::H_D1] | 1);
     S.ys = fl; fl += TE * (tab[o3::H_D2] | 1);
-    S.os = fl; fl += TE * (tab[o3::H_DOUT] | 1);
-    S.F = fl;
+    S.os = fl;
     for (int io = 0; io < tab[o3::H_NIO]; ++io) {
         const int32_t* IO = tab + tab[o3::H_IO] + io * o3::IO_W;
-        const int mul = IO[o3::IO_MUL], K = IO[o3::IO_K], mulp = (mul + 3) & ~3;
+        const int mul = IO[o3::IO_MUL], K = IO[o3::IO_K], mulp = IO[o3::IO_MULP];
         for (int idx = threadIdx.x; idx < K * mulp; idx += blockDim.x) {
             const int kk = idx / mulp, c = idx - kk * mulp;
             Ws[IO[o3::IO_WSOFF] + idx] = c < mul ? w[IO[o3::IO_WOFF] + kk * mul + c] : 0.f;
@@ -120,12 +120,12 @@ struct se3_o3tp_plan {
 };
 
 static int pick_tile(const std::vector<int32_t>& blob, bool bwd, int* te, size_t* smem) {
-    const int cand[4] = {32, 16, 8, 4};
+    const int cand[4] = {bwd ? 32 : 64, bwd ? 16 : 32, bwd ? 8 : 0, bwd ? 4 : 0};
     auto bytes = [&](int t) { return 4 * (blob.size() + (bwd ? o3::bwd_floats(blob, t) : o3::fwd_floats(blob, t))); };
     for (int c : cand)
-        if (bytes(c) <= SMEM_TWO) { *te = c; *smem = bytes(c); return 0; }
+        if (c && bytes(c) <= SMEM_TWO) { *te = c; *smem = bytes(c); return 0; }
     for (int c : cand)
-        if (bytes(c) <= SMEM_MAX) { *te = c; *smem = bytes(c); return 0; }
+        if (c && bytes(c) <= SMEM_MAX) { *te = c; *smem = bytes(c); return 0; }
     return SE3_ERR_TOO_LARGE;
 }
 
@@ -146,7 +146,15 @@ extern "C" int se3_o3tp_plan_create(const se3_o3tp_desc* d, se3_o3tp_plan** out)
         delete p;
         return SE3_ERR_INVALID;
     }
-    if (pick_tile(p->P.blob, false, &p->te_f, &p->smem_f) || pick_tile(p->P.blob, true, &p->te_b, &p->smem_b)) {
+    // the forward schedule depends on the tile size and adds a few table words: try 64 rows, fall back to 32
+    o3::schedule_forward(p->P, 64);
+    int rc_f = pick_tile(p->P.blob, false, &p->te_f, &p->smem_f);
+    if (rc_f == 0 && p->te_f != 64) {
+        o3::schedule_forward(p->P, p->te_f);
+        rc_f = pick_tile(p->P.blob, false, &p->te_f, &p->smem_f);
+        if (rc_f == 0 && p->te_f != p->P.blob[o3::H_TEF]) rc_f = SE3_ERR_TOO_LARGE;
+    }
+    if (rc_f || pick_tile(p->P.blob, true, &p->te_b, &p->smem_b)) {
         set_error("o3tp: irreps too large for the shared-memory tiling (%d weights, d_in1 %d)", p->P.nW, p->P.D1);
         delete p;
         return SE3_ERR_TOO_LARGE;

@@ -22,8 +22,8 @@
 struct O3Fwd {
     const int32_t* tab;  // table blob (shared memory)
     const float* Ws;     // all weights, per io [K, mulp] zero padded (shared, resident)
-    float *xs, *ys, *os, *F;
-    int TE, Rp;
+    float *xs, *ys, *os;
+    int TE;
 };
 
 struct O3Bwd {
@@ -61,56 +61,120 @@ O3_DEV void o3_features(const int32_t* tab, const int32_t* IO, const float* xs, 
     }
 }
 
+// ---- forward: one warp per work unit (output irrep, chunk of CW output channels, group of 32 rows), lane = row.
+// Per path the lane folds its spherical-harmonics values into M[i][c] = sum_j C[i][j][c] y[j] once (generated code,
+// o3tp_cg_gen.inl), then per input channel u: d1 shared loads, f[c] = sum_i M[i][c] x[i], one broadcast weight row,
+// acc[c][t] += f[c] w[t].  No feature buffer, no cross-lane traffic.
+template <int L1, int L2, int LO, int CW>
+O3_DEV void o3_fwd_path(const float* xr, const float* yr, int mul1, const float* w, int mulp,
+                        float (&acc)[2 * LO + 1][CW]) {
+    constexpr int D1 = 2 * L1 + 1, DO = 2 * LO + 1;
+    float M[D1][DO];
+    o3_M<L1, L2, LO>(yr, M);
+    for (int u = 0; u < mul1; ++u, xr += D1, w += mulp) {
+        float f[DO];
+        O3_UNROLL
+        for (int c = 0; c < DO; ++c) f[c] = 0.f;
+        O3_UNROLL
+        for (int i = 0; i < D1; ++i) {
+            const float x = xr[i];
+            O3_UNROLL
+            for (int c = 0; c < DO; ++c)
+                if ((o3_nz<L1, L2, LO>::mask >> (i * DO + c)) & 1u) f[c] += M[i][c] * x;
+        }
+        O3_UNROLL
+        for (int t4 = 0; t4 < CW; t4 += 4) {
+            const o3f4 wv = O3_LD4(w + t4);
+            O3_UNROLL
+            for (int c = 0; c < DO; ++c) {
+                acc[c][t4] += f[c] * wv.x; acc[c][t4 + 1] += f[c] * wv.y;
+                acc[c][t4 + 2] += f[c] * wv.z; acc[c][t4 + 3] += f[c] * wv.w;
+            }
+        }
+    }
+}
+
+template <int LO, int CW>
+O3_DEV void o3_fwd_unit(const int32_t* tab, const int32_t* IO, const float* xe, const float* ye, const float* Ws,
+                        float* oe, int q) {
+    constexpr int DO = 2 * LO + 1;
+    float acc[DO][CW];
+    O3_UNROLL
+    for (int c = 0; c < DO; ++c)
+        O3_UNROLL
+        for (int t = 0; t < CW; ++t) acc[c][t] = 0.f;
+    const int mulp = IO[o3::IO_MULP], mul = IO[o3::IO_MUL];
+    const float* wq = Ws + IO[o3::IO_WSOFF] + q * CW;
+    for (int p = IO[o3::IO_PBEG]; p < IO[o3::IO_PEND]; ++p) {
+        const int32_t* P = tab + tab[o3::H_PATH] + p * o3::PATH_W;
+        const float* xr = xe + P[o3::P_OFF1];
+        const float* yr = ye + P[o3::P_OFF2];
+        const float* w = wq + P[o3::P_KOFF] * mulp;
+        const int mul1 = P[o3::P_MUL1];
+        switch (P[o3::P_L1] * 9 + P[o3::P_L2] * 3 + LO) {
+#define O3_CASE(A, B, C)                                                                      \
+    case A * 9 + B * 3 + C:                                                                   \
+        if constexpr (C == LO) o3_fwd_path<A, B, C, CW>(xr, yr, mul1, w, mulp, acc);          \
+        break;
+            O3_TRIPLES(O3_CASE)
+#undef O3_CASE
+        }
+    }
+    const float a = O3_I2F(IO[o3::IO_A]);
+    float* o = oe + IO[o3::IO_OFF] + q * CW * DO;
+    O3_UNROLL
+    for (int t = 0; t < CW; ++t)
+        if (q * CW + t < mul) {
+            O3_UNROLL
+            for (int c = 0; c < DO; ++c) o[t * DO + c] = a * acc[c][t];
+        }
+}
+
 O3_DEV void o3_fwd_tile(const O3Fwd& S, const float* __restrict__ in1, const float* __restrict__ in2,
-                               float* __restrict__ out, long long row0, int nrow O3_NT_DECL) {
+                        float* __restrict__ out, long long row0, int nrow O3_NT_DECL) {
     const int32_t* tab = S.tab;
-    const int D1 = tab[o3::H_D1], D2 = tab[o3::H_D2], DO = tab[o3::H_DOUT], nio = tab[o3::H_NIO];
-    const int D1p = D1 | 1, D2p = D2 | 1, DOp = DO | 1, TE = S.TE, Rp = S.Rp;
+    const int D1 = tab[o3::H_D1], D2 = tab[o3::H_D2], DO = tab[o3::H_DOUT];
+    const int D1p = D1 | 1, D2p = D2 | 1, DOp = DO | 1, TE = S.TE;
 
     O3_THREADS
-        for (int idx = tid; idx < TE * D1; idx += NT) {
-            const int e = idx / D1, c = idx - e * D1;
-            S.xs[e * D1p + c] = e < nrow ? in1[(row0 + e) * D1 + c] : 0.f;
-        }
-        for (int idx = tid; idx < TE * D2; idx += NT) {
-            const int e = idx / D2, c = idx - e * D2;
-            S.ys[e * D2p + c] = e < nrow ? in2[(row0 + e) * D2 + c] : 0.f;
+        const int warp = tid >> 5, lane = tid & 31, nw = NT >> 5;
+        for (int e = warp; e < TE; e += nw) {
+            const bool ok = e < nrow;
+            const float* src = in1 + (row0 + e) * D1;
+            for (int c = lane; c < D1; c += 32) S.xs[e * D1p + c] = ok ? src[c] : 0.f;
+            if (lane < D2) S.ys[e * D2p + lane] = ok ? in2[(row0 + e) * D2 + lane] : 0.f;
         }
     O3_END
 
-    for (int io = 0; io < nio; ++io) {
-        const int32_t* IO = tab + tab[o3::H_IO] + io * o3::IO_W;
-        const int mul = IO[o3::IO_MUL], d = IO[o3::IO_D], K = IO[o3::IO_K];
-        const int mulp = (mul + 3) & ~3, nq = mulp >> 2, R = TE * d;
-        O3_THREADS
-            o3_features(tab, IO, S.xs, S.ys, S.F, TE, Rp, D1p, D2p, K, tid, NT);
-        O3_END
-        O3_THREADS
-            const float a = O3_I2F(IO[o3::IO_A]);
-            for (int item = tid; item < R * nq; item += NT) {
-                const int q = item / R, r = item - q * R;
-                const float* w = S.Ws + IO[o3::IO_WSOFF] + 4 * q;
-                const float* f = S.F + r;
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-                for (int kk = 0; kk < K; ++kk) {
-                    const float fv = f[(size_t)kk * Rp];
-                    const o3f4 wv = O3_LD4(w + kk * mulp);
-                    a0 += fv * wv.x; a1 += fv * wv.y; a2 += fv * wv.z; a3 += fv * wv.w;
-                }
-                const int e = r / d, c = r - e * d, w0 = 4 * q;
-                float* o = S.os + e * DOp + IO[o3::IO_OFF] + c;
-                o[w0 * d] = a * a0;
-                if (w0 + 1 < mul) o[(w0 + 1) * d] = a * a1;
-                if (w0 + 2 < mul) o[(w0 + 2) * d] = a * a2;
-                if (w0 + 3 < mul) o[(w0 + 3) * d] = a * a3;
+    O3_THREADS
+        const int warp = tid >> 5, lane = tid & 31;
+        (void)NT;
+        const int32_t* U = tab + tab[o3::H_UNIT];
+        for (int k = U[warp]; k < U[warp + 1]; ++k) {
+            const int packed = U[o3::NWARP + 1 + k];
+            const int io = packed & 255, q = (packed >> 8) & 255, e = (packed >> 16) * 32 + lane;
+            const int32_t* IO = tab + tab[o3::H_IO] + io * o3::IO_W;
+            const float* xe = S.xs + e * D1p;
+            const float* ye = S.ys + e * D2p;
+            float* oe = S.os + e * DOp;
+            switch (IO[o3::IO_D] * 16 + IO[o3::IO_CW]) {
+                case 1 * 16 + 4: o3_fwd_unit<0, 4>(tab, IO, xe, ye, S.Ws, oe, q); break;
+                case 1 * 16 + 8: o3_fwd_unit<0, 8>(tab, IO, xe, ye, S.Ws, oe, q); break;
+                case 1 * 16 + 12: o3_fwd_unit<0, 12>(tab, IO, xe, ye, S.Ws, oe, q); break;
+                case 3 * 16 + 4: o3_fwd_unit<1, 4>(tab, IO, xe, ye, S.Ws, oe, q); break;
+                case 3 * 16 + 8: o3_fwd_unit<1, 8>(tab, IO, xe, ye, S.Ws, oe, q); break;
+                case 3 * 16 + 12: o3_fwd_unit<1, 12>(tab, IO, xe, ye, S.Ws, oe, q); break;
+                case 5 * 16 + 4: o3_fwd_unit<2, 4>(tab, IO, xe, ye, S.Ws, oe, q); break;
+                case 5 * 16 + 8: o3_fwd_unit<2, 8>(tab, IO, xe, ye, S.Ws, oe, q); break;
             }
-        O3_END
-    }
+        }
+    O3_END
 
     O3_THREADS
-        for (int idx = tid; idx < nrow * DO; idx += NT) {
-            const int e = idx / DO, c = idx - e * DO;
-            out[(row0 + e) * DO + c] = S.os[e * DOp + c];
+        const int warp = tid >> 5, lane = tid & 31, nw = NT >> 5;
+        for (int e = warp; e < nrow; e += nw) {
+            float* dst = out + (row0 + e) * DO;
+            for (int c = lane; c < DO; c += 32) dst[c] = S.os[e * DOp + c];
         }
     O3_END
 }

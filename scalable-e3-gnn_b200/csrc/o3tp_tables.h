@@ -7,6 +7,7 @@
 // no l = 2 code (L1TP:13-14), so l = 2 follows the same convention: unit-norm invariant tensors, real bases
 // l=1 -> (x,y,z), l=2 -> Q_a below.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -18,11 +19,15 @@ namespace o3 {
 enum { MAX_IRR = 8 };
 // blob header words
 enum { H_NIO = 0, H_D1, H_D2, H_DOUT, H_IO, H_PATH, H_GRP, H_ENT, H_WORDS, H_NW, H_KPMAX, H_DMAX, H_MULPMAX,
-       H_NPATH, H_NWP, H_NWT, HDR_W };
+       H_NPATH, H_NWP, H_NWT, H_UNIT, H_TEF, H_BASE, HDR_W = 20 };
+enum { NWARP = 8 };  // warps per CTA the forward unit schedule is made for
 // per output irrep
-enum { IO_MUL = 0, IO_D, IO_OFF, IO_K, IO_WOFF, IO_A, IO_PBEG, IO_PEND, IO_GBEG, IO_GEND, IO_WSOFF, IO_WTOFF, IO_W };
+// IO_CW: output channels per forward work unit (4, 8 or 12); IO_MULP: mul padded to a multiple of IO_CW (row length of
+// the staged forward weights at IO_WSOFF); IO_NQ = IO_MULP / IO_CW
+enum { IO_MUL = 0, IO_D, IO_OFF, IO_K, IO_WOFF, IO_A, IO_PBEG, IO_PEND, IO_GBEG, IO_GEND, IO_WSOFF, IO_WTOFF, IO_CW,
+       IO_MULP, IO_NQ, IO_W = 16 };
 // per path: entries (i, j, -, v) grouped by output component c: [P_EB0+c, P_EB0+c+1)
-enum { P_OFF1 = 0, P_D1, P_MUL1, P_OFF2, P_KOFF, P_EB0, PATH_W = P_EB0 + 7 };
+enum { P_OFF1 = 0, P_D1, P_MUL1, P_OFF2, P_KOFF, P_L1, P_L2, P_EB0, PATH_W = P_EB0 + 7 };
 // per (output irrep, in1 irrep) group for the backward: entries grouped by in1 component i (a=jabs, b=koff, c, v)
 // and grouped by in2 column (a=i, b=koff, c, v)
 enum { G_OFF1 = 0, G_D1, G_MUL1, G_NJ, G_IB0, G_JABS = G_IB0 + 6, G_JB0 = G_JABS + 9, GRP_W = G_JB0 + 10 };
@@ -160,7 +165,7 @@ inline bool build_plan(Plan& P) {
             cg(a.l, b.l, o.l, C);
             int32_t rec[PATH_W] = {0};
             rec[P_OFF1] = off1[ph.i1]; rec[P_D1] = 2 * a.l + 1; rec[P_MUL1] = a.mul; rec[P_OFF2] = off2[ph.i2];
-            rec[P_KOFF] = ph.koff;
+            rec[P_KOFF] = ph.koff; rec[P_L1] = a.l; rec[P_L2] = b.l;
             for (int c = 0; c < d; ++c) {
                 rec[P_EB0 + c] = (int32_t)(ent_w.size() / ENT_W);
                 for (int i = 0; i < 2 * a.l + 1; ++i)
@@ -218,12 +223,21 @@ inline bool build_plan(Plan& P) {
             grp_w.insert(grp_w.end(), rec, rec + GRP_W);
         }
         const int mulp = (o.mul + 3) & ~3, Kp = (K + 3) & ~3;
+        // forward chunk width: least padding among {12, 8, 4} (ties: the wider), accumulators d * CW <= 40 registers
+        int cw = 4, best = 1 << 30;
+        for (int c : {12, 8, 4}) {
+            if (c * d > 40) continue;
+            const int padded = (o.mul + c - 1) / c * c;
+            if (padded < best) { best = padded; cw = c; }
+        }
+        const int mulpf = best;
         int32_t rec[IO_W] = {0};
+        rec[IO_CW] = cw; rec[IO_MULP] = mulpf; rec[IO_NQ] = mulpf / cw;
         rec[IO_MUL] = o.mul; rec[IO_D] = d; rec[IO_OFF] = offo[io]; rec[IO_K] = K; rec[IO_WOFF] = woff0;
         rec[IO_A] = f2i(P.a[io]); rec[IO_PBEG] = pbeg; rec[IO_PEND] = pend; rec[IO_GBEG] = gbeg;
         rec[IO_GEND] = (int32_t)(grp_w.size() / GRP_W); rec[IO_WSOFF] = wsoff; rec[IO_WTOFF] = wtoff;
         io_w.insert(io_w.end(), rec, rec + IO_W);
-        wsoff += K * mulp;
+        wsoff += K * mulpf;
         wtoff += o.mul * Kp;
         if (Kp > kpmax) kpmax = Kp;
         if (d > dmax) dmax = d;
@@ -242,15 +256,57 @@ inline bool build_plan(Plan& P) {
     B[H_GRP] = (int32_t)B.size(); B.insert(B.end(), grp_w.begin(), grp_w.end());
     B[H_ENT] = (int32_t)B.size(); B.insert(B.end(), ent_w.begin(), ent_w.end());
     while (B.size() % 4) B.push_back(0);
-    B[H_WORDS] = (int32_t)B.size(); B[H_NW] = P.nW; B[H_KPMAX] = kpmax; B[H_DMAX] = dmax; B[H_MULPMAX] = mulpmax;
+    B[H_WORDS] = B[H_BASE] = (int32_t)B.size(); B[H_NW] = P.nW; B[H_KPMAX] = kpmax; B[H_DMAX] = dmax; B[H_MULPMAX] = mulpmax;
     B[H_NPATH] = (int32_t)P.paths.size(); B[H_NWP] = wsoff; B[H_NWT] = wtoff;
     return true;
 }
 
+// Forward work units of one tile of TE rows (TE a multiple of 32): (output irrep, channel chunk, 32-row group), spread
+// over the NWARP warps by longest-processing-time-first on an instruction-count estimate.  Appended to the blob:
+// [H_UNIT + w] .. [H_UNIT + w + 1] = range of warp w in the packed list (io | chunk << 8 | group << 16).
+inline void schedule_forward(Plan& P, int TE) {
+    std::vector<int32_t>& B = P.blob;
+    struct U { int packed; double cost; };
+    std::vector<U> us;
+    for (int io = 0; io < B[H_NIO]; ++io) {
+        const int32_t* IO = B.data() + B[H_IO] + io * IO_W;
+        const int d = IO[IO_D], cw = IO[IO_CW];
+        double cost = 40;
+        for (int p = IO[IO_PBEG]; p < IO[IO_PEND]; ++p) {
+            const int32_t* R = B.data() + B[H_PATH] + p * PATH_W;
+            cost += 30 + R[P_D1] * d + R[P_MUL1] * (R[P_D1] + R[P_D1] * d + cw / 4 + d * cw + 4);
+        }
+        for (int q = 0; q < IO[IO_NQ]; ++q)
+            for (int g = 0; g < TE / 32; ++g) us.push_back({io | (q << 8) | (g << 16), cost});
+    }
+    std::stable_sort(us.begin(), us.end(), [](const U& a, const U& b) { return a.cost > b.cost; });
+    std::vector<std::vector<int>> per(NWARP);
+    double load[NWARP] = {0};
+    for (const U& u : us) {
+        int w = 0;
+        for (int k = 1; k < NWARP; ++k)
+            if (load[k] < load[w]) w = k;
+        per[w].push_back(u.packed);
+        load[w] += u.cost;
+    }
+    B.resize(B[H_BASE]);  // drop an earlier schedule
+    const int base = (int)B.size();
+    B[H_UNIT] = base; B[H_TEF] = TE;
+    B.resize(base + NWARP + 1);
+    int acc = 0;
+    for (int w = 0; w < NWARP; ++w) {
+        B[base + w] = acc;
+        acc += (int)per[w].size();
+    }
+    B[base + NWARP] = acc;
+    for (int w = 0; w < NWARP; ++w) B.insert(B.end(), per[w].begin(), per[w].end());
+    while (B.size() % 4) B.push_back(0);
+    B[H_WORDS] = (int32_t)B.size();
+}
+
 // shared-memory floats of the tile programs (excluding the table), for a tile of TE rows
 inline size_t fwd_floats(const std::vector<int32_t>& B, int TE) {
-    const size_t Rp = (size_t)(TE * B[H_DMAX]) | 1;
-    return (size_t)B[H_NWP] + (size_t)TE * ((B[H_D1] | 1) + (B[H_D2] | 1) + (B[H_DOUT] | 1)) + (size_t)B[H_KPMAX] * Rp + 8;
+    return (size_t)B[H_NWP] + (size_t)TE * ((B[H_D1] | 1) + (B[H_D2] | 1) + (B[H_DOUT] | 1)) + 8;
 }
 inline size_t bwd_floats(const std::vector<int32_t>& B, int TE) {
     const size_t Rp = (size_t)(TE * B[H_DMAX]) | 1;

@@ -12,7 +12,7 @@
 namespace {
 struct o3f4 { float x, y, z, w; };
 inline float i2f(int32_t i) { float f; std::memcpy(&f, &i, 4); return f; }
-#define O3_DEV static inline
+#define O3_DEV inline
 #define O3_THREADS for (int tid = 0; tid < NT_; ++tid) { const int NT = NT_;
 #define O3_END }
 #define O3_ATOMIC_ADD(p, v) (*(p) += (v))
@@ -21,6 +21,7 @@ inline float i2f(int32_t i) { float f; std::memcpy(&f, &i, 4); return f; }
 #define O3_LD4(p) (o3f4{(p)[0], (p)[1], (p)[2], (p)[3]})
 #define O3_UNROLL
 #define __restrict__
+#include "../../scalable-e3-gnn_b200/csrc/o3tp_cg_gen.inl"
 #include "../../scalable-e3-gnn_b200/csrc/o3tp_body.inl"
 }  // namespace
 
@@ -59,6 +60,8 @@ int emu_forward(int n1, const int* in1i, int n2, const int* in2i, int no, const 
                 const float* in1, const float* in2, const float* w, float* out, int TE, int NT, int nblocks) {
     o3::Plan P;
     if (!make_plan(P, n1, in1i, n2, in2i, no, outi)) return -1;
+    if (TE % 32 || NT != 32 * o3::NWARP) return -2;  // the forward schedule is made for 8 warps and 32-row groups
+    o3::schedule_forward(P, TE);
     const int32_t* tab = P.blob.data();
     const long long ntiles = (rows + TE - 1) / TE;
     for (int b = 0; b < nblocks; ++b) {
@@ -66,14 +69,13 @@ int emu_forward(int n1, const int* in1i, int n2, const int* in2i, int no, const 
         float* fl = sm.data();
         float* Ws = fl; fl += tab[o3::H_NWP];
         O3Fwd S;
-        S.tab = tab; S.Ws = Ws; S.TE = TE; S.Rp = (TE * tab[o3::H_DMAX]) | 1;
+        S.tab = tab; S.Ws = Ws; S.TE = TE;
         S.xs = fl; fl += TE * (tab[o3::H_D1] | 1);
         S.ys = fl; fl += TE * (tab[o3::H_D2] | 1);
-        S.os = fl; fl += TE * (tab[o3::H_DOUT] | 1);
-        S.F = fl;
+        S.os = fl;
         for (int io = 0; io < tab[o3::H_NIO]; ++io) {
             const int32_t* IO = tab + tab[o3::H_IO] + io * o3::IO_W;
-            const int mul = IO[o3::IO_MUL], K = IO[o3::IO_K], mulp = (mul + 3) & ~3;
+            const int mul = IO[o3::IO_MUL], K = IO[o3::IO_K], mulp = IO[o3::IO_MULP];
             for (int idx = 0; idx < K * mulp; ++idx) {
                 const int kk = idx / mulp, c = idx - kk * mulp;
                 Ws[IO[o3::IO_WSOFF] + idx] = c < mul ? w[IO[o3::IO_WOFF] + kk * mul + c] : 0.f;

@@ -14,7 +14,7 @@ from oracle import lmax2_oracle as l2
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "emu", "o3tp_emu.cpp")
-DEPS = [SRC] + [os.path.join(HERE, "..", "scalable-e3-gnn_b200", "csrc", f) for f in ("o3tp_body.inl", "o3tp_tables.h")]
+DEPS = [SRC] + [os.path.join(HERE, "..", "scalable-e3-gnn_b200", "csrc", f) for f in ("o3tp_body.inl", "o3tp_tables.h", "o3tp_cg_gen.inl")]
 LIB = os.path.join(HERE, "emu", "_build", "libo3tp_emu.so")
 
 
@@ -46,6 +46,7 @@ CASES = {
                      [(3, 0, 1), (2, 1, -1), (1, 2, 1), (2, 1, 1), (1, 2, -1), (5, 0, -1)]),
     "dead_output": ([(4, 0, 1)], 1, [(3, 0, 1), (2, 1, 1), (2, 1, -1)]),       # 1e has no path: columns must be 0
     "scalar_attr": ([(5, 0, 1), (3, 2, 1)], 0, [(4, 0, 1), (2, 2, 1)]),
+    "wide": ([(64, 0, 1), (32, 1, -1), (16, 2, 1)], 2, [(64, 0, 1), (32, 1, -1), (16, 2, 1)]),
 }
 
 
@@ -103,11 +104,12 @@ def test_plan_matches_oracle(emu, name):
     np.testing.assert_allclose([pa[k] for k in range(len(ps))], [a[p[2]] for p in ps], rtol=1e-6)
 
 
-@pytest.mark.parametrize("name,rows,TE,NT,nblocks", [
-    ("sh1", 37, 16, 64, 2), ("balanced2", 45, 16, 256, 1), ("balanced2", 33, 32, 96, 3), ("message2", 21, 8, 256, 2),
-    ("mixed_parity", 19, 4, 7, 1), ("dead_output", 9, 8, 32, 1), ("scalar_attr", 16, 16, 33, 1), ("message2", 1, 32, 256, 4),
+@pytest.mark.parametrize("name,rows,TEF,TE,NT,nblocks", [
+    ("sh1", 37, 32, 16, 64, 2), ("balanced2", 145, 64, 16, 256, 1), ("balanced2", 33, 32, 32, 96, 3),
+    ("message2", 121, 64, 8, 256, 2), ("mixed_parity", 19, 32, 4, 7, 1), ("dead_output", 9, 64, 8, 32, 1),
+    ("scalar_attr", 16, 32, 16, 33, 1), ("message2", 1, 32, 32, 256, 4), ("wide", 70, 64, 8, 256, 1),
 ])
-def test_emulated_kernels_match_oracle(emu, name, rows, TE, NT, nblocks):
+def test_emulated_kernels_match_oracle(emu, name, rows, TEF, TE, NT, nblocks):
     in1, lmax, out = CASES[name]
     in2 = l2.sh_irreps(lmax)
     rng = np.random.default_rng(hash(name) % 1000)
@@ -123,7 +125,8 @@ def test_emulated_kernels_match_oracle(emu, name, rows, TE, NT, nblocks):
 
     spec = (len(in1), _flat(in1), len(in2), _flat(in2, True), len(out), _flat(out))
     got_o = np.full((rows, do), np.nan, np.float32)
-    assert emu.emu_forward(*spec, C.c_longlong(rows), _fp(x1), _fp(y), _fp(w), _fp(got_o), TE, NT, nblocks) == 0
+    # forward: one warp per (output irrep, channel chunk, 32-row group); the schedule is made for 8 warps
+    assert emu.emu_forward(*spec, C.c_longlong(rows), _fp(x1), _fp(y), _fp(w), _fp(got_o), TEF, 256, nblocks) == 0
     _close(got_o, want_o)
 
     gx = np.full((rows, d1), np.nan, np.float32)

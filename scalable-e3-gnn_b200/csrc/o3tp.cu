@@ -17,7 +17,15 @@ typedef float4 o3f4;
 #define O3_THREADS { const int tid = threadIdx.x; const int NT = blockDim.x;
 #define O3_END } __syncthreads();
 #define O3_ATOMIC_ADD(p, v) atomicAdd((p), (v))
+#define O3_GW_ADD(S, p, v)               \
+    do {                                 \
+        if ((S).gw_global)               \
+            atomicAdd((p), (v));         \
+        else                             \
+            *(p) += (v);                 \
+    } while (0)
 #define O3_I2F(i) __int_as_float(i)
+#define O3_MULHI(a, b) __umulhi((a), (b))
 #define O3_NT_DECL
 #define O3_LD4(p) (*reinterpret_cast<const float4*>(p))
 #define O3_UNROLL _Pragma("unroll")
@@ -67,34 +75,42 @@ __global__ void __launch_bounds__(O3_NT) o3tp_bwd_kernel(const int32_t* __restri
                                                          const float* __restrict__ in2, const float* __restrict__ w,
                                                          const float* __restrict__ gout, float* __restrict__ gin1,
                                                          float* __restrict__ gin2, float* __restrict__ gw, long long rows,
-                                                         int TE) {
+                                                         int gw_global) {
     extern __shared__ __align__(16) int32_t o3_sm[];
     const int32_t* tab = load_table(tab_g, o3_sm);
     float* fl = reinterpret_cast<float*>(o3_sm + tab[o3::H_WORDS]);
     float* WT = fl;
     fl += tab[o3::H_NWT];
-    float* gWs = fl;
-    fl += tab[o3::H_NW];
+    float* gWs = gw_global ? gw : fl;
+    if (!gw_global) fl += tab[o3::H_NW];
+    constexpr int TE = o3::TE_BWD;
     const int D1p = tab[o3::H_D1] | 1, D2p = tab[o3::H_D2] | 1, DOp = tab[o3::H_DOUT] | 1;
     O3Bwd S;
-    S.tab = tab; S.WT = WT; S.gWs = gWs; S.TE = TE; S.Rp = (TE * tab[o3::H_DMAX]) | 1;
+    S.tab = tab; S.WT = WT; S.gWs = gWs; S.gw_global = gw_global;
     S.xs = fl; fl += TE * D1p;
     S.gxs = fl; fl += TE * D1p;
     S.ys = fl; fl += TE * D2p;
     S.gys = fl; fl += TE * D2p;
     S.gs = fl; fl += TE * DOp;
-    S.F = fl; fl += (size_t)tab[o3::H_KPMAX] * S.Rp;
-    S.G = fl; fl += (size_t)tab[o3::H_KPMAX] * S.Rp;
-    S.GT = fl;
+    S.F = fl; fl += (size_t)4 * tab[o3::H_MAXNP] * o3::NWARP * tab[o3::H_FROW];
+    S.GT = fl; fl += tab[o3::H_GTMAX];
+    S.scr = fl;
     for (int io = 0; io < tab[o3::H_NIO]; ++io) {
         const int32_t* IO = tab + tab[o3::H_IO] + io * o3::IO_W;
-        const int mul = IO[o3::IO_MUL], K = IO[o3::IO_K], Kp = (K + 3) & ~3;
-        for (int idx = threadIdx.x; idx < mul * Kp; idx += blockDim.x) {
-            const int wi = idx / Kp, kk = idx - wi * Kp;
-            WT[IO[o3::IO_WTOFF] + idx] = kk < K ? w[IO[o3::IO_WOFF] + kk * mul + wi] : 0.f;
+        const int32_t* BL = tab + tab[o3::H_BLK] + IO[o3::IO_BLK];
+        const int32_t* SUB = tab + tab[o3::H_SUB] + IO[o3::IO_SUB];
+        const int mul = IO[o3::IO_MUL], KPP = 4 * IO[o3::IO_NSUB];
+        for (int idx = threadIdx.x; idx < mul * KPP; idx += blockDim.x) {
+            const int wi = idx / KPP, kkp = idx - wi * KPP, word = SUB[kkp >> 2];
+            const int32_t* B = BL + (word & 0xffff) * o3::BLK_W;
+            const int32_t* G = tab + tab[o3::H_GRP] + (B[o3::B_GRP] & 0xffff) * o3::GRP_W;
+            const int32_t* P = tab + tab[o3::H_PATH] + G[o3::G_P0 + (word >> 16)] * o3::PATH_W;
+            const int u = (B[o3::B_GRP] >> 16) + (kkp & 3);
+            WT[IO[o3::IO_WTOFF] + idx] = u < G[o3::G_MUL1] ? w[P[o3::P_WOFF] + u * mul + wi] : 0.f;
         }
     }
-    for (int idx = threadIdx.x; idx < tab[o3::H_NW]; idx += blockDim.x) gWs[idx] = 0.f;
+    if (!gw_global)
+        for (int idx = threadIdx.x; idx < tab[o3::H_NW]; idx += blockDim.x) gWs[idx] = 0.f;
     __syncthreads();
     const long long ntiles = (rows + TE - 1) / TE;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -103,7 +119,8 @@ __global__ void __launch_bounds__(O3_NT) o3tp_bwd_kernel(const int32_t* __restri
         o3_bwd_tile(S, in1, in2, gout, gin1, gin2, row0, nrow);
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < tab[o3::H_NW]; idx += blockDim.x) atomicAdd(gw + idx, gWs[idx]);
+    if (!gw_global)
+        for (int idx = threadIdx.x; idx < tab[o3::H_NW]; idx += blockDim.x) atomicAdd(gw + idx, gWs[idx]);
 }
 
 constexpr size_t SMEM_MAX = 227 * 1024;
@@ -114,14 +131,14 @@ constexpr size_t SMEM_TWO = 110 * 1024;  // budget that lets two CTAs share an S
 struct se3_o3tp_plan {
     o3::Plan P;
     int32_t* d_tab = nullptr;
-    int te_f = 0, te_b = 0;
+    int te_f = 0, te_b = 0, gw_global = 0;
     size_t smem_f = 0, smem_b = 0;
     int grid_f = 0, grid_b = 0;
 };
 
 static int pick_tile(const std::vector<int32_t>& blob, bool bwd, int* te, size_t* smem) {
-    const int cand[4] = {bwd ? 32 : 64, bwd ? 16 : 32, bwd ? 8 : 0, bwd ? 4 : 0};
-    auto bytes = [&](int t) { return 4 * (blob.size() + (bwd ? o3::bwd_floats(blob, t) : o3::fwd_floats(blob, t))); };
+    const int cand[4] = {bwd ? o3::TE_BWD : 64, bwd ? 0 : 32, 0, 0};
+    auto bytes = [&](int t) { return 4 * (blob.size() + (bwd ? o3::bwd_floats(blob) : o3::fwd_floats(blob, t))); };
     for (int c : cand)
         if (c && bytes(c) <= SMEM_TWO) { *te = c; *smem = bytes(c); return 0; }
     for (int c : cand)
@@ -154,7 +171,14 @@ extern "C" int se3_o3tp_plan_create(const se3_o3tp_desc* d, se3_o3tp_plan** out)
         rc_f = pick_tile(p->P.blob, false, &p->te_f, &p->smem_f);
         if (rc_f == 0 && p->te_f != p->P.blob[o3::H_TEF]) rc_f = SE3_ERR_TOO_LARGE;
     }
-    if (rc_f || pick_tile(p->P.blob, true, &p->te_b, &p->smem_b)) {
+    int rc_b = pick_tile(p->P.blob, true, &p->te_b, &p->smem_b);
+    if (rc_b) {  // keep the weight-gradient accumulators in global memory instead
+        p->smem_b = 4 * (p->P.blob.size() + o3::bwd_floats(p->P.blob, false));
+        p->te_b = o3::TE_BWD;
+        p->gw_global = 1;
+        rc_b = p->smem_b <= SMEM_MAX ? 0 : SE3_ERR_TOO_LARGE;
+    }
+    if (rc_f || rc_b) {
         set_error("o3tp: irreps too large for the shared-memory tiling (%d weights, d_in1 %d)", p->P.nW, p->P.D1);
         delete p;
         return SE3_ERR_TOO_LARGE;
@@ -236,7 +260,7 @@ extern "C" int se3_o3tp_backward(se3_o3tp_plan* p, int64_t rows, const float* in
     const long long ntiles = (rows + p->te_b - 1) / p->te_b;
     const int grid = (int)std::min<long long>(ntiles, p->grid_b);
     o3tp_bwd_kernel<<<grid, O3_NT, p->smem_b, (cudaStream_t)stream>>>(p->d_tab, in1, in2, w, gout, gin1, gin2, gw, rows,
-                                                                     p->te_b);
+                                                                     p->gw_global);
     SE3_LAUNCHED();
     return SE3_OK;
 }

@@ -2,64 +2,41 @@
 // o3tp.cu (one CUDA thread per `tid`) and by g++ inside tests/emu/o3tp_emu.cpp (threads run one after another, phase by
 // phase) so the table walking and indexing are checked against the oracle on a machine without a GPU.
 //
-// The includer defines:
+// The includer defines (and includes o3tp_cg_gen.inl first):
 //   O3_DEV                     function qualifier
 //   O3_THREADS / O3_END        open / close a region every thread of the block executes; O3_END is a block barrier
 //   O3_ATOMIC_ADD(p, v)        shared-memory float add that tolerates several threads on one address
+//   O3_GW_ADD(S, p, v)         weight-gradient accumulation: plain add, or a global atomic add when S.gw_global
+//   O3_MULHI(a, b)             high 32 bits of the unsigned 32 x 32 product
 //   O3_I2F(i)                  reinterpret an int32 table word as float
 //   O3_NT_DECL                 extra parameter `, int NT_` carrying the emulated block size (empty under nvcc)
 //   o3f4 / O3_LD4(p)           four consecutive floats read from a 16-byte aligned shared-memory address
 //   O3_UNROLL                  unroll pragma
 //
 // Math (oracle/lmax2_oracle.py forward): for every output irrep io with stacked paths,
-//   F[kk, e, c]   = sum_{i,j} C_p[i,j,c] x1[e, off1_p + u d1 + i] y[e, off2_p + j]     kk = koff_p + u
-//   out[e, w, c]  = a_io sum_kk F[kk, e, c] W_io[kk, w]
+//   f[kk, e, c]   = sum_{i,j} C_p[i,j,c] x1[e, off1_p + u d1 + i] y[e, off2_p + j]     kk = koff_p + u
+//   out[e, w, c]  = a_io sum_kk f[kk, e, c] W_io[kk, w]
 // backward, with g' = a_io g:
-//   gW_io[kk, w]  = sum_{e,c} F[kk, e, c] g'[e, w, c]
+//   gW_io[kk, w]  = sum_{e,c} f[kk, e, c] g'[e, w, c]
 //   G[kk, e, c]   = sum_w W_io[kk, w] g'[e, w, c]
 //   gx1[e, off1 + u d1 + i] += sum C[i,j,c] y[e, j] G[koff + u, e, c];   gy[e, j] += sum C[i,j,c] x1[...] G[...]
+// Per lane (= row e) and path the second input is folded once into M[i][c] = sum_j C[i][j][c] y[j], so that
+// f[c] = sum_i M[i][c] x[i] and gx[i] = sum_c M[i][c] G[c].
 
 struct O3Fwd {
     const int32_t* tab;  // table blob (shared memory)
-    const float* Ws;     // all weights, per io [K, mulp] zero padded (shared, resident)
+    const float* Ws;     // all weights, per io [K, IO_MULP] zero padded (shared, resident)
     float *xs, *ys, *os;
     int TE;
 };
 
 struct O3Bwd {
     const int32_t* tab;
-    const float* WT;  // all weights transposed, per io [mul, Kp] (shared, resident)
+    const float* WT;  // all weights transposed, per io [mul, 4 * IO_NBLK] in block order (shared, resident)
     float* gWs;       // weight gradient accumulators, flat like the weights (shared, resident)
-    float *xs, *ys, *gs, *gxs, *gys, *F, *G, *GT;
-    int TE, Rp;
+    float *xs, *ys, *gs, *gxs, *gys, *F, *GT, *scr;
+    int gw_global;  // gWs is the global result (weights too large to keep accumulators resident): add atomically
 };
-
-O3_DEV void o3_features(const int32_t* tab, const int32_t* IO, const float* xs, const float* ys, float* F,
-                               int TE, int Rp, int D1p, int D2p, int Krows, int tid, int NT) {
-    const int d = IO[o3::IO_D], K = IO[o3::IO_K];
-    const int32_t* ent = tab + tab[o3::H_ENT];
-    for (int item = tid; item < TE * Krows; item += NT) {
-        const int kk = item / TE, e = item - kk * TE;
-        float* f = F + (size_t)kk * Rp + e * d;
-        if (kk >= K) {
-            for (int c = 0; c < d; ++c) f[c] = 0.f;
-            continue;
-        }
-        const int32_t* P = tab + tab[o3::H_PATH] + IO[o3::IO_PBEG] * o3::PATH_W;
-        while (kk >= P[o3::P_KOFF] + P[o3::P_MUL1]) P += o3::PATH_W;
-        const int u = kk - P[o3::P_KOFF];
-        const float* xr = xs + e * D1p + P[o3::P_OFF1] + u * P[o3::P_D1];
-        const float* yr = ys + e * D2p + P[o3::P_OFF2];
-        for (int c = 0; c < d; ++c) {
-            float s = 0.f;
-            for (int t = P[o3::P_EB0 + c]; t < P[o3::P_EB0 + c + 1]; ++t) {
-                const int32_t* E = ent + t * o3::ENT_W;
-                s += O3_I2F(E[3]) * xr[E[0]] * yr[E[1]];
-            }
-            f[c] = s;
-        }
-    }
-}
 
 // ---- forward: one warp per work unit (output irrep, chunk of CW output channels, group of 32 rows), lane = row.
 // Per path the lane folds its spherical-harmonics values into M[i][c] = sum_j C[i][j][c] y[j] once (generated code,
@@ -179,56 +156,245 @@ O3_DEV void o3_fwd_tile(const O3Fwd& S, const float* __restrict__ in1, const flo
     O3_END
 }
 
+// ---- backward.  Tile of 32 rows, lane = row.  Per output irrep: GT[w][e*d + c] = a g[e][w][c] (shared), then rounds of
+// NWARP blocks (<= 4 channels of one input irrep, all its paths into this output; one block per warp):
+//   step 1 (warp = block), per path: Gc[uu][c] = sum_w W[kk0+uu][w] GT[w][e, c] from one transposed weight float4 per w;
+//           per channel f -> F rows of the warp's slot, gx accumulated in registers over the paths (then added to the
+//           shared gx tile, which this block owns), P[i][c] += x[i] Gc[uu][c] -> gy[j] += C . P (generated code).
+//   step 2 (all threads): weight gradient of the round's sub-blocks (4 feature rows of one path), 4 x 4 register blocks
+//           of F . GT^T; the (e, c) axis is cut into slices so that every thread has work, the slices' partial sums
+//           go through a scratch array and are added to the resident accumulators at the start of the next region.
+template <int A, int B, int C> struct o3_tri { static constexpr bool v = C >= (A > B ? A - B : B - A) && C <= A + B; };
+
+template <int L1, int L2, int LO>
+O3_DEV void o3_bwd_path(const float* xr, const float* yr, float (&gx)[4][2 * L1 + 1], float* gyr, const float* GTe,
+                        int Rp, const float* wt, int KPP, int mul, int nu, float* Fe) {
+    constexpr int D1 = 2 * L1 + 1, D2 = 2 * L2 + 1, DO = 2 * LO + 1;
+    constexpr unsigned NZ = o3_nz<L1, L2, LO>::mask;
+    float M[D1][DO];
+    o3_M<L1, L2, LO>(yr, M);
+    float Gc[4][DO];
+    O3_UNROLL
+    for (int uu = 0; uu < 4; ++uu)
+        O3_UNROLL
+        for (int c = 0; c < DO; ++c) Gc[uu][c] = 0.f;
+    for (int w = 0; w < mul; ++w) {
+        const o3f4 t = O3_LD4(wt + w * KPP);
+        O3_UNROLL
+        for (int c = 0; c < DO; ++c) {
+            const float gv = GTe[(size_t)w * Rp + c];
+            Gc[0][c] += t.x * gv; Gc[1][c] += t.y * gv; Gc[2][c] += t.z * gv; Gc[3][c] += t.w * gv;
+        }
+    }
+    float Pm[D1][DO];
+    O3_UNROLL
+    for (int i = 0; i < D1; ++i)
+        O3_UNROLL
+        for (int c = 0; c < DO; ++c) Pm[i][c] = 0.f;
+    O3_UNROLL
+    for (int uu = 0; uu < 4; ++uu) {
+        float* f = Fe + (size_t)uu * Rp;
+        if (uu < nu) {
+            float x[D1], fc[DO];
+            O3_UNROLL
+            for (int i = 0; i < D1; ++i) x[i] = xr[uu * D1 + i];
+            O3_UNROLL
+            for (int c = 0; c < DO; ++c) fc[c] = 0.f;
+            O3_UNROLL
+            for (int i = 0; i < D1; ++i) {
+                O3_UNROLL
+                for (int c = 0; c < DO; ++c)
+                    if ((NZ >> (i * DO + c)) & 1u) {
+                        fc[c] += M[i][c] * x[i];
+                        gx[uu][i] += M[i][c] * Gc[uu][c];
+                        Pm[i][c] += x[i] * Gc[uu][c];
+                    }
+            }
+            O3_UNROLL
+            for (int c = 0; c < DO; ++c) f[c] = fc[c];
+        } else {
+            O3_UNROLL
+            for (int c = 0; c < DO; ++c) f[c] = 0.f;
+        }
+    }
+    if (gyr != nullptr) {
+        float gy[D2];
+        O3_UNROLL
+        for (int j = 0; j < D2; ++j) gy[j] = 0.f;
+        o3_gy<L1, L2, LO>(Pm, gy);
+        O3_UNROLL
+        for (int j = 0; j < D2; ++j) O3_ATOMIC_ADD(gyr + j, gy[j]);
+    }
+}
+
+template <int L1, int LO>
+O3_DEV void o3_bwd_group(const int32_t* tab, const int32_t* G, int u0, const float* xe, const float* ye, float* gxe,
+                         float* gye, const float* GTe, int Rp, const float* wt0, int KPP, int mul, float* Fe) {
+    constexpr int D1 = 2 * L1 + 1;
+    const int nu = G[o3::G_MUL1] - u0 < 4 ? G[o3::G_MUL1] - u0 : 4;
+    const float* xr = xe + G[o3::G_OFF1] + u0 * D1;
+    float gx[4][D1];
+    O3_UNROLL
+    for (int uu = 0; uu < 4; ++uu)
+        O3_UNROLL
+        for (int i = 0; i < D1; ++i) gx[uu][i] = 0.f;
+    for (int pi = 0; pi < G[o3::G_NP]; ++pi) {
+        const int32_t* P = tab + tab[o3::H_PATH] + G[o3::G_P0 + pi] * o3::PATH_W;
+        const float* yr = ye + P[o3::P_OFF2];
+        float* gyr = gye != nullptr ? gye + P[o3::P_OFF2] : nullptr;
+        const float* wt = wt0 + 4 * pi;
+        float* Fp = Fe + (size_t)(4 * pi) * Rp;
+        switch (P[o3::P_L2]) {
+            case 0:
+                if constexpr (o3_tri<L1, 0, LO>::v) o3_bwd_path<L1, 0, LO>(xr, yr, gx, gyr, GTe, Rp, wt, KPP, mul, nu, Fp);
+                break;
+            case 1:
+                if constexpr (o3_tri<L1, 1, LO>::v) o3_bwd_path<L1, 1, LO>(xr, yr, gx, gyr, GTe, Rp, wt, KPP, mul, nu, Fp);
+                break;
+            case 2:
+                if constexpr (o3_tri<L1, 2, LO>::v) o3_bwd_path<L1, 2, LO>(xr, yr, gx, gyr, GTe, Rp, wt, KPP, mul, nu, Fp);
+                break;
+        }
+    }
+    float* gxr = gxe + G[o3::G_OFF1] + u0 * D1;
+    O3_UNROLL
+    for (int uu = 0; uu < 4; ++uu)
+        if (uu < nu) {
+            O3_UNROLL
+            for (int i = 0; i < D1; ++i) gxr[uu * D1 + i] += gx[uu][i];
+        }
+}
+
+// pending partial sums of the previous step 2 -> resident weight-gradient accumulators
+struct O3Pending {
+    const int32_t* IO;
+    int sbeg, nsb, lg;  // lg = log2(slices); -1: nothing pending
+};
+
+// scratch index of partial sum (t, s): rows of 32 words, the slice index rotated by the row so that both the writers
+// (lanes = consecutive (t, s)) and the readers (lanes = consecutive t, fixed s) are bank-conflict free
+O3_DEV int o3_scr_index(int t, int s, int lg) { return (t << lg) + ((s + ((t << lg) >> 5)) & ((1 << lg) - 1)); }
+
+O3_DEV void o3_bwd_reduce(const O3Bwd& S, const O3Pending& Q, int tid, int NT) {
+    if (Q.lg <= 0) return;
+    const int32_t* tab = S.tab;
+    const int32_t* IO = Q.IO;
+    const int mul = IO[o3::IO_MUL], nwb = ((mul + 3) & ~3) >> 2, base = Q.nsb * nwb;
+    const unsigned magic = (unsigned)IO[o3::IO_NWB_MAGIC];
+    const int32_t* BL = tab + tab[o3::H_BLK] + IO[o3::IO_BLK];
+    const int32_t* SUB = tab + tab[o3::H_SUB] + IO[o3::IO_SUB];
+    for (int t = tid; t < base; t += NT) {     // base <= NT / 2 here: one output block per thread
+        const int sb = nwb == 1 ? t : (int)O3_MULHI((unsigned)t, magic), wb = t - sb * nwb;
+        const int word = SUB[Q.sbeg + sb];
+        const int32_t* B = BL + (word & 0xffff) * o3::BLK_W;
+        const int32_t* G = tab + tab[o3::H_GRP] + (B[o3::B_GRP] & 0xffff) * o3::GRP_W;
+        const int32_t* P = tab + tab[o3::H_PATH] + G[o3::G_P0 + (word >> 16)] * o3::PATH_W;
+        const int u0 = B[o3::B_GRP] >> 16;
+        float* gw = S.gWs + P[o3::P_WOFF] + u0 * mul + 4 * wb;
+        O3_UNROLL
+        for (int k = 0; k < 16; ++k) {
+            float sum = 0.f;
+            for (int s = 0; s < (1 << Q.lg); ++s) sum += S.scr[k * NT + o3_scr_index(t, s, Q.lg)];
+            if (u0 + (k >> 2) < G[o3::G_MUL1] && 4 * wb + (k & 3) < mul) O3_GW_ADD(S, gw + (k >> 2) * mul + (k & 3), sum);
+        }
+    }
+}
+
 O3_DEV void o3_bwd_tile(const O3Bwd& S, const float* __restrict__ in1, const float* __restrict__ in2,
-                               const float* __restrict__ gout, float* __restrict__ gin1, float* __restrict__ gin2,
-                               long long row0, int nrow O3_NT_DECL) {
+                        const float* __restrict__ gout, float* __restrict__ gin1, float* __restrict__ gin2,
+                        long long row0, int nrow O3_NT_DECL) {
     const int32_t* tab = S.tab;
     const int D1 = tab[o3::H_D1], D2 = tab[o3::H_D2], DO = tab[o3::H_DOUT], nio = tab[o3::H_NIO];
-    const int D1p = D1 | 1, D2p = D2 | 1, DOp = DO | 1, TE = S.TE, Rp = S.Rp;
-    const int32_t* ent = tab + tab[o3::H_ENT];
+    const int D1p = D1 | 1, D2p = D2 | 1, DOp = DO | 1;
+    constexpr int TE = o3::TE_BWD;
+    O3Pending Q;
+    Q.IO = nullptr; Q.sbeg = 0; Q.nsb = 0; Q.lg = -1;
 
     O3_THREADS
-        for (int idx = tid; idx < TE * D1; idx += NT) {
-            const int e = idx / D1, c = idx - e * D1;
-            S.xs[e * D1p + c] = e < nrow ? in1[(row0 + e) * D1 + c] : 0.f;
-            S.gxs[e * D1p + c] = 0.f;
-        }
-        for (int idx = tid; idx < TE * D2; idx += NT) {
-            const int e = idx / D2, c = idx - e * D2;
-            S.ys[e * D2p + c] = e < nrow ? in2[(row0 + e) * D2 + c] : 0.f;
-            S.gys[e * D2p + c] = 0.f;
-        }
-        for (int idx = tid; idx < TE * DO; idx += NT) {
-            const int e = idx / DO, c = idx - e * DO;
-            S.gs[e * DOp + c] = e < nrow ? gout[(row0 + e) * DO + c] : 0.f;
+        const int warp = tid >> 5, lane = tid & 31, nw = NT >> 5;
+        for (int e = warp; e < TE; e += nw) {
+            const bool ok = e < nrow;
+            const float* src = in1 + (row0 + e) * D1;
+            for (int c = lane; c < D1; c += 32) {
+                S.xs[e * D1p + c] = ok ? src[c] : 0.f;
+                S.gxs[e * D1p + c] = 0.f;
+            }
+            if (lane < D2) {
+                S.ys[e * D2p + lane] = ok ? in2[(row0 + e) * D2 + lane] : 0.f;
+                S.gys[e * D2p + lane] = 0.f;
+            }
+            const float* gsrc = gout + (row0 + e) * DO;
+            for (int c = lane; c < DO; c += 32) S.gs[e * DOp + c] = ok ? gsrc[c] : 0.f;
         }
     O3_END
 
     for (int io = 0; io < nio; ++io) {
         const int32_t* IO = tab + tab[o3::H_IO] + io * o3::IO_W;
-        const int mul = IO[o3::IO_MUL], d = IO[o3::IO_D], K = IO[o3::IO_K];
-        const int mulp = (mul + 3) & ~3, Kp = (K + 3) & ~3, R = TE * d;
-        if (K == 0) continue;  // block-uniform
+        const int mul = IO[o3::IO_MUL], d = IO[o3::IO_D], nblk = IO[o3::IO_NBLK], nsub = IO[o3::IO_NSUB];
+        const int mulp = (mul + 3) & ~3, nwb = mulp >> 2, R = TE * d, Rp = R | 1, KPP = 4 * nsub;
+        const int32_t* BL = tab + tab[o3::H_BLK] + IO[o3::IO_BLK];
+        const int32_t* SUB = tab + tab[o3::H_SUB] + IO[o3::IO_SUB];
+        if (nblk == 0) continue;  // block-uniform
         O3_THREADS
+            o3_bwd_reduce(S, Q, tid, NT);
             const float a = O3_I2F(IO[o3::IO_A]);
-            for (int item = tid; item < mulp * R; item += NT) {
-                const int w = item / R, r = item - w * R;
-                const int e = r / d, c = r - e * d;
-                S.GT[(size_t)w * Rp + r] = w < mul ? a * S.gs[e * DOp + IO[o3::IO_OFF] + w * d + c] : 0.f;
-            }
-            o3_features(tab, IO, S.xs, S.ys, S.F, TE, Rp, D1p, D2p, Kp, tid, NT);
+            const int warp = tid >> 5, lane = tid & 31, nw = NT >> 5;
+            for (int w = warp; w < mulp; w += nw)
+                for (int c = 0; c < d; ++c)
+                    S.GT[(size_t)w * Rp + lane * d + c] = w < mul ? a * S.gs[lane * DOp + IO[o3::IO_OFF] + w * d + c] : 0.f;
         O3_END
-        O3_THREADS
-            {   // weight gradient: 4 x 4 register blocks of F . GT^T
-                const int nkb = Kp >> 2, nwb = mulp >> 2;
-                for (int item = tid; item < nkb * nwb; item += NT) {
-                    const int kb = item / nwb, wb = item - kb * nwb;
-                    const float* f = S.F + (size_t)(4 * kb) * Rp;
+        Q.lg = -1;
+        for (int b0 = 0; b0 < nblk; b0 += o3::NWARP) {
+            O3_THREADS
+                o3_bwd_reduce(S, Q, tid, NT);
+                const int warp = tid >> 5, e = tid & 31, b = b0 + warp;
+                if (b < nblk) {
+                    const int32_t* B = BL + b * o3::BLK_W;
+                    const int32_t* G = tab + tab[o3::H_GRP] + (B[o3::B_GRP] & 0xffff) * o3::GRP_W;
+                    const int u0 = B[o3::B_GRP] >> 16;
+                    const float* xe = S.xs + e * D1p;
+                    const float* ye = S.ys + e * D2p;
+                    float* gxe = S.gxs + e * D1p;
+                    float* gye = gin2 != nullptr ? S.gys + e * D2p : nullptr;
+                    const float* GTe = S.GT + e * d;
+                    const float* wt0 = S.WT + IO[o3::IO_WTOFF] + 4 * B[o3::B_SUB0];
+                    float* Fe = S.F + (size_t)(4 * tab[o3::H_MAXNP] * warp) * Rp + e * d;
+                    switch (G[o3::G_L1] * 3 + (d >> 1)) {
+#define O3_CASE(A, C)                                                                            \
+    case A * 3 + C:                                                                              \
+        o3_bwd_group<A, C>(tab, G, u0, xe, ye, gxe, gye, GTe, Rp, wt0, KPP, mul, Fe);            \
+        break;
+                        O3_CASE(0, 0) O3_CASE(0, 1) O3_CASE(0, 2) O3_CASE(1, 0) O3_CASE(1, 1) O3_CASE(1, 2)
+                        O3_CASE(2, 0) O3_CASE(2, 1) O3_CASE(2, 2)
+#undef O3_CASE
+                    }
+                }
+            O3_END
+            const int nb = nblk - b0 < o3::NWARP ? nblk - b0 : o3::NWARP;
+            const int sbeg = BL[b0 * o3::BLK_W + o3::B_SUB0];
+            const int send = b0 + nb < nblk ? BL[(b0 + nb) * o3::BLK_W + o3::B_SUB0] : nsub;
+            Q.IO = IO; Q.sbeg = sbeg; Q.nsb = send - sbeg;
+            {   // slices: the largest power of two that keeps one item per thread
+                const int base = Q.nsb * nwb;
+                Q.lg = 0;
+                while (Q.lg < 5 && (base << (Q.lg + 1)) <= (int)(32 * o3::NWARP)) ++Q.lg;
+            }
+            O3_THREADS
+                const int lg = Q.lg, ns = 1 << lg;
+                const unsigned magic = (unsigned)IO[o3::IO_NWB_MAGIC];
+                for (int item = tid; item < ((Q.nsb * nwb) << lg); item += NT) {
+                    const int s = item & (ns - 1), t = item >> lg;
+                    const int sb = nwb == 1 ? t : (int)O3_MULHI((unsigned)t, magic), wb = t - sb * nwb;
+                    const int word = SUB[sbeg + sb], bl = (word & 0xffff) - b0, pi = word >> 16;
+                    const float* f = S.F + (size_t)(4 * (tab[o3::H_MAXNP] * bl + pi)) * Rp;
                     const float* g = S.GT + (size_t)(4 * wb) * Rp;
+                    const int r0 = (s * R) >> lg, r1 = ((s + 1) * R) >> lg;
                     float acc[4][4];
+                    O3_UNROLL
                     for (int i = 0; i < 4; ++i)
+                        O3_UNROLL
                         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-                    for (int r = 0; r < R; ++r) {
+                    for (int r = r0; r < r1; ++r) {
                         const float f0 = f[r], f1 = f[Rp + r], f2 = f[2 * Rp + r], f3 = f[3 * Rp + r];
                         const float g0 = g[r], g1 = g[Rp + r], g2 = g[2 * Rp + r], g3 = g[3 * Rp + r];
                         acc[0][0] += f0 * g0; acc[0][1] += f0 * g1; acc[0][2] += f0 * g2; acc[0][3] += f0 * g3;
@@ -236,75 +402,36 @@ O3_DEV void o3_bwd_tile(const O3Bwd& S, const float* __restrict__ in1, const flo
                         acc[2][0] += f2 * g0; acc[2][1] += f2 * g1; acc[2][2] += f2 * g2; acc[2][3] += f2 * g3;
                         acc[3][0] += f3 * g0; acc[3][1] += f3 * g1; acc[3][2] += f3 * g2; acc[3][3] += f3 * g3;
                     }
-                    float* gw = S.gWs + IO[o3::IO_WOFF];
-                    O3_UNROLL
-                    for (int i = 0; i < 4; ++i)
+                    if (lg > 0) {   // item < NT here: one scratch column per thread
+                        const int idx = o3_scr_index(t, s, lg);
                         O3_UNROLL
-                        for (int j = 0; j < 4; ++j) {
-                            const int kk = 4 * kb + i, w = 4 * wb + j;
-                            if (kk < K && w < mul) gw[kk * mul + w] += acc[i][j];
-                        }
-                }
-            }
-            {   // G = W . g'
-                const int nkc = Kp >> 2;
-                for (int item = tid; item < R * nkc; item += NT) {
-                    const int kc = item / R, r = item - kc * R;
-                    const float* wt = S.WT + IO[o3::IO_WTOFF] + 4 * kc;
-                    const float* g = S.GT + r;
-                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-                    for (int w = 0; w < mul; ++w) {
-                        const float gv = g[(size_t)w * Rp];
-                        const o3f4 wv = O3_LD4(wt + w * Kp);
-                        a0 += gv * wv.x; a1 += gv * wv.y; a2 += gv * wv.z; a3 += gv * wv.w;
-                    }
-                    float* G = S.G + (size_t)(4 * kc) * Rp + r;
-                    G[0] = a0; G[Rp] = a1; G[2 * Rp] = a2; G[3 * Rp] = a3;
-                }
-            }
-        O3_END
-        O3_THREADS
-            for (int gi = IO[o3::IO_GBEG]; gi < IO[o3::IO_GEND]; ++gi) {
-                const int32_t* Gp = tab + tab[o3::H_GRP] + gi * o3::GRP_W;
-                const int off1 = Gp[o3::G_OFF1], d1 = Gp[o3::G_D1], mul1 = Gp[o3::G_MUL1], nj = Gp[o3::G_NJ];
-                for (int item = tid; item < TE * mul1; item += NT) {
-                    const int u = item / TE, e = item - u * TE;
-                    const float* yr = S.ys + e * D2p;
-                    const float* xr = S.xs + e * D1p + off1 + u * d1;
-                    float* gx = S.gxs + e * D1p + off1 + u * d1;
-                    const float* Gr = S.G + (size_t)u * Rp + e * d;
-                    for (int i = 0; i < d1; ++i) {
-                        float s = 0.f;
-                        for (int t = Gp[o3::G_IB0 + i]; t < Gp[o3::G_IB0 + i + 1]; ++t) {
-                            const int32_t* E = ent + t * o3::ENT_W;
-                            s += O3_I2F(E[3]) * yr[E[0]] * Gr[(size_t)E[1] * Rp + E[2]];
-                        }
-                        gx[i] += s;
-                    }
-                    if (gin2 != nullptr) {
-                        for (int jj = 0; jj < nj; ++jj) {
-                            float s = 0.f;
-                            for (int t = Gp[o3::G_JB0 + jj]; t < Gp[o3::G_JB0 + jj + 1]; ++t) {
-                                const int32_t* E = ent + t * o3::ENT_W;
-                                s += O3_I2F(E[3]) * xr[E[0]] * Gr[(size_t)E[1] * Rp + E[2]];
-                            }
-                            O3_ATOMIC_ADD(&S.gys[e * D2p + Gp[o3::G_JABS + jj]], s);
-                        }
+                        for (int i = 0; i < 4; ++i)
+                            O3_UNROLL
+                            for (int j = 0; j < 4; ++j) S.scr[(4 * i + j) * NT + idx] = acc[i][j];
+                    } else {        // this thread owns the 4 x 4 weight block
+                        const int32_t* B = BL + (word & 0xffff) * o3::BLK_W;
+                        const int32_t* G = tab + tab[o3::H_GRP] + (B[o3::B_GRP] & 0xffff) * o3::GRP_W;
+                        const int32_t* P = tab + tab[o3::H_PATH] + G[o3::G_P0 + pi] * o3::PATH_W;
+                        const int u0 = B[o3::B_GRP] >> 16;
+                        float* gw = S.gWs + P[o3::P_WOFF] + u0 * mul + 4 * wb;
+                        O3_UNROLL
+                        for (int i = 0; i < 4; ++i)
+                            O3_UNROLL
+                            for (int j = 0; j < 4; ++j)
+                                if (u0 + i < G[o3::G_MUL1] && 4 * wb + j < mul) O3_GW_ADD(S, gw + i * mul + j, acc[i][j]);
                     }
                 }
-            }
-        O3_END
+            O3_END
+        }
     }
 
     O3_THREADS
-        for (int idx = tid; idx < nrow * D1; idx += NT) {
-            const int e = idx / D1, c = idx - e * D1;
-            gin1[(row0 + e) * D1 + c] = S.gxs[e * D1p + c];
+        o3_bwd_reduce(S, Q, tid, NT);
+        const int warp = tid >> 5, lane = tid & 31, nw = NT >> 5;
+        for (int e = warp; e < nrow; e += nw) {
+            float* dst = gin1 + (row0 + e) * D1;
+            for (int c = lane; c < D1; c += 32) dst[c] = S.gxs[e * D1p + c];
+            if (gin2 != nullptr && lane < D2) gin2[(row0 + e) * D2 + lane] = S.gys[e * D2p + lane];
         }
-        if (gin2 != nullptr)
-            for (int idx = tid; idx < nrow * D2; idx += NT) {
-                const int e = idx / D2, c = idx - e * D2;
-                gin2[(row0 + e) * D2 + c] = S.gys[e * D2p + c];
-            }
     O3_END
 }

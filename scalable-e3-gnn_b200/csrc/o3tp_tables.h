@@ -18,20 +18,23 @@ namespace o3 {
 
 enum { MAX_IRR = 8 };
 // blob header words
-enum { H_NIO = 0, H_D1, H_D2, H_DOUT, H_IO, H_PATH, H_GRP, H_ENT, H_WORDS, H_NW, H_KPMAX, H_DMAX, H_MULPMAX,
-       H_NPATH, H_NWP, H_NWT, H_UNIT, H_TEF, H_BASE, HDR_W = 20 };
-enum { NWARP = 8 };  // warps per CTA the forward unit schedule is made for
+enum { H_NIO = 0, H_D1, H_D2, H_DOUT, H_IO, H_PATH, H_BLK, H_WORDS, H_NW, H_NPATH, H_NWP, H_NWT, H_UNIT, H_TEF, H_BASE,
+       H_FROW, H_GTMAX, H_GRP, H_SUB, H_MAXNP, HDR_W = 20 };
+enum { NWARP = 8 };   // warps per CTA both schedules are made for
+enum { TE_BWD = 32 }; // rows per backward tile (lane = row)
 // per output irrep
 // IO_CW: output channels per forward work unit (4, 8 or 12); IO_MULP: mul padded to a multiple of IO_CW (row length of
-// the staged forward weights at IO_WSOFF); IO_NQ = IO_MULP / IO_CW
-enum { IO_MUL = 0, IO_D, IO_OFF, IO_K, IO_WOFF, IO_A, IO_PBEG, IO_PEND, IO_GBEG, IO_GEND, IO_WSOFF, IO_WTOFF, IO_CW,
-       IO_MULP, IO_NQ, IO_W = 16 };
-// per path: entries (i, j, -, v) grouped by output component c: [P_EB0+c, P_EB0+c+1)
-enum { P_OFF1 = 0, P_D1, P_MUL1, P_OFF2, P_KOFF, P_L1, P_L2, P_EB0, PATH_W = P_EB0 + 7 };
-// per (output irrep, in1 irrep) group for the backward: entries grouped by in1 component i (a=jabs, b=koff, c, v)
-// and grouped by in2 column (a=i, b=koff, c, v)
-enum { G_OFF1 = 0, G_D1, G_MUL1, G_NJ, G_IB0, G_JABS = G_IB0 + 6, G_JB0 = G_JABS + 9, GRP_W = G_JB0 + 10 };
-enum { ENT_W = 4 };
+// the staged forward weights at IO_WSOFF); IO_NQ = IO_MULP / IO_CW.
+// Backward: the paths into an output irrep are grouped by input irrep (GRP record: <= 3 paths, one per in2 irrep).  A
+// block = <= 4 channels of one group (all its paths): BLK record = (group | first channel << 16, first sub-block).  A
+// sub-block = 4 feature rows of one (block, path): word [H_SUB + IO_SUB + s] = block | path slot << 16.  The transposed
+// weights at IO_WTOFF are [mul, 4 * IO_NSUB] in sub-block order.
+enum { IO_MUL = 0, IO_D, IO_OFF, IO_K, IO_WOFF, IO_A, IO_PBEG, IO_PEND, IO_WSOFF, IO_WTOFF, IO_CW, IO_MULP, IO_NQ,
+       IO_NBLK, IO_BLK, IO_NSUB, IO_SUB, IO_NWB_MAGIC /* ceil(2^32 / ceil(mul / 4)) */, IO_W = 20 };
+enum { P_OFF1 = 0, P_D1, P_MUL1, P_OFF2, P_KOFF, P_L1, P_L2, P_WOFF, PATH_W };
+enum { G_OFF1 = 0, G_L1, G_MUL1, G_NP, G_P0, GRP_W = 8 };
+enum { B_GRP = 0, B_SUB0, BLK_W };
+enum { MAXP = 3 };  // paths per group = in2 irreps
 
 struct Irrep { int mul, l, p; };
 struct PathH { int i1, i2, io, woff, koff; };
@@ -139,13 +142,12 @@ inline bool build_plan(Plan& P) {
     }
     P.paths.clear();
     P.a.assign(P.out.size(), 0.f);
-    std::vector<int32_t> io_w, path_w, grp_w, ent_w;
-    int woff = 0, kpmax = 4, dmax = 1, mulpmax = 4, wsoff = 0, wtoff = 0;
-    double C[5][5][5];
+    std::vector<int32_t> io_w, path_w, blk_w, grp_w, sub_w;
+    int woff = 0, wsoff = 0, wtoff = 0, frow = 1, gtmax = 4, maxnp = 1;
     for (size_t io = 0; io < P.out.size(); ++io) {
         const Irrep o = P.out[io];
         const int d = 2 * o.l + 1;
-        const int pbeg = (int)P.paths.size(), gbeg = (int)(grp_w.size() / GRP_W);
+        const int pbeg = (int)P.paths.size();
         int K = 0;
         const int woff0 = woff;
         for (size_t i2 = 0; i2 < P.in2.size(); ++i2)
@@ -156,73 +158,35 @@ inline bool build_plan(Plan& P) {
                 woff += a.mul * o.mul;
                 K += a.mul;
             }
-        // paths were appended in (i2, i1) order; K offsets follow that order
         const int pend = (int)P.paths.size();
         P.a[io] = K > 0 ? (float)std::sqrt((double)d / (double)K) : 0.f;
+        const int blk0 = (int)(blk_w.size() / BLK_W), sub0 = (int)sub_w.size();
         for (int p = pbeg; p < pend; ++p) {
             const PathH& ph = P.paths[p];
             const Irrep a = P.in1[ph.i1], b = P.in2[ph.i2];
-            cg(a.l, b.l, o.l, C);
             int32_t rec[PATH_W] = {0};
             rec[P_OFF1] = off1[ph.i1]; rec[P_D1] = 2 * a.l + 1; rec[P_MUL1] = a.mul; rec[P_OFF2] = off2[ph.i2];
-            rec[P_KOFF] = ph.koff; rec[P_L1] = a.l; rec[P_L2] = b.l;
-            for (int c = 0; c < d; ++c) {
-                rec[P_EB0 + c] = (int32_t)(ent_w.size() / ENT_W);
-                for (int i = 0; i < 2 * a.l + 1; ++i)
-                    for (int j = 0; j < 2 * b.l + 1; ++j)
-                        if (C[i][j][c] != 0.0) {
-                            ent_w.push_back(i); ent_w.push_back(j); ent_w.push_back(c);
-                            ent_w.push_back(f2i((float)C[i][j][c]));
-                        }
-            }
-            for (int c = d; c < 7; ++c) rec[P_EB0 + c] = (int32_t)(ent_w.size() / ENT_W);
+            rec[P_KOFF] = ph.koff; rec[P_L1] = a.l; rec[P_L2] = b.l; rec[P_WOFF] = ph.woff;
             path_w.insert(path_w.end(), rec, rec + PATH_W);
         }
-        // backward groups: one per in1 irrep that reaches this output
         for (size_t i1 = 0; i1 < P.in1.size(); ++i1) {
-            std::vector<int> ps;
-            for (int p = pbeg; p < pend; ++p)
-                if (P.paths[p].i1 == (int)i1) ps.push_back(p);
-            if (ps.empty()) continue;
-            const Irrep a = P.in1[i1];
-            const int d1 = 2 * a.l + 1;
             int32_t rec[GRP_W] = {0};
-            rec[G_OFF1] = off1[i1]; rec[G_D1] = d1; rec[G_MUL1] = a.mul;
-            for (int i = 0; i < d1; ++i) {
-                rec[G_IB0 + i] = (int32_t)(ent_w.size() / ENT_W);
-                for (int p : ps) {
-                    const Irrep b = P.in2[P.paths[p].i2];
-                    cg(a.l, b.l, o.l, C);
-                    for (int j = 0; j < 2 * b.l + 1; ++j)
-                        for (int c = 0; c < d; ++c)
-                            if (C[i][j][c] != 0.0) {
-                                ent_w.push_back(off2[P.paths[p].i2] + j); ent_w.push_back(P.paths[p].koff);
-                                ent_w.push_back(c); ent_w.push_back(f2i((float)C[i][j][c]));
-                            }
-                }
-            }
-            for (int i = d1; i < 6; ++i) rec[G_IB0 + i] = (int32_t)(ent_w.size() / ENT_W);
-            int nj = 0;
-            for (int p : ps) {
-                const Irrep b = P.in2[P.paths[p].i2];
-                cg(a.l, b.l, o.l, C);
-                for (int j = 0; j < 2 * b.l + 1; ++j) {
-                    rec[G_JABS + nj] = off2[P.paths[p].i2] + j;
-                    rec[G_JB0 + nj] = (int32_t)(ent_w.size() / ENT_W);
-                    for (int i = 0; i < d1; ++i)
-                        for (int c = 0; c < d; ++c)
-                            if (C[i][j][c] != 0.0) {
-                                ent_w.push_back(i); ent_w.push_back(P.paths[p].koff); ent_w.push_back(c);
-                                ent_w.push_back(f2i((float)C[i][j][c]));
-                            }
-                    ++nj;
-                }
-            }
-            rec[G_NJ] = nj;
-            for (int j = nj; j < 10; ++j) rec[G_JB0 + j] = (int32_t)(ent_w.size() / ENT_W);
+            int np = 0;
+            for (int p = pbeg; p < pend; ++p)
+                if (P.paths[p].i1 == (int)i1) rec[G_P0 + np++] = p;
+            if (np == 0) continue;
+            maxnp = std::max(maxnp, np);
+            rec[G_OFF1] = off1[i1]; rec[G_L1] = P.in1[i1].l; rec[G_MUL1] = P.in1[i1].mul; rec[G_NP] = np;
+            const int g = (int)(grp_w.size() / GRP_W);
             grp_w.insert(grp_w.end(), rec, rec + GRP_W);
+            for (int u0 = 0; u0 < P.in1[i1].mul; u0 += 4) {
+                const int b = (int)(blk_w.size() / BLK_W) - blk0;
+                blk_w.push_back(g | (u0 << 16));
+                blk_w.push_back((int)sub_w.size() - sub0);
+                for (int pi = 0; pi < np; ++pi) sub_w.push_back(b | (pi << 16));
+            }
         }
-        const int mulp = (o.mul + 3) & ~3, Kp = (K + 3) & ~3;
+        const int nblk = (int)(blk_w.size() / BLK_W) - blk0, nsub = (int)sub_w.size() - sub0;
         // forward chunk width: least padding among {12, 8, 4} (ties: the wider), accumulators d * CW <= 40 registers
         int cw = 4, best = 1 << 30;
         for (int c : {12, 8, 4}) {
@@ -230,22 +194,26 @@ inline bool build_plan(Plan& P) {
             const int padded = (o.mul + c - 1) / c * c;
             if (padded < best) { best = padded; cw = c; }
         }
-        const int mulpf = best;
         int32_t rec[IO_W] = {0};
-        rec[IO_CW] = cw; rec[IO_MULP] = mulpf; rec[IO_NQ] = mulpf / cw;
+        rec[IO_CW] = cw; rec[IO_MULP] = best; rec[IO_NQ] = best / cw;
         rec[IO_MUL] = o.mul; rec[IO_D] = d; rec[IO_OFF] = offo[io]; rec[IO_K] = K; rec[IO_WOFF] = woff0;
-        rec[IO_A] = f2i(P.a[io]); rec[IO_PBEG] = pbeg; rec[IO_PEND] = pend; rec[IO_GBEG] = gbeg;
-        rec[IO_GEND] = (int32_t)(grp_w.size() / GRP_W); rec[IO_WSOFF] = wsoff; rec[IO_WTOFF] = wtoff;
+        rec[IO_A] = f2i(P.a[io]); rec[IO_PBEG] = pbeg; rec[IO_PEND] = pend; rec[IO_WSOFF] = wsoff;
+        rec[IO_WTOFF] = wtoff; rec[IO_NBLK] = nblk; rec[IO_BLK] = blk0 * BLK_W; rec[IO_NSUB] = nsub; rec[IO_SUB] = sub0;
+        rec[IO_NWB_MAGIC] = (int32_t)(uint32_t)((0x100000000ull + (uint64_t)((o.mul + 3) / 4) - 1) / (uint64_t)((o.mul + 3) / 4));
         io_w.insert(io_w.end(), rec, rec + IO_W);
-        wsoff += K * mulpf;
-        wtoff += o.mul * Kp;
-        if (Kp > kpmax) kpmax = Kp;
-        if (d > dmax) dmax = d;
-        if (mulp > mulpmax) mulpmax = mulp;
+        wsoff += K * best;
+        wtoff += o.mul * 4 * nsub;
+        const int rp = (TE_BWD * d) | 1;
+        frow = std::max(frow, rp);
+        gtmax = std::max(gtmax, ((o.mul + 3) & ~3) * rp);
     }
     P.nW = woff;
     if (P.nW == 0) {
         P.err = "o3tp: no path connects in1 x in2 to out";
+        return false;
+    }
+    if (P.paths.size() >= 65536 || P.in2.size() > MAXP) {
+        P.err = "o3tp: too many paths";
         return false;
     }
     std::vector<int32_t>& B = P.blob;
@@ -253,10 +221,11 @@ inline bool build_plan(Plan& P) {
     B[H_NIO] = (int32_t)P.out.size(); B[H_D1] = P.D1; B[H_D2] = P.D2; B[H_DOUT] = P.Dout;
     B[H_IO] = (int32_t)B.size(); B.insert(B.end(), io_w.begin(), io_w.end());
     B[H_PATH] = (int32_t)B.size(); B.insert(B.end(), path_w.begin(), path_w.end());
+    B[H_BLK] = (int32_t)B.size(); B.insert(B.end(), blk_w.begin(), blk_w.end());
     B[H_GRP] = (int32_t)B.size(); B.insert(B.end(), grp_w.begin(), grp_w.end());
-    B[H_ENT] = (int32_t)B.size(); B.insert(B.end(), ent_w.begin(), ent_w.end());
+    B[H_SUB] = (int32_t)B.size(); B.insert(B.end(), sub_w.begin(), sub_w.end());
     while (B.size() % 4) B.push_back(0);
-    B[H_WORDS] = B[H_BASE] = (int32_t)B.size(); B[H_NW] = P.nW; B[H_KPMAX] = kpmax; B[H_DMAX] = dmax; B[H_MULPMAX] = mulpmax;
+    B[H_WORDS] = B[H_BASE] = (int32_t)B.size(); B[H_NW] = P.nW; B[H_FROW] = frow; B[H_GTMAX] = gtmax; B[H_MAXNP] = maxnp;
     B[H_NPATH] = (int32_t)P.paths.size(); B[H_NWP] = wsoff; B[H_NWT] = wtoff;
     return true;
 }
@@ -308,10 +277,12 @@ inline void schedule_forward(Plan& P, int TE) {
 inline size_t fwd_floats(const std::vector<int32_t>& B, int TE) {
     return (size_t)B[H_NWP] + (size_t)TE * ((B[H_D1] | 1) + (B[H_D2] | 1) + (B[H_DOUT] | 1)) + 8;
 }
-inline size_t bwd_floats(const std::vector<int32_t>& B, int TE) {
-    const size_t Rp = (size_t)(TE * B[H_DMAX]) | 1;
-    return (size_t)B[H_NWT] + (size_t)B[H_NW] + (size_t)TE * (2 * (B[H_D1] | 1) + 2 * (B[H_D2] | 1) + (B[H_DOUT] | 1)) +
-           (size_t)(2 * B[H_KPMAX] + B[H_MULPMAX]) * Rp + 8;
+// backward (TE_BWD rows): resident transposed weights + gradient accumulators, x / gx / y / gy / g tiles, one round of
+// features (4 rows per warp and path slot), the scaled transposed cotangent of one output irrep, and the scratch of
+// the sliced weight-gradient partial sums (16 per thread)
+inline size_t bwd_floats(const std::vector<int32_t>& B, bool resident_gw = true) {
+    return (size_t)B[H_NWT] + (resident_gw ? (size_t)B[H_NW] : 0) + (size_t)TE_BWD * (2 * (B[H_D1] | 1) + 2 * (B[H_D2] | 1) + (B[H_DOUT] | 1)) +
+           (size_t)4 * B[H_MAXNP] * NWARP * B[H_FROW] + (size_t)B[H_GTMAX] + 16 * 32 * NWARP + 8;
 }
 
 }  // namespace o3

@@ -16,6 +16,8 @@ inline float i2f(int32_t i) { float f; std::memcpy(&f, &i, 4); return f; }
 #define O3_THREADS for (int tid = 0; tid < NT_; ++tid) { const int NT = NT_;
 #define O3_END }
 #define O3_ATOMIC_ADD(p, v) (*(p) += (v))
+#define O3_GW_ADD(S, p, v) (*(p) += (v))
+#define O3_MULHI(a, b) ((unsigned)(((unsigned long long)(a) * (unsigned long long)(b)) >> 32))
 #define O3_I2F(i) i2f(i)
 #define O3_NT_DECL , int NT_
 #define O3_LD4(p) (o3f4{(p)[0], (p)[1], (p)[2], (p)[3]})
@@ -91,34 +93,42 @@ int emu_forward(int n1, const int* in1i, int n2, const int* in2i, int no, const 
 
 int emu_backward(int n1, const int* in1i, int n2, const int* in2i, int no, const int* outi, long long rows,
                  const float* in1, const float* in2, const float* w, const float* gout, float* gin1, float* gin2,
-                 float* gw, int TE, int NT, int nblocks) {
+                 float* gw, int NT, int nblocks) {
     o3::Plan P;
     if (!make_plan(P, n1, in1i, n2, in2i, no, outi)) return -1;
+    if (NT != 32 * o3::NWARP) return -2;  // one block of <= 4 channels per warp and round
     const int32_t* tab = P.blob.data();
+    constexpr int TE = o3::TE_BWD;
     const long long ntiles = (rows + TE - 1) / TE;
     for (int i = 0; i < P.nW; ++i) gw[i] = 0.f;
     for (int b = 0; b < nblocks; ++b) {
-        std::vector<float> sm(o3::bwd_floats(P.blob, TE), -1e30f);
+        std::vector<float> sm(o3::bwd_floats(P.blob), -1e30f);
         float* fl = sm.data();
         float* WT = fl; fl += tab[o3::H_NWT];
         float* gWs = fl; fl += tab[o3::H_NW];
         const int D1p = tab[o3::H_D1] | 1, D2p = tab[o3::H_D2] | 1, DOp = tab[o3::H_DOUT] | 1;
         O3Bwd S;
-        S.tab = tab; S.WT = WT; S.gWs = gWs; S.TE = TE; S.Rp = (TE * tab[o3::H_DMAX]) | 1;
+        S.tab = tab; S.WT = WT; S.gWs = gWs; S.gw_global = 0;
         S.xs = fl; fl += TE * D1p;
         S.gxs = fl; fl += TE * D1p;
         S.ys = fl; fl += TE * D2p;
         S.gys = fl; fl += TE * D2p;
         S.gs = fl; fl += TE * DOp;
-        S.F = fl; fl += (size_t)tab[o3::H_KPMAX] * S.Rp;
-        S.G = fl; fl += (size_t)tab[o3::H_KPMAX] * S.Rp;
-        S.GT = fl;
+        S.F = fl; fl += (size_t)4 * tab[o3::H_MAXNP] * o3::NWARP * tab[o3::H_FROW];
+        S.GT = fl; fl += tab[o3::H_GTMAX];
+        S.scr = fl;
         for (int io = 0; io < tab[o3::H_NIO]; ++io) {
             const int32_t* IO = tab + tab[o3::H_IO] + io * o3::IO_W;
-            const int mul = IO[o3::IO_MUL], K = IO[o3::IO_K], Kp = (K + 3) & ~3;
-            for (int idx = 0; idx < mul * Kp; ++idx) {
-                const int wi = idx / Kp, kk = idx - wi * Kp;
-                WT[IO[o3::IO_WTOFF] + idx] = kk < K ? w[IO[o3::IO_WOFF] + kk * mul + wi] : 0.f;
+            const int32_t* BL = tab + tab[o3::H_BLK] + IO[o3::IO_BLK];
+            const int32_t* SUB = tab + tab[o3::H_SUB] + IO[o3::IO_SUB];
+            const int mul = IO[o3::IO_MUL], KPP = 4 * IO[o3::IO_NSUB];
+            for (int idx = 0; idx < mul * KPP; ++idx) {
+                const int wi = idx / KPP, kkp = idx - wi * KPP, word = SUB[kkp >> 2];
+                const int32_t* B = BL + (word & 0xffff) * o3::BLK_W;
+                const int32_t* G = tab + tab[o3::H_GRP] + (B[o3::B_GRP] & 0xffff) * o3::GRP_W;
+                const int32_t* PP = tab + tab[o3::H_PATH] + G[o3::G_P0 + (word >> 16)] * o3::PATH_W;
+                const int u = (B[o3::B_GRP] >> 16) + (kkp & 3);
+                WT[IO[o3::IO_WTOFF] + idx] = u < G[o3::G_MUL1] ? w[PP[o3::P_WOFF] + u * mul + wi] : 0.f;
             }
         }
         for (int idx = 0; idx < tab[o3::H_NW]; ++idx) gWs[idx] = 0.f;

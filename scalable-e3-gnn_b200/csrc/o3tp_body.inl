@@ -283,20 +283,17 @@ O3_DEV void o3_bwd_reduce(const O3Bwd& S, const O3Pending& Q, int tid, int NT) {
     const unsigned magic = (unsigned)IO[o3::IO_NWB_MAGIC];
     const int32_t* BL = tab + tab[o3::H_BLK] + IO[o3::IO_BLK];
     const int32_t* SUB = tab + tab[o3::H_SUB] + IO[o3::IO_SUB];
-    for (int t = tid; t < base; t += NT) {     // base <= NT / 2 here: one output block per thread
+    for (int o = tid; o < (base << 4); o += NT) {     // one of the 16 entries of a 4 x 4 block per thread
+        const int k = o & 15, t = o >> 4;
+        float sum = 0.f;
+        for (int s = 0; s < (1 << Q.lg); ++s) sum += S.scr[k * (NT + 1) + o3_scr_index(t, s, Q.lg)];
         const int sb = nwb == 1 ? t : (int)O3_MULHI((unsigned)t, magic), wb = t - sb * nwb;
         const int word = SUB[Q.sbeg + sb];
         const int32_t* B = BL + (word & 0xffff) * o3::BLK_W;
         const int32_t* G = tab + tab[o3::H_GRP] + (B[o3::B_GRP] & 0xffff) * o3::GRP_W;
         const int32_t* P = tab + tab[o3::H_PATH] + G[o3::G_P0 + (word >> 16)] * o3::PATH_W;
-        const int u0 = B[o3::B_GRP] >> 16;
-        float* gw = S.gWs + P[o3::P_WOFF] + u0 * mul + 4 * wb;
-        O3_UNROLL
-        for (int k = 0; k < 16; ++k) {
-            float sum = 0.f;
-            for (int s = 0; s < (1 << Q.lg); ++s) sum += S.scr[k * NT + o3_scr_index(t, s, Q.lg)];
-            if (u0 + (k >> 2) < G[o3::G_MUL1] && 4 * wb + (k & 3) < mul) O3_GW_ADD(S, gw + (k >> 2) * mul + (k & 3), sum);
-        }
+        const int u = (B[o3::B_GRP] >> 16) + (k >> 2), w = 4 * wb + (k & 3);
+        if (u < G[o3::G_MUL1] && w < mul) O3_GW_ADD(S, S.gWs + P[o3::P_WOFF] + u * mul + w, sum);
     }
 }
 
@@ -407,7 +404,7 @@ O3_DEV void o3_bwd_tile(const O3Bwd& S, const float* __restrict__ in1, const flo
                         O3_UNROLL
                         for (int i = 0; i < 4; ++i)
                             O3_UNROLL
-                            for (int j = 0; j < 4; ++j) S.scr[(4 * i + j) * NT + idx] = acc[i][j];
+                            for (int j = 0; j < 4; ++j) S.scr[(4 * i + j) * (NT + 1) + idx] = acc[i][j];
                     } else {        // this thread owns the 4 x 4 weight block
                         const int32_t* B = BL + (word & 0xffff) * o3::BLK_W;
                         const int32_t* G = tab + tab[o3::H_GRP] + (B[o3::B_GRP] & 0xffff) * o3::GRP_W;

@@ -161,6 +161,8 @@ inline bool build_plan(Plan& P) {
         const int pend = (int)P.paths.size();
         P.a[io] = K > 0 ? (float)std::sqrt((double)d / (double)K) : 0.f;
         const int blk0 = (int)(blk_w.size() / BLK_W), sub0 = (int)sub_w.size();
+        struct Blk { int g, u0, np; double cost; };
+        std::vector<Blk> pending;
         for (int p = pbeg; p < pend; ++p) {
             const PathH& ph = P.paths[p];
             const Irrep a = P.in1[ph.i1], b = P.in2[ph.i2];
@@ -179,12 +181,18 @@ inline bool build_plan(Plan& P) {
             rec[G_OFF1] = off1[i1]; rec[G_L1] = P.in1[i1].l; rec[G_MUL1] = P.in1[i1].mul; rec[G_NP] = np;
             const int g = (int)(grp_w.size() / GRP_W);
             grp_w.insert(grp_w.end(), rec, rec + GRP_W);
-            for (int u0 = 0; u0 < P.in1[i1].mul; u0 += 4) {
-                const int b = (int)(blk_w.size() / BLK_W) - blk0;
-                blk_w.push_back(g | (u0 << 16));
-                blk_w.push_back((int)sub_w.size() - sub0);
-                for (int pi = 0; pi < np; ++pi) sub_w.push_back(b | (pi << 16));
-            }
+            // instruction estimate of one block: per path the G contraction over mul outputs + 4 channels of coupling work
+            const int d1 = 2 * P.in1[i1].l + 1;
+            const double cost = np * (o.mul * (5.0 * d + 2) + 4.0 * (d1 + 3.0 * d1 * d + d) + 40);
+            for (int u0 = 0; u0 < P.in1[i1].mul; u0 += 4) pending.push_back({g, u0, np, cost});
+        }
+        // heaviest blocks first, so that the NWARP blocks of a round cost about the same (a round ends at a barrier)
+        std::stable_sort(pending.begin(), pending.end(), [](const Blk& x, const Blk& y) { return x.cost > y.cost; });
+        for (const Blk& k : pending) {
+            const int b = (int)(blk_w.size() / BLK_W) - blk0;
+            blk_w.push_back(k.g | (k.u0 << 16));
+            blk_w.push_back((int)sub_w.size() - sub0);
+            for (int pi = 0; pi < k.np; ++pi) sub_w.push_back(b | (pi << 16));
         }
         const int nblk = (int)(blk_w.size() / BLK_W) - blk0, nsub = (int)sub_w.size() - sub0;
         // forward chunk width: least padding among {12, 8, 4} (ties: the wider), accumulators d * CW <= 40 registers
@@ -282,7 +290,7 @@ inline size_t fwd_floats(const std::vector<int32_t>& B, int TE) {
 // the sliced weight-gradient partial sums (16 per thread)
 inline size_t bwd_floats(const std::vector<int32_t>& B, bool resident_gw = true) {
     return (size_t)B[H_NWT] + (resident_gw ? (size_t)B[H_NW] : 0) + (size_t)TE_BWD * (2 * (B[H_D1] | 1) + 2 * (B[H_D2] | 1) + (B[H_DOUT] | 1)) +
-           (size_t)4 * B[H_MAXNP] * NWARP * B[H_FROW] + (size_t)B[H_GTMAX] + 16 * 32 * NWARP + 8;
+           (size_t)4 * B[H_MAXNP] * NWARP * B[H_FROW] + (size_t)B[H_GTMAX] + 16 * (32 * NWARP + 1) + 8;
 }
 
 }  // namespace o3

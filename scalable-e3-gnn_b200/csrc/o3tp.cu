@@ -29,6 +29,7 @@ typedef float4 o3f4;
 #define O3_NT_DECL
 #define O3_LD4(p) (*reinterpret_cast<const float4*>(p))
 #define O3_UNROLL _Pragma("unroll")
+#define O3_UNROLL2 _Pragma("unroll 2")
 #include "o3tp_cg_gen.inl"
 #include "o3tp_body.inl"
 
@@ -81,6 +82,8 @@ __global__ void __launch_bounds__(O3_NT) o3tp_bwd_kernel(const int32_t* __restri
     float* fl = reinterpret_cast<float*>(o3_sm + tab[o3::H_WORDS]);
     float* WT = fl;
     fl += tab[o3::H_NWT];
+    float* scr = fl;  // 16-byte aligned: read with float4
+    fl += 16 * O3_SCR_LD;
     float* gWs = gw_global ? gw : fl;
     if (!gw_global) fl += tab[o3::H_NW];
     constexpr int TE = o3::TE_BWD;
@@ -93,8 +96,8 @@ __global__ void __launch_bounds__(O3_NT) o3tp_bwd_kernel(const int32_t* __restri
     S.gys = fl; fl += TE * D2p;
     S.gs = fl; fl += TE * DOp;
     S.F = fl; fl += (size_t)4 * tab[o3::H_MAXNP] * o3::NWARP * tab[o3::H_FROW];
-    S.GT = fl; fl += tab[o3::H_GTMAX];
-    S.scr = fl;
+    S.GT = fl;
+    S.scr = scr;
     for (int io = 0; io < tab[o3::H_NIO]; ++io) {
         const int32_t* IO = tab + tab[o3::H_IO] + io * o3::IO_W;
         const int32_t* BL = tab + tab[o3::H_BLK] + IO[o3::IO_BLK];

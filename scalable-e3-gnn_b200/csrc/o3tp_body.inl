@@ -11,7 +11,7 @@
 //   O3_I2F(i)                  reinterpret an int32 table word as float
 //   O3_NT_DECL                 extra parameter `, int NT_` carrying the emulated block size (empty under nvcc)
 //   o3f4 / O3_LD4(p)           four consecutive floats read from a 16-byte aligned shared-memory address
-//   O3_UNROLL                  unroll pragma
+//   O3_UNROLL / O3_UNROLL2     unroll pragmas (full / by two)
 //
 // Math (oracle/lmax2_oracle.py forward): for every output irrep io with stacked paths,
 //   f[kk, e, c]   = sum_{i,j} C_p[i,j,c] x1[e, off1_p + u d1 + i] y[e, off2_p + j]     kk = koff_p + u
@@ -271,9 +271,9 @@ struct O3Pending {
     int sbeg, nsb, lg;  // lg = log2(slices); -1: nothing pending
 };
 
-// scratch index of partial sum (t, s): rows of 32 words, the slice index rotated by the row so that both the writers
-// (lanes = consecutive (t, s)) and the readers (lanes = consecutive t, fixed s) are bank-conflict free
-O3_DEV int o3_scr_index(int t, int s, int lg) { return (t << lg) + ((s + ((t << lg) >> 5)) & ((1 << lg) - 1)); }
+// Scratch of the sliced partial sums: scr[k * O3_SCR_LD + (t << lg) + s] for entry k of the 4 x 4 block of item t, slice
+// s.  Writers (lanes = consecutive items) and readers (lanes = consecutive k, 16-byte loads over s) are conflict free.
+#define O3_SCR_LD (32 * o3::NWARP + 4)
 
 O3_DEV void o3_bwd_reduce(const O3Bwd& S, const O3Pending& Q, int tid, int NT) {
     if (Q.lg <= 0) return;
@@ -286,7 +286,15 @@ O3_DEV void o3_bwd_reduce(const O3Bwd& S, const O3Pending& Q, int tid, int NT) {
     for (int o = tid; o < (base << 4); o += NT) {     // one of the 16 entries of a 4 x 4 block per thread
         const int k = o & 15, t = o >> 4;
         float sum = 0.f;
-        for (int s = 0; s < (1 << Q.lg); ++s) sum += S.scr[k * (NT + 1) + o3_scr_index(t, s, Q.lg)];
+        const float* ps = S.scr + k * O3_SCR_LD + (t << Q.lg);
+        if (Q.lg >= 2) {
+            for (int s4 = 0; s4 < (1 << Q.lg); s4 += 4) {
+                const o3f4 v = O3_LD4(ps + s4);
+                sum += (v.x + v.y) + (v.z + v.w);
+            }
+        } else {
+            sum = ps[0] + ps[1];
+        }
         const int sb = nwb == 1 ? t : (int)O3_MULHI((unsigned)t, magic), wb = t - sb * nwb;
         const int word = SUB[Q.sbeg + sb];
         const int32_t* B = BL + (word & 0xffff) * o3::BLK_W;
@@ -391,6 +399,7 @@ O3_DEV void o3_bwd_tile(const O3Bwd& S, const float* __restrict__ in1, const flo
                     for (int i = 0; i < 4; ++i)
                         O3_UNROLL
                         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+                    O3_UNROLL2
                     for (int r = r0; r < r1; ++r) {
                         const float f0 = f[r], f1 = f[Rp + r], f2 = f[2 * Rp + r], f3 = f[3 * Rp + r];
                         const float g0 = g[r], g1 = g[Rp + r], g2 = g[2 * Rp + r], g3 = g[3 * Rp + r];
@@ -400,11 +409,10 @@ O3_DEV void o3_bwd_tile(const O3Bwd& S, const float* __restrict__ in1, const flo
                         acc[3][0] += f3 * g0; acc[3][1] += f3 * g1; acc[3][2] += f3 * g2; acc[3][3] += f3 * g3;
                     }
                     if (lg > 0) {   // item < NT here: one scratch column per thread
-                        const int idx = o3_scr_index(t, s, lg);
                         O3_UNROLL
                         for (int i = 0; i < 4; ++i)
                             O3_UNROLL
-                            for (int j = 0; j < 4; ++j) S.scr[(4 * i + j) * (NT + 1) + idx] = acc[i][j];
+                            for (int j = 0; j < 4; ++j) S.scr[(4 * i + j) * O3_SCR_LD + item] = acc[i][j];
                     } else {        // this thread owns the 4 x 4 weight block
                         const int32_t* B = BL + (word & 0xffff) * o3::BLK_W;
                         const int32_t* G = tab + tab[o3::H_GRP] + (B[o3::B_GRP] & 0xffff) * o3::GRP_W;

@@ -290,7 +290,7 @@ inline size_t fwd_floats(const std::vector<int32_t>& B, int TE) {
 // the sliced weight-gradient partial sums (16 per thread)
 inline size_t bwd_floats(const std::vector<int32_t>& B, bool resident_gw = true) {
     return (size_t)B[H_NWT] + (resident_gw ? (size_t)B[H_NW] : 0) + (size_t)TE_BWD * (2 * (B[H_D1] | 1) + 2 * (B[H_D2] | 1) + (B[H_DOUT] | 1)) +
-           (size_t)4 * B[H_MAXNP] * NWARP * B[H_FROW] + (size_t)B[H_GTMAX] + 16 * (32 * NWARP + 1) + 8;
+           (size_t)4 * B[H_MAXNP] * NWARP * B[H_FROW] + (size_t)B[H_GTMAX] + 16 * (32 * NWARP + 4) + 8;
 }
 
 }  // namespace o3

@@ -22,6 +22,7 @@ inline float i2f(int32_t i) { float f; std::memcpy(&f, &i, 4); return f; }
 #define O3_NT_DECL , int NT_
 #define O3_LD4(p) (o3f4{(p)[0], (p)[1], (p)[2], (p)[3]})
 #define O3_UNROLL
+#define O3_UNROLL2
 #define __restrict__
 #include "../../scalable-e3-gnn_b200/csrc/o3tp_cg_gen.inl"
 #include "../../scalable-e3-gnn_b200/csrc/o3tp_body.inl"
@@ -105,6 +106,7 @@ int emu_backward(int n1, const int* in1i, int n2, const int* in2i, int no, const
         std::vector<float> sm(o3::bwd_floats(P.blob), -1e30f);
         float* fl = sm.data();
         float* WT = fl; fl += tab[o3::H_NWT];
+        float* scr = fl; fl += 16 * O3_SCR_LD;
         float* gWs = fl; fl += tab[o3::H_NW];
         const int D1p = tab[o3::H_D1] | 1, D2p = tab[o3::H_D2] | 1, DOp = tab[o3::H_DOUT] | 1;
         O3Bwd S;
@@ -115,8 +117,8 @@ int emu_backward(int n1, const int* in1i, int n2, const int* in2i, int no, const
         S.gys = fl; fl += TE * D2p;
         S.gs = fl; fl += TE * DOp;
         S.F = fl; fl += (size_t)4 * tab[o3::H_MAXNP] * o3::NWARP * tab[o3::H_FROW];
-        S.GT = fl; fl += tab[o3::H_GTMAX];
-        S.scr = fl;
+        S.GT = fl;
+        S.scr = scr;
         for (int io = 0; io < tab[o3::H_NIO]; ++io) {
             const int32_t* IO = tab + tab[o3::H_IO] + io * o3::IO_W;
             const int32_t* BL = tab + tab[o3::H_BLK] + IO[o3::IO_BLK];

@@ -25,6 +25,12 @@ typedef float4 o3f4;
             *(p) += (v);                 \
     } while (0)
 #define O3_I2F(i) __int_as_float(i)
+#define O3_CP4(dst, src)                                                                                      \
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), \
+                 "l"(src)                                                                                    \
+                 : "memory")
+#define O3_CP_COMMIT() asm volatile("cp.async.commit_group;" ::: "memory")
+#define O3_CP_WAIT() asm volatile("cp.async.wait_all;" ::: "memory")
 #define O3_MULHI(a, b) __umulhi((a), (b))
 #define O3_NT_DECL
 #define O3_LD4(p) (*reinterpret_cast<const float4*>(p))
@@ -52,9 +58,15 @@ __global__ void __launch_bounds__(O3_NT) o3tp_fwd_kernel(const int32_t* __restri
     fl += tab[o3::H_NWP];
     O3Fwd S;
     S.tab = tab; S.Ws = Ws; S.TE = TE;
-    S.xs = fl; fl += TE * (tab[o3::H_D1] | 1);
-    S.ys = fl; fl += TE * (tab[o3::H_D2] | 1);
+    S.xs0 = fl; fl += TE * (tab[o3::H_D1] | 1);
+    S.xs1 = fl; fl += TE * (tab[o3::H_D1] | 1);
+    S.ys0 = fl; fl += TE * (tab[o3::H_D2] | 1);
+    S.ys1 = fl; fl += TE * (tab[o3::H_D2] | 1);
     S.os = fl;
+    const long long ntiles = (rows + TE - 1) / TE;
+    if ((long long)blockIdx.x < ntiles)
+        o3_fwd_load(S, 0, in1, in2, (long long)blockIdx.x * TE, (int)min((long long)TE, rows - (long long)blockIdx.x * TE),
+                    threadIdx.x, blockDim.x);
     for (int io = 0; io < tab[o3::H_NIO]; ++io) {
         const int32_t* IO = tab + tab[o3::H_IO] + io * o3::IO_W;
         const int mul = IO[o3::IO_MUL], K = IO[o3::IO_K], mulp = IO[o3::IO_MULP];
@@ -64,11 +76,12 @@ __global__ void __launch_bounds__(O3_NT) o3tp_fwd_kernel(const int32_t* __restri
         }
     }
     __syncthreads();
-    const long long ntiles = (rows + TE - 1) / TE;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const long long row0 = tile * TE;
+    int buf = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+        const long long row0 = tile * TE, next = tile + gridDim.x;
         const int nrow = (int)min((long long)TE, rows - row0);
-        o3_fwd_tile(S, in1, in2, out, row0, nrow);
+        const int nrow_next = next < ntiles ? (int)min((long long)TE, rows - next * TE) : 0;
+        o3_fwd_tile(S, buf, in1, in2, out, row0, nrow, next * TE, nrow_next);
     }
 }
 

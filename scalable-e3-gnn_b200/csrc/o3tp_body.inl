@@ -8,6 +8,7 @@
 //   O3_ATOMIC_ADD(p, v)        shared-memory float add that tolerates several threads on one address
 //   O3_GW_ADD(S, p, v)         weight-gradient accumulation: plain add, or a global atomic add when S.gw_global
 //   O3_MULHI(a, b)             high 32 bits of the unsigned 32 x 32 product
+//   O3_CP4(dst, src) / O3_CP_COMMIT() / O3_CP_WAIT()   4-byte asynchronous global -> shared copy, group commit, wait all
 //   O3_I2F(i)                  reinterpret an int32 table word as float
 //   O3_NT_DECL                 extra parameter `, int NT_` carrying the emulated block size (empty under nvcc)
 //   o3f4 / O3_LD4(p)           four consecutive floats read from a 16-byte aligned shared-memory address
@@ -26,7 +27,7 @@
 struct O3Fwd {
     const int32_t* tab;  // table blob (shared memory)
     const float* Ws;     // all weights, per io [K, IO_MULP] zero padded (shared, resident)
-    float *xs, *ys, *os;
+    float *xs0, *xs1, *ys0, *ys1, *os;  // double-buffered input tiles, output tile
     int TE;
 };
 
@@ -107,32 +108,53 @@ O3_DEV void o3_fwd_unit(const int32_t* tab, const int32_t* IO, const float* xe, 
         }
 }
 
-O3_DEV void o3_fwd_tile(const O3Fwd& S, const float* __restrict__ in1, const float* __restrict__ in2,
-                        float* __restrict__ out, long long row0, int nrow O3_NT_DECL) {
+// asynchronous copy of one tile of both inputs into buffer `buf` (rows past the end are zero filled)
+O3_DEV void o3_fwd_load(const O3Fwd& S, int buf, const float* __restrict__ in1, const float* __restrict__ in2,
+                        long long row0, int nrow, int tid, int NT) {
+    const int32_t* tab = S.tab;
+    const int D1 = tab[o3::H_D1], D2 = tab[o3::H_D2], D1p = D1 | 1, D2p = D2 | 1;
+    float* xs = buf ? S.xs1 : S.xs0;
+    float* ys = buf ? S.ys1 : S.ys0;
+    const int warp = tid >> 5, lane = tid & 31, nw = NT >> 5;
+    for (int e = warp; e < S.TE; e += nw) {
+        if (e < nrow) {
+            const float* src = in1 + (row0 + e) * D1;
+            for (int c = lane; c < D1; c += 32) O3_CP4(xs + e * D1p + c, src + c);
+            if (lane < D2) O3_CP4(ys + e * D2p + lane, in2 + (row0 + e) * D2 + lane);
+        } else {
+            for (int c = lane; c < D1; c += 32) xs[e * D1p + c] = 0.f;
+            if (lane < D2) ys[e * D2p + lane] = 0.f;
+        }
+    }
+    O3_CP_COMMIT();
+}
+
+// One tile: the inputs of this tile were requested earlier into buffer `buf` (by the previous call, or by the
+// prologue for the first tile); the next tile (nrow_next > 0) is requested into the other buffer before computing.
+O3_DEV void o3_fwd_tile(const O3Fwd& S, int buf, const float* __restrict__ in1, const float* __restrict__ in2,
+                        float* __restrict__ out, long long row0, int nrow, long long row0_next,
+                        int nrow_next O3_NT_DECL) {
     const int32_t* tab = S.tab;
     const int D1 = tab[o3::H_D1], D2 = tab[o3::H_D2], DO = tab[o3::H_DOUT];
-    const int D1p = D1 | 1, D2p = D2 | 1, DOp = DO | 1, TE = S.TE;
+    const int D1p = D1 | 1, D2p = D2 | 1, DOp = DO | 1;
+    const float* xs = buf ? S.xs1 : S.xs0;
+    const float* ys = buf ? S.ys1 : S.ys0;
 
     O3_THREADS
-        const int warp = tid >> 5, lane = tid & 31, nw = NT >> 5;
-        for (int e = warp; e < TE; e += nw) {
-            const bool ok = e < nrow;
-            const float* src = in1 + (row0 + e) * D1;
-            for (int c = lane; c < D1; c += 32) S.xs[e * D1p + c] = ok ? src[c] : 0.f;
-            if (lane < D2) S.ys[e * D2p + lane] = ok ? in2[(row0 + e) * D2 + lane] : 0.f;
-        }
+        (void)tid; (void)NT;
+        O3_CP_WAIT();
     O3_END
 
     O3_THREADS
+        if (nrow_next > 0) o3_fwd_load(S, buf ^ 1, in1, in2, row0_next, nrow_next, tid, NT);
         const int warp = tid >> 5, lane = tid & 31;
-        (void)NT;
         const int32_t* U = tab + tab[o3::H_UNIT];
         for (int k = U[warp]; k < U[warp + 1]; ++k) {
             const int packed = U[o3::NWARP + 1 + k];
             const int io = packed & 255, q = (packed >> 8) & 255, e = (packed >> 16) * 32 + lane;
             const int32_t* IO = tab + tab[o3::H_IO] + io * o3::IO_W;
-            const float* xe = S.xs + e * D1p;
-            const float* ye = S.ys + e * D2p;
+            const float* xe = xs + e * D1p;
+            const float* ye = ys + e * D2p;
             float* oe = S.os + e * DOp;
             switch (IO[o3::IO_D] * 16 + IO[o3::IO_CW]) {
                 case 1 * 16 + 4: o3_fwd_unit<0, 4>(tab, IO, xe, ye, S.Ws, oe, q); break;

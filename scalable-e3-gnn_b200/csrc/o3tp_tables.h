@@ -283,7 +283,7 @@ inline void schedule_forward(Plan& P, int TE) {
 
 // shared-memory floats of the tile programs (excluding the table), for a tile of TE rows
 inline size_t fwd_floats(const std::vector<int32_t>& B, int TE) {
-    return (size_t)B[H_NWP] + (size_t)TE * ((B[H_D1] | 1) + (B[H_D2] | 1) + (B[H_DOUT] | 1)) + 8;
+    return (size_t)B[H_NWP] + (size_t)TE * (2 * (B[H_D1] | 1) + 2 * (B[H_D2] | 1) + (B[H_DOUT] | 1)) + 8;
 }
 // backward (TE_BWD rows): resident transposed weights + gradient accumulators, x / gx / y / gy / g tiles, one round of
 // features (4 rows per warp and path slot), the scaled transposed cotangent of one output irrep, and the scratch of

@@ -23,6 +23,9 @@ inline float i2f(int32_t i) { float f; std::memcpy(&f, &i, 4); return f; }
 #define O3_LD4(p) (o3f4{(p)[0], (p)[1], (p)[2], (p)[3]})
 #define O3_UNROLL
 #define O3_UNROLL2
+#define O3_CP4(dst, src) (*(dst) = *(src))
+#define O3_CP_COMMIT()
+#define O3_CP_WAIT()
 #define __restrict__
 #include "../../scalable-e3-gnn_b200/csrc/o3tp_cg_gen.inl"
 #include "../../scalable-e3-gnn_b200/csrc/o3tp_body.inl"
@@ -73,9 +76,14 @@ int emu_forward(int n1, const int* in1i, int n2, const int* in2i, int no, const 
         float* Ws = fl; fl += tab[o3::H_NWP];
         O3Fwd S;
         S.tab = tab; S.Ws = Ws; S.TE = TE;
-        S.xs = fl; fl += TE * (tab[o3::H_D1] | 1);
-        S.ys = fl; fl += TE * (tab[o3::H_D2] | 1);
+        S.xs0 = fl; fl += TE * (tab[o3::H_D1] | 1);
+        S.xs1 = fl; fl += TE * (tab[o3::H_D1] | 1);
+        S.ys0 = fl; fl += TE * (tab[o3::H_D2] | 1);
+        S.ys1 = fl; fl += TE * (tab[o3::H_D2] | 1);
         S.os = fl;
+        if (b < ntiles)
+            for (int tid = 0; tid < NT; ++tid)
+                o3_fwd_load(S, 0, in1, in2, (long long)b * TE, (int)std::min<long long>(TE, rows - (long long)b * TE), tid, NT);
         for (int io = 0; io < tab[o3::H_NIO]; ++io) {
             const int32_t* IO = tab + tab[o3::H_IO] + io * o3::IO_W;
             const int mul = IO[o3::IO_MUL], K = IO[o3::IO_K], mulp = IO[o3::IO_MULP];
@@ -84,9 +92,11 @@ int emu_forward(int n1, const int* in1i, int n2, const int* in2i, int no, const 
                 Ws[IO[o3::IO_WSOFF] + idx] = c < mul ? w[IO[o3::IO_WOFF] + kk * mul + c] : 0.f;
             }
         }
-        for (long long tile = b; tile < ntiles; tile += nblocks) {
-            const long long row0 = tile * TE;
-            o3_fwd_tile(S, in1, in2, out, row0, (int)std::min<long long>(TE, rows - row0), NT);
+        int buf = 0;
+        for (long long tile = b; tile < ntiles; tile += nblocks, buf ^= 1) {
+            const long long row0 = tile * TE, next = tile + nblocks;
+            const int nrow_next = next < ntiles ? (int)std::min<long long>(TE, rows - next * TE) : 0;
+            o3_fwd_tile(S, buf, in1, in2, out, row0, (int)std::min<long long>(TE, rows - row0), next * TE, nrow_next, NT);
         }
     }
     return 0;

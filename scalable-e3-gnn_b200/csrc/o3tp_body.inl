@@ -35,7 +35,8 @@ struct O3Bwd {
     const int32_t* tab;
     const float* WT;  // all weights transposed, per io [mul, 4 * IO_NBLK] in block order (shared, resident)
     float* gWs;       // weight gradient accumulators, flat like the weights (shared, resident)
-    float *xs, *ys, *gs, *gxs, *gys, *F, *GT, *scr;
+    float *xs0, *xs1, *ys0, *ys1, *gs0, *gs1;  // double-buffered x / y / cotangent tiles
+    float *gxs, *gys, *F, *GT, *scr;
     int gw_global;  // gWs is the global result (weights too large to keep accumulators resident): add atomically
 };
 
@@ -327,33 +328,56 @@ O3_DEV void o3_bwd_reduce(const O3Bwd& S, const O3Pending& Q, int tid, int NT) {
     }
 }
 
-O3_DEV void o3_bwd_tile(const O3Bwd& S, const float* __restrict__ in1, const float* __restrict__ in2,
+// asynchronous copy of one tile of both inputs and of the cotangent into buffer `buf` (rows past the end: zeros)
+O3_DEV void o3_bwd_load(const O3Bwd& S, int buf, const float* __restrict__ in1, const float* __restrict__ in2,
+                        const float* __restrict__ gout, long long row0, int nrow, int tid, int NT) {
+    const int32_t* tab = S.tab;
+    const int D1 = tab[o3::H_D1], D2 = tab[o3::H_D2], DO = tab[o3::H_DOUT];
+    const int D1p = D1 | 1, D2p = D2 | 1, DOp = DO | 1;
+    float* xs = buf ? S.xs1 : S.xs0;
+    float* ys = buf ? S.ys1 : S.ys0;
+    float* gs = buf ? S.gs1 : S.gs0;
+    const int warp = tid >> 5, lane = tid & 31, nw = NT >> 5;
+    for (int e = warp; e < o3::TE_BWD; e += nw) {
+        if (e < nrow) {
+            const float* src = in1 + (row0 + e) * D1;
+            for (int c = lane; c < D1; c += 32) O3_CP4(xs + e * D1p + c, src + c);
+            if (lane < D2) O3_CP4(ys + e * D2p + lane, in2 + (row0 + e) * D2 + lane);
+            const float* gsrc = gout + (row0 + e) * DO;
+            for (int c = lane; c < DO; c += 32) O3_CP4(gs + e * DOp + c, gsrc + c);
+        } else {
+            for (int c = lane; c < D1; c += 32) xs[e * D1p + c] = 0.f;
+            if (lane < D2) ys[e * D2p + lane] = 0.f;
+            for (int c = lane; c < DO; c += 32) gs[e * DOp + c] = 0.f;
+        }
+    }
+    O3_CP_COMMIT();
+}
+
+// One tile; its inputs were requested earlier into buffer `buf`, the next tile (nrow_next > 0) is requested into the
+// other buffer at the start of the first compute region.
+O3_DEV void o3_bwd_tile(const O3Bwd& S, int buf, const float* __restrict__ in1, const float* __restrict__ in2,
                         const float* __restrict__ gout, float* __restrict__ gin1, float* __restrict__ gin2,
-                        long long row0, int nrow O3_NT_DECL) {
+                        long long row0, int nrow, long long row0_next, int nrow_next O3_NT_DECL) {
     const int32_t* tab = S.tab;
     const int D1 = tab[o3::H_D1], D2 = tab[o3::H_D2], DO = tab[o3::H_DOUT], nio = tab[o3::H_NIO];
     const int D1p = D1 | 1, D2p = D2 | 1, DOp = DO | 1;
     constexpr int TE = o3::TE_BWD;
+    const float* xs = buf ? S.xs1 : S.xs0;
+    const float* ys = buf ? S.ys1 : S.ys0;
+    const float* gs = buf ? S.gs1 : S.gs0;
     O3Pending Q;
     Q.IO = nullptr; Q.sbeg = 0; Q.nsb = 0; Q.lg = -1;
 
     O3_THREADS
+        O3_CP_WAIT();
         const int warp = tid >> 5, lane = tid & 31, nw = NT >> 5;
         for (int e = warp; e < TE; e += nw) {
-            const bool ok = e < nrow;
-            const float* src = in1 + (row0 + e) * D1;
-            for (int c = lane; c < D1; c += 32) {
-                S.xs[e * D1p + c] = ok ? src[c] : 0.f;
-                S.gxs[e * D1p + c] = 0.f;
-            }
-            if (lane < D2) {
-                S.ys[e * D2p + lane] = ok ? in2[(row0 + e) * D2 + lane] : 0.f;
-                S.gys[e * D2p + lane] = 0.f;
-            }
-            const float* gsrc = gout + (row0 + e) * DO;
-            for (int c = lane; c < DO; c += 32) S.gs[e * DOp + c] = ok ? gsrc[c] : 0.f;
+            for (int c = lane; c < D1; c += 32) S.gxs[e * D1p + c] = 0.f;
+            if (lane < D2) S.gys[e * D2p + lane] = 0.f;
         }
     O3_END
+    bool prefetch = nrow_next > 0;
 
     for (int io = 0; io < nio; ++io) {
         const int32_t* IO = tab + tab[o3::H_IO] + io * o3::IO_W;
@@ -363,14 +387,16 @@ O3_DEV void o3_bwd_tile(const O3Bwd& S, const float* __restrict__ in1, const flo
         const int32_t* SUB = tab + tab[o3::H_SUB] + IO[o3::IO_SUB];
         if (nblk == 0) continue;  // block-uniform
         O3_THREADS
+            if (prefetch) o3_bwd_load(S, buf ^ 1, in1, in2, gout, row0_next, nrow_next, tid, NT);
             o3_bwd_reduce(S, Q, tid, NT);
             const float a = O3_I2F(IO[o3::IO_A]);
             const int warp = tid >> 5, lane = tid & 31, nw = NT >> 5;
             for (int w = warp; w < mulp; w += nw)
                 for (int c = 0; c < d; ++c)
-                    S.GT[(size_t)w * Rp + lane * d + c] = w < mul ? a * S.gs[lane * DOp + IO[o3::IO_OFF] + w * d + c] : 0.f;
+                    S.GT[(size_t)w * Rp + lane * d + c] = w < mul ? a * gs[lane * DOp + IO[o3::IO_OFF] + w * d + c] : 0.f;
         O3_END
         Q.lg = -1;
+        prefetch = false;
         for (int b0 = 0; b0 < nblk; b0 += o3::NWARP) {
             O3_THREADS
                 o3_bwd_reduce(S, Q, tid, NT);
@@ -379,8 +405,8 @@ O3_DEV void o3_bwd_tile(const O3Bwd& S, const float* __restrict__ in1, const flo
                     const int32_t* B = BL + b * o3::BLK_W;
                     const int32_t* G = tab + tab[o3::H_GRP] + (B[o3::B_GRP] & 0xffff) * o3::GRP_W;
                     const int u0 = B[o3::B_GRP] >> 16;
-                    const float* xe = S.xs + e * D1p;
-                    const float* ye = S.ys + e * D2p;
+                    const float* xe = xs + e * D1p;
+                    const float* ye = ys + e * D2p;
                     float* gxe = S.gxs + e * D1p;
                     float* gye = gin2 != nullptr ? S.gys + e * D2p : nullptr;
                     const float* GTe = S.GT + e * d;
@@ -453,6 +479,7 @@ O3_DEV void o3_bwd_tile(const O3Bwd& S, const float* __restrict__ in1, const flo
     }
 
     O3_THREADS
+        if (prefetch) o3_bwd_load(S, buf ^ 1, in1, in2, gout, row0_next, nrow_next, tid, NT);  // no output irrep had paths
         o3_bwd_reduce(S, Q, tid, NT);
         const int warp = tid >> 5, lane = tid & 31, nw = NT >> 5;
         for (int e = warp; e < nrow; e += nw) {

@@ -288,8 +288,9 @@ inline size_t fwd_floats(const std::vector<int32_t>& B, int TE) {
 // backward (TE_BWD rows): resident transposed weights + gradient accumulators, x / gx / y / gy / g tiles, one round of
 // features (4 rows per warp and path slot), the scaled transposed cotangent of one output irrep, and the scratch of
 // the sliced weight-gradient partial sums (16 per thread)
-inline size_t bwd_floats(const std::vector<int32_t>& B, bool resident_gw = true) {
-    return (size_t)B[H_NWT] + (resident_gw ? (size_t)B[H_NW] : 0) + (size_t)TE_BWD * (2 * (B[H_D1] | 1) + 2 * (B[H_D2] | 1) + (B[H_DOUT] | 1)) +
+inline size_t bwd_floats(const std::vector<int32_t>& B, bool resident_gw = true, bool dbuf = true) {
+    const int nb = dbuf ? 2 : 1;
+    return (size_t)B[H_NWT] + (resident_gw ? (size_t)B[H_NW] : 0) + (size_t)TE_BWD * ((nb + 1) * (B[H_D1] | 1) + (nb + 1) * (B[H_D2] | 1) + nb * (B[H_DOUT] | 1)) +
            (size_t)4 * B[H_MAXNP] * NWARP * B[H_FROW] + (size_t)B[H_GTMAX] + 16 * (32 * NWARP + 4) + 8;
 }
 

@@ -121,11 +121,14 @@ int emu_backward(int n1, const int* in1i, int n2, const int* in2i, int no, const
         const int D1p = tab[o3::H_D1] | 1, D2p = tab[o3::H_D2] | 1, DOp = tab[o3::H_DOUT] | 1;
         O3Bwd S;
         S.tab = tab; S.WT = WT; S.gWs = gWs; S.gw_global = 0;
-        S.xs = fl; fl += TE * D1p;
+        S.xs0 = fl; fl += TE * D1p;
+        S.xs1 = fl; fl += TE * D1p;
         S.gxs = fl; fl += TE * D1p;
-        S.ys = fl; fl += TE * D2p;
+        S.ys0 = fl; fl += TE * D2p;
+        S.ys1 = fl; fl += TE * D2p;
         S.gys = fl; fl += TE * D2p;
-        S.gs = fl; fl += TE * DOp;
+        S.gs0 = fl; fl += TE * DOp;
+        S.gs1 = fl; fl += TE * DOp;
         S.F = fl; fl += (size_t)4 * tab[o3::H_MAXNP] * o3::NWARP * tab[o3::H_FROW];
         S.GT = fl;
         S.scr = scr;
@@ -144,9 +147,16 @@ int emu_backward(int n1, const int* in1i, int n2, const int* in2i, int no, const
             }
         }
         for (int idx = 0; idx < tab[o3::H_NW]; ++idx) gWs[idx] = 0.f;
-        for (long long tile = b; tile < ntiles; tile += nblocks) {
-            const long long row0 = tile * TE;
-            o3_bwd_tile(S, in1, in2, gout, gin1, gin2, row0, (int)std::min<long long>(TE, rows - row0), NT);
+        if (b < ntiles)
+            for (int tid = 0; tid < NT; ++tid)
+                o3_bwd_load(S, 0, in1, in2, gout, (long long)b * TE, (int)std::min<long long>(TE, rows - (long long)b * TE),
+                            tid, NT);
+        int buf = 0;
+        for (long long tile = b; tile < ntiles; tile += nblocks, buf ^= 1) {
+            const long long row0 = tile * TE, next = tile + nblocks;
+            const int nrow_next = next < ntiles ? (int)std::min<long long>(TE, rows - next * TE) : 0;
+            o3_bwd_tile(S, buf, in1, in2, gout, gin1, gin2, row0, (int)std::min<long long>(TE, rows - row0), next * TE,
+                        nrow_next, NT);
         }
         for (int idx = 0; idx < tab[o3::H_NW]; ++idx) gw[idx] += gWs[idx];
     }

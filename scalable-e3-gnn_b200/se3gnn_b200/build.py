@@ -37,7 +37,7 @@ def sources():
 
 
 def _deps_mtime() -> float:
-    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".inl"))]
     hdrs.append(os.path.join(ROOT, "include", "se3gnn_b200.h"))
     return max(os.path.getmtime(h) for h in hdrs if os.path.exists(h))
 

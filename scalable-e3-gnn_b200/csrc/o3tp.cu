@@ -3,6 +3,7 @@
 // then the weight contraction as a register-blocked fp32 SIMT GEMM out of shared memory.  The tile
 // programs live in o3tp_body.inl (shared with the CPU emulation under tests/emu), the planning in o3tp_tables.h.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -25,6 +26,9 @@ typedef float4 o3f4;
             *(p) += (v);                 \
     } while (0)
 #define O3_I2F(i) __int_as_float(i)
+#define O3_ACC_DECL float (&acc)[o3::MAXIO_GW][16]
+#define O3_ACC(acc, slot, tid) acc[slot]
+#define O3_GLOBAL_ADD(p, v) atomicAdd((p), (v))
 #define O3_CP4(dst, src)                                                                                      \
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), \
                  "l"(src)                                                                                    \
@@ -148,6 +152,74 @@ __global__ void __launch_bounds__(O3_NT) o3tp_bwd_kernel(const int32_t* __restri
         for (int idx = threadIdx.x; idx < tab[o3::H_NW]; idx += blockDim.x) atomicAdd(gw + idx, gWs[idx]);
 }
 
+__global__ void __launch_bounds__(O3_NT, 2) o3tp_gin_kernel(const int32_t* __restrict__ tab_g, const float* __restrict__ in1,
+                                                            const float* __restrict__ in2, const float* __restrict__ w,
+                                                            const float* __restrict__ gout, float* __restrict__ gin1,
+                                                            float* __restrict__ gin2, long long rows) {
+    extern __shared__ __align__(16) int32_t o3_sm[];
+    const int32_t* tab = load_table(tab_g, o3_sm);
+    float* fl = reinterpret_cast<float*>(o3_sm + tab[o3::H_WORDS]);
+    float* WT = fl;
+    fl += tab[o3::H_NWT];
+    constexpr int TE = o3::TE_GIN;
+    const int D1p = tab[o3::H_D1] | 1, D2p = tab[o3::H_D2] | 1, DOp = tab[o3::H_DOUT] | 1;
+    O3Gin S;
+    S.tab = tab; S.WT = WT; S.need_gy = gin2 != nullptr;
+    S.xs = fl; fl += TE * D1p;
+    S.gxs = fl; fl += TE * D1p;
+    S.ys = fl; fl += TE * D2p;
+    S.gys = fl; fl += TE * D2p;
+    S.gs = fl;
+    for (int io = 0; io < tab[o3::H_NIO]; ++io) {   // a * W^T in sub-block order
+        const int32_t* IO = tab + tab[o3::H_IO] + io * o3::IO_W;
+        const int32_t* BL = tab + tab[o3::H_BLK] + IO[o3::IO_BLK];
+        const int32_t* SUB = tab + tab[o3::H_SUB] + IO[o3::IO_SUB];
+        const int mul = IO[o3::IO_MUL], KPP = 4 * IO[o3::IO_NSUB];
+        const float a = __int_as_float(IO[o3::IO_A]);
+        for (int idx = threadIdx.x; idx < mul * KPP; idx += blockDim.x) {
+            const int wi = idx / KPP, kkp = idx - wi * KPP, word = SUB[kkp >> 2];
+            const int32_t* B = BL + (word & 0xffff) * o3::BLK_W;
+            const int32_t* G = tab + tab[o3::H_GRP] + (B[o3::B_GRP] & 0xffff) * o3::GRP_W;
+            const int32_t* P = tab + tab[o3::H_PATH] + G[o3::G_P0 + (word >> 16)] * o3::PATH_W;
+            const int u = (B[o3::B_GRP] >> 16) + (kkp & 3);
+            WT[IO[o3::IO_WTOFF] + idx] = u < G[o3::G_MUL1] ? a * w[P[o3::P_WOFF] + u * mul + wi] : 0.f;
+        }
+    }
+    __syncthreads();
+    const long long ntiles = (rows + TE - 1) / TE;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long row0 = tile * TE;
+        o3_gin_tile(S, in1, in2, gout, gin1, gin2, row0, (int)min((long long)TE, rows - row0));
+    }
+}
+
+__global__ void __launch_bounds__(O3_NT, 2) o3tp_gw_kernel(const int32_t* __restrict__ tab_g, const float* __restrict__ in1,
+                                                           const float* __restrict__ in2, const float* __restrict__ gout,
+                                                           float* __restrict__ gw, long long rows) {
+    extern __shared__ __align__(16) int32_t o3_sm[];
+    const int32_t* tab = load_table(tab_g, o3_sm);
+    float* fl = reinterpret_cast<float*>(o3_sm + tab[o3::H_WORDS]);
+    constexpr int TE = o3::TE_BWD;
+    O3Gw S;
+    S.tab = tab;
+    S.F = fl; fl += max(tab[o3::H_FMAX], 16 * O3_SCR_LD);
+    S.GT = fl; fl += tab[o3::H_GTMAX];
+    S.xs = fl; fl += TE * (tab[o3::H_D1] | 1);
+    S.ys = fl; fl += TE * (tab[o3::H_D2] | 1);
+    S.gs = fl;
+    float acc[o3::MAXIO_GW][16];
+#pragma unroll
+    for (int i = 0; i < o3::MAXIO_GW; ++i)
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc[i][k] = 0.f;
+    const long long ntiles = (rows + TE - 1) / TE;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long row0 = tile * TE;
+        o3_gw_tile(S, acc, in1, in2, gout, row0, (int)min((long long)TE, rows - row0));
+    }
+    o3_gw_flush(S, acc, gw);
+}
+
 constexpr size_t SMEM_MAX = 227 * 1024;
 constexpr size_t SMEM_TWO = 110 * 1024;  // budget that lets two CTAs share an SM
 
@@ -156,7 +228,8 @@ constexpr size_t SMEM_TWO = 110 * 1024;  // budget that lets two CTAs share an S
 struct se3_o3tp_plan {
     o3::Plan P;
     int32_t* d_tab = nullptr;
-    int te_f = 0, te_b = 0, gw_global = 0, dbuf_b = 1;
+    int te_f = 0, te_b = 0, gw_global = 0, dbuf_b = 1, split = 0, grid_gin = 0, grid_gw = 0;
+    size_t smem_gin = 0, smem_gw = 0;
     size_t smem_f = 0, smem_b = 0;
     int grid_f = 0, grid_b = 0;
 };
@@ -220,9 +293,23 @@ extern "C" int se3_o3tp_plan_create(const se3_o3tp_desc* d, se3_o3tp_plan** out)
     if (e == cudaSuccess) e = cudaMemcpy(p->d_tab, p->P.blob.data(), p->P.blob.size() * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(o3tp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(o3tp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
+    // split backward (input gradients / weight gradients as two kernels) when the plan allows it and both fit twice per SM
+    p->smem_gin = 4 * (p->P.blob.size() + o3::gin_floats(p->P.blob));
+    p->smem_gw = 4 * (p->P.blob.size() + o3::gw_floats(p->P.blob));
+    p->split = p->P.blob[o3::H_SPLIT] && p->smem_gin <= SMEM_TWO && p->smem_gw <= SMEM_TWO && !getenv("SE3_O3TP_FUSED_BWD");
     int bf = 0, bb = 0;
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bf, o3tp_fwd_kernel, O3_NT, p->smem_f);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bb, o3tp_bwd_kernel, O3_NT, p->smem_b);
+    if (p->split) {
+        int b1 = 0, b2 = 0;
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(o3tp_gin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(o3tp_gw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, o3tp_gin_kernel, O3_NT, p->smem_gin);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, o3tp_gw_kernel, O3_NT, p->smem_gw);
+        if (b1 < 1 || b2 < 1) p->split = 0;
+        p->grid_gin = b1 * se3::num_sms();
+        p->grid_gw = b2 * se3::num_sms();
+    }
     if (e != cudaSuccess || bf < 1 || bb < 1) {
         set_error("o3tp: CUDA setup failed: %s", e != cudaSuccess ? cudaGetErrorString(e) : "kernel does not fit an SM");
         if (p->d_tab) cudaFree(p->d_tab);
@@ -244,7 +331,7 @@ extern "C" void se3_o3tp_plan_destroy(se3_o3tp_plan* p) {
 extern "C" int se3_o3tp_plan_info(const se3_o3tp_plan* p, int32_t dims[8]) {
     if (!p || !dims) { set_error("null argument"); return SE3_ERR_INVALID; }
     dims[0] = p->P.D1; dims[1] = p->P.D2; dims[2] = p->P.Dout; dims[3] = (int32_t)p->P.paths.size();
-    dims[4] = p->P.nW; dims[5] = p->te_f; dims[6] = p->te_b; dims[7] = (int32_t)(p->smem_b >> 10) | (p->gw_global << 16) | (p->dbuf_b << 17);
+    dims[4] = p->P.nW; dims[5] = p->te_f; dims[6] = p->te_b; dims[7] = (int32_t)(p->smem_b >> 10) | (p->gw_global << 16) | (p->dbuf_b << 17) | (p->split << 18);
     return SE3_OK;
 }
 
@@ -290,6 +377,16 @@ extern "C" int se3_o3tp_backward(se3_o3tp_plan* p, int64_t rows, const float* in
     }
     SE3_CUDA_TRY(cudaMemsetAsync(gw, 0, sizeof(float) * p->P.nW, (cudaStream_t)stream));
     if (rows == 0) return SE3_OK;
+    if (p->split) {
+        const long long t1 = (rows + o3::TE_GIN - 1) / o3::TE_GIN, t2 = (rows + o3::TE_BWD - 1) / o3::TE_BWD;
+        o3tp_gin_kernel<<<(int)std::min<long long>(t1, p->grid_gin), O3_NT, p->smem_gin, (cudaStream_t)stream>>>(
+            p->d_tab, in1, in2, w, gout, gin1, gin2, rows);
+        SE3_LAUNCHED();
+        o3tp_gw_kernel<<<(int)std::min<long long>(t2, p->grid_gw), O3_NT, p->smem_gw, (cudaStream_t)stream>>>(
+            p->d_tab, in1, in2, gout, gw, rows);
+        SE3_LAUNCHED();
+        return SE3_OK;
+    }
     const long long ntiles = (rows + p->te_b - 1) / p->te_b;
     const int grid = (int)std::min<long long>(ntiles, p->grid_b);
     o3tp_bwd_kernel<<<grid, O3_NT, p->smem_b, (cudaStream_t)stream>>>(p->d_tab, in1, in2, w, gout, gin1, gin2, gw, rows,

@@ -9,6 +9,9 @@
 //   O3_GW_ADD(S, p, v)         weight-gradient accumulation: plain add, or a global atomic add when S.gw_global
 //   O3_MULHI(a, b)             high 32 bits of the unsigned 32 x 32 product
 //   O3_CP4(dst, src) / O3_CP_COMMIT() / O3_CP_WAIT()   4-byte asynchronous global -> shared copy, group commit, wait all
+//   O3_ACC_DECL / O3_ACC(acc, slot, tid)   per-thread accumulator sets [MAXIO_GW][16] that live across regions and
+//                              tiles (registers under nvcc, one array per emulated thread otherwise)
+//   O3_GLOBAL_ADD(p, v)        atomic float add to global memory
 //   O3_I2F(i)                  reinterpret an int32 table word as float
 //   O3_NT_DECL                 extra parameter `, int NT_` carrying the emulated block size (empty under nvcc)
 //   o3f4 / O3_LD4(p)           four consecutive floats read from a 16-byte aligned shared-memory address
@@ -488,4 +491,337 @@ O3_DEV void o3_bwd_tile(const O3Bwd& S, int buf, const float* __restrict__ in1, 
             if (gin2 != nullptr && lane < D2) gin2[(row0 + e) * D2 + lane] = S.gys[e * D2p + lane];
         }
     O3_END
+}
+
+// ======================================================================================================================
+// Split backward (used when the plan allows it, H_SPLIT): two kernels with small shared-memory footprints instead of
+// the fused one above (which stays as the general fallback).
+//
+// (1) input gradients: forward-like.  One warp per unit (in1 irrep, block of 4 channels, 32-row group), lane = row.
+//     For every output irrep the block reaches and every path: G[uu][c] = sum_w aW^T[w][kk0+uu] g[e][w][c] straight from
+//     the cotangent tile (row stride odd: conflict free), gx[uu][i] += sum_c M[i][c] G[uu][c] in registers, then one
+//     exclusive store into the shared gx tile.  No feature buffer, no scratch, no atomics (except the optional in2
+//     gradient).  The staged transposed weights carry the normalisation factor a.
+struct O3Gin {
+    const int32_t* tab;
+    const float* WT;  // a * W^T per io [mul, 4 * IO_NSUB] (shared, resident)
+    float *xs, *ys, *gs, *gxs, *gys;
+    int need_gy;
+};
+
+template <int L1, int L2, int LO>
+O3_DEV void o3_gin_path(const float* xr, const float* yr, float (&gx)[4][2 * L1 + 1], float* gyr, const float* ge,
+                        const float* wt, int KPP, int mul, int nu) {
+    constexpr int D1 = 2 * L1 + 1, D2 = 2 * L2 + 1, DO = 2 * LO + 1;
+    constexpr unsigned NZ = o3_nz<L1, L2, LO>::mask;
+    float M[D1][DO];
+    o3_M<L1, L2, LO>(yr, M);
+    float Gc[4][DO];
+    O3_UNROLL
+    for (int uu = 0; uu < 4; ++uu)
+        O3_UNROLL
+        for (int c = 0; c < DO; ++c) Gc[uu][c] = 0.f;
+    for (int w = 0; w < mul; ++w) {
+        const o3f4 t = O3_LD4(wt + w * KPP);
+        O3_UNROLL
+        for (int c = 0; c < DO; ++c) {
+            const float gv = ge[w * DO + c];
+            Gc[0][c] += t.x * gv; Gc[1][c] += t.y * gv; Gc[2][c] += t.z * gv; Gc[3][c] += t.w * gv;
+        }
+    }
+    O3_UNROLL
+    for (int uu = 0; uu < 4; ++uu)
+        O3_UNROLL
+        for (int i = 0; i < D1; ++i)
+            O3_UNROLL
+            for (int c = 0; c < DO; ++c)
+                if ((NZ >> (i * DO + c)) & 1u) gx[uu][i] += M[i][c] * Gc[uu][c];
+    if (gyr != nullptr) {
+        float Pm[D1][DO];
+        O3_UNROLL
+        for (int i = 0; i < D1; ++i)
+            O3_UNROLL
+            for (int c = 0; c < DO; ++c) Pm[i][c] = 0.f;
+        O3_UNROLL
+        for (int uu = 0; uu < 4; ++uu)
+            if (uu < nu) {
+                O3_UNROLL
+                for (int i = 0; i < D1; ++i) {
+                    const float x = xr[uu * D1 + i];
+                    O3_UNROLL
+                    for (int c = 0; c < DO; ++c)
+                        if ((NZ >> (i * DO + c)) & 1u) Pm[i][c] += x * Gc[uu][c];
+                }
+            }
+        float gy[D2];
+        O3_UNROLL
+        for (int j = 0; j < D2; ++j) gy[j] = 0.f;
+        o3_gy<L1, L2, LO>(Pm, gy);
+        O3_UNROLL
+        for (int j = 0; j < D2; ++j) O3_ATOMIC_ADD(gyr + j, gy[j]);
+    }
+}
+
+template <int L1>
+O3_DEV void o3_gin_unit(const O3Gin& S, const int32_t* GI, int ub, int e, int D1p, int D2p, int DOp) {
+    constexpr int D1 = 2 * L1 + 1;
+    const int32_t* tab = S.tab;
+    const int u0 = 4 * ub, nu = GI[o3::GI_MUL1] - u0 < 4 ? GI[o3::GI_MUL1] - u0 : 4;
+    float gx[4][D1];
+    O3_UNROLL
+    for (int uu = 0; uu < 4; ++uu)
+        O3_UNROLL
+        for (int i = 0; i < D1; ++i) gx[uu][i] = 0.f;
+    const float* xr = S.xs + e * D1p + GI[o3::GI_OFF1] + u0 * D1;
+    for (int r = 0; r < GI[o3::GI_NR]; ++r) {
+        const int32_t* RE = tab + tab[o3::H_RE] + (GI[o3::GI_R0] + r) * o3::RE_W;
+        const int32_t* IO = tab + tab[o3::H_IO] + RE[o3::RE_IO] * o3::IO_W;
+        const int32_t* G = tab + tab[o3::H_GRP] + RE[o3::RE_GRP] * o3::GRP_W;
+        const int mul = IO[o3::IO_MUL], KPP = 4 * IO[o3::IO_NSUB], lo = IO[o3::IO_D] >> 1;
+        const float* ge = S.gs + e * DOp + IO[o3::IO_OFF];
+        const float* wt0 = S.WT + tab[tab[o3::H_GIWT] + RE[o3::RE_WT0] + ub];
+        for (int pi = 0; pi < G[o3::G_NP]; ++pi) {
+            const int32_t* P = tab + tab[o3::H_PATH] + G[o3::G_P0 + pi] * o3::PATH_W;
+            const float* yr = S.ys + e * D2p + P[o3::P_OFF2];
+            float* gyr = S.need_gy ? S.gys + e * D2p + P[o3::P_OFF2] : nullptr;
+            const float* wt = wt0 + 4 * pi;
+            switch (P[o3::P_L2] * 3 + lo) {
+#define O3_CASE(B, C)                                                                                   \
+    case B * 3 + C:                                                                                     \
+        if constexpr (o3_tri<L1, B, C>::v) o3_gin_path<L1, B, C>(xr, yr, gx, gyr, ge, wt, KPP, mul, nu); \
+        break;
+                O3_CASE(0, 0) O3_CASE(0, 1) O3_CASE(0, 2) O3_CASE(1, 0) O3_CASE(1, 1) O3_CASE(1, 2)
+                O3_CASE(2, 0) O3_CASE(2, 1) O3_CASE(2, 2)
+#undef O3_CASE
+            }
+        }
+    }
+    float* gxr = S.gxs + e * D1p + GI[o3::GI_OFF1] + u0 * D1;
+    O3_UNROLL
+    for (int uu = 0; uu < 4; ++uu)
+        if (uu < nu) {
+            O3_UNROLL
+            for (int i = 0; i < D1; ++i) gxr[uu * D1 + i] = gx[uu][i];
+        }
+}
+
+O3_DEV void o3_gin_tile(const O3Gin& S, const float* __restrict__ in1, const float* __restrict__ in2,
+                        const float* __restrict__ gout, float* __restrict__ gin1, float* __restrict__ gin2,
+                        long long row0, int nrow O3_NT_DECL) {
+    const int32_t* tab = S.tab;
+    const int D1 = tab[o3::H_D1], D2 = tab[o3::H_D2], DO = tab[o3::H_DOUT];
+    const int D1p = D1 | 1, D2p = D2 | 1, DOp = DO | 1;
+    constexpr int TE = o3::TE_GIN;
+
+    O3_THREADS
+        const int warp = tid >> 5, lane = tid & 31, nw = NT >> 5;
+        for (int e = warp; e < TE; e += nw) {
+            const bool ok = e < nrow;
+            for (int c = lane; c < D1; c += 32) S.gxs[e * D1p + c] = 0.f;   // columns without any path stay zero
+            if (S.need_gy) {
+                const float* src = in1 + (row0 + e) * D1;
+                for (int c = lane; c < D1; c += 32) S.xs[e * D1p + c] = ok ? src[c] : 0.f;
+            }
+            if (lane < D2) {
+                S.ys[e * D2p + lane] = ok ? in2[(row0 + e) * D2 + lane] : 0.f;
+                S.gys[e * D2p + lane] = 0.f;
+            }
+            const float* gsrc = gout + (row0 + e) * DO;
+            for (int c = lane; c < DO; c += 32) S.gs[e * DOp + c] = ok ? gsrc[c] : 0.f;
+        }
+    O3_END
+
+    O3_THREADS
+        const int warp = tid >> 5, lane = tid & 31;
+        (void)NT;
+        const int32_t* U = tab + tab[o3::H_GUNIT];
+        for (int k = U[warp]; k < U[warp + 1]; ++k) {
+            const int packed = U[o3::NWARP + 1 + k];
+            const int gi = packed & 255, ub = (packed >> 8) & 0xffff, e = (packed >> 24) * 32 + lane;
+            const int32_t* GI = tab + tab[o3::H_GI] + gi * o3::GI_W;
+            switch (GI[o3::GI_L1]) {
+                case 0: o3_gin_unit<0>(S, GI, ub, e, D1p, D2p, DOp); break;
+                case 1: o3_gin_unit<1>(S, GI, ub, e, D1p, D2p, DOp); break;
+                case 2: o3_gin_unit<2>(S, GI, ub, e, D1p, D2p, DOp); break;
+            }
+        }
+    O3_END
+
+    O3_THREADS
+        const int warp = tid >> 5, lane = tid & 31, nw = NT >> 5;
+        for (int e = warp; e < nrow; e += nw) {
+            float* dst = gin1 + (row0 + e) * D1;
+            for (int c = lane; c < D1; c += 32) dst[c] = S.gxs[e * D1p + c];
+            if (gin2 != nullptr && lane < D2) gin2[(row0 + e) * D2 + lane] = S.gys[e * D2p + lane];
+        }
+    O3_END
+}
+
+// (2) weight gradients.  Tile of 32 rows; per output irrep: features of ALL its channels into the shared F buffer
+//     (warp = block of 4 channels, lane = row) and GT = a g transposed, then every thread adds its slice of the (e, c)
+//     axis to the 4 x 4 block of weight gradients it owns FOR THE WHOLE KERNEL (register accumulators, one set per output
+//     irrep, at most MAXIO_GW).  The slices are combined once, after the last tile (o3_gw_flush).
+struct O3Gw {
+    const int32_t* tab;
+    float *xs, *ys, *gs, *F, *GT;
+};
+
+template <int L1, int L2, int LO>
+O3_DEV void o3_feat_block(const float* xr, const float* yr, int nu, float* Fe, int Rp) {
+    constexpr int D1 = 2 * L1 + 1, DO = 2 * LO + 1;
+    constexpr unsigned NZ = o3_nz<L1, L2, LO>::mask;
+    float M[D1][DO];
+    o3_M<L1, L2, LO>(yr, M);
+    O3_UNROLL
+    for (int uu = 0; uu < 4; ++uu) {
+        float fc[DO];
+        O3_UNROLL
+        for (int c = 0; c < DO; ++c) fc[c] = 0.f;
+        if (uu < nu) {
+            O3_UNROLL
+            for (int i = 0; i < D1; ++i) {
+                const float x = xr[uu * D1 + i];
+                O3_UNROLL
+                for (int c = 0; c < DO; ++c)
+                    if ((NZ >> (i * DO + c)) & 1u) fc[c] += M[i][c] * x;
+            }
+        }
+        O3_UNROLL
+        for (int c = 0; c < DO; ++c) Fe[(size_t)uu * Rp + c] = fc[c];
+    }
+}
+
+// features + GT of output irrep `io` (one region), then this thread's slice of its 4 x 4 block (next region)
+O3_DEV void o3_gw_build(const O3Gw& S, const int32_t* IO, int tid, int NT) {
+    const int32_t* tab = S.tab;
+    const int D1p = tab[o3::H_D1] | 1, D2p = tab[o3::H_D2] | 1, DOp = tab[o3::H_DOUT] | 1;
+    const int mul = IO[o3::IO_MUL], d = IO[o3::IO_D], nblk = IO[o3::IO_NBLK], mulp = (mul + 3) & ~3;
+    const int Rp = (o3::TE_BWD * d) | 1;
+    const int32_t* BL = tab + tab[o3::H_BLK] + IO[o3::IO_BLK];
+    const float a = O3_I2F(IO[o3::IO_A]);
+    const int warp = tid >> 5, e = tid & 31, nw = NT >> 5;
+    for (int w = warp; w < mulp; w += nw)
+        for (int c = 0; c < d; ++c)
+            S.GT[(size_t)w * Rp + e * d + c] = w < mul ? a * S.gs[e * DOp + IO[o3::IO_OFF] + w * d + c] : 0.f;
+    for (int b = warp; b < nblk; b += nw) {
+        const int32_t* B = BL + b * o3::BLK_W;
+        const int32_t* G = tab + tab[o3::H_GRP] + (B[o3::B_GRP] & 0xffff) * o3::GRP_W;
+        const int u0 = B[o3::B_GRP] >> 16, l1 = G[o3::G_L1];
+        const int nu = G[o3::G_MUL1] - u0 < 4 ? G[o3::G_MUL1] - u0 : 4;
+        const float* xr = S.xs + e * D1p + G[o3::G_OFF1] + u0 * (2 * l1 + 1);
+        for (int pi = 0; pi < G[o3::G_NP]; ++pi) {
+            const int32_t* P = tab + tab[o3::H_PATH] + G[o3::G_P0 + pi] * o3::PATH_W;
+            const float* yr = S.ys + e * D2p + P[o3::P_OFF2];
+            float* Fe = S.F + (size_t)(4 * (B[o3::B_SUB0] + pi)) * Rp + e * d;
+            switch (l1 * 9 + P[o3::P_L2] * 3 + (d >> 1)) {
+#define O3_CASE(A, B2, C)                                    \
+    case A * 9 + B2 * 3 + C:                                 \
+        o3_feat_block<A, B2, C>(xr, yr, nu, Fe, Rp);         \
+        break;
+                O3_TRIPLES(O3_CASE)
+#undef O3_CASE
+            }
+        }
+    }
+}
+
+O3_DEV void o3_gw_accum(const O3Gw& S, const int32_t* IO, float (&acc)[16], int tid) {
+    const int mul = IO[o3::IO_MUL], d = IO[o3::IO_D], nwb = ((mul + 3) & ~3) >> 2, lg = IO[o3::IO_GWLG];
+    const int R = o3::TE_BWD * d, Rp = R | 1;
+    const int s = tid & ((1 << lg) - 1), t = tid >> lg;
+    if (t >= IO[o3::IO_NSUB] * nwb) return;
+    const int sb = nwb == 1 ? t : (int)O3_MULHI((unsigned)t, (unsigned)IO[o3::IO_NWB_MAGIC]), wb = t - sb * nwb;
+    const float* f = S.F + (size_t)(4 * sb) * Rp;
+    const float* g = S.GT + (size_t)(4 * wb) * Rp;
+    const int r0 = (s * R) >> lg, r1 = ((s + 1) * R) >> lg;
+    O3_UNROLL2
+    for (int r = r0; r < r1; ++r) {
+        const float f0 = f[r], f1 = f[Rp + r], f2 = f[2 * Rp + r], f3 = f[3 * Rp + r];
+        const float g0 = g[r], g1 = g[Rp + r], g2 = g[2 * Rp + r], g3 = g[3 * Rp + r];
+        acc[0] += f0 * g0; acc[1] += f0 * g1; acc[2] += f0 * g2; acc[3] += f0 * g3;
+        acc[4] += f1 * g0; acc[5] += f1 * g1; acc[6] += f1 * g2; acc[7] += f1 * g3;
+        acc[8] += f2 * g0; acc[9] += f2 * g1; acc[10] += f2 * g2; acc[11] += f2 * g3;
+        acc[12] += f3 * g0; acc[13] += f3 * g1; acc[14] += f3 * g2; acc[15] += f3 * g3;
+    }
+}
+
+// acc[slot] belongs to the slot-th output irrep that has paths
+O3_DEV void o3_gw_tile(const O3Gw& S, O3_ACC_DECL, const float* __restrict__ in1,
+                       const float* __restrict__ in2, const float* __restrict__ gout, long long row0,
+                       int nrow O3_NT_DECL) {
+    const int32_t* tab = S.tab;
+    const int D1 = tab[o3::H_D1], D2 = tab[o3::H_D2], DO = tab[o3::H_DOUT], nio = tab[o3::H_NIO];
+    const int D1p = D1 | 1, D2p = D2 | 1, DOp = DO | 1;
+    constexpr int TE = o3::TE_BWD;
+
+    O3_THREADS
+        const int warp = tid >> 5, lane = tid & 31, nw = NT >> 5;
+        for (int e = warp; e < TE; e += nw) {
+            const bool ok = e < nrow;
+            const float* src = in1 + (row0 + e) * D1;
+            for (int c = lane; c < D1; c += 32) S.xs[e * D1p + c] = ok ? src[c] : 0.f;
+            if (lane < D2) S.ys[e * D2p + lane] = ok ? in2[(row0 + e) * D2 + lane] : 0.f;
+            const float* gsrc = gout + (row0 + e) * DO;
+            for (int c = lane; c < DO; c += 32) S.gs[e * DOp + c] = ok ? gsrc[c] : 0.f;
+        }
+    O3_END
+
+    int io = 0;
+    O3_UNROLL
+    for (int slot = 0; slot < o3::MAXIO_GW; ++slot) {
+        while (io < nio && tab[tab[o3::H_IO] + io * o3::IO_W + o3::IO_NSUB] == 0) ++io;   // block-uniform
+        if (io < nio) {
+            const int32_t* IO = tab + tab[o3::H_IO] + io * o3::IO_W;
+            O3_THREADS
+                o3_gw_build(S, IO, tid, NT);
+            O3_END
+            O3_THREADS
+                (void)NT;
+                o3_gw_accum(S, IO, O3_ACC(acc, slot, tid), tid);
+            O3_END
+            ++io;
+        }
+    }
+}
+
+// after the last tile: combine the slices of every 4 x 4 block (through shared scratch, aliasing F) and add the block to
+// the global weight gradient
+O3_DEV void o3_gw_flush(const O3Gw& S, O3_ACC_DECL, float* __restrict__ gw O3_NT_DECL) {
+    const int32_t* tab = S.tab;
+    const int nio = tab[o3::H_NIO];
+    float* scr = S.F;
+    int io = 0;
+    O3_UNROLL
+    for (int slot = 0; slot < o3::MAXIO_GW; ++slot) {
+        while (io < nio && tab[tab[o3::H_IO] + io * o3::IO_W + o3::IO_NSUB] == 0) ++io;
+        if (io < nio) {
+            const int32_t* IO = tab + tab[o3::H_IO] + io * o3::IO_W;
+            const int mul = IO[o3::IO_MUL], nwb = ((mul + 3) & ~3) >> 2, lg = IO[o3::IO_GWLG];
+            const int base = IO[o3::IO_NSUB] * nwb;
+            O3_THREADS
+                (void)NT;
+                if ((tid >> lg) < base) {
+                    O3_UNROLL
+                    for (int k = 0; k < 16; ++k) scr[k * O3_SCR_LD + tid] = O3_ACC(acc, slot, tid)[k];
+                }
+            O3_END
+            O3_THREADS
+                const int32_t* BL = tab + tab[o3::H_BLK] + IO[o3::IO_BLK];
+                const int32_t* SUB = tab + tab[o3::H_SUB] + IO[o3::IO_SUB];
+                for (int o = tid; o < (base << 4); o += NT) {
+                    const int k = o & 15, t = o >> 4;
+                    float sum = 0.f;
+                    for (int s = 0; s < (1 << lg); ++s) sum += scr[k * O3_SCR_LD + (t << lg) + s];
+                    const int sb = nwb == 1 ? t : (int)O3_MULHI((unsigned)t, (unsigned)IO[o3::IO_NWB_MAGIC]), wb = t - sb * nwb;
+                    const int word = SUB[sb];
+                    const int32_t* B = BL + (word & 0xffff) * o3::BLK_W;
+                    const int32_t* G = tab + tab[o3::H_GRP] + (B[o3::B_GRP] & 0xffff) * o3::GRP_W;
+                    const int32_t* P = tab + tab[o3::H_PATH] + G[o3::G_P0 + (word >> 16)] * o3::PATH_W;
+                    const int u = (B[o3::B_GRP] >> 16) + (k >> 2), w = 4 * wb + (k & 3);
+                    if (u < G[o3::G_MUL1] && w < mul) O3_GLOBAL_ADD(gw + P[o3::P_WOFF] + u * mul + w, sum);
+                }
+            O3_END
+            ++io;
+        }
+    }
 }

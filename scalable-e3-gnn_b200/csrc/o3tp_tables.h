@@ -19,7 +19,8 @@ namespace o3 {
 enum { MAX_IRR = 8 };
 // blob header words
 enum { H_NIO = 0, H_D1, H_D2, H_DOUT, H_IO, H_PATH, H_BLK, H_WORDS, H_NW, H_NPATH, H_NWP, H_NWT, H_UNIT, H_TEF, H_BASE,
-       H_FROW, H_GTMAX, H_GRP, H_SUB, H_MAXNP, HDR_W = 20 };
+       H_FROW, H_GTMAX, H_GRP, H_SUB, H_MAXNP, H_GI, H_NGI, H_RE, H_GIWT, H_GUNIT, H_SPLIT, H_FMAX, HDR_W = 32 };
+enum { TE_GIN = 64 };  // rows per tile of the input-gradient kernel (two 32-row groups)
 enum { NWARP = 8 };   // warps per CTA both schedules are made for
 enum { TE_BWD = 32 }; // rows per backward tile (lane = row)
 // per output irrep
@@ -30,11 +31,17 @@ enum { TE_BWD = 32 }; // rows per backward tile (lane = row)
 // sub-block = 4 feature rows of one (block, path): word [H_SUB + IO_SUB + s] = block | path slot << 16.  The transposed
 // weights at IO_WTOFF are [mul, 4 * IO_NSUB] in sub-block order.
 enum { IO_MUL = 0, IO_D, IO_OFF, IO_K, IO_WOFF, IO_A, IO_PBEG, IO_PEND, IO_WSOFF, IO_WTOFF, IO_CW, IO_MULP, IO_NQ,
-       IO_NBLK, IO_BLK, IO_NSUB, IO_SUB, IO_NWB_MAGIC /* ceil(2^32 / ceil(mul / 4)) */, IO_W = 20 };
+       IO_NBLK, IO_BLK, IO_NSUB, IO_SUB, IO_NWB_MAGIC /* ceil(2^32 / ceil(mul / 4)) */,
+       IO_GWLG /* log2 of the (e, c) slices per 4 x 4 block in the weight-gradient kernel */, IO_W = 20 };
 enum { P_OFF1 = 0, P_D1, P_MUL1, P_OFF2, P_KOFF, P_L1, P_L2, P_WOFF, PATH_W };
 enum { G_OFF1 = 0, G_L1, G_MUL1, G_NP, G_P0, GRP_W = 8 };
 enum { B_GRP = 0, B_SUB0, BLK_W };
 enum { MAXP = 3 };  // paths per group = in2 irreps
+// split backward, input-gradient kernel: GI record per in1 irrep that has paths, its reach entries (output irrep, group,
+// index of the per-channel-block offsets of the transposed weights)
+enum { GI_OFF1 = 0, GI_L1, GI_MUL1, GI_NR, GI_R0, GI_W = 6 };
+enum { RE_IO = 0, RE_GRP, RE_WT0, RE_W = 4 };
+enum { MAXIO_GW = 4 };  // output irreps the weight-gradient kernel keeps register accumulators for
 
 struct Irrep { int mul, l, p; };
 struct PathH { int i1, i2, io, woff, koff; };
@@ -143,6 +150,10 @@ inline bool build_plan(Plan& P) {
     P.paths.clear();
     P.a.assign(P.out.size(), 0.f);
     std::vector<int32_t> io_w, path_w, blk_w, grp_w, sub_w;
+    struct GrpH { int io, i1, g, blk0, nblk, wtoff; };
+    std::vector<GrpH> grps;
+    bool split_ok = true;
+    int nio_active = 0, fmax = 4;
     int woff = 0, wsoff = 0, wtoff = 0, frow = 1, gtmax = 4, maxnp = 1;
     for (size_t io = 0; io < P.out.size(); ++io) {
         const Irrep o = P.out[io];
@@ -181,6 +192,7 @@ inline bool build_plan(Plan& P) {
             rec[G_OFF1] = off1[i1]; rec[G_L1] = P.in1[i1].l; rec[G_MUL1] = P.in1[i1].mul; rec[G_NP] = np;
             const int g = (int)(grp_w.size() / GRP_W);
             grp_w.insert(grp_w.end(), rec, rec + GRP_W);
+            grps.push_back({(int)io, (int)i1, g, blk0, 0, wtoff});
             // instruction estimate of one block: per path the G contraction over mul outputs + 4 channels of coupling work
             const int d1 = 2 * P.in1[i1].l + 1;
             const double cost = np * (o.mul * (5.0 * d + 2) + 4.0 * (d1 + 3.0 * d1 * d + d) + 40);
@@ -207,6 +219,15 @@ inline bool build_plan(Plan& P) {
         rec[IO_MUL] = o.mul; rec[IO_D] = d; rec[IO_OFF] = offo[io]; rec[IO_K] = K; rec[IO_WOFF] = woff0;
         rec[IO_A] = f2i(P.a[io]); rec[IO_PBEG] = pbeg; rec[IO_PEND] = pend; rec[IO_WSOFF] = wsoff;
         rec[IO_WTOFF] = wtoff; rec[IO_NBLK] = nblk; rec[IO_BLK] = blk0 * BLK_W; rec[IO_NSUB] = nsub; rec[IO_SUB] = sub0;
+        {   // weight-gradient kernel: one 4 x 4 block and one slice per thread
+            const int base = nsub * ((o.mul + 3) / 4);
+            int lg = 0;
+            while (lg < 5 && (base << (lg + 1)) <= 32 * NWARP) ++lg;
+            rec[IO_GWLG] = lg;
+            if (base > 32 * NWARP) split_ok = false;
+            if (nsub > 0) ++nio_active;
+            fmax = std::max(fmax, 4 * nsub * ((TE_BWD * d) | 1));
+        }
         rec[IO_NWB_MAGIC] = (int32_t)(uint32_t)((0x100000000ull + (uint64_t)((o.mul + 3) / 4) - 1) / (uint64_t)((o.mul + 3) / 4));
         io_w.insert(io_w.end(), rec, rec + IO_W);
         wsoff += K * best;
@@ -214,6 +235,29 @@ inline bool build_plan(Plan& P) {
         const int rp = (TE_BWD * d) | 1;
         frow = std::max(frow, rp);
         gtmax = std::max(gtmax, ((o.mul + 3) & ~3) * rp);
+    }
+    if (nio_active > MAXIO_GW) split_ok = false;
+    // input-gradient kernel tables
+    std::vector<int32_t> gi_w, re_w, giwt_w;
+    for (size_t i1 = 0; i1 < P.in1.size(); ++i1) {
+        int32_t rec[GI_W] = {0};
+        rec[GI_OFF1] = off1[i1]; rec[GI_L1] = P.in1[i1].l; rec[GI_MUL1] = P.in1[i1].mul;
+        rec[GI_R0] = (int32_t)(re_w.size() / RE_W);
+        for (const GrpH& gh : grps) {
+            if (gh.i1 != (int)i1) continue;
+            int32_t re[RE_W] = {0};
+            re[RE_IO] = gh.io; re[RE_GRP] = gh.g; re[RE_WT0] = (int32_t)giwt_w.size();
+            const int32_t* IOr = io_w.data() + gh.io * IO_W;
+            for (int u0 = 0; u0 < P.in1[i1].mul; u0 += 4) {
+                int found = -1;
+                for (int b = 0; b < IOr[IO_NBLK]; ++b)
+                    if (blk_w[IOr[IO_BLK] + b * BLK_W + B_GRP] == (gh.g | (u0 << 16))) found = b;
+                giwt_w.push_back(IOr[IO_WTOFF] + 4 * blk_w[IOr[IO_BLK] + found * BLK_W + B_SUB0]);
+            }
+            re_w.insert(re_w.end(), re, re + RE_W);
+            ++rec[GI_NR];
+        }
+        if (rec[GI_NR] > 0) gi_w.insert(gi_w.end(), rec, rec + GI_W);
     }
     P.nW = woff;
     if (P.nW == 0) {
@@ -232,6 +276,11 @@ inline bool build_plan(Plan& P) {
     B[H_BLK] = (int32_t)B.size(); B.insert(B.end(), blk_w.begin(), blk_w.end());
     B[H_GRP] = (int32_t)B.size(); B.insert(B.end(), grp_w.begin(), grp_w.end());
     B[H_SUB] = (int32_t)B.size(); B.insert(B.end(), sub_w.begin(), sub_w.end());
+    B[H_GI] = (int32_t)B.size(); B.insert(B.end(), gi_w.begin(), gi_w.end());
+    B[H_NGI] = (int32_t)(gi_w.size() / GI_W);
+    B[H_RE] = (int32_t)B.size(); B.insert(B.end(), re_w.begin(), re_w.end());
+    B[H_GIWT] = (int32_t)B.size(); B.insert(B.end(), giwt_w.begin(), giwt_w.end());
+    B[H_SPLIT] = split_ok ? 1 : 0; B[H_FMAX] = fmax;
     while (B.size() % 4) B.push_back(0);
     B[H_WORDS] = B[H_BASE] = (int32_t)B.size(); B[H_NW] = P.nW; B[H_FROW] = frow; B[H_GTMAX] = gtmax; B[H_MAXNP] = maxnp;
     B[H_NPATH] = (int32_t)P.paths.size(); B[H_NWP] = wsoff; B[H_NWT] = wtoff;
@@ -267,18 +316,56 @@ inline void schedule_forward(Plan& P, int TE) {
         load[w] += u.cost;
     }
     B.resize(B[H_BASE]);  // drop an earlier schedule
-    const int base = (int)B.size();
-    B[H_UNIT] = base; B[H_TEF] = TE;
-    B.resize(base + NWARP + 1);
-    int acc = 0;
-    for (int w = 0; w < NWARP; ++w) {
-        B[base + w] = acc;
-        acc += (int)per[w].size();
+    auto emit = [&](const std::vector<std::vector<int>>& lists) {
+        const int base = (int)B.size();
+        B.resize(base + NWARP + 1);
+        int acc = 0;
+        for (int w = 0; w < NWARP; ++w) {
+            B[base + w] = acc;
+            acc += (int)lists[w].size();
+        }
+        B[base + NWARP] = acc;
+        for (int w = 0; w < NWARP; ++w) B.insert(B.end(), lists[w].begin(), lists[w].end());
+        return base;
+    };
+    B[H_UNIT] = emit(per); B[H_TEF] = TE;
+    // input-gradient kernel: units (in1 irrep, block of 4 channels, 32-row group), packed gi | block << 8 | group << 24
+    us.clear();
+    for (int gi = 0; gi < B[H_NGI]; ++gi) {
+        const int32_t* GI = B.data() + B[H_GI] + gi * GI_W;
+        const int d1 = 2 * GI[GI_L1] + 1;
+        double cost = 40;
+        for (int r = 0; r < GI[GI_NR]; ++r) {
+            const int32_t* RE = B.data() + B[H_RE] + (GI[GI_R0] + r) * RE_W;
+            const int32_t* IO = B.data() + B[H_IO] + RE[RE_IO] * IO_W;
+            const int32_t* G = B.data() + B[H_GRP] + RE[RE_GRP] * GRP_W;
+            cost += G[G_NP] * (IO[IO_MUL] * (5.0 * IO[IO_D] + 2) + 4.0 * d1 * IO[IO_D] + 30);
+        }
+        for (int ub = 0; ub * 4 < GI[GI_MUL1]; ++ub)
+            for (int g = 0; g < TE_GIN / 32; ++g) us.push_back({gi | (ub << 8) | (g << 24), cost});
     }
-    B[base + NWARP] = acc;
-    for (int w = 0; w < NWARP; ++w) B.insert(B.end(), per[w].begin(), per[w].end());
+    std::stable_sort(us.begin(), us.end(), [](const U& a, const U& b) { return a.cost > b.cost; });
+    std::vector<std::vector<int>> per2(NWARP);
+    double load2[NWARP] = {0};
+    for (const U& u : us) {
+        int w = 0;
+        for (int k = 1; k < NWARP; ++k)
+            if (load2[k] < load2[w]) w = k;
+        per2[w].push_back(u.packed);
+        load2[w] += u.cost;
+    }
+    B[H_GUNIT] = emit(per2);
     while (B.size() % 4) B.push_back(0);
     B[H_WORDS] = (int32_t)B.size();
+}
+
+// shared-memory floats of the split backward kernels
+inline size_t gin_floats(const std::vector<int32_t>& B) {
+    return (size_t)B[H_NWT] + (size_t)TE_GIN * (2 * (B[H_D1] | 1) + 2 * (B[H_D2] | 1) + (B[H_DOUT] | 1)) + 8;
+}
+inline size_t gw_floats(const std::vector<int32_t>& B) {
+    return (size_t)std::max(B[H_FMAX], 16 * (32 * NWARP + 4)) + (size_t)B[H_GTMAX] +
+           (size_t)TE_BWD * ((B[H_D1] | 1) + (B[H_D2] | 1) + (B[H_DOUT] | 1)) + 8;
 }
 
 // shared-memory floats of the tile programs (excluding the table), for a tile of TE rows

@@ -257,6 +257,7 @@ class O3tpPlan:
         dims = (C.c_int32 * 8)()
         check(lib().se3_o3tp_plan_info(h, dims))
         self.d_in1, self.d_in2, self.d_out, self.n_paths, self.weight_floats, self.tile_fwd, self.tile_bwd = list(dims)[:7]
+        self.split_backward = bool((dims[7] >> 18) & 1)   # input / weight gradients as two kernels
         n = max(1, self.n_paths)
         arrs = [(C.c_int32 * n)() for _ in range(4)]
         pw = (C.c_float * n)()

@@ -23,6 +23,9 @@ inline float i2f(int32_t i) { float f; std::memcpy(&f, &i, 4); return f; }
 #define O3_LD4(p) (o3f4{(p)[0], (p)[1], (p)[2], (p)[3]})
 #define O3_UNROLL
 #define O3_UNROLL2
+#define O3_ACC_DECL float (*acc)[o3::MAXIO_GW][16]
+#define O3_ACC(acc, slot, tid) acc[tid][slot]
+#define O3_GLOBAL_ADD(p, v) (*(p) += (v))
 #define O3_CP4(dst, src) (*(dst) = *(src))
 #define O3_CP_COMMIT()
 #define O3_CP_WAIT()
@@ -159,6 +162,79 @@ int emu_backward(int n1, const int* in1i, int n2, const int* in2i, int no, const
                         nrow_next, NT);
         }
         for (int idx = 0; idx < tab[o3::H_NW]; ++idx) gw[idx] += gWs[idx];
+    }
+    return 0;
+}
+
+// the split backward: input-gradient kernel, then weight-gradient kernel (mirrors o3tp_gin_kernel / o3tp_gw_kernel);
+// returns 1 if the plan does not allow the split (too many output irreps / blocks)
+int emu_backward_split(int n1, const int* in1i, int n2, const int* in2i, int no, const int* outi, long long rows,
+                       const float* in1, const float* in2, const float* w, const float* gout, float* gin1, float* gin2,
+                       float* gw, int NT, int nblocks) {
+    o3::Plan P;
+    if (!make_plan(P, n1, in1i, n2, in2i, no, outi)) return -1;
+    if (NT != 32 * o3::NWARP) return -2;
+    o3::schedule_forward(P, 64);
+    const int32_t* tab = P.blob.data();
+    if (!tab[o3::H_SPLIT]) return 1;
+    for (int i = 0; i < P.nW; ++i) gw[i] = 0.f;
+    {
+        constexpr int TE = o3::TE_GIN;
+        const long long ntiles = (rows + TE - 1) / TE;
+        for (int b = 0; b < nblocks; ++b) {
+            std::vector<float> sm(o3::gin_floats(P.blob), -1e30f);
+            float* fl = sm.data();
+            float* WT = fl; fl += tab[o3::H_NWT];
+            const int D1p = tab[o3::H_D1] | 1, D2p = tab[o3::H_D2] | 1;
+            O3Gin S;
+            S.tab = tab; S.WT = WT; S.need_gy = gin2 != nullptr;
+            S.xs = fl; fl += TE * D1p;
+            S.gxs = fl; fl += TE * D1p;
+            S.ys = fl; fl += TE * D2p;
+            S.gys = fl; fl += TE * D2p;
+            S.gs = fl;
+            for (int io = 0; io < tab[o3::H_NIO]; ++io) {
+                const int32_t* IO = tab + tab[o3::H_IO] + io * o3::IO_W;
+                const int32_t* BL = tab + tab[o3::H_BLK] + IO[o3::IO_BLK];
+                const int32_t* SUB = tab + tab[o3::H_SUB] + IO[o3::IO_SUB];
+                const int mul = IO[o3::IO_MUL], KPP = 4 * IO[o3::IO_NSUB];
+                const float a = i2f(IO[o3::IO_A]);
+                for (int idx = 0; idx < mul * KPP; ++idx) {
+                    const int wi = idx / KPP, kkp = idx - wi * KPP, word = SUB[kkp >> 2];
+                    const int32_t* B = BL + (word & 0xffff) * o3::BLK_W;
+                    const int32_t* G = tab + tab[o3::H_GRP] + (B[o3::B_GRP] & 0xffff) * o3::GRP_W;
+                    const int32_t* PP = tab + tab[o3::H_PATH] + G[o3::G_P0 + (word >> 16)] * o3::PATH_W;
+                    const int u = (B[o3::B_GRP] >> 16) + (kkp & 3);
+                    WT[IO[o3::IO_WTOFF] + idx] = u < G[o3::G_MUL1] ? a * w[PP[o3::P_WOFF] + u * mul + wi] : 0.f;
+                }
+            }
+            for (long long tile = b; tile < ntiles; tile += nblocks) {
+                const long long row0 = tile * TE;
+                o3_gin_tile(S, in1, in2, gout, gin1, gin2, row0, (int)std::min<long long>(TE, rows - row0), NT);
+            }
+        }
+    }
+    {
+        constexpr int TE = o3::TE_BWD;
+        const long long ntiles = (rows + TE - 1) / TE;
+        for (int b = 0; b < nblocks; ++b) {
+            std::vector<float> sm(o3::gw_floats(P.blob), -1e30f);
+            float* fl = sm.data();
+            O3Gw S;
+            S.tab = tab;
+            S.F = fl; fl += std::max(tab[o3::H_FMAX], 16 * O3_SCR_LD);
+            S.GT = fl; fl += tab[o3::H_GTMAX];
+            S.xs = fl; fl += TE * (tab[o3::H_D1] | 1);
+            S.ys = fl; fl += TE * (tab[o3::H_D2] | 1);
+            S.gs = fl;
+            std::vector<float> accs((size_t)NT * o3::MAXIO_GW * 16, 0.f);
+            auto* acc = reinterpret_cast<float (*)[o3::MAXIO_GW][16]>(accs.data());
+            for (long long tile = b; tile < ntiles; tile += nblocks) {
+                const long long row0 = tile * TE;
+                o3_gw_tile(S, acc, in1, in2, gout, row0, (int)std::min<long long>(TE, rows - row0), NT);
+            }
+            o3_gw_flush(S, acc, gw, NT);
+        }
     }
     return 0;
 }

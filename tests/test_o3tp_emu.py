@@ -137,6 +137,21 @@ def test_emulated_kernels_match_oracle(emu, name, rows, TEF, nblocks):
     _close(gx, want_gx)
     _close(gy, want_gy)
     _close(gw, want_gw)
+    # the split backward (input-gradient kernel + weight-gradient kernel), where the plan allows it
+    gx3 = np.full((rows, d1), np.nan, np.float32)
+    gy3 = np.full((rows, d2), np.nan, np.float32)
+    gw3 = np.full(nw, np.nan, np.float32)
+    rc = emu.emu_backward_split(*spec, C.c_longlong(rows), _fp(x1), _fp(y), _fp(w), _fp(g), _fp(gx3), _fp(gy3), _fp(gw3),
+                                256, nblocks)
+    assert rc == (1 if name in ("mixed_parity", "wide") else 0)
+    if rc == 0:
+        _close(gx3, want_gx)
+        _close(gy3, want_gy)
+        _close(gw3, want_gw)
+        gx4 = np.full((rows, d1), np.nan, np.float32)
+        assert emu.emu_backward_split(*spec, C.c_longlong(rows), _fp(x1), _fp(y), _fp(w), _fp(g), _fp(gx4), None,
+                                      _fp(gw3), 256, nblocks) == 0
+        np.testing.assert_array_equal(gx4, gx3)
     # gin2 is optional
     gx2 = np.full((rows, d1), np.nan, np.float32)
     gw2 = np.full(nw, np.nan, np.float32)

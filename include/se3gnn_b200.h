@@ -202,6 +202,13 @@ int se3_edge_geometry(int64_t n, int64_t m, int64_t e, const int64_t* rowptr, co
                       float mass_scale, float* edge_attr, float* edge_extra, float* node_attr, float* x_in,
                       void* stream);
 
+/* SH(2) attributes for the l <= 2 tensor product: edge_attr9 [e,9] = SH(2)(pos[src]-pos[dst]), columns Y0 | Y1 (x,y,z) |
+ * Y2 (xy, yz, 2zz-xx-yy, zx, xx-yy), 'integral' normalisation (the first four columns are se3_edge_geometry's);
+ * node_attr9 [n+m,9] = mean incoming edge_attr9 + SH(2)(vel). */
+int se3_edge_geometry_l2(int64_t n, int64_t m, int64_t e, const int64_t* rowptr, const int32_t* col,
+                         const int32_t* dst, const float* npos, const float* nvel, float* edge_attr9,
+                         float* node_attr9, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

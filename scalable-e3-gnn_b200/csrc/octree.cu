@@ -583,6 +583,53 @@ __global__ void node_feat_kernel(long long nn, long long n, const long long* __r
     reinterpret_cast<float4*>(x)[1] = make_float4(vy, vz, vn, nmass[i] * mass_scale);
 }
 
+// ---- SH(2) attributes for the l_max = 2 tensor product (csrc/o3tp.cu): 9 columns = Y0 | Y1 (x,y,z) | Y2 in the
+// orthonormal basis (xy, yz, 2zz-xx-yy, zx, xx-yy), 'integral' normalisation like SH0 / SH1 above
+static constexpr float SH2 = 0.6307831305050401f * 1.2247448713915890f;  // sqrt(5/(4 pi)) * sqrt(3/2)
+
+__device__ __forceinline__ void sh2_of(float x, float y, float z, float* o) {
+    const float r = sqrtf(x * x + y * y + z * z);
+    const float inv = r > 0.f ? 1.0f / r : 0.f;
+    const float nx = x * inv, ny = y * inv, nz = z * inv;
+    o[0] = SH0;
+    o[1] = SH1 * nx; o[2] = SH1 * ny; o[3] = SH1 * nz;
+    o[4] = SH2 * 1.4142135623730951f * nx * ny;
+    o[5] = SH2 * 1.4142135623730951f * ny * nz;
+    o[6] = SH2 * 0.4082482904638631f * (2.f * nz * nz - nx * nx - ny * ny);
+    o[7] = SH2 * 1.4142135623730951f * nz * nx;
+    o[8] = SH2 * 0.7071067811865476f * (nx * nx - ny * ny);
+}
+
+__global__ void edge_sh2_kernel(long long e, const int* __restrict__ dst, const int* __restrict__ col,
+                                const float* __restrict__ npos, float* __restrict__ eattr) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= e) return;
+    const long long d = dst[i], s = col[i];
+    float o[9];
+    sh2_of(npos[3 * s] - npos[3 * d], npos[3 * s + 1] - npos[3 * d + 1], npos[3 * s + 2] - npos[3 * d + 2], o);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) eattr[9 * i + k] = o[k];
+}
+
+// node_attr = mean of the incoming edge attributes + SH(2)(velocity)
+__global__ void node_sh2_kernel(long long nn, const long long* __restrict__ rowptr, const float* __restrict__ eattr,
+                                const float* __restrict__ nvel, float* __restrict__ nattr) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nn) return;
+    const long long a = rowptr[i], b = rowptr[i + 1];
+    float s[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) s[k] = 0.f;
+    for (long long j = a; j < b; ++j)
+#pragma unroll
+        for (int k = 0; k < 9; ++k) s[k] += eattr[9 * j + k];
+    const float invd = b > a ? 1.0f / (float)(b - a) : 0.f;
+    float o[9];
+    sh2_of(nvel[3 * i], nvel[3 * i + 1], nvel[3 * i + 2], o);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) nattr[9 * i + k] = s[k] * invd + o[k];
+}
+
 }  // namespace se3
 
 using namespace se3;
@@ -736,6 +783,20 @@ extern "C" int se3_edge_geometry(int64_t n, int64_t m, int64_t e, const int64_t*
     cudaStream_t st = (cudaStream_t)stream;
     if (e > 0) { edge_geom_kernel<<<nblk(e, 256), 256, 0, st>>>(e, dst, col, npos, nmass, mass_scale, edge_attr, edge_extra); SE3_LAUNCHED(); }
     node_feat_kernel<<<nblk(n + m, 256), 256, 0, st>>>(n + m, n, (const long long*)rowptr, edge_attr, npos, nvel, nmass, mass_scale, node_attr, x_in);
+    SE3_LAUNCHED();
+    return SE3_OK;
+}
+
+extern "C" int se3_edge_geometry_l2(int64_t n, int64_t m, int64_t e, const int64_t* rowptr, const int32_t* col,
+                                    const int32_t* dst, const float* npos, const float* nvel, float* edge_attr9,
+                                    float* node_attr9, void* stream) {
+    if (!rowptr || !col || !dst || !npos || !nvel || !edge_attr9 || !node_attr9) {
+        set_error("null argument");
+        return SE3_ERR_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (e > 0) { edge_sh2_kernel<<<nblk(e, 256), 256, 0, st>>>(e, dst, col, npos, edge_attr9); SE3_LAUNCHED(); }
+    node_sh2_kernel<<<nblk(n + m, 256), 256, 0, st>>>(n + m, (const long long*)rowptr, edge_attr9, nvel, node_attr9);
     SE3_LAUNCHED();
     return SE3_OK;
 }

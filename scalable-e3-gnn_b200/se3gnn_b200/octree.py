@@ -150,3 +150,19 @@ def build_octree_graph(pos: torch.Tensor, vel: Optional[torch.Tensor] = None, ma
                                              C.c_float(float(n)), g.edge_attr.data_ptr(), g.edge_extra.data_ptr(),
                                              g.node_attr.data_ptr(), g.x_in.data_ptr(), st), "se3_edge_geometry")
     return g
+
+
+def sh2_attributes(g: OctreeGraph):
+    """SH(2) edge / node attributes of a graph built with features: (edge_attr9 [E,9], node_attr9 [N+M,9]) for the l <= 2
+    tensor product (`se3gnn_b200.o3tp`); the first four columns equal `g.edge_attr` / `g.node_attr`."""
+    if getattr(g, "node_pos", None) is None:
+        raise capi.Se3Error("sh2_attributes needs a graph built with features=True")
+    dev = g.node_pos.device
+    nn = g.n + g.m
+    ea = torch.empty((g.e, 9), device=dev, dtype=torch.float32)
+    na = torch.empty((nn, 9), device=dev, dtype=torch.float32)
+    with capi.mark("graph.edge_geometry_l2", g.e * (8.0 + 24.0 + 36.0 + 36.0) + nn * (12.0 + 36.0)):
+        capi.check(capi.lib().se3_edge_geometry_l2(g.n, g.m, g.e, g.rowptr.data_ptr(), g.col.data_ptr(), g.dst.data_ptr(),
+                                                   g.node_pos.data_ptr(), g.node_vel.data_ptr(), ea.data_ptr(),
+                                                   na.data_ptr(), capi.current_stream_ptr()), "se3_edge_geometry_l2")
+    return ea, na

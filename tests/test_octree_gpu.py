@@ -99,3 +99,41 @@ def test_node_and_edge_features():
     xin = np.concatenate([P - P[n], V, vn[:, None], (M * n)[:, None]], 1)
     np.testing.assert_allclose(g.x_in.cpu().numpy(), xin, rtol=1e-5, atol=1e-6)
     assert g.edge_index.shape == (2, g.e)
+
+
+def test_sh2_attributes():
+    """SH(2) edge / node attributes for the l <= 2 tensor product against `oracle/lmax2_oracle.spherical_harmonics`
+    (fp64) evaluated on the GPU's own fp32 node positions; the l <= 1 columns must be the l_max = 1 builder's."""
+    from oracle import lmax2_oracle as O2
+    from se3gnn_b200.octree import build_octree_graph, sh2_attributes
+    rng = np.random.default_rng(5)
+    n = 4000
+    pos = _plummer(n, 9)
+    pos[:5] = pos[0]                                          # coincident particles: zero-length edges, Y0 only
+    vel = rng.standard_normal((n, 3)).astype(np.float32)
+    vel[:7] = 0.0                                             # zero velocity: Y0 only
+    g = build_octree_graph(torch.from_numpy(pos).cuda(), torch.from_numpy(vel).cuda())
+    ea, na = sh2_attributes(g)
+    assert ea.shape == (g.e, 9) and na.shape == (g.n + g.m, 9)
+    assert torch.equal(ea[:, :4], g.edge_attr)
+    P = g.node_pos.cpu().numpy().astype(np.float64)
+    V = g.node_vel.cpu().numpy().astype(np.float64)
+    d, s = g.dst.cpu().numpy(), g.col.cpu().numpy()
+    rel = P[s] - P[d]
+    want = O2.spherical_harmonics(rel, 2)
+    ok = np.linalg.norm(rel, axis=1) > 1e-4
+    got = ea.cpu().numpy()
+    np.testing.assert_allclose(got[ok], want[ok], rtol=1e-4, atol=5e-4)
+    zero_len = np.linalg.norm(rel, axis=1) == 0
+    assert zero_len.any() and not got[zero_len][:, 1:].any()
+    wn = np.zeros((len(P), 9))
+    np.add.at(wn, d, got.astype(np.float64))
+    wn /= np.maximum(np.diff(g.rowptr.cpu().numpy()), 1)[:, None]
+    wn += O2.spherical_harmonics(V, 2)
+    np.testing.assert_allclose(na.cpu().numpy(), wn, rtol=1e-4, atol=1e-5)
+    # the attributes feed the l <= 2 tensor product
+    from se3gnn_b200.irreps import Irreps
+    from se3gnn_b200.o3tp import O3TensorProduct
+    tp = O3TensorProduct(Irreps("8x0e+4x1o+2x2e"), Irreps("8x0e+4x1o+2x2e")).cuda()
+    out = tp(torch.randn(g.e, tp.in1_dim, device="cuda"), ea)
+    assert out.shape == (g.e, tp.iro.dim) and torch.isfinite(out).all()

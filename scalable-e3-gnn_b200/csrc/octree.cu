@@ -589,10 +589,10 @@ static constexpr float SH2 = 0.6307831305050401f * 1.2247448713915890f;  // sqrt
 
 __device__ __forceinline__ void sh2_of(float x, float y, float z, float* o) {
     const float r = sqrtf(x * x + y * y + z * z);
-    const float inv = r > 0.f ? 1.0f / r : 0.f;
+    const float inv = r > 0.f ? 1.0f / r : 0.f, inv1 = r > 0.f ? SH1 / r : 0.f;   // inv1: same arithmetic as edge_geom_kernel
     const float nx = x * inv, ny = y * inv, nz = z * inv;
     o[0] = SH0;
-    o[1] = SH1 * nx; o[2] = SH1 * ny; o[3] = SH1 * nz;
+    o[1] = x * inv1; o[2] = y * inv1; o[3] = z * inv1;
     o[4] = SH2 * 1.4142135623730951f * nx * ny;
     o[5] = SH2 * 1.4142135623730951f * ny * nz;
     o[6] = SH2 * 0.4082482904638631f * (2.f * nz * nz - nx * nx - ny * ny);

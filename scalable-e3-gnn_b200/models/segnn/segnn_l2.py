@@ -1,0 +1,81 @@
+"""SEGNN with l_max = 2 on the octree graph (BASELINE configs[2]), first version: every tensor product is the l <= 2 CUDA
+operator (``se3gnn_b200.o3tp.O3TensorProduct``, csrc/o3tp.cu); the gathers, the gate and the aggregation around it are
+still plain torch tensor ops (the fused gather / gate / sorted-segment-sum epilogues of the l_max = 1 path, DESIGN 4.1-4.3,
+are the next step for this model).  Same layer layout as ``models/segnn/segnn.py`` (public SEGNN):
+embedding -> N x [message (2 gated TPs) -> add aggregation over dst -> update (gated TP, TP, residual)] -> 2 read-out TPs,
+no bias terms.  Specification for the tests: ``oracle/segnn_l2_oracle.py``.
+
+Inputs come from ``se3gnn_b200.octree``: ``g.x_in`` [Nn,8], ``g.edge_extra`` [E,2], ``g.dst`` / ``g.col`` and the SH(2)
+attributes of ``octree.sh2_attributes(g)`` (edge_attr9 [E,9], node_attr9 [Nn,9]).
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from se3gnn_b200.gate import SIGMOID_CST, SILU_CST
+from se3gnn_b200.irreps import Irreps
+from se3gnn_b200.o3tp import O3TensorProduct
+
+INPUT_IRREPS = "2x1o+2x0e"   # (pos - centroid, vel, |vel|, mass)
+EXTRA_IRREPS = "2x0e"        # (|rel|, m_i m_j)
+
+
+def split_hidden(hidden: Irreps):
+    """(ns, nv, nt) of hidden irreps of the form  a x0e + b x1o + c x2e  (the public-SEGNN BalancedIrreps layout)."""
+    hidden = Irreps(hidden).simplify()
+    ns, nv, nt = hidden.count("0e"), hidden.count("1o"), hidden.count("2e")
+    if str(hidden) != "+".join(f"{m}x{ir}" for m, ir in ((ns, "0e"), (nv, "1o"), (nt, "2e")) if m):
+        raise ValueError("hidden irreps must be of the form  a x0e + b x1o + c x2e")
+    return ns, nv, nt
+
+
+def gate_irreps(hidden: Irreps) -> Irreps:
+    """TP output that feeds a gate: scalars, one gate scalar per l > 0 channel, then the l > 0 channels."""
+    ns, nv, nt = split_hidden(hidden)
+    return Irreps("+".join(f"{m}x{ir}" for m, ir in ((ns + nv + nt, "0e"), (nv, "1o"), (nt, "2e")) if m))
+
+
+class SEGNNL2(nn.Module):
+    def __init__(self, hidden: str = "23x0e+7x1o+4x2e", num_layers: int = 4, out_irreps: str = "1x1o",
+                 input_irreps: str = INPUT_IRREPS):
+        super().__init__()
+        self.hidden = Irreps(hidden).simplify()
+        self.ns, self.nv, self.nt = split_hidden(self.hidden)
+        self.num_layers = num_layers
+        h, hg, sh = str(self.hidden), gate_irreps(self.hidden), Irreps.spherical_harmonics(2)
+        tp = lambda a, b: O3TensorProduct(Irreps(a), Irreps(b), sh)
+        self.embed = tp(input_irreps, h)
+        self.msg1 = nn.ModuleList(tp(f"{h}+{h}+{EXTRA_IRREPS}", hg) for _ in range(num_layers))
+        self.msg2 = nn.ModuleList(tp(h, hg) for _ in range(num_layers))
+        self.upd1 = nn.ModuleList(tp(f"{h}+{h}", hg) for _ in range(num_layers))
+        self.upd2 = nn.ModuleList(tp(h, h) for _ in range(num_layers))
+        self.pre1 = tp(h, hg)
+        self.pre2 = tp(h, out_irreps)
+
+    def gate(self, raw: torch.Tensor) -> torch.Tensor:
+        ns, nv, nt = self.ns, self.nv, self.nt
+        s, g = raw[:, :ns], SIGMOID_CST * torch.sigmoid(raw[:, ns:ns + nv + nt])
+        o = ns + nv + nt
+        v = raw[:, o:o + 3 * nv].reshape(-1, nv, 3) * g[:, :nv, None]
+        t = raw[:, o + 3 * nv:].reshape(-1, nt, 5) * g[:, nv:, None]
+        return torch.cat([SILU_CST * torch.nn.functional.silu(s), v.reshape(len(raw), -1), t.reshape(len(raw), -1)], 1)
+
+    def forward(self, x_in, node_attr, edge_attr, edge_extra, dst, src):
+        """x_in [Nn,8], node_attr [Nn,9], edge_attr [E,9], edge_extra [E,2], dst/src [E] int32 (sorted by dst)."""
+        if not x_in.is_cuda:
+            raise RuntimeError("SEGNNL2 runs on CUDA (sm_100a) only; there is no CPU fallback")
+        x = self.embed(x_in, node_attr)
+        for l in range(self.num_layers):
+            m = torch.cat([x.index_select(0, dst), x.index_select(0, src), edge_extra], 1)
+            m = self.gate(self.msg1[l](m, edge_attr))
+            m = self.gate(self.msg2[l](m, edge_attr))
+            agg = torch.zeros_like(x).index_add_(0, dst, m)
+            u = self.gate(self.upd1[l](torch.cat([x, agg], 1), node_attr))
+            x = x + self.upd2[l](u, node_attr)
+        return self.pre2(self.gate(self.pre1(x, node_attr)), node_attr)
+
+    def forward_graph(self, g, attrs=None):
+        from se3gnn_b200.octree import sh2_attributes
+        ea, na = sh2_attributes(g) if attrs is None else attrs
+        return self.forward(g.x_in, na, ea, g.edge_extra, g.dst, g.col)

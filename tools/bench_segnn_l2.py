@@ -68,7 +68,7 @@ def main():
         "workload": f"SEGNN l_max=2, 4 layers, hidden {a.hidden}, {n} particles (plummer), fp32, octree leaf size 32 "
                     "[BASELINE configs[2] at reduced size]",
         "ms_per_step": round(ms, 3), "particles_per_s": n / ms * 1e3, "edges": int(g.e), "cells": int(g.m),
-        "gpu_launches_per_step": (capi.launch_count() - n0) / a.steps, "loss": float(loss),
+        "gpu_launches_per_step": (capi.launch_count() - n0) / a.steps, "loss": float(loss.detach()),
         "peak_mem_GB": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2),
         "note": "tensor products: csrc/o3tp.cu (fp32 SIMT); gather / gate / aggregation: torch ops (not fused yet)",
     }), flush=True)

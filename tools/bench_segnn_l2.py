@@ -1,8 +1,7 @@
 """BASELINE configs[2] as a measured case (first version, fp32 SIMT tensor products, torch glue for gather / gate /
 aggregation): octree graph build + SH(2) attributes + 4-layer SEGNN l_max = 2 forward/backward + Adam on one GPU.
-One JSON line; CUDA events on the current stream, warm-up first.  `--particles` defaults to 100k: the unfused model
-keeps every per-edge tensor for autograd (about 13 KB per edge over 4 layers), so 1M particles need the fused
-epilogues of the l_max = 1 path or activation checkpointing.
+One JSON line; CUDA events on the current stream, warm-up first.  The unfused model keeps every per-edge tensor for
+autograd (about 7.7 KB per edge over 4 layers): 1M particles (17.9M edges) peak at 137 GB of the 180 GB.
 
     python tools/bench_segnn_l2.py [--particles 100000] [--steps 5]
 """
@@ -66,7 +65,7 @@ def main():
     ms = e0.elapsed_time(e1) / a.steps
     print(json.dumps({
         "workload": f"SEGNN l_max=2, 4 layers, hidden {a.hidden}, {n} particles (plummer), fp32, octree leaf size 32 "
-                    "[BASELINE configs[2] at reduced size]",
+                    + ("[BASELINE configs[2], fp32 contraction]" if n == 1_000_000 else "[BASELINE configs[2] at a different size]"),
         "ms_per_step": round(ms, 3), "particles_per_s": n / ms * 1e3, "edges": int(g.e), "cells": int(g.m),
         "gpu_launches_per_step": (capi.launch_count() - n0) / a.steps, "loss": float(loss.detach()),
         "peak_mem_GB": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2),

@@ -156,6 +156,16 @@ int se3_o3tp_forward(se3_o3tp_plan* plan, int64_t rows, const float* in1, const 
 int se3_o3tp_backward(se3_o3tp_plan* plan, int64_t rows, const float* in1, const float* in2, const float* w,
                       const float* gout, float* gin1, float* gin2, float* gw, void* stream);
 
+/* ---------------------------------------------------------------- gate ---- */
+/* Gated non-linearity on flat rows (public SEGNN O3TensorProductSwishGate's Gate; the reference mount has no source for
+ * it): raw = [ns scalars | ng gate scalars | block b: cnt[b] channels x dim[b] components ...], ng = sum cnt;
+ * out = [cs silu(s) | raw * cg sigmoid(gate of the channel)].  For l <= 1 hidden irreps the tensor-product kernels fuse
+ * this (SE3_EPI_GATE); this stand-alone pair serves layouts with l = 2 blocks.  nblk <= 4, host arrays cnt/dim. */
+int se3_gate_forward(int64_t rows, int32_t ns, int32_t nblk, const int32_t* cnt, const int32_t* dim, float cs, float cg,
+                     const float* raw /*[rows, ns+ng+sum cnt*dim]*/, float* out /*[rows, ns+sum cnt*dim]*/, void* stream);
+int se3_gate_backward(int64_t rows, int32_t ns, int32_t nblk, const int32_t* cnt, const int32_t* dim, float cs, float cg,
+                      const float* raw, const float* gout, float* graw, void* stream);
+
 /* -------------------------------------------------------------- octree ---- */
 /* Builder-defined API (the reference's numba graph builder is not in the mount; the
  * specification is oracle/octree_oracle.py).  All arrays are caller-allocated device memory. */

@@ -1,6 +1,6 @@
 """SEGNN with l_max = 2 on the octree graph (BASELINE configs[2]), first version: every tensor product is the l <= 2 CUDA
-operator (``se3gnn_b200.o3tp.O3TensorProduct``, csrc/o3tp.cu); the gathers, the gate and the aggregation around it are
-still plain torch tensor ops (the fused gather / gate / sorted-segment-sum epilogues of the l_max = 1 path, DESIGN 4.1-4.3,
+operator (``se3gnn_b200.o3tp.O3TensorProduct``, csrc/o3tp.cu) and every gate one elementwise kernel (csrc/gate.cu); the
+gathers and the aggregation around them are still plain torch tensor ops (the fused gather / gate / sorted-segment-sum epilogues of the l_max = 1 path, DESIGN 4.1-4.3,
 are the next step for this model).  Same layer layout as ``models/segnn/segnn.py`` (public SEGNN):
 embedding -> N x [message (2 gated TPs) -> add aggregation over dst -> update (gated TP, TP, residual)] -> 2 read-out TPs,
 no bias terms.  Specification for the tests: ``oracle/segnn_l2_oracle.py``.
@@ -13,7 +13,7 @@ from __future__ import annotations
 import torch
 from torch import nn
 
-from se3gnn_b200.gate import SIGMOID_CST, SILU_CST
+from se3gnn_b200.gate import irreps_gate
 from se3gnn_b200.irreps import Irreps
 from se3gnn_b200.o3tp import O3TensorProduct
 
@@ -54,12 +54,8 @@ class SEGNNL2(nn.Module):
         self.pre2 = tp(h, out_irreps)
 
     def gate(self, raw: torch.Tensor) -> torch.Tensor:
-        ns, nv, nt = self.ns, self.nv, self.nt
-        s, g = raw[:, :ns], SIGMOID_CST * torch.sigmoid(raw[:, ns:ns + nv + nt])
-        o = ns + nv + nt
-        v = raw[:, o:o + 3 * nv].reshape(-1, nv, 3) * g[:, :nv, None]
-        t = raw[:, o + 3 * nv:].reshape(-1, nt, 5) * g[:, nv:, None]
-        return torch.cat([SILU_CST * torch.nn.functional.silu(s), v.reshape(len(raw), -1), t.reshape(len(raw), -1)], 1)
+        """silu on the scalars, sigmoid gates on the l = 1 / l = 2 channels: one CUDA kernel each way (csrc/gate.cu)."""
+        return irreps_gate(raw, self.ns, [(self.nv, 3), (self.nt, 5)])
 
     def forward(self, x_in, node_attr, edge_attr, edge_extra, dst, src):
         """x_in [Nn,8], node_attr [Nn,9], edge_attr [E,9], edge_extra [E,2], dst/src [E] int32 (sorted by dst)."""

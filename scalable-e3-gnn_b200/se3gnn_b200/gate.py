@@ -22,3 +22,44 @@ def _sigmoid(z):
 
 SILU_CST = normalize2mom_const(lambda z: z * _sigmoid(z))
 SIGMOID_CST = normalize2mom_const(_sigmoid)
+
+
+def irreps_gate(raw, ns: int, blocks):
+    """Gate on the CUDA kernels (`se3_gate_forward/backward`, csrc/gate.cu): raw [rows, ns + ng + sum(cnt*dim)] ->
+    [rows, ns + sum(cnt*dim)] with blocks = [(cnt, dim), ...] (<= 4) and ng = sum(cnt).  Differentiable."""
+    import torch
+
+    from . import capi
+
+    blocks = [(int(c), int(d)) for c, d in blocks if int(c) > 0]
+    cnt = (capi.C.c_int32 * 4)(*[c for c, _ in blocks])
+    dim = (capi.C.c_int32 * 4)(*[d for _, d in blocks])
+    d_out = ns + sum(c * d for c, d in blocks)
+    d_raw = d_out + sum(c for c, _ in blocks)
+
+    class _Gate(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, raw):
+            raw = raw.contiguous()
+            if not raw.is_cuda or raw.dtype != torch.float32 or raw.dim() != 2 or raw.shape[1] != d_raw:
+                raise capi.Se3Error(f"irreps_gate: need a CUDA fp32 [rows, {d_raw}] tensor")
+            out = torch.empty((raw.shape[0], d_out), device=raw.device, dtype=torch.float32)
+            with capi.mark("gate.fwd", 4.0 * raw.shape[0] * (d_raw + d_out)):
+                capi.check(capi.lib().se3_gate_forward(raw.shape[0], ns, len(blocks), cnt, dim, SILU_CST, SIGMOID_CST,
+                                                       capi.ptr(raw), capi.ptr(out), capi.current_stream_ptr()),
+                           "se3_gate_forward")
+            ctx.save_for_backward(raw)
+            return out
+
+        @staticmethod
+        def backward(ctx, gout):
+            (raw,) = ctx.saved_tensors
+            gout = gout.contiguous()
+            graw = torch.empty_like(raw)
+            with capi.mark("gate.bwd", 4.0 * raw.shape[0] * (2 * d_raw + d_out)):
+                capi.check(capi.lib().se3_gate_backward(raw.shape[0], ns, len(blocks), cnt, dim, SILU_CST, SIGMOID_CST,
+                                                        capi.ptr(raw), capi.ptr(gout), capi.ptr(graw),
+                                                        capi.current_stream_ptr()), "se3_gate_backward")
+            return graw
+
+    return _Gate.apply(raw)

@@ -52,7 +52,7 @@ __device__ __forceinline__ const int32_t* load_table(const int32_t* __restrict__
     return sm;
 }
 
-__global__ void __launch_bounds__(O3_NT) o3tp_fwd_kernel(const int32_t* __restrict__ tab_g, const float* __restrict__ in1,
+__global__ void __launch_bounds__(O3_NT) o3tp_fwd_kernel(const int32_t* __restrict__ tab_g, const O3Rows in1,
                                                          const float* __restrict__ in2, const float* __restrict__ w,
                                                          float* __restrict__ out, long long rows, int TE) {
     extern __shared__ __align__(16) int32_t o3_sm[];
@@ -89,9 +89,9 @@ __global__ void __launch_bounds__(O3_NT) o3tp_fwd_kernel(const int32_t* __restri
     }
 }
 
-__global__ void __launch_bounds__(O3_NT) o3tp_bwd_kernel(const int32_t* __restrict__ tab_g, const float* __restrict__ in1,
+__global__ void __launch_bounds__(O3_NT) o3tp_bwd_kernel(const int32_t* __restrict__ tab_g, const O3Rows in1,
                                                          const float* __restrict__ in2, const float* __restrict__ w,
-                                                         const float* __restrict__ gout, float* __restrict__ gin1,
+                                                         const float* __restrict__ gout, const O3GRows gin1,
                                                          float* __restrict__ gin2, float* __restrict__ gw, long long rows,
                                                          int gw_global, int dbuf) {
     extern __shared__ __align__(16) int32_t o3_sm[];
@@ -152,9 +152,9 @@ __global__ void __launch_bounds__(O3_NT) o3tp_bwd_kernel(const int32_t* __restri
         for (int idx = threadIdx.x; idx < tab[o3::H_NW]; idx += blockDim.x) atomicAdd(gw + idx, gWs[idx]);
 }
 
-__global__ void __launch_bounds__(O3_NT, 2) o3tp_gin_kernel(const int32_t* __restrict__ tab_g, const float* __restrict__ in1,
+__global__ void __launch_bounds__(O3_NT, 2) o3tp_gin_kernel(const int32_t* __restrict__ tab_g, const O3Rows in1,
                                                             const float* __restrict__ in2, const float* __restrict__ w,
-                                                            const float* __restrict__ gout, float* __restrict__ gin1,
+                                                            const float* __restrict__ gout, const O3GRows gin1,
                                                             float* __restrict__ gin2, long long rows) {
     extern __shared__ __align__(16) int32_t o3_sm[];
     const int32_t* tab = load_table(tab_g, o3_sm);
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(O3_NT, 2) o3tp_gin_kernel(const int32_t* __res
     }
 }
 
-__global__ void __launch_bounds__(O3_NT, 2) o3tp_gw_kernel(const int32_t* __restrict__ tab_g, const float* __restrict__ in1,
+__global__ void __launch_bounds__(O3_NT, 2) o3tp_gw_kernel(const int32_t* __restrict__ tab_g, const O3Rows in1,
                                                            const float* __restrict__ in2, const float* __restrict__ gout,
                                                            float* __restrict__ gw, long long rows) {
     extern __shared__ __align__(16) int32_t o3_sm[];
@@ -358,39 +358,93 @@ extern "C" int se3_o3tp_coupling(int32_t l1, int32_t l2, int32_t l3, double* out
     return SE3_OK;
 }
 
-extern "C" int se3_o3tp_forward(se3_o3tp_plan* p, int64_t rows, const float* in1, const float* in2, const float* w,
-                                float* out, void* stream) {
-    if (!p || rows < 0 || (rows > 0 && (!in1 || !in2 || !w || !out))) { set_error("o3tp forward: bad argument"); return SE3_ERR_INVALID; }
+static int make_rows(const se3_o3tp_plan* p, int nseg, const se3_rowseg* seg, O3Rows& X) {
+    if (nseg < 1 || nseg > SE3_MAX_SEG || !seg) return SE3_ERR_INVALID;
+    int c0 = 0;
+    X.nseg = nseg;
+    for (int s = 0; s < 4; ++s) {
+        const bool on = s < nseg;
+        if (on && (!seg[s].base || seg[s].width < 1 || seg[s].ld < seg[s].width)) return SE3_ERR_INVALID;
+        X.base[s] = on ? seg[s].base : nullptr; X.idx[s] = on ? seg[s].idx : nullptr;
+        X.ld[s] = on ? seg[s].ld : 0; X.c0[s] = c0; X.width[s] = on ? seg[s].width : 0;
+        c0 += X.width[s];
+    }
+    return c0 == p->P.D1 ? SE3_OK : SE3_ERR_INVALID;
+}
+
+extern "C" int se3_o3tp_forward_seg(se3_o3tp_plan* p, int64_t rows, int32_t nseg, const se3_rowseg* seg, const float* in2,
+                                    const float* w, float* out, void* stream) {
+    O3Rows X;
+    if (!p || rows < 0 || make_rows(p, nseg, seg, X) || (rows > 0 && (!in2 || !w || !out))) {
+        set_error("o3tp forward: bad argument (segments must add up to d_in1)");
+        return SE3_ERR_INVALID;
+    }
     if (rows == 0) return SE3_OK;
     const long long ntiles = (rows + p->te_f - 1) / p->te_f;
     const int grid = (int)std::min<long long>(ntiles, p->grid_f);
-    o3tp_fwd_kernel<<<grid, O3_NT, p->smem_f, (cudaStream_t)stream>>>(p->d_tab, in1, in2, w, out, rows, p->te_f);
+    o3tp_fwd_kernel<<<grid, O3_NT, p->smem_f, (cudaStream_t)stream>>>(p->d_tab, X, in2, w, out, rows, p->te_f);
     SE3_LAUNCHED();
     return SE3_OK;
 }
 
-extern "C" int se3_o3tp_backward(se3_o3tp_plan* p, int64_t rows, const float* in1, const float* in2, const float* w,
-                                 const float* gout, float* gin1, float* gin2, float* gw, void* stream) {
-    if (!p || rows < 0 || !gw || (rows > 0 && (!in1 || !in2 || !w || !gout || !gin1))) {
-        set_error("o3tp backward: bad argument");
+extern "C" int se3_o3tp_backward_seg(se3_o3tp_plan* p, int64_t rows, int32_t nseg, const se3_rowseg* seg, const float* in2,
+                                     const float* w, const float* gout, float* const* gseg, const int32_t* gseg_mode,
+                                     float* gin2, float* gw, void* stream) {
+    O3Rows X;
+    if (!p || rows < 0 || !gw || make_rows(p, nseg, seg, X) || !gseg || !gseg_mode || (rows > 0 && (!in2 || !w || !gout))) {
+        set_error("o3tp backward: bad argument (segments must add up to d_in1)");
         return SE3_ERR_INVALID;
+    }
+    O3GRows G;
+    G.nseg = nseg;
+    for (int s = 0; s < 4; ++s) {
+        const bool on = s < nseg && gseg[s] && gseg_mode[s] != SE3_GRAD_NONE;
+        if (on && gseg_mode[s] != SE3_GRAD_STORE && gseg_mode[s] != SE3_GRAD_ATOMIC && gseg_mode[s] != SE3_GRAD_SORTED) {
+            set_error("o3tp backward: unknown gradient mode");
+            return SE3_ERR_INVALID;
+        }
+        if (on && gseg_mode[s] == SE3_GRAD_STORE && X.idx[s]) {
+            set_error("o3tp backward: SE3_GRAD_STORE needs identity rows");
+            return SE3_ERR_INVALID;
+        }
+        G.base[s] = on ? gseg[s] : nullptr; G.idx[s] = X.idx[s]; G.ld[s] = X.ld[s]; G.c0[s] = X.c0[s]; G.width[s] = X.width[s];
+        G.mode[s] = !on ? 0 : (gseg_mode[s] == SE3_GRAD_STORE ? 1 : 2);   // SORTED is served by the atomic path here
     }
     SE3_CUDA_TRY(cudaMemsetAsync(gw, 0, sizeof(float) * p->P.nW, (cudaStream_t)stream));
     if (rows == 0) return SE3_OK;
     if (p->split) {
         const long long t1 = (rows + o3::TE_GIN - 1) / o3::TE_GIN, t2 = (rows + o3::TE_BWD - 1) / o3::TE_BWD;
         o3tp_gin_kernel<<<(int)std::min<long long>(t1, p->grid_gin), O3_NT, p->smem_gin, (cudaStream_t)stream>>>(
-            p->d_tab, in1, in2, w, gout, gin1, gin2, rows);
+            p->d_tab, X, in2, w, gout, G, gin2, rows);
         SE3_LAUNCHED();
         o3tp_gw_kernel<<<(int)std::min<long long>(t2, p->grid_gw), O3_NT, p->smem_gw, (cudaStream_t)stream>>>(
-            p->d_tab, in1, in2, gout, gw, rows);
+            p->d_tab, X, in2, gout, gw, rows);
         SE3_LAUNCHED();
         return SE3_OK;
     }
     const long long ntiles = (rows + p->te_b - 1) / p->te_b;
     const int grid = (int)std::min<long long>(ntiles, p->grid_b);
-    o3tp_bwd_kernel<<<grid, O3_NT, p->smem_b, (cudaStream_t)stream>>>(p->d_tab, in1, in2, w, gout, gin1, gin2, gw, rows,
+    o3tp_bwd_kernel<<<grid, O3_NT, p->smem_b, (cudaStream_t)stream>>>(p->d_tab, X, in2, w, gout, G, gin2, gw, rows,
                                                                      p->gw_global, p->dbuf_b);
     SE3_LAUNCHED();
     return SE3_OK;
+}
+
+extern "C" int se3_o3tp_forward(se3_o3tp_plan* p, int64_t rows, const float* in1, const float* in2, const float* w,
+                                float* out, void* stream) {
+    if (!p) { set_error("o3tp forward: bad argument"); return SE3_ERR_INVALID; }
+    const se3_rowseg seg = {in1, nullptr, p->P.D1, p->P.D1};
+    if (rows > 0 && !in1) { set_error("o3tp forward: bad argument"); return SE3_ERR_INVALID; }
+    if (rows == 0) return rows < 0 ? SE3_ERR_INVALID : SE3_OK;
+    return se3_o3tp_forward_seg(p, rows, 1, &seg, in2, w, out, stream);
+}
+
+extern "C" int se3_o3tp_backward(se3_o3tp_plan* p, int64_t rows, const float* in1, const float* in2, const float* w,
+                                 const float* gout, float* gin1, float* gin2, float* gw, void* stream) {
+    if (!p || !gw || (rows > 0 && (!in1 || !gin1))) { set_error("o3tp backward: bad argument"); return SE3_ERR_INVALID; }
+    static const float dummy = 0.f;   // rows == 0: the segment still needs a non-null base
+    const se3_rowseg seg = {in1 ? in1 : &dummy, nullptr, p->P.D1, p->P.D1};
+    float* gs[SE3_MAX_SEG] = {gin1, nullptr, nullptr, nullptr};
+    const int32_t mode[SE3_MAX_SEG] = {SE3_GRAD_STORE, 0, 0, 0};
+    return se3_o3tp_backward_seg(p, rows, 1, &seg, in2, w, gout, gs, mode, gin2, gw, stream);
 }

@@ -27,6 +27,52 @@
 // Per lane (= row e) and path the second input is folded once into M[i][c] = sum_j C[i][j][c] y[j], so that
 // f[c] = sum_i M[i][c] x[i] and gx[i] = sum_c M[i][c] G[c].
 
+// in1 as a virtual concatenation of up to 4 row segments (se3_rowseg of the C ABI): row r, columns [c0, c0 + width) of
+// segment s = base[s][(idx[s] ? idx[s][r] : r) * ld[s] + 0 .. width).  The gradient goes back per segment: stored
+// (identity rows), added atomically (gathered rows) or skipped.  Loops over the segments are fully unrolled so that the
+// kernel-parameter arrays are only indexed statically.
+struct O3Rows {
+    const float* base[4];
+    const int* idx[4];
+    int ld[4], c0[4], width[4];
+    int nseg;
+};
+struct O3GRows {
+    float* base[4];
+    const int* idx[4];
+    int ld[4], c0[4], width[4], mode[4];  // mode: SE3_GRAD_NONE / STORE / ATOMIC
+    int nseg;
+};
+
+O3_DEV void o3_row_load_async(const O3Rows& X, long long row, float* dst, int lane) {
+    O3_UNROLL
+    for (int s = 0; s < 4; ++s)
+        if (s < X.nseg) {
+            const float* src = X.base[s] + (X.idx[s] ? (long long)X.idx[s][row] : row) * X.ld[s];
+            for (int c = lane; c < X.width[s]; c += 32) O3_CP4(dst + X.c0[s] + c, src + c);
+        }
+}
+O3_DEV void o3_row_load(const O3Rows& X, long long row, float* dst, int lane) {
+    O3_UNROLL
+    for (int s = 0; s < 4; ++s)
+        if (s < X.nseg) {
+            const float* src = X.base[s] + (X.idx[s] ? (long long)X.idx[s][row] : row) * X.ld[s];
+            for (int c = lane; c < X.width[s]; c += 32) dst[X.c0[s] + c] = src[c];
+        }
+}
+O3_DEV void o3_row_store_grad(const O3GRows& G, long long row, const float* src, int lane) {
+    O3_UNROLL
+    for (int s = 0; s < 4; ++s)
+        if (s < G.nseg && G.mode[s] != 0) {
+            float* dst = G.base[s] + (G.idx[s] ? (long long)G.idx[s][row] : row) * G.ld[s];
+            if (G.mode[s] == 1) {
+                for (int c = lane; c < G.width[s]; c += 32) dst[c] = src[G.c0[s] + c];
+            } else {
+                for (int c = lane; c < G.width[s]; c += 32) O3_GLOBAL_ADD(dst + c, src[G.c0[s] + c]);
+            }
+        }
+}
+
 struct O3Fwd {
     const int32_t* tab;  // table blob (shared memory)
     const float* Ws;     // all weights, per io [K, IO_MULP] zero padded (shared, resident)
@@ -113,7 +159,7 @@ O3_DEV void o3_fwd_unit(const int32_t* tab, const int32_t* IO, const float* xe, 
 }
 
 // asynchronous copy of one tile of both inputs into buffer `buf` (rows past the end are zero filled)
-O3_DEV void o3_fwd_load(const O3Fwd& S, int buf, const float* __restrict__ in1, const float* __restrict__ in2,
+O3_DEV void o3_fwd_load(const O3Fwd& S, int buf, const O3Rows& in1, const float* __restrict__ in2,
                         long long row0, int nrow, int tid, int NT) {
     const int32_t* tab = S.tab;
     const int D1 = tab[o3::H_D1], D2 = tab[o3::H_D2], D1p = D1 | 1, D2p = D2 | 1;
@@ -122,8 +168,7 @@ O3_DEV void o3_fwd_load(const O3Fwd& S, int buf, const float* __restrict__ in1, 
     const int warp = tid >> 5, lane = tid & 31, nw = NT >> 5;
     for (int e = warp; e < S.TE; e += nw) {
         if (e < nrow) {
-            const float* src = in1 + (row0 + e) * D1;
-            for (int c = lane; c < D1; c += 32) O3_CP4(xs + e * D1p + c, src + c);
+            o3_row_load_async(in1, row0 + e, xs + e * D1p, lane);
             if (lane < D2) O3_CP4(ys + e * D2p + lane, in2 + (row0 + e) * D2 + lane);
         } else {
             for (int c = lane; c < D1; c += 32) xs[e * D1p + c] = 0.f;
@@ -135,7 +180,7 @@ O3_DEV void o3_fwd_load(const O3Fwd& S, int buf, const float* __restrict__ in1, 
 
 // One tile: the inputs of this tile were requested earlier into buffer `buf` (by the previous call, or by the
 // prologue for the first tile); the next tile (nrow_next > 0) is requested into the other buffer before computing.
-O3_DEV void o3_fwd_tile(const O3Fwd& S, int buf, const float* __restrict__ in1, const float* __restrict__ in2,
+O3_DEV void o3_fwd_tile(const O3Fwd& S, int buf, const O3Rows& in1, const float* __restrict__ in2,
                         float* __restrict__ out, long long row0, int nrow, long long row0_next,
                         int nrow_next O3_NT_DECL) {
     const int32_t* tab = S.tab;
@@ -332,7 +377,7 @@ O3_DEV void o3_bwd_reduce(const O3Bwd& S, const O3Pending& Q, int tid, int NT) {
 }
 
 // asynchronous copy of one tile of both inputs and of the cotangent into buffer `buf` (rows past the end: zeros)
-O3_DEV void o3_bwd_load(const O3Bwd& S, int buf, const float* __restrict__ in1, const float* __restrict__ in2,
+O3_DEV void o3_bwd_load(const O3Bwd& S, int buf, const O3Rows& in1, const float* __restrict__ in2,
                         const float* __restrict__ gout, long long row0, int nrow, int tid, int NT) {
     const int32_t* tab = S.tab;
     const int D1 = tab[o3::H_D1], D2 = tab[o3::H_D2], DO = tab[o3::H_DOUT];
@@ -343,8 +388,7 @@ O3_DEV void o3_bwd_load(const O3Bwd& S, int buf, const float* __restrict__ in1, 
     const int warp = tid >> 5, lane = tid & 31, nw = NT >> 5;
     for (int e = warp; e < o3::TE_BWD; e += nw) {
         if (e < nrow) {
-            const float* src = in1 + (row0 + e) * D1;
-            for (int c = lane; c < D1; c += 32) O3_CP4(xs + e * D1p + c, src + c);
+            o3_row_load_async(in1, row0 + e, xs + e * D1p, lane);
             if (lane < D2) O3_CP4(ys + e * D2p + lane, in2 + (row0 + e) * D2 + lane);
             const float* gsrc = gout + (row0 + e) * DO;
             for (int c = lane; c < DO; c += 32) O3_CP4(gs + e * DOp + c, gsrc + c);
@@ -359,8 +403,8 @@ O3_DEV void o3_bwd_load(const O3Bwd& S, int buf, const float* __restrict__ in1, 
 
 // One tile; its inputs were requested earlier into buffer `buf`, the next tile (nrow_next > 0) is requested into the
 // other buffer at the start of the first compute region.
-O3_DEV void o3_bwd_tile(const O3Bwd& S, int buf, const float* __restrict__ in1, const float* __restrict__ in2,
-                        const float* __restrict__ gout, float* __restrict__ gin1, float* __restrict__ gin2,
+O3_DEV void o3_bwd_tile(const O3Bwd& S, int buf, const O3Rows& in1, const float* __restrict__ in2,
+                        const float* __restrict__ gout, const O3GRows& gin1, float* __restrict__ gin2,
                         long long row0, int nrow, long long row0_next, int nrow_next O3_NT_DECL) {
     const int32_t* tab = S.tab;
     const int D1 = tab[o3::H_D1], D2 = tab[o3::H_D2], DO = tab[o3::H_DOUT], nio = tab[o3::H_NIO];
@@ -486,8 +530,7 @@ O3_DEV void o3_bwd_tile(const O3Bwd& S, int buf, const float* __restrict__ in1, 
         o3_bwd_reduce(S, Q, tid, NT);
         const int warp = tid >> 5, lane = tid & 31, nw = NT >> 5;
         for (int e = warp; e < nrow; e += nw) {
-            float* dst = gin1 + (row0 + e) * D1;
-            for (int c = lane; c < D1; c += 32) dst[c] = S.gxs[e * D1p + c];
+            o3_row_store_grad(gin1, row0 + e, S.gxs + e * D1p, lane);
             if (gin2 != nullptr && lane < D2) gin2[(row0 + e) * D2 + lane] = S.gys[e * D2p + lane];
         }
     O3_END
@@ -605,8 +648,8 @@ O3_DEV void o3_gin_unit(const O3Gin& S, const int32_t* GI, int ub, int e, int D1
         }
 }
 
-O3_DEV void o3_gin_tile(const O3Gin& S, const float* __restrict__ in1, const float* __restrict__ in2,
-                        const float* __restrict__ gout, float* __restrict__ gin1, float* __restrict__ gin2,
+O3_DEV void o3_gin_tile(const O3Gin& S, const O3Rows& in1, const float* __restrict__ in2,
+                        const float* __restrict__ gout, const O3GRows& gin1, float* __restrict__ gin2,
                         long long row0, int nrow O3_NT_DECL) {
     const int32_t* tab = S.tab;
     const int D1 = tab[o3::H_D1], D2 = tab[o3::H_D2], DO = tab[o3::H_DOUT];
@@ -619,8 +662,9 @@ O3_DEV void o3_gin_tile(const O3Gin& S, const float* __restrict__ in1, const flo
             const bool ok = e < nrow;
             for (int c = lane; c < D1; c += 32) S.gxs[e * D1p + c] = 0.f;   // columns without any path stay zero
             if (S.need_gy) {
-                const float* src = in1 + (row0 + e) * D1;
-                for (int c = lane; c < D1; c += 32) S.xs[e * D1p + c] = ok ? src[c] : 0.f;
+                if (ok) o3_row_load(in1, row0 + e, S.xs + e * D1p, lane);
+                else
+                    for (int c = lane; c < D1; c += 32) S.xs[e * D1p + c] = 0.f;
             }
             if (lane < D2) {
                 S.ys[e * D2p + lane] = ok ? in2[(row0 + e) * D2 + lane] : 0.f;
@@ -650,8 +694,7 @@ O3_DEV void o3_gin_tile(const O3Gin& S, const float* __restrict__ in1, const flo
     O3_THREADS
         const int warp = tid >> 5, lane = tid & 31, nw = NT >> 5;
         for (int e = warp; e < nrow; e += nw) {
-            float* dst = gin1 + (row0 + e) * D1;
-            for (int c = lane; c < D1; c += 32) dst[c] = S.gxs[e * D1p + c];
+            o3_row_store_grad(gin1, row0 + e, S.gxs + e * D1p, lane);
             if (gin2 != nullptr && lane < D2) gin2[(row0 + e) * D2 + lane] = S.gys[e * D2p + lane];
         }
     O3_END
@@ -746,7 +789,7 @@ O3_DEV void o3_gw_accum(const O3Gw& S, const int32_t* IO, float (&acc)[16], int 
 }
 
 // acc[slot] belongs to the slot-th output irrep that has paths
-O3_DEV void o3_gw_tile(const O3Gw& S, O3_ACC_DECL, const float* __restrict__ in1,
+O3_DEV void o3_gw_tile(const O3Gw& S, O3_ACC_DECL, const O3Rows& in1,
                        const float* __restrict__ in2, const float* __restrict__ gout, long long row0,
                        int nrow O3_NT_DECL) {
     const int32_t* tab = S.tab;
@@ -758,8 +801,9 @@ O3_DEV void o3_gw_tile(const O3Gw& S, O3_ACC_DECL, const float* __restrict__ in1
         const int warp = tid >> 5, lane = tid & 31, nw = NT >> 5;
         for (int e = warp; e < TE; e += nw) {
             const bool ok = e < nrow;
-            const float* src = in1 + (row0 + e) * D1;
-            for (int c = lane; c < D1; c += 32) S.xs[e * D1p + c] = ok ? src[c] : 0.f;
+            if (ok) o3_row_load(in1, row0 + e, S.xs + e * D1p, lane);
+            else
+                for (int c = lane; c < D1; c += 32) S.xs[e * D1p + c] = 0.f;
             if (lane < D2) S.ys[e * D2p + lane] = ok ? in2[(row0 + e) * D2 + lane] : 0.f;
             const float* gsrc = gout + (row0 + e) * DO;
             for (int c = lane; c < DO; c += 32) S.gs[e * DOp + c] = ok ? gsrc[c] : 0.f;

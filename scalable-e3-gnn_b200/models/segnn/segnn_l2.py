@@ -1,6 +1,6 @@
 """SEGNN with l_max = 2 on the octree graph (BASELINE configs[2]), first version: every tensor product is the l <= 2 CUDA
 operator (``se3gnn_b200.o3tp.O3TensorProduct``, csrc/o3tp.cu) and every gate one elementwise kernel (csrc/gate.cu); the
-gathers and the aggregation around them are still plain torch tensor ops (the fused gather / gate / sorted-segment-sum epilogues of the l_max = 1 path, DESIGN 4.1-4.3,
+concatenated / gathered inputs are read in place (``forward_cat``); only the aggregation is still a torch op (the fused gather / gate / sorted-segment-sum epilogues of the l_max = 1 path, DESIGN 4.1-4.3,
 are the next step for this model).  Same layer layout as ``models/segnn/segnn.py`` (public SEGNN):
 embedding -> N x [message (2 gated TPs) -> add aggregation over dst -> update (gated TP, TP, residual)] -> 2 read-out TPs,
 no bias terms.  Specification for the tests: ``oracle/segnn_l2_oracle.py``.
@@ -63,11 +63,11 @@ class SEGNNL2(nn.Module):
             raise RuntimeError("SEGNNL2 runs on CUDA (sm_100a) only; there is no CPU fallback")
         x = self.embed(x_in, node_attr)
         for l in range(self.num_layers):
-            m = torch.cat([x.index_select(0, dst), x.index_select(0, src), edge_extra], 1)
-            m = self.gate(self.msg1[l](m, edge_attr))
+            # cat(x[dst], x[src], edge_extra) is read in place by the kernel; its gradient is scattered by the backward
+            m = self.gate(self.msg1[l].forward_cat([(x, dst), (x, src), (edge_extra, None)], edge_attr))
             m = self.gate(self.msg2[l](m, edge_attr))
             agg = torch.zeros_like(x).index_add_(0, dst, m)
-            u = self.gate(self.upd1[l](torch.cat([x, agg], 1), node_attr))
+            u = self.gate(self.upd1[l].forward_cat([(x, None), (agg, None)], node_attr))
             x = x + self.upd2[l](u, node_attr)
         return self.pre2(self.gate(self.pre1(x, node_attr)), node_attr)
 

@@ -96,6 +96,10 @@ EXPORTS = [
     ("se3_o3tp_forward", C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("se3_o3tp_backward", C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("se3_o3tp_forward_seg", C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(RowSeg), C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p]),
+    ("se3_o3tp_backward_seg", C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(RowSeg), C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.POINTER(C.c_void_p), _i32p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("se3_gate_forward", C.c_int, [C.c_int64, C.c_int32, C.c_int32, _i32p, _i32p, C.c_float, C.c_float, C.c_void_p,
                                    C.c_void_p, C.c_void_p]),
     ("se3_gate_backward", C.c_int, [C.c_int64, C.c_int32, C.c_int32, _i32p, _i32p, C.c_float, C.c_float, C.c_void_p,

@@ -47,6 +47,60 @@ class _O3tpFn(torch.autograd.Function):
         return gin1, gin2, gw, None
 
 
+def _rowsegs(tensors, idxs):
+    segs = (capi.RowSeg * capi.MAX_SEG)()
+    for s, (t, ix) in enumerate(zip(tensors, idxs)):
+        segs[s].base, segs[s].idx = capi.ptr(t), capi.ptr(ix)
+        segs[s].width, segs[s].ld = t.shape[1], t.stride(0)
+    return segs
+
+
+class _O3tpCatFn(torch.autograd.Function):
+    """in1 = cat_s(tensors[s][idxs[s]] if idxs[s] is not None else tensors[s]) read in place by the kernels."""
+
+    @staticmethod
+    def forward(ctx, in2, weight, mod, idxs, *tensors):
+        plan = mod._plan
+        rows = in2.shape[0]
+        out = torch.empty((rows, plan.d_out), device=in2.device, dtype=torch.float32)
+        with capi.mark("o3tp.fwd", mod.algo_bytes(rows, "fwd"), mod.flops(rows)):
+            capi.check(capi.lib().se3_o3tp_forward_seg(plan.handle, rows, len(tensors), _rowsegs(tensors, idxs), capi.ptr(in2),
+                                                       capi.ptr(weight), capi.ptr(out), capi.current_stream_ptr()),
+                       "se3_o3tp_forward_seg")
+        ctx.save_for_backward(in2, weight, *tensors)
+        ctx.mod, ctx.idxs = mod, idxs
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        in2, weight, *tensors = ctx.saved_tensors
+        mod, idxs = ctx.mod, ctx.idxs
+        plan = mod._plan
+        rows = in2.shape[0]
+        gout = gout.contiguous()
+        grads, gptr, modes = [], (capi.C.c_void_p * capi.MAX_SEG)(), (capi.C.c_int32 * capi.MAX_SEG)()
+        for s, (t, ix) in enumerate(zip(tensors, idxs)):
+            if not ctx.needs_input_grad[4 + s]:
+                grads.append(None)
+                modes[s] = capi.GRAD_NONE
+                continue
+            # same row stride as the source: the kernels address source and gradient alike
+            g = torch.empty_like(t) if ix is None else torch.zeros_like(t)
+            if g.stride() != t.stride():
+                raise capi.Se3Error("o3tp: segment tensors need a dense row-major layout")
+            grads.append(g)
+            gptr[s] = capi.ptr(g)
+            modes[s] = capi.GRAD_STORE if ix is None else capi.GRAD_ATOMIC
+        gin2 = torch.empty_like(in2) if ctx.needs_input_grad[0] else None
+        gw = torch.empty_like(weight)
+        with capi.mark("o3tp.bwd", mod.algo_bytes(rows, "bwd"), 2 * mod.flops(rows)):
+            capi.check(capi.lib().se3_o3tp_backward_seg(plan.handle, rows, len(tensors), _rowsegs(tensors, idxs),
+                                                        capi.ptr(in2), capi.ptr(weight), capi.ptr(gout), gptr, modes,
+                                                        capi.ptr(gin2), capi.ptr(gw), capi.current_stream_ptr()),
+                       "se3_o3tp_backward_seg")
+        return (gin2, gw, None, None, *grads)
+
+
 class O3TensorProduct(torch.nn.Module):
     def __init__(self, in1_irreps, out_irreps=None, in2_irreps=None):
         super().__init__()
@@ -82,6 +136,30 @@ class O3TensorProduct(torch.nn.Module):
         d1, d2, do = self.in1_dim, self.in2_dim, self.iro.dim
         per_row = (d1 + d2 + do) if part == "fwd" else (do + d1 + d2 + d1 + d2)
         return 4.0 * (rows * per_row + self._plan.weight_floats)
+
+    def forward_cat(self, parts, in2: torch.Tensor) -> torch.Tensor:
+        """TP(cat(parts), in2) without materialising the concatenation: parts = [(tensor [n_s, width_s], idx or None)]
+        (<= 4), idx an int32 [rows] gather index into the tensor's rows (e.g. the edge list), None = one row per output
+        row.  The gradient of a gathered part is scatter-added (atomics) inside the backward kernel."""
+        tensors, idxs = [], []
+        for t, ix in parts:
+            if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2):
+                raise capi.Se3Error("O3TensorProduct.forward_cat: parts must be CUDA fp32 matrices")
+            if t.stride(1) != 1:
+                t = t.contiguous()
+            if ix is not None:
+                if ix.dtype != torch.int32 or ix.shape[0] != in2.shape[0]:
+                    raise capi.Se3Error("O3TensorProduct.forward_cat: gather indices must be int32 [rows]")
+                ix = ix.contiguous()
+            elif t.shape[0] != in2.shape[0]:
+                raise capi.Se3Error("O3TensorProduct.forward_cat: an ungathered part needs one row per output row")
+            tensors.append(t)
+            idxs.append(ix)
+        torch._assert(sum(t.shape[1] for t in tensors) == self.in1_dim, "Incorrect last dimension for in1")
+        torch._assert(in2.dim() == 2 and in2.shape[-1] == self.in2_dim, "Incorrect last dimension for in2")
+        if len(tensors) > capi.MAX_SEG:
+            raise capi.Se3Error(f"O3TensorProduct.forward_cat: at most {capi.MAX_SEG} parts")
+        return _O3tpCatFn.apply(in2.contiguous(), self.weight, self, tuple(idxs), *tensors)
 
     def forward(self, in1: torch.Tensor, in2: torch.Tensor) -> torch.Tensor:
         torch._assert(in1.dim() == 2 and in1.shape[-1] == self.in1_dim, "Incorrect last dimension for in1")

@@ -34,6 +34,20 @@ inline float i2f(int32_t i) { float f; std::memcpy(&f, &i, 4); return f; }
 #include "../../scalable-e3-gnn_b200/csrc/o3tp_body.inl"
 }  // namespace
 
+static void make_rows(int nseg, const float* const* base, const int* const* idx, const int* width, const int* ld,
+                      float* const* gbase, const int* gmode, O3Rows& X, O3GRows& G) {
+    int c0 = 0;
+    X.nseg = G.nseg = nseg;
+    for (int s = 0; s < 4; ++s) {
+        const bool on = s < nseg;
+        X.base[s] = on ? base[s] : nullptr; X.idx[s] = on ? idx[s] : nullptr;
+        X.ld[s] = on ? ld[s] : 0; X.c0[s] = c0; X.width[s] = on ? width[s] : 0;
+        G.base[s] = on && gbase ? gbase[s] : nullptr; G.idx[s] = X.idx[s]; G.ld[s] = X.ld[s]; G.c0[s] = c0;
+        G.width[s] = X.width[s]; G.mode[s] = on && gbase && gbase[s] ? gmode[s] : 0;
+        c0 += X.width[s];
+    }
+}
+
 static bool make_plan(o3::Plan& P, int n1, const int* in1, int n2, const int* in2, int no, const int* out) {
     for (int i = 0; i < n1; ++i) P.in1.push_back({in1[3 * i], in1[3 * i + 1], in1[3 * i + 2]});
     for (int i = 0; i < n2; ++i) P.in2.push_back({1, in2[2 * i], in2[2 * i + 1]});
@@ -65,8 +79,11 @@ int emu_coupling(int l1, int l2, int l3, double* out) {
     return 0;
 }
 
-int emu_forward(int n1, const int* in1i, int n2, const int* in2i, int no, const int* outi, long long rows,
-                const float* in1, const float* in2, const float* w, float* out, int TE, int NT, int nblocks) {
+int emu_forward(int n1, const int* in1i, int n2, const int* in2i, int no, const int* outi, long long rows, int nseg,
+                const float* const* sbase, const int* const* sidx, const int* swidth, const int* sld, const float* in2,
+                const float* w, float* out, int TE, int NT, int nblocks) {
+    O3Rows in1; O3GRows unusedG;
+    make_rows(nseg, sbase, sidx, swidth, sld, nullptr, nullptr, in1, unusedG);
     o3::Plan P;
     if (!make_plan(P, n1, in1i, n2, in2i, no, outi)) return -1;
     if (TE % 32 || NT != 32 * o3::NWARP) return -2;  // the forward schedule is made for 8 warps and 32-row groups
@@ -105,9 +122,12 @@ int emu_forward(int n1, const int* in1i, int n2, const int* in2i, int no, const 
     return 0;
 }
 
-int emu_backward(int n1, const int* in1i, int n2, const int* in2i, int no, const int* outi, long long rows,
-                 const float* in1, const float* in2, const float* w, const float* gout, float* gin1, float* gin2,
-                 float* gw, int NT, int nblocks) {
+int emu_backward(int n1, const int* in1i, int n2, const int* in2i, int no, const int* outi, long long rows, int nseg,
+                 const float* const* sbase, const int* const* sidx, const int* swidth, const int* sld, float* const* gbase,
+                 const int* gmode, const float* in2, const float* w, const float* gout, float* gin2, float* gw, int NT,
+                 int nblocks) {
+    O3Rows in1; O3GRows gin1;
+    make_rows(nseg, sbase, sidx, swidth, sld, gbase, gmode, in1, gin1);
     o3::Plan P;
     if (!make_plan(P, n1, in1i, n2, in2i, no, outi)) return -1;
     if (NT != 32 * o3::NWARP) return -2;  // one block of <= 4 channels per warp and round
@@ -168,9 +188,12 @@ int emu_backward(int n1, const int* in1i, int n2, const int* in2i, int no, const
 
 // the split backward: input-gradient kernel, then weight-gradient kernel (mirrors o3tp_gin_kernel / o3tp_gw_kernel);
 // returns 1 if the plan does not allow the split (too many output irreps / blocks)
-int emu_backward_split(int n1, const int* in1i, int n2, const int* in2i, int no, const int* outi, long long rows,
-                       const float* in1, const float* in2, const float* w, const float* gout, float* gin1, float* gin2,
-                       float* gw, int NT, int nblocks) {
+int emu_backward_split(int n1, const int* in1i, int n2, const int* in2i, int no, const int* outi, long long rows, int nseg,
+                       const float* const* sbase, const int* const* sidx, const int* swidth, const int* sld,
+                       float* const* gbase, const int* gmode, const float* in2, const float* w, const float* gout,
+                       float* gin2, float* gw, int NT, int nblocks) {
+    O3Rows in1; O3GRows gin1;
+    make_rows(nseg, sbase, sidx, swidth, sld, gbase, gmode, in1, gin1);
     o3::Plan P;
     if (!make_plan(P, n1, in1i, n2, in2i, no, outi)) return -1;
     if (NT != 32 * o3::NWARP) return -2;

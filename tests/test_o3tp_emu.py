@@ -37,6 +37,29 @@ def _fp(a):
     return a.ctypes.data_as(C.POINTER(C.c_float))
 
 
+class Segs:
+    """C arrays describing in1 as row segments (+ gradient destinations) for the emulation entry points."""
+
+    def __init__(self, parts, grads=None, modes=None):
+        # parts: [(array [n, ld] float32, idx int32 array or None, width)]
+        n = len(parts)
+        self.keep = parts, grads
+        self.base = (C.POINTER(C.c_float) * 4)(*[_fp(a) for a, _, _ in parts])
+        self.idx = (C.POINTER(C.c_int) * 4)(*[i.ctypes.data_as(C.POINTER(C.c_int)) if i is not None else None for _, i, _ in parts])
+        self.width = (C.c_int * 4)(*[w for _, _, w in parts])
+        self.ld = (C.c_int * 4)(*[a.shape[1] for a, _, _ in parts])
+        self.n = n
+        if grads is not None:
+            self.gbase = (C.POINTER(C.c_float) * 4)(*[_fp(g) if g is not None else None for g in grads])
+            self.gmode = (C.c_int * 4)(*modes)
+
+    def fwd(self):
+        return self.n, self.base, self.idx, self.width, self.ld
+
+    def bwd(self):
+        return self.n, self.base, self.idx, self.width, self.ld, self.gbase, self.gmode
+
+
 CASES = {
     "sh1": ([(8, 0, 1), (4, 1, -1)], 1, [(6, 0, 1), (5, 1, -1)]),
     "balanced2": ([(23, 0, 1), (7, 1, -1), (4, 2, 1)], 2, [(23, 0, 1), (7, 1, -1), (4, 2, 1)]),
@@ -126,14 +149,15 @@ def test_emulated_kernels_match_oracle(emu, name, rows, TEF, nblocks):
     spec = (len(in1), _flat(in1), len(in2), _flat(in2, True), len(out), _flat(out))
     got_o = np.full((rows, do), np.nan, np.float32)
     # forward: one warp per (output irrep, channel chunk, 32-row group); the schedule is made for 8 warps
-    assert emu.emu_forward(*spec, C.c_longlong(rows), _fp(x1), _fp(y), _fp(w), _fp(got_o), TEF, 256, nblocks) == 0
+    assert emu.emu_forward(*spec, C.c_longlong(rows), *Segs([(x1, None, d1)]).fwd(), _fp(y), _fp(w), _fp(got_o), TEF, 256,
+                           nblocks) == 0
     _close(got_o, want_o)
 
     gx = np.full((rows, d1), np.nan, np.float32)
     gy = np.full((rows, d2), np.nan, np.float32)
     gw = np.full(nw, np.nan, np.float32)
-    assert emu.emu_backward(*spec, C.c_longlong(rows), _fp(x1), _fp(y), _fp(w), _fp(g), _fp(gx), _fp(gy), _fp(gw),
-                            256, nblocks) == 0
+    assert emu.emu_backward(*spec, C.c_longlong(rows), *Segs([(x1, None, d1)], [gx], [1]).bwd(), _fp(y), _fp(w), _fp(g),
+                            _fp(gy), _fp(gw), 256, nblocks) == 0
     _close(gx, want_gx)
     _close(gy, want_gy)
     _close(gw, want_gw)
@@ -141,21 +165,60 @@ def test_emulated_kernels_match_oracle(emu, name, rows, TEF, nblocks):
     gx3 = np.full((rows, d1), np.nan, np.float32)
     gy3 = np.full((rows, d2), np.nan, np.float32)
     gw3 = np.full(nw, np.nan, np.float32)
-    rc = emu.emu_backward_split(*spec, C.c_longlong(rows), _fp(x1), _fp(y), _fp(w), _fp(g), _fp(gx3), _fp(gy3), _fp(gw3),
-                                256, nblocks)
+    rc = emu.emu_backward_split(*spec, C.c_longlong(rows), *Segs([(x1, None, d1)], [gx3], [1]).bwd(), _fp(y), _fp(w), _fp(g),
+                                _fp(gy3), _fp(gw3), 256, nblocks)
     assert rc == (1 if name in ("mixed_parity", "wide") else 0)
     if rc == 0:
         _close(gx3, want_gx)
         _close(gy3, want_gy)
         _close(gw3, want_gw)
         gx4 = np.full((rows, d1), np.nan, np.float32)
-        assert emu.emu_backward_split(*spec, C.c_longlong(rows), _fp(x1), _fp(y), _fp(w), _fp(g), _fp(gx4), None,
-                                      _fp(gw3), 256, nblocks) == 0
+        assert emu.emu_backward_split(*spec, C.c_longlong(rows), *Segs([(x1, None, d1)], [gx4], [1]).bwd(), _fp(y), _fp(w),
+                                      _fp(g), None, _fp(gw3), 256, nblocks) == 0
         np.testing.assert_array_equal(gx4, gx3)
     # gin2 is optional
     gx2 = np.full((rows, d1), np.nan, np.float32)
     gw2 = np.full(nw, np.nan, np.float32)
-    assert emu.emu_backward(*spec, C.c_longlong(rows), _fp(x1), _fp(y), _fp(w), _fp(g), _fp(gx2), None, _fp(gw2),
-                            256, nblocks) == 0
+    assert emu.emu_backward(*spec, C.c_longlong(rows), *Segs([(x1, None, d1)], [gx2], [1]).bwd(), _fp(y), _fp(w), _fp(g),
+                            None, _fp(gw2), 256, nblocks) == 0
     np.testing.assert_array_equal(gx2, gx)
     np.testing.assert_array_equal(gw2, gw)
+
+
+@pytest.mark.parametrize("split", [True, False])
+def test_emulated_gathered_segments(emu, split):
+    """in1 = cat(x[dst], x[src], extra) read through row segments; gradients: atomic adds into per-source buffers for the
+    gathered segments, a plain store for the identity segment, one segment skipped."""
+    in1 = [(6, 0, 1), (3, 1, -1), (2, 2, 1), (6, 0, 1), (3, 1, -1), (2, 2, 1), (2, 0, 1)]
+    out = [(9, 0, 1), (3, 1, -1), (2, 2, 1)]
+    in2 = l2.sh_irreps(2)
+    rng = np.random.default_rng(7)
+    nn_, rows, dh = 23, 150, 6 + 9 + 10
+    x = rng.standard_normal((nn_, dh + 3)).astype(np.float32)          # ld > width: padded node rows
+    extra = rng.standard_normal((rows, 2)).astype(np.float32)
+    dst = np.sort(rng.integers(0, nn_, rows)).astype(np.int32)
+    src = rng.integers(0, nn_, rows).astype(np.int32)
+    y = rng.standard_normal((rows, 9)).astype(np.float32)
+    x1 = np.concatenate([x[dst, :dh], x[src, :dh], extra], 1)
+    d1, do = x1.shape[1], 9 + 9 + 10
+    nw = sum(a * b for a, b in l2.weight_shapes(in1, in2, out))
+    w = rng.standard_normal(nw).astype(np.float32)
+    g = rng.standard_normal((rows, do)).astype(np.float32)
+    want_o, want_gx, _, want_gw = _oracle(in1, in2, out, x1, y, w, g)
+    spec = (len(in1), _flat(in1), len(in2), _flat(in2, True), len(out), _flat(out))
+    parts = [(x, dst, dh), (x, src, dh), (extra, None, 2)]
+    got_o = np.full((rows, do), np.nan, np.float32)
+    assert emu.emu_forward(*spec, C.c_longlong(rows), *Segs(parts).fwd(), _fp(y), _fp(w), _fp(got_o), 64, 256, 2) == 0
+    _close(got_o, want_o)
+    ga, gb = np.zeros_like(x), np.zeros_like(x)
+    gw = np.full(nw, np.nan, np.float32)
+    fn = emu.emu_backward_split if split else emu.emu_backward
+    assert fn(*spec, C.c_longlong(rows), *Segs(parts, [ga, gb, None], [2, 2, 0]).bwd(), _fp(y), _fp(w), _fp(g), None,
+              _fp(gw), 256, 2) == 0
+    wa, wb = np.zeros((nn_, dh)), np.zeros((nn_, dh))
+    np.add.at(wa, dst, want_gx[:, :dh])
+    np.add.at(wb, src, want_gx[:, dh:2 * dh])
+    _close(ga[:, :dh], wa)
+    _close(gb[:, :dh], wb)
+    assert not ga[:, dh:].any() and not gb[:, dh:].any()
+    _close(gw, want_gw)

@@ -189,3 +189,28 @@ def test_large_equivariance_and_gradient_linearity():
     parts = gw(0, 100_001) + gw(100_001, rows)
     err = ((whole - parts).abs().max() / whole.abs().max()).item()
     assert err < 2e-5, err
+
+
+def test_gathered_segments_match_dense():
+    """forward_cat([(x, dst), (x, src), (extra, None)]) == forward(cat(x[dst], x[src], extra)), values and gradients
+    (the gathered gradients are scatter-added inside the kernel)."""
+    in1, lmax, out = CASES["message2"]
+    tp = _module(in1, lmax, out)
+    torch.manual_seed(3)
+    nn_, rows, dh = 3000, 40_001, 64
+    x = torch.randn(nn_, dh, device="cuda", requires_grad=True)
+    extra = torch.randn(rows, 2, device="cuda", requires_grad=True)
+    dst = torch.sort(torch.randint(0, nn_, (rows,), device="cuda"))[0].int()
+    src = torch.randint(0, nn_, (rows,), device="cuda").int()
+    y = torch.randn(rows, 9, device="cuda")
+    g = torch.randn(rows, tp.iro.dim, device="cuda")
+    a = tp(torch.cat([x[dst.long()], x[src.long()], extra], 1), y)
+    a.backward(g)
+    want = (a.detach().clone(), x.grad.clone(), extra.grad.clone(), tp.weight.grad.clone())
+    x.grad = extra.grad = tp.weight.grad = None
+    b = tp.forward_cat([(x, dst), (x, src), (extra, None)], y)
+    b.backward(g)
+    assert torch.equal(b, want[0])
+    for got, ref, what in ((x.grad, want[1], "x"), (extra.grad, want[2], "extra"), (tp.weight.grad, want[3], "weight")):
+        err = ((got - ref).abs().max() / ref.abs().max()).item()
+        assert err < 2e-5, (what, err)

@@ -1,7 +1,7 @@
-"""BASELINE configs[2] as a measured case (first version, fp32 SIMT tensor products, torch glue for gather / gate /
-aggregation): octree graph build + SH(2) attributes + 4-layer SEGNN l_max = 2 forward/backward + Adam on one GPU.
-One JSON line; CUDA events on the current stream, warm-up first.  The unfused model keeps every per-edge tensor for
-autograd (about 7.7 KB per edge over 4 layers): 1M particles (17.9M edges) peak at 137 GB of the 180 GB.
+"""BASELINE configs[2] as a measured case (first version: fp32 SIMT tensor products reading their gathered inputs in
+place, gate kernels; the aggregation is still torch's index_add): octree graph build + SH(2) attributes + 4-layer SEGNN l_max = 2 forward/backward + Adam on one GPU.
+One JSON line; CUDA events on the current stream, warm-up first.  The model keeps the per-edge tensor-product outputs
+for autograd (about 4.8 KB per edge over 4 layers).
 
     python tools/bench_segnn_l2.py [--particles 100000] [--steps 5]
 """
@@ -69,7 +69,8 @@ def main():
         "ms_per_step": round(ms, 3), "particles_per_s": n / ms * 1e3, "edges": int(g.e), "cells": int(g.m),
         "gpu_launches_per_step": (capi.launch_count() - n0) / a.steps, "loss": float(loss.detach()),
         "peak_mem_GB": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2),
-        "note": "tensor products: csrc/o3tp.cu (fp32 SIMT); gather / gate / aggregation: torch ops (not fused yet)",
+        "note": "tensor products csrc/o3tp.cu (fp32 SIMT, gathered inputs read in place), gates csrc/gate.cu; "
+                "aggregation (index_add) and residual are torch ops",
     }), flush=True)
 
 

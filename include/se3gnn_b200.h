@@ -159,7 +159,8 @@ int se3_o3tp_backward(se3_o3tp_plan* plan, int64_t rows, const float* in1, const
 /* The same with in1 given as a virtual concatenation of up to SE3_MAX_SEG (optionally gathered) row segments, as in
  * se3_l1tp_fwd_args: the message product reads cat(x[dst], x[src], edge_extra) without materialising it.  Backward:
  * gseg[s] receives the gradient of segment s with gseg_mode[s] = SE3_GRAD_NONE (or gseg[s] == NULL) / SE3_GRAD_STORE
- * (identity rows: written) / SE3_GRAD_ATOMIC or SE3_GRAD_SORTED (gathered rows: += with atomics, caller zeroes). */
+ * (identity rows: written) / SE3_GRAD_ATOMIC (gathered rows: += with atomics, caller zeroes) / SE3_GRAD_SORTED (the same
+ * for an index that is sorted: runs inside a tile are summed before the one atomic add). */
 int se3_o3tp_forward_seg(se3_o3tp_plan* plan, int64_t rows, int32_t nseg, const se3_rowseg* seg, const float* in2,
                          const float* w, float* out, void* stream);
 int se3_o3tp_backward_seg(se3_o3tp_plan* plan, int64_t rows, int32_t nseg, const se3_rowseg* seg, const float* in2,

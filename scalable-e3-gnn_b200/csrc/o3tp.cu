@@ -29,6 +29,7 @@ typedef float4 o3f4;
 #define O3_ACC_DECL float (&acc)[o3::MAXIO_GW][16]
 #define O3_ACC(acc, slot, tid) acc[slot]
 #define O3_GLOBAL_ADD(p, v) atomicAdd((p), (v))
+#define O3_GLOBAL_ADD4(p, a, b, c, d) se3::red_add_v4((p), (a), (b), (c), (d))
 #define O3_CP4(dst, src)                                                                                      \
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), \
                  "l"(src)                                                                                    \
@@ -408,7 +409,8 @@ extern "C" int se3_o3tp_backward_seg(se3_o3tp_plan* p, int64_t rows, int32_t nse
             return SE3_ERR_INVALID;
         }
         G.base[s] = on ? gseg[s] : nullptr; G.idx[s] = X.idx[s]; G.ld[s] = X.ld[s]; G.c0[s] = X.c0[s]; G.width[s] = X.width[s];
-        G.mode[s] = !on ? 0 : (gseg_mode[s] == SE3_GRAD_STORE ? 1 : 2);   // SORTED is served by the atomic path here
+        G.mode[s] = !on ? 0 : (gseg_mode[s] == SE3_GRAD_STORE ? 1 : (gseg_mode[s] == SE3_GRAD_SORTED ? 3 : 2));
+        if (on && G.mode[s] != 1 && (X.width[s] & 3) == 0 && (X.ld[s] & 3) == 0 && ((uintptr_t)gseg[s] & 15) == 0) G.mode[s] |= 16;
     }
     SE3_CUDA_TRY(cudaMemsetAsync(gw, 0, sizeof(float) * p->P.nW, (cudaStream_t)stream));
     if (rows == 0) return SE3_OK;

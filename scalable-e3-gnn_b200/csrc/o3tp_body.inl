@@ -11,7 +11,7 @@
 //   O3_CP4(dst, src) / O3_CP_COMMIT() / O3_CP_WAIT()   4-byte asynchronous global -> shared copy, group commit, wait all
 //   O3_ACC_DECL / O3_ACC(acc, slot, tid)   per-thread accumulator sets [MAXIO_GW][16] that live across regions and
 //                              tiles (registers under nvcc, one array per emulated thread otherwise)
-//   O3_GLOBAL_ADD(p, v)        atomic float add to global memory
+//   O3_GLOBAL_ADD(p, v) / O3_GLOBAL_ADD4(p, a, b, c, d)   atomic float add to global memory (one / four consecutive)
 //   O3_I2F(i)                  reinterpret an int32 table word as float
 //   O3_NT_DECL                 extra parameter `, int NT_` carrying the emulated block size (empty under nvcc)
 //   o3f4 / O3_LD4(p)           four consecutive floats read from a 16-byte aligned shared-memory address
@@ -40,7 +40,7 @@ struct O3Rows {
 struct O3GRows {
     float* base[4];
     const int* idx[4];
-    int ld[4], c0[4], width[4], mode[4];  // mode: SE3_GRAD_NONE / STORE / ATOMIC
+    int ld[4], c0[4], width[4], mode[4];  // see o3_tile_store_grad
     int nseg;
 };
 
@@ -60,15 +60,47 @@ O3_DEV void o3_row_load(const O3Rows& X, long long row, float* dst, int lane) {
             for (int c = lane; c < X.width[s]; c += 32) dst[X.c0[s] + c] = src[c];
         }
 }
-O3_DEV void o3_row_store_grad(const O3GRows& G, long long row, const float* src, int lane) {
+// Gradient tile [nrow, D1p] (shared) -> the segments' destinations.  mode & 15: 1 store (identity rows), 2 atomic add per
+// row, 3 rows sorted by index: the rows of a run inside the tile are summed first and added once (an octree node has
+// ~18 incoming edges, so this removes most of the atomics of the dst segment); mode & 16: 16-byte reductions (width, ld
+// multiples of 4, base 16-byte aligned: checked by the host).
+O3_DEV void o3_tile_store_grad(const O3GRows& G, long long row0, int nrow, const float* gxs, int D1p, int tid, int NT) {
+    const int warp = tid >> 5, lane = tid & 31, nw = NT >> 5;
     O3_UNROLL
     for (int s = 0; s < 4; ++s)
         if (s < G.nseg && G.mode[s] != 0) {
-            float* dst = G.base[s] + (G.idx[s] ? (long long)G.idx[s][row] : row) * G.ld[s];
-            if (G.mode[s] == 1) {
-                for (int c = lane; c < G.width[s]; c += 32) dst[c] = src[G.c0[s] + c];
-            } else {
-                for (int c = lane; c < G.width[s]; c += 32) O3_GLOBAL_ADD(dst + c, src[G.c0[s] + c]);
+            const int mode = G.mode[s] & 15, c0 = G.c0[s], width = G.width[s];
+            const bool v4 = (G.mode[s] & 16) != 0;
+            for (int e = warp; e < nrow; e += nw) {
+                const float* src = gxs + e * D1p + c0;
+                if (mode == 1) {
+                    float* dst = G.base[s] + (row0 + e) * G.ld[s];
+                    for (int c = lane; c < width; c += 32) dst[c] = src[c];
+                    continue;
+                }
+                const int id = G.idx[s][row0 + e];
+                int len = 1;
+                if (mode == 3) {
+                    if (e > 0 && G.idx[s][row0 + e - 1] == id) continue;   // not the head of its run (warp-uniform)
+                    while (e + len < nrow && G.idx[s][row0 + e + len] == id) ++len;
+                }
+                float* dst = G.base[s] + (long long)id * G.ld[s];
+                if (v4) {
+                    for (int c = 4 * lane; c < width; c += 128) {
+                        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                        for (int k = 0; k < len; ++k) {
+                            const float* p = src + k * D1p + c;
+                            a0 += p[0]; a1 += p[1]; a2 += p[2]; a3 += p[3];
+                        }
+                        O3_GLOBAL_ADD4(dst + c, a0, a1, a2, a3);
+                    }
+                } else {
+                    for (int c = lane; c < width; c += 32) {
+                        float a0 = 0.f;
+                        for (int k = 0; k < len; ++k) a0 += src[k * D1p + c];
+                        O3_GLOBAL_ADD(dst + c, a0);
+                    }
+                }
             }
         }
 }
@@ -528,11 +560,11 @@ O3_DEV void o3_bwd_tile(const O3Bwd& S, int buf, const O3Rows& in1, const float*
     O3_THREADS
         if (prefetch) o3_bwd_load(S, buf ^ 1, in1, in2, gout, row0_next, nrow_next, tid, NT);  // no output irrep had paths
         o3_bwd_reduce(S, Q, tid, NT);
+        o3_tile_store_grad(gin1, row0, nrow, S.gxs, D1p, tid, NT);
         const int warp = tid >> 5, lane = tid & 31, nw = NT >> 5;
-        for (int e = warp; e < nrow; e += nw) {
-            o3_row_store_grad(gin1, row0 + e, S.gxs + e * D1p, lane);
-            if (gin2 != nullptr && lane < D2) gin2[(row0 + e) * D2 + lane] = S.gys[e * D2p + lane];
-        }
+        if (gin2 != nullptr)
+            for (int e = warp; e < nrow; e += nw)
+                if (lane < D2) gin2[(row0 + e) * D2 + lane] = S.gys[e * D2p + lane];
     O3_END
 }
 
@@ -692,11 +724,11 @@ O3_DEV void o3_gin_tile(const O3Gin& S, const O3Rows& in1, const float* __restri
     O3_END
 
     O3_THREADS
+        o3_tile_store_grad(gin1, row0, nrow, S.gxs, D1p, tid, NT);
         const int warp = tid >> 5, lane = tid & 31, nw = NT >> 5;
-        for (int e = warp; e < nrow; e += nw) {
-            o3_row_store_grad(gin1, row0 + e, S.gxs + e * D1p, lane);
-            if (gin2 != nullptr && lane < D2) gin2[(row0 + e) * D2 + lane] = S.gys[e * D2p + lane];
-        }
+        if (gin2 != nullptr)
+            for (int e = warp; e < nrow; e += nw)
+                if (lane < D2) gin2[(row0 + e) * D2 + lane] = S.gys[e * D2p + lane];
     O3_END
 }
 

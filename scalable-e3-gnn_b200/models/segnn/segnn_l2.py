@@ -64,7 +64,7 @@ class SEGNNL2(nn.Module):
         x = self.embed(x_in, node_attr)
         for l in range(self.num_layers):
             # cat(x[dst], x[src], edge_extra) is read in place by the kernel; its gradient is scattered by the backward
-            m = self.gate(self.msg1[l].forward_cat([(x, dst), (x, src), (edge_extra, None)], edge_attr))
+            m = self.gate(self.msg1[l].forward_cat([(x, dst, True), (x, src), (edge_extra, None)], edge_attr))
             m = self.gate(self.msg2[l](m, edge_attr))
             agg = torch.zeros_like(x).index_add_(0, dst, m)
             u = self.gate(self.upd1[l].forward_cat([(x, None), (agg, None)], node_attr))

@@ -59,7 +59,7 @@ class _O3tpCatFn(torch.autograd.Function):
     """in1 = cat_s(tensors[s][idxs[s]] if idxs[s] is not None else tensors[s]) read in place by the kernels."""
 
     @staticmethod
-    def forward(ctx, in2, weight, mod, idxs, *tensors):
+    def forward(ctx, in2, weight, mod, idxs, sorted_flags, *tensors):
         plan = mod._plan
         rows = in2.shape[0]
         out = torch.empty((rows, plan.d_out), device=in2.device, dtype=torch.float32)
@@ -68,19 +68,19 @@ class _O3tpCatFn(torch.autograd.Function):
                                                        capi.ptr(weight), capi.ptr(out), capi.current_stream_ptr()),
                        "se3_o3tp_forward_seg")
         ctx.save_for_backward(in2, weight, *tensors)
-        ctx.mod, ctx.idxs = mod, idxs
+        ctx.mod, ctx.idxs, ctx.sorted_flags = mod, idxs, sorted_flags
         return out
 
     @staticmethod
     def backward(ctx, gout):
         in2, weight, *tensors = ctx.saved_tensors
-        mod, idxs = ctx.mod, ctx.idxs
+        mod, idxs, sorted_flags = ctx.mod, ctx.idxs, ctx.sorted_flags
         plan = mod._plan
         rows = in2.shape[0]
         gout = gout.contiguous()
         grads, gptr, modes = [], (capi.C.c_void_p * capi.MAX_SEG)(), (capi.C.c_int32 * capi.MAX_SEG)()
         for s, (t, ix) in enumerate(zip(tensors, idxs)):
-            if not ctx.needs_input_grad[4 + s]:
+            if not ctx.needs_input_grad[5 + s]:
                 grads.append(None)
                 modes[s] = capi.GRAD_NONE
                 continue
@@ -90,7 +90,7 @@ class _O3tpCatFn(torch.autograd.Function):
                 raise capi.Se3Error("o3tp: segment tensors need a dense row-major layout")
             grads.append(g)
             gptr[s] = capi.ptr(g)
-            modes[s] = capi.GRAD_STORE if ix is None else capi.GRAD_ATOMIC
+            modes[s] = capi.GRAD_STORE if ix is None else (capi.GRAD_SORTED if sorted_flags[s] else capi.GRAD_ATOMIC)
         gin2 = torch.empty_like(in2) if ctx.needs_input_grad[0] else None
         gw = torch.empty_like(weight)
         with capi.mark("o3tp.bwd", mod.algo_bytes(rows, "bwd"), 2 * mod.flops(rows)):
@@ -98,7 +98,7 @@ class _O3tpCatFn(torch.autograd.Function):
                                                         capi.ptr(in2), capi.ptr(weight), capi.ptr(gout), gptr, modes,
                                                         capi.ptr(gin2), capi.ptr(gw), capi.current_stream_ptr()),
                        "se3_o3tp_backward_seg")
-        return (gin2, gw, None, None, *grads)
+        return (gin2, gw, None, None, None, *grads)
 
 
 class O3TensorProduct(torch.nn.Module):
@@ -138,11 +138,14 @@ class O3TensorProduct(torch.nn.Module):
         return 4.0 * (rows * per_row + self._plan.weight_floats)
 
     def forward_cat(self, parts, in2: torch.Tensor) -> torch.Tensor:
-        """TP(cat(parts), in2) without materialising the concatenation: parts = [(tensor [n_s, width_s], idx or None)]
-        (<= 4), idx an int32 [rows] gather index into the tensor's rows (e.g. the edge list), None = one row per output
-        row.  The gradient of a gathered part is scatter-added (atomics) inside the backward kernel."""
-        tensors, idxs = [], []
-        for t, ix in parts:
+        """TP(cat(parts), in2) without materialising the concatenation: parts = [(tensor [n_s, width_s], idx or None[,
+        sorted])] (<= 4), idx an int32 [rows] gather index into the tensor's rows (e.g. the edge list), None = one row per
+        output row.  The gradient of a gathered part is scatter-added inside the backward kernel; `sorted=True` promises a
+        sorted index (the dst list of the graph), whose runs are summed on chip before one atomic add per run."""
+        tensors, idxs, flags = [], [], []
+        for part in parts:
+            t, ix = part[0], part[1]
+            flags.append(bool(part[2]) if len(part) > 2 else False)
             if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2):
                 raise capi.Se3Error("O3TensorProduct.forward_cat: parts must be CUDA fp32 matrices")
             if t.stride(1) != 1:
@@ -159,7 +162,7 @@ class O3TensorProduct(torch.nn.Module):
         torch._assert(in2.dim() == 2 and in2.shape[-1] == self.in2_dim, "Incorrect last dimension for in2")
         if len(tensors) > capi.MAX_SEG:
             raise capi.Se3Error(f"O3TensorProduct.forward_cat: at most {capi.MAX_SEG} parts")
-        return _O3tpCatFn.apply(in2.contiguous(), self.weight, self, tuple(idxs), *tensors)
+        return _O3tpCatFn.apply(in2.contiguous(), self.weight, self, tuple(idxs), tuple(flags), *tensors)
 
     def forward(self, in1: torch.Tensor, in2: torch.Tensor) -> torch.Tensor:
         torch._assert(in1.dim() == 2 and in1.shape[-1] == self.in1_dim, "Incorrect last dimension for in1")

@@ -26,6 +26,7 @@ inline float i2f(int32_t i) { float f; std::memcpy(&f, &i, 4); return f; }
 #define O3_ACC_DECL float (*acc)[o3::MAXIO_GW][16]
 #define O3_ACC(acc, slot, tid) acc[tid][slot]
 #define O3_GLOBAL_ADD(p, v) (*(p) += (v))
+#define O3_GLOBAL_ADD4(p, a, b, c, d) ((p)[0] += (a), (p)[1] += (b), (p)[2] += (c), (p)[3] += (d))
 #define O3_CP4(dst, src) (*(dst) = *(src))
 #define O3_CP_COMMIT()
 #define O3_CP_WAIT()

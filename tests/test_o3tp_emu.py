@@ -185,8 +185,8 @@ def test_emulated_kernels_match_oracle(emu, name, rows, TEF, nblocks):
     np.testing.assert_array_equal(gw2, gw)
 
 
-@pytest.mark.parametrize("split", [True, False])
-def test_emulated_gathered_segments(emu, split):
+@pytest.mark.parametrize("split,modes", [(True, [3 | 16, 2 | 16, 0]), (False, [3, 2, 0]), (True, [2, 3 | 16, 0])])
+def test_emulated_gathered_segments(emu, split, modes):
     """in1 = cat(x[dst], x[src], extra) read through row segments; gradients: atomic adds into per-source buffers for the
     gathered segments, a plain store for the identity segment, one segment skipped."""
     in1 = [(6, 0, 1), (3, 1, -1), (2, 2, 1), (6, 0, 1), (3, 1, -1), (2, 2, 1), (2, 0, 1)]
@@ -194,10 +194,15 @@ def test_emulated_gathered_segments(emu, split):
     in2 = l2.sh_irreps(2)
     rng = np.random.default_rng(7)
     nn_, rows, dh = 23, 150, 6 + 9 + 10
-    x = rng.standard_normal((nn_, dh + 3)).astype(np.float32)          # ld > width: padded node rows
+    pad = 3 if not (modes[0] | modes[1]) & 16 else 0                     # ld > width: padded node rows (scalar adds)
+    in1 = [(9, 0, 1) if m == 6 else (m, l, p) for m, l, p in in1] if not pad else in1   # 16-byte path: width 28
+    dh = sum(m * (2 * l + 1) for m, l, p in in1[:3])
+    x = rng.standard_normal((nn_, dh + pad)).astype(np.float32)
     extra = rng.standard_normal((rows, 2)).astype(np.float32)
     dst = np.sort(rng.integers(0, nn_, rows)).astype(np.int32)
     src = rng.integers(0, nn_, rows).astype(np.int32)
+    if modes[1] & 15 == 3:
+        src = np.sort(src)
     y = rng.standard_normal((rows, 9)).astype(np.float32)
     x1 = np.concatenate([x[dst, :dh], x[src, :dh], extra], 1)
     d1, do = x1.shape[1], 9 + 9 + 10
@@ -213,7 +218,7 @@ def test_emulated_gathered_segments(emu, split):
     ga, gb = np.zeros_like(x), np.zeros_like(x)
     gw = np.full(nw, np.nan, np.float32)
     fn = emu.emu_backward_split if split else emu.emu_backward
-    assert fn(*spec, C.c_longlong(rows), *Segs(parts, [ga, gb, None], [2, 2, 0]).bwd(), _fp(y), _fp(w), _fp(g), None,
+    assert fn(*spec, C.c_longlong(rows), *Segs(parts, [ga, gb, None], modes).bwd(), _fp(y), _fp(w), _fp(g), None,
               _fp(gw), 256, 2) == 0
     wa, wb = np.zeros((nn_, dh)), np.zeros((nn_, dh))
     np.add.at(wa, dst, want_gx[:, :dh])

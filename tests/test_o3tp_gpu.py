@@ -208,7 +208,7 @@ def test_gathered_segments_match_dense():
     a.backward(g)
     want = (a.detach().clone(), x.grad.clone(), extra.grad.clone(), tp.weight.grad.clone())
     x.grad = extra.grad = tp.weight.grad = None
-    b = tp.forward_cat([(x, dst), (x, src), (extra, None)], y)
+    b = tp.forward_cat([(x, dst, True), (x, src), (extra, None)], y)     # dst sorted: run-combined adds; src: 16-byte reds
     b.backward(g)
     assert torch.equal(b, want[0])
     for got, ref, what in ((x.grad, want[1], "x"), (extra.grad, want[2], "extra"), (tp.weight.grad, want[3], "weight")):

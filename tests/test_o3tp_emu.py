@@ -227,3 +227,50 @@ def test_emulated_gathered_segments(emu, split, modes):
     _close(gb[:, :dh], wb)
     assert not ga[:, dh:].any() and not gb[:, dh:].any()
     _close(gw, want_gw)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_emulated_kernels_random_irreps(emu, seed):
+    """Seeded random configurations (irreps of both parities in any order, repeated irreps, 1..8 of them, in2 = SH(0..2),
+    ragged row counts): forward, fused backward and - where the plan allows it - split backward against the oracle."""
+    rng = np.random.default_rng(1000 + seed)
+
+    def rand_irreps(k):
+        return [(int(rng.integers(1, 10)), int(rng.integers(0, 3)), int(rng.choice([-1, 1]))) for _ in range(k)]
+
+    lmax = int(rng.integers(0, 3))
+    in2 = l2.sh_irreps(lmax)
+    for _ in range(50):
+        in1, out = rand_irreps(int(rng.integers(1, 9))), rand_irreps(int(rng.integers(1, 9)))
+        if l2.paths(in1, in2, out):
+            break
+    else:
+        pytest.skip("no connected configuration drawn")
+    rows = int(rng.integers(1, 150))
+    d1 = sum(m * (2 * l + 1) for m, l, _ in in1)
+    d2 = sum(2 * l + 1 for _, l, _ in in2)
+    do = sum(m * (2 * l + 1) for m, l, _ in out)
+    x1 = rng.standard_normal((rows, d1)).astype(np.float32)
+    y = rng.standard_normal((rows, d2)).astype(np.float32)
+    nw = sum(a * b for a, b in l2.weight_shapes(in1, in2, out))
+    w = rng.standard_normal(nw).astype(np.float32)
+    g = rng.standard_normal((rows, do)).astype(np.float32)
+    want_o, want_gx, want_gy, want_gw = _oracle(in1, in2, out, x1, y, w, g)
+    spec = (len(in1), _flat(in1), len(in2), _flat(in2, True), len(out), _flat(out))
+    nblocks = int(rng.integers(1, 4))
+    got_o = np.full((rows, do), np.nan, np.float32)
+    assert emu.emu_forward(*spec, C.c_longlong(rows), *Segs([(x1, None, d1)]).fwd(), _fp(y), _fp(w), _fp(got_o),
+                           int(rng.choice([32, 64])), 256, nblocks) == 0
+    _close(got_o, want_o)
+    for fn in (emu.emu_backward, emu.emu_backward_split):
+        gx = np.full((rows, d1), np.nan, np.float32)
+        gy = np.full((rows, d2), np.nan, np.float32)
+        gw = np.full(nw, np.nan, np.float32)
+        rc = fn(*spec, C.c_longlong(rows), *Segs([(x1, None, d1)], [gx], [1]).bwd(), _fp(y), _fp(w), _fp(g), _fp(gy),
+                _fp(gw), 256, nblocks)
+        if rc == 1 and fn is emu.emu_backward_split:
+            continue                                  # plan not eligible for the split (many output irreps)
+        assert rc == 0
+        _close(gx, want_gx)
+        _close(gy, want_gy)
+        _close(gw, want_gw)

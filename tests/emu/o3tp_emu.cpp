@@ -13,7 +13,16 @@ namespace {
 struct o3f4 { float x, y, z, w; };
 inline float i2f(int32_t i) { float f; std::memcpy(&f, &i, 4); return f; }
 #define O3_DEV inline
-#define O3_THREADS for (int tid = 0; tid < NT_; ++tid) { const int NT = NT_;
+// thread order inside a region: a region must not depend on it (no barrier-free read-after-write between threads), so the
+// tests run every case in several orders
+static int g_order = 0;
+static inline int emu_tid(int k, int nt) {
+    if (g_order == 1) return nt - 1 - k;                                  // reversed
+    if (g_order == 2) return ((k & 31) * (nt >> 5) + (k >> 5)) % nt;      // lane-major: warps interleaved
+    if (g_order == 3) return (k * 37 + 11) % nt;                          // a fixed permutation (37 coprime to 256)
+    return k;
+}
+#define O3_THREADS for (int k_ = 0; k_ < NT_; ++k_) { const int tid = emu_tid(k_, NT_); const int NT = NT_;
 #define O3_END }
 #define O3_ATOMIC_ADD(p, v) (*(p) += (v))
 #define O3_GW_ADD(S, p, v) (*(p) += (v))
@@ -57,6 +66,8 @@ static bool make_plan(o3::Plan& P, int n1, const int* in1, int n2, const int* in
 }
 
 extern "C" {
+
+void emu_set_order(int mode) { g_order = mode; }
 
 // irreps as flat int triples (mul, l, p) / pairs (l, p); returns weight count or -1; dims = D1, D2, Dout, npaths
 int emu_plan(int n1, const int* in1, int n2, const int* in2, int no, const int* out, int* dims, int* path_io,

@@ -229,6 +229,22 @@ def test_emulated_gathered_segments(emu, split, modes):
     _close(gw, want_gw)
 
 
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_regions_do_not_depend_on_thread_order(emu, order):
+    """The emulation runs the threads of a region one after another; a missing barrier (a thread reading what another
+    thread of the same region writes) would make the result depend on that order.  Re-run representative cases with the
+    threads reversed, warp-interleaved and permuted."""
+    emu.emu_set_order(order)
+    try:
+        test_emulated_kernels_match_oracle(emu, "message2", 121, 64, 2)
+        test_emulated_kernels_match_oracle(emu, "mixed_parity", 19, 32, 1)
+        test_emulated_gathered_segments(emu, True, [3 | 16, 2 | 16, 0])
+        test_emulated_gathered_segments(emu, False, [3, 2, 0])
+        test_emulated_kernels_random_irreps(emu, 3)
+    finally:
+        emu.emu_set_order(0)
+
+
 @pytest.mark.parametrize("seed", range(12))
 def test_emulated_kernels_random_irreps(emu, seed):
     """Seeded random configurations (irreps of both parities in any order, repeated irreps, 1..8 of them, in2 = SH(0..2),

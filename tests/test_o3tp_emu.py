@@ -290,3 +290,28 @@ def test_emulated_kernels_random_irreps(emu, seed):
         _close(gx, want_gx)
         _close(gy, want_gy)
         _close(gw, want_gw)
+
+
+def test_emulated_kernels_match_frozen_vectors(emu):
+    """The emulated kernels against the frozen convention vectors (`tests/golden/o3tp_*.npz`)."""
+    import glob
+    import json
+    files = sorted(f for f in glob.glob(os.path.join(HERE, "golden", "o3tp_*.npz")) if not f.endswith("couplings.npz"))
+    assert len(files) == 3
+    for f in files:
+        r = np.load(f)
+        meta = json.loads(bytes(r["meta"]).decode())
+        in1, out = [tuple(t) for t in meta["in1"]], [tuple(t) for t in meta["out"]]
+        in2 = l2.sh_irreps(meta["lmax"])
+        x1, y, w, g = (np.ascontiguousarray(r[k]) for k in ("x1", "y", "w", "g"))
+        rows, d1, d2 = x1.shape[0], x1.shape[1], y.shape[1]
+        spec = (len(in1), _flat(in1), len(in2), _flat(in2, True), len(out), _flat(out))
+        got = np.full(r["out_f64"].shape, np.nan, np.float32)
+        assert emu.emu_forward(*spec, C.c_longlong(rows), *Segs([(x1, None, d1)]).fwd(), _fp(y), _fp(w), _fp(got), 32, 256, 1) == 0
+        _close(got, r["out_f64"])
+        gx, gy, gw = np.full((rows, d1), np.nan, np.float32), np.full((rows, d2), np.nan, np.float32), np.full(len(w), np.nan, np.float32)
+        assert emu.emu_backward(*spec, C.c_longlong(rows), *Segs([(x1, None, d1)], [gx], [1]).bwd(), _fp(y), _fp(w), _fp(g),
+                                _fp(gy), _fp(gw), 256, 1) == 0
+        _close(gx, r["gx_f64"])
+        _close(gy, r["gy_f64"])
+        _close(gw, r["gw_f64"])

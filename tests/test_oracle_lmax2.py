@@ -131,3 +131,34 @@ def test_component_normalisation_variance():
     for lo, (a, b) in zip((0, 1, 2), ((0, 8), (8, 32), (32, 72))):
         v = o[:, a:b].var()
         assert 0.5 < v < 2.0, (lo, v)
+
+
+def test_frozen_convention():
+    """`tests/golden/o3tp_*.npz` freeze this repo's l = 2 convention (bases, coupling signs, normalisation, path order):
+    the oracle must keep reproducing them.  (Not reference outputs: there is no l = 2 reference.)"""
+    import glob
+    import json
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    z = np.load(os.path.join(here, "o3tp_couplings.npz"))
+    assert len(z.files) == 15
+    for k in z.files:
+        a, b, c = (int(ch) for ch in k[3:])
+        np.testing.assert_allclose(l2.cg(a, b, c), z[k], atol=1e-13)
+    files = sorted(f for f in glob.glob(os.path.join(here, "o3tp_*.npz")) if not f.endswith("couplings.npz"))
+    assert len(files) == 3
+    for f in files:
+        r = np.load(f)
+        meta = json.loads(bytes(r["meta"]).decode())
+        in1 = [tuple(t) for t in meta["in1"]]
+        out = [tuple(t) for t in meta["out"]]
+        in2 = l2.sh_irreps(meta["lmax"])
+        assert [list(p) for p in l2.paths(in1, in2, out)] == meta["paths"]
+        np.testing.assert_allclose(l2.norm_factors(in1, in2, out), meta["norm"], rtol=1e-14)
+        ws, o = [], 0
+        for a, b in l2.weight_shapes(in1, in2, out):
+            ws.append(torch.from_numpy(r["w"][o:o + a * b].astype(np.float64).reshape(a, b)))
+            o += a * b
+        got = l2.forward(torch.from_numpy(r["x1"].astype(np.float64)), torch.from_numpy(r["y"].astype(np.float64)), ws,
+                         in1, in2, out).numpy()
+        np.testing.assert_allclose(got, r["out_f64"], rtol=1e-12, atol=1e-12)

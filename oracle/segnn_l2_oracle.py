@@ -51,13 +51,28 @@ class SEGNNL2Oracle(torch.nn.Module):
         t = raw[:, o + 3 * nv:].reshape(-1, nt, 5) * g[:, nv:, None]
         return torch.cat([SILU_CST * torch.nn.functional.silu(raw[:, :ns]), v.reshape(len(raw), -1), t.reshape(len(raw), -1)], 1)
 
-    def forward(self, x_in, node_attr, edge_attr, edge_extra, dst, src):
+    def forward(self, x_in, node_attr, edge_attr, edge_extra, dst, src, halo=None):
+        """``halo`` (domain-decomposition tests): callable appending the halo rows to the owned rows of x."""
         dst, src = dst.long(), src.long()
         x = self.embed(x_in, node_attr)
         for l in range(self.num_layers):
-            m = self.gate(self.msg1[l](torch.cat([x[dst], x[src], edge_extra], 1), edge_attr))
+            xe = x if halo is None else halo(x)
+            m = self.gate(self.msg1[l](torch.cat([xe[dst], xe[src], edge_extra], 1), edge_attr))
             m = self.gate(self.msg2[l](m, edge_attr))
             agg = torch.zeros_like(x).index_add(0, dst, m)
             u = self.gate(self.upd1[l](torch.cat([x, agg], 1), node_attr))
             x = x + self.upd2[l](u, node_attr)
         return self.pre2(self.gate(self.pre1(x, node_attr)), node_attr)
+
+
+def sh2_features(f, g):
+    """SH(2) edge / node attributes from the l_max = 1 feature dict `f` of `oracle.segnn_oracle.graph_features` and the graph
+    `g`: (edge_attr9, node_attr9) as numpy fp64 - what `se3_edge_geometry_l2` computes on the GPU."""
+    import numpy as np
+    P, V = f["node_pos"], f["node_vel"]
+    d, s = g["dst"], g["col"]
+    ea = O2.spherical_harmonics(P[s] - P[d], 2)
+    na = np.zeros((len(P), 9))
+    np.add.at(na, d, ea)
+    na /= np.maximum(np.diff(g["rowptr"]), 1)[:, None]
+    return ea, na + O2.spherical_harmonics(V, 2)

@@ -57,14 +57,19 @@ class SEGNNL2(nn.Module):
         """silu on the scalars, sigmoid gates on the l = 1 / l = 2 channels: one CUDA kernel each way (csrc/gate.cu)."""
         return irreps_gate(raw, self.ns, [(self.nv, 3), (self.nt, 5)])
 
-    def forward(self, x_in, node_attr, edge_attr, edge_extra, dst, src):
-        """x_in [Nn,8], node_attr [Nn,9], edge_attr [E,9], edge_extra [E,2], dst/src [E] int32 (sorted by dst)."""
+    def forward(self, x_in, node_attr, edge_attr, edge_extra, dst, src, halo=None):
+        """x_in [Nn,8], node_attr [Nn,9], edge_attr [E,9], edge_extra [E,2], dst/src [E] int32 (sorted by dst).
+
+        Domain-decomposed run (``se3gnn_b200.domain``, as for the l_max = 1 model): the node arrays hold the rank's owned
+        nodes, ``src`` may point past Nn into the halo and ``halo(x) -> [Nn + n_halo, d]`` appends the halo rows fetched
+        from their owners (one all-to-all-v per layer, differentiable)."""
         if not x_in.is_cuda:
             raise RuntimeError("SEGNNL2 runs on CUDA (sm_100a) only; there is no CPU fallback")
         x = self.embed(x_in, node_attr)
         for l in range(self.num_layers):
             # cat(x[dst], x[src], edge_extra) is read in place by the kernel; its gradient is scattered by the backward
-            m = self.gate(self.msg1[l].forward_cat([(x, dst, True), (x, src), (edge_extra, None)], edge_attr))
+            xe = x if halo is None else halo(x)
+            m = self.gate(self.msg1[l].forward_cat([(xe, dst, True), (xe, src), (edge_extra, None)], edge_attr))
             m = self.gate(self.msg2[l](m, edge_attr))
             agg = torch.zeros_like(x).index_add_(0, dst, m)
             u = self.gate(self.upd1[l].forward_cat([(x, None), (agg, None)], node_attr))

@@ -1,5 +1,6 @@
-"""Morton-range domain decomposition (se3gnn_b200.domain) on CPU: world-2 and world-3 gloo runs of the CPU oracle model
-on the oracle's octree graph, partitioned and halo-exchanged by the PRODUCT's host logic, against the 1-rank result."""
+"""Morton-range domain decomposition (se3gnn_b200.domain) on CPU: world-2 and world-3 gloo runs of the CPU oracle models
+(l_max = 1, and the l_max = 2 model of BASELINE configs[2]) on the oracle's octree graph, partitioned and halo-exchanged
+by the PRODUCT's host logic, against the 1-rank result."""
 import os
 import socket
 
@@ -32,21 +33,35 @@ def _global(n, leaf):
                    cell_start=t(g["cell_start"], torch.int64), leaf_of_rank=t(g["leaf_of_rank"], torch.int64))
 
 
-def _model():
-    from oracle.segnn_oracle import SEGNNOracle
+def _model(l2=False):
     torch.manual_seed(0)
+    if l2:
+        from oracle.segnn_l2_oracle import SEGNNL2Oracle
+        return SEGNNL2Oracle(hidden="5x0e+2x1o+1x2e", num_layers=2)
+    from oracle.segnn_oracle import SEGNNOracle
     return SEGNNOracle(hidden="6x0e+3x1o", num_layers=2).double()
 
 
-def _worker(rank, world, port, n, leaf, q):
+def _global_l2(n, leaf):
+    """The same graph with SH(2) attributes (BASELINE configs[2] model)."""
+    from oracle.segnn_l2_oracle import sh2_features
+    from oracle.segnn_oracle import graph_features
+    g, G = _global(n, leaf)
+    pos, vel, mass = _cloud(n)
+    ea, na = sh2_features(graph_features(g, pos, vel, mass), g)
+    G["edge_attr"], G["node_attr"] = torch.from_numpy(ea), torch.from_numpy(na)
+    return g, G
+
+
+def _worker(rank, world, port, n, leaf, q, l2=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.set_num_threads(1)
     from se3gnn_b200 import domain
-    g, G = _global(n, leaf)
+    g, G = _global_l2(n, leaf) if l2 else _global(n, leaf)
     lg = domain.local_graph(rank, world, g["n"], G["cell_start"], G["leaf_of_rank"], G["dst"], G["src"])
     domain.exchange_halo_lists(lg)
-    model = _model()
+    model = _model(l2)
     out = model(G["x_in"][lg.own_ids], G["node_attr"][lg.own_ids], G["edge_attr"][lg.edge_ids], G["edge_extra"][lg.edge_ids],
                 lg.dst, lg.src, halo=lambda x: domain.halo_exchange(x, lg))
     loss = out[:lg.n_part].square().sum() / (3.0 * n)
@@ -60,22 +75,22 @@ def _worker(rank, world, port, n, leaf, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n,leaf", [(2, 1500, 16), (3, 900, 8)])
-def test_decomposed_matches_single_rank(world, n, leaf):
+@pytest.mark.parametrize("world,n,leaf,l2", [(2, 1500, 16, False), (3, 900, 8, False), (2, 600, 8, True)])
+def test_decomposed_matches_single_rank(world, n, leaf, l2):
     from conftest import PKG, ROOT
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     os.environ["PYTHONPATH"] = os.pathsep.join([PKG, ROOT, os.path.join(ROOT, "tests"), os.environ.get("PYTHONPATH", "")])
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n, leaf, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, leaf, q, l2)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=300) for _ in procs], key=lambda r: r[0])
     for p in procs:
         p.join(timeout=60)
     # single-rank reference
-    g, G = _global(n, leaf)
-    model = _model()
+    g, G = _global_l2(n, leaf) if l2 else _global(n, leaf)
+    model = _model(l2)
     out = model(G["x_in"], G["node_attr"], G["edge_attr"], G["edge_extra"], G["dst"], G["src"])
     loss = out[:n].square().sum() / (3.0 * n)
     loss.backward()

@@ -315,3 +315,75 @@ def test_emulated_kernels_match_frozen_vectors(emu):
         _close(gx, r["gx_f64"])
         _close(gy, r["gy_f64"])
         _close(gw, r["gw_f64"])
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_emulated_random_segments(emu, seed):
+    """Seeded random cuts of in1 into 1..4 row segments, each identity or gathered (sorted or not, padded row stride or
+    16-byte aligned), gradients stored / added / skipped: forward and both backward variants against the oracle."""
+    rng = np.random.default_rng(90000 + seed)
+    in2 = l2.sh_irreps(int(rng.integers(0, 3)))
+    for _ in range(50):
+        in1 = [(int(rng.integers(1, 12)), int(rng.integers(0, 3)), int(rng.choice([-1, 1]))) for _ in range(int(rng.integers(1, 7)))]
+        out = [(int(rng.integers(1, 12)), int(rng.integers(0, 3)), int(rng.choice([-1, 1]))) for _ in range(int(rng.integers(1, 5)))]
+        if l2.paths(in1, in2, out):
+            break
+    else:
+        pytest.skip("no connected configuration drawn")
+    rows, nn_ = int(rng.integers(1, 200)), int(rng.integers(1, 40))
+    d1 = sum(m * (2 * l + 1) for m, l, _ in in1)
+    d2 = sum(2 * l + 1 for _, l, _ in in2)
+    do = sum(m * (2 * l + 1) for m, l, _ in out)
+    nseg = int(rng.integers(1, min(4, d1) + 1))
+    cuts = sorted(rng.choice(np.arange(1, d1), nseg - 1, replace=False).tolist()) if nseg > 1 else []
+    widths = np.diff([0] + cuts + [d1]).tolist()
+    parts, cols, modes, skip = [], [], [], []
+    for wdt in widths:
+        pad = int(rng.integers(0, 3))
+        if rng.integers(0, 2):
+            t = rng.standard_normal((nn_, wdt + pad)).astype(np.float32)
+            idx = rng.integers(0, nn_, rows).astype(np.int32)
+            srt = bool(rng.integers(0, 2))
+            idx = np.sort(idx) if srt else idx
+            parts.append((t, idx, wdt))
+            cols.append(t[idx, :wdt])
+            modes.append((3 if srt else 2) | (16 if wdt % 4 == 0 and (wdt + pad) % 4 == 0 else 0))
+        else:
+            t = rng.standard_normal((rows, wdt + pad)).astype(np.float32)
+            parts.append((t, None, wdt))
+            cols.append(t[:, :wdt])
+            modes.append(1)
+        skip.append(rng.integers(0, 5) == 0)
+    modes = [0 if s else m for m, s in zip(modes, skip)] + [0] * (4 - nseg)
+    x1 = np.ascontiguousarray(np.concatenate(cols, 1))
+    y = rng.standard_normal((rows, d2)).astype(np.float32)
+    nw = sum(a * b for a, b in l2.weight_shapes(in1, in2, out))
+    w = rng.standard_normal(nw).astype(np.float32)
+    g = rng.standard_normal((rows, do)).astype(np.float32)
+    want_o, want_gx, want_gy, want_gw = _oracle(in1, in2, out, x1, y, w, g)
+    spec = (len(in1), _flat(in1), len(in2), _flat(in2, True), len(out), _flat(out))
+    got_o = np.full((rows, do), np.nan, np.float32)
+    assert emu.emu_forward(*spec, C.c_longlong(rows), *Segs(parts).fwd(), _fp(y), _fp(w), _fp(got_o), 64, 256, 2) == 0
+    _close(got_o, want_o)
+    for fn in (emu.emu_backward, emu.emu_backward_split):
+        gs = [None if s else (np.zeros_like(t) if ix is not None else np.full_like(t, np.nan)) for (t, ix, _), s in zip(parts, skip)]
+        gy, gw = np.full((rows, d2), np.nan, np.float32), np.full(nw, np.nan, np.float32)
+        rc = fn(*spec, C.c_longlong(rows), *Segs(parts, gs, modes).bwd(), _fp(y), _fp(w), _fp(g), _fp(gy), _fp(gw), 256, 2)
+        if rc == 1 and fn is emu.emu_backward_split:
+            continue
+        assert rc == 0
+        _close(gw, want_gw)
+        _close(gy, want_gy)
+        c0 = 0
+        for (t, ix, wdt), gb in zip(parts, gs):
+            ref = want_gx[:, c0:c0 + wdt]
+            c0 += wdt
+            if gb is None:
+                continue
+            if ix is None:
+                _close(gb[:, :wdt], ref)
+            else:
+                acc = np.zeros((t.shape[0], wdt))
+                np.add.at(acc, ix, ref)
+                _close(gb[:, :wdt], acc)
+                assert not gb[:, wdt:].any()

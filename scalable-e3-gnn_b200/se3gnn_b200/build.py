@@ -43,9 +43,12 @@ def _deps_mtime() -> float:
 
 
 def build(verbose: bool = False, force: bool = False) -> str:
+    hm = _deps_mtime()
+    # a library newer than every source and header is current even if the object files did not travel with the tree
+    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= max([hm] + [os.path.getmtime(s) for s in sources()]):
+        return LIB
     os.makedirs(OBJ, exist_ok=True)
     nvcc = _nvcc()
-    hm = _deps_mtime()
     jobs = []
     objs = []
     for src in sources():

@@ -30,7 +30,7 @@ def main():
     cg = {f"cg_{a}{b}{c}": O2.cg(a, b, c) for a in range(3) for b in range(3) for c in range(3) if abs(a - b) <= c <= a + b}
     np.savez_compressed(os.path.join(HERE, "o3tp_couplings.npz"), **cg)
     for name, in1, lmax, out in CASES:
-        rng = np.random.default_rng(abs(hash(name)) % 2 ** 16 if False else sum(map(ord, name)))
+        rng = np.random.default_rng(sum(map(ord, name)))
         in2 = O2.sh_irreps(lmax)
         rows = 29
         d1 = sum(m * (2 * l + 1) for m, l, _ in in1)

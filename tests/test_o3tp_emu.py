@@ -135,7 +135,7 @@ def test_plan_matches_oracle(emu, name):
 def test_emulated_kernels_match_oracle(emu, name, rows, TEF, nblocks):
     in1, lmax, out = CASES[name]
     in2 = l2.sh_irreps(lmax)
-    rng = np.random.default_rng(hash(name) % 1000)
+    rng = np.random.default_rng(sum(map(ord, name)))          # stable across processes (str hashes are salted)
     d1 = sum(m * (2 * l + 1) for m, l, _ in in1)
     d2 = sum(2 * l + 1 for _, l, _ in in2)
     do = sum(m * (2 * l + 1) for m, l, _ in out)

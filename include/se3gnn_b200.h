@@ -88,8 +88,10 @@ typedef struct se3_l1tp_fwd_args {
     float* out_raw;              /* [rows,d_out] pre-activation (or the output in RAW mode); may be NULL */
     float* out_post;             /* GATE: [rows, gate_ns + 3*m1o]; may be NULL  */
     const float* resid;          /* RAW: added to the output, [rows,d_out]; may be NULL */
-    const int32_t* seg_idx;      /* if non-NULL: rows are sorted by seg_idx and the (post or raw)
-                                    rows are summed into out_seg[seg_idx[r]] (+=, caller zeroes) */
+    const int32_t* seg_idx;      /* if non-NULL: the (post or raw) rows are summed into out_seg[seg_idx[r]].
+                                    CONTRACT: seg_idx is GLOBALLY non-decreasing and out_seg is zero on entry
+                                    (segments interior to a 64-row tile are written with a plain store; only
+                                    tile-boundary segments accumulate) */
     float* out_seg;
 } se3_l1tp_fwd_args;
 

@@ -376,6 +376,7 @@ static int make_rows(const se3_o3tp_plan* p, int nseg, const se3_rowseg* seg, O3
 extern "C" int se3_o3tp_forward_seg(se3_o3tp_plan* p, int64_t rows, int32_t nseg, const se3_rowseg* seg, const float* in2,
                                     const float* w, float* out, void* stream) {
     O3Rows X;
+    if (p && rows == 0) return SE3_OK;   // an empty slab of a decomposed run: empty tensors have NULL data pointers
     if (!p || rows < 0 || make_rows(p, nseg, seg, X) || (rows > 0 && (!in2 || !w || !out))) {
         set_error("o3tp forward: bad argument (segments must add up to d_in1)");
         return SE3_ERR_INVALID;
@@ -392,6 +393,10 @@ extern "C" int se3_o3tp_backward_seg(se3_o3tp_plan* p, int64_t rows, int32_t nse
                                      const float* w, const float* gout, float* const* gseg, const int32_t* gseg_mode,
                                      float* gin2, float* gw, void* stream) {
     O3Rows X;
+    if (p && rows == 0 && gw) {          // as above; the weight gradient of no rows is zero
+        SE3_CUDA_TRY(cudaMemsetAsync(gw, 0, sizeof(float) * p->P.nW, (cudaStream_t)stream));
+        return SE3_OK;
+    }
     if (!p || rows < 0 || !gw || make_rows(p, nseg, seg, X) || !gseg || !gseg_mode || (rows > 0 && (!in2 || !w || !gout))) {
         set_error("o3tp backward: bad argument (segments must add up to d_in1)");
         return SE3_ERR_INVALID;

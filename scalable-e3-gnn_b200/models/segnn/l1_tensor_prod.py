@@ -106,7 +106,6 @@ class L1TensorProduct(Module):
         out_var = _vars(out_var, self.iro, "Len of out_var must be equal to len(irreps_out)")
 
         self.is_norm = irrep_normalization in ("component", "norm") or path_normalization in ("element", "path")
-        self._plan = None
         if not self.is_norm:
             return  # reference quirk Q3 (L1TP:116): is_comp_norm / instructions stay undefined
         self.is_comp_norm = irrep_normalization != "norm" and path_normalization != "path"
@@ -150,9 +149,9 @@ class L1TensorProduct(Module):
 
     # ------------------------------------------------------------------ CUDA path
     def _cfg(self, need_gin2: bool) -> TPConfig:
-        if self._plan is None:
-            self._plan = get_plan(self.iri1, self.iro)
-        return TPConfig(plan=self._plan, widths=(self.in1_dim,), need_gin2=need_gin2)
+        # the plan (a ctypes handle with device tables) is looked up per call in the (irreps, device) cache and never
+        # becomes module state: copy.deepcopy / pickle / torch.save of the module work as they do for the reference
+        return TPConfig(plan=get_plan(self.iri1, self.iro), widths=(self.in1_dim,), need_gin2=need_gin2)
 
     def forward(self, in1: Tensor, in2: Tensor) -> Tensor:
         torch._assert(in1.shape[-1] == self.in1_dim,

@@ -1,12 +1,10 @@
 """Multi-GPU plumbing (torch.distributed; NCCL on GPUs, gloo in the CPU tests).
 
-Round 1: data parallel over independent clouds — every rank owns a whole cloud, weight gradients live in one flat
-buffer and are averaged with a single all-reduce per step.  `morton_ranges` is the host logic of the next step
-(Morton-range domain decomposition of one cloud): contiguous, equal-count slabs of the sorted key array.
+Weight gradients live in one flat fp32 buffer, so a step needs exactly one collective for them: a sum in the
+Morton-range domain decomposition (``se3gnn_b200.domain``, the default for N > 1) or a mean in the data-parallel mode
+(one independent cloud per rank).  ``broadcast_params_`` makes the replicas start from rank 0's weights.
 """
 from __future__ import annotations
-
-from typing import List, Tuple
 
 import torch
 import torch.distributed as dist
@@ -23,19 +21,26 @@ def flatten_grads(params) -> torch.Tensor:
     return flat
 
 
-def allreduce_mean_(flat: torch.Tensor) -> torch.Tensor:
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(flat)
-        flat.div_(dist.get_world_size())
+def _active(group=None) -> bool:
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
+
+def allreduce_mean_(flat: torch.Tensor, group=None) -> torch.Tensor:
+    if _active(group):
+        dist.all_reduce(flat, group=group)
+        flat.div_(dist.get_world_size(group))
     return flat
 
 
-def morton_ranges(n: int, world: int) -> List[Tuple[int, int]]:
-    """Rank r owns Morton ranks [lo, hi): equal particle counts, remainder spread over the first ranks."""
-    base, rem = divmod(n, world)
-    out, lo = [], 0
-    for r in range(world):
-        hi = lo + base + (1 if r < rem else 0)
-        out.append((lo, hi))
-        lo = hi
-    return out
+def broadcast_params_(params, group=None) -> None:
+    """Every rank of ``group`` takes the parameters of the group's first rank (one flat broadcast)."""
+    if not _active(group):
+        return
+    params = list(params)
+    flat = torch.cat([p.detach().reshape(-1) for p in params])
+    dist.broadcast(flat, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    o = 0
+    with torch.no_grad():
+        for p in params:
+            p.copy_(flat[o:o + p.numel()].view_as(p))
+            o += p.numel()

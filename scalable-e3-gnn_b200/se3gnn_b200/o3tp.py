@@ -101,6 +101,9 @@ class _O3tpCatFn(torch.autograd.Function):
         return (gin2, gw, None, None, None, *grads)
 
 
+_PLANS: dict = {}
+
+
 class O3TensorProduct(torch.nn.Module):
     def __init__(self, in1_irreps, out_irreps=None, in2_irreps=None):
         super().__init__()
@@ -110,9 +113,7 @@ class O3TensorProduct(torch.nn.Module):
         assert max(self.iri1.lmax, self.iri2.lmax, self.iro.lmax) <= 2, "Maximal l supported by this tensor product is 2."
         assert all(mi.mul == 1 for mi in self.iri2), "in2 must have multiplicity 1 per irrep (spherical harmonics type)"
         self.in1_dim, self.in2_dim = self.iri1.dim, self.iri2.dim
-        self._plan = capi.O3tpPlan([(mi.mul, mi.ir.l, mi.ir.p) for mi in self.iri1],
-                                   [(mi.ir.l, mi.ir.p) for mi in self.iri2],
-                                   [(mi.mul, mi.ir.l, mi.ir.p) for mi in self.iro])
+        _ = self._plan   # created now: configuration errors surface at construction
         assert (self._plan.d_in1, self._plan.d_in2, self._plan.d_out) == (self.in1_dim, self.in2_dim, self.iro.dim)
         self.instructions = [
             Instruction(i1, i2, io, "uvw", True, a, (self.iri1[i1].mul, 1, self.iro[io].mul))
@@ -120,6 +121,18 @@ class O3TensorProduct(torch.nn.Module):
         ]
         self.weight_offsets = [p[3] for p in self._plan.paths]
         self.weight = torch.nn.Parameter(torch.randn(self._plan.weight_floats))
+
+    @property
+    def _plan(self) -> "capi.O3tpPlan":
+        """The plan (ctypes handle + device tables on the CURRENT device) lives in a per-(irreps, device) cache, not in
+        the module: deepcopy / pickle / torch.save of the module work, and ``.to(other_gpu)`` gets tables there."""
+        key = (str(self.iri1), str(self.iri2), str(self.iro), torch.cuda.current_device() if torch.cuda.is_available() else -1)
+        p = _PLANS.get(key)
+        if p is None:
+            p = _PLANS[key] = capi.O3tpPlan([(mi.mul, mi.ir.l, mi.ir.p) for mi in self.iri1],
+                                            [(mi.ir.l, mi.ir.p) for mi in self.iri2],
+                                            [(mi.mul, mi.ir.l, mi.ir.p) for mi in self.iro])
+        return p
 
     def weight_views(self):
         """Per-path [mul_in1, mul_out] views of the flat weight, in `instructions` order."""

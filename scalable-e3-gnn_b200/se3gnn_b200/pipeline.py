@@ -14,7 +14,7 @@ import torch
 import torch.distributed as dist
 
 from . import domain
-from .dist import allreduce_mean_, flatten_grads
+from .dist import allreduce_mean_, broadcast_params_, flatten_grads
 from .octree import build_octree_graph
 
 
@@ -68,6 +68,8 @@ class TrainStep:
         self.group = group
         self.last_local = None
         params = [p for p in model.parameters()]
+        if distributed or decompose:
+            broadcast_params_(params, group)   # replicas must start identical: the gradients are summed / averaged
         self.flat_grad = flatten_grads(params)
         self.opt = torch.optim.Adam(params, lr=lr, fused=True)
         self._pin = None
@@ -84,7 +86,7 @@ class TrainStep:
         loss = (out[:n] - tgt).square().mean()
         loss.backward()
         if self.distributed:
-            allreduce_mean_(self.flat_grad)
+            allreduce_mean_(self.flat_grad, self.group)
         self.opt.step()
         return loss.detach()
 

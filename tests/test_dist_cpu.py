@@ -1,5 +1,5 @@
-"""N>1 host logic on CPU: world_size-2 gloo run of the flat-gradient all-reduce used by TrainStep, and the
-Morton-range partition."""
+"""N>1 host logic on CPU: world_size-2 gloo run of the flat-gradient all-reduce and the parameter broadcast used by
+TrainStep (the Morton-range decomposition itself is covered by test_domain_cpu.py)."""
 import os
 import socket
 
@@ -12,9 +12,13 @@ import torch.multiprocessing as mp
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from se3gnn_b200.dist import allreduce_mean_, flatten_grads
-    torch.manual_seed(0)
+    from se3gnn_b200.dist import allreduce_mean_, broadcast_params_, flatten_grads
+    torch.manual_seed(rank)                       # replicas start DIFFERENT; the broadcast makes them rank 0's
     lin = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3))
+    broadcast_params_(lin.parameters())
+    torch.manual_seed(0)
+    ref = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3))
+    assert all(torch.equal(a, b) for a, b in zip(lin.parameters(), ref.parameters()))
     flat = flatten_grads(lin.parameters())
     x = torch.full((4, 5), float(rank + 1))
     lin(x).sum().backward()                       # autograd accumulates in place into the flat views
@@ -43,14 +47,3 @@ def test_flat_grad_allreduce_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert sorted(r[0] for r in res) == [0, 1] and all(r[1] and r[2] for r in res)
-
-
-def test_morton_ranges():
-    from se3gnn_b200.dist import morton_ranges
-    r = morton_ranges(10, 4)
-    assert r == [(0, 3), (3, 6), (6, 8), (8, 10)]
-    assert morton_ranges(3, 8)[-1] == (3, 3)
-    n = 1_000_003
-    rr = morton_ranges(n, 8)
-    assert rr[0][0] == 0 and rr[-1][1] == n and all(a[1] == b[0] for a, b in zip(rr, rr[1:]))
-    assert max(h - l for l, h in rr) - min(h - l for l, h in rr) <= 1

@@ -56,3 +56,54 @@ def test_segnn_forward_backward_vs_oracle(n, layers):
         worst = max(worst, _relerr(p.grad, pr[k].grad))
     assert worst <= 5e-5, f"weight grads rel err {worst:.2e}"
     print(f"n={n} layers={layers}: out rel err {e_out:.2e}, worst grad rel err {worst:.2e}")
+
+
+def _model_vs_oracle(pos, vel, mass, target, layers, tol_out=1e-5, tol_grad=5e-5):
+    """GPU octree bit-exact vs the CPU specification, then model outputs / loss / weight gradients vs the fp64 oracle."""
+    from models.segnn.segnn import SEGNN
+    from se3gnn_b200.octree import build_octree_graph
+    n = len(pos)
+    torch.manual_seed(0)
+    model = SEGNN(num_layers=layers).cuda()
+    tc = lambda a: torch.from_numpy(a).cuda()
+    g = build_octree_graph(tc(pos), tc(vel), tc(mass))
+    ref_g = T.build_graph(pos)
+    assert (ref_g["m"], len(ref_g["col"])) == (g.m, g.e)
+    for k in ("order", "cell_of_particle", "leaf_of_rank", "rowptr", "col", "dst"):
+        np.testing.assert_array_equal(getattr(g, k).cpu().numpy(), ref_g[k], err_msg=k)
+    out = model.forward_graph(g)
+    tgt = tc(target).index_select(0, g.order.long())
+    loss = (out[:n] - tgt).square().mean()
+    loss.backward()
+    oracle = SEGNNOracle(num_layers=layers).double()
+    oracle.load_state_dict({k: v.detach().cpu().double() for k, v in model.state_dict().items()})
+    f64 = lambda t: t.detach().cpu().double()
+    o_ref = oracle(f64(g.x_in), f64(g.node_attr), f64(g.edge_attr), f64(g.edge_extra), g.dst.cpu(), g.col.cpu())
+    l_ref = (o_ref[:n] - f64(tgt)).square().mean()
+    l_ref.backward()
+    e_out = _relerr(out, o_ref)
+    assert e_out <= tol_out, f"node outputs rel err {e_out:.2e}"
+    assert abs(loss.item() - l_ref.item()) <= 1e-5 * abs(l_ref.item())
+    pr = dict(oracle.named_parameters())
+    worst = max(_relerr(p.grad, pr[k].grad) for k, p in model.named_parameters())
+    assert worst <= tol_grad, f"weight grads rel err {worst:.2e}"
+    return g, e_out, worst
+
+
+def test_bench_size_parity_100k_plummer():
+    """BASELINE configs[1] at its full size, on bench.py's own cloud: 100 000 Plummer particles, 4 layers (1.78M edges:
+    tile tails, persistent-CTA scheduling, segment-sum boundaries, > 2^31-byte per-edge tensors)."""
+    from se3gnn_b200.pipeline import synthetic_cloud
+    pos, vel, mass, target = synthetic_cloud(100_000, "plummer", 1)
+    g, e_out, worst = _model_vs_oracle(pos, vel, mass, target, 4)
+    assert g.e > 1_500_000
+    print(f"100k plummer: {g.e} edges, out rel err {e_out:.2e}, worst grad rel err {worst:.2e}")
+
+
+@pytest.mark.parametrize("kind,n", [("uniform", 20_000), ("nfw", 24_001)])
+def test_other_clouds_parity(kind, n):
+    """SURVEY 8d's other two synthetic inputs through the whole model (uniform cube, NFW halo)."""
+    from se3gnn_b200.pipeline import synthetic_cloud
+    pos, vel, mass, target = synthetic_cloud(n, kind, 2)
+    g, e_out, worst = _model_vs_oracle(pos, vel, mass, target, 4)
+    print(f"{kind} {n}: {g.e} edges, out rel err {e_out:.2e}, worst grad rel err {worst:.2e}")

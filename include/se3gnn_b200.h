@@ -123,6 +123,42 @@ typedef struct se3_l1tp_bwd_args {
 
 int se3_l1tp_backward(se3_l1tp_plan* plan, const se3_l1tp_bwd_args* args, void* stream);
 
+/* ---------------------------------------------------------------- msg1 ---- */
+/* First tensor product of the SEGNN message by linearity (csrc/msg_table.cu).  It replaces L1TensorProduct.forward
+ * (L1TP:242-297) + its autograd backward for in1 = cat(x[dst], x[src], edge_extra), hidden irreps ns x0e + nv x1o,
+ * output (ns+nv) x0e + nv x1o followed by the swish / sigmoid gate: the weight contraction runs once per NODE
+ * (T = x . wbig, a dense [n_all, ns+3nv] x [ns+3nv, 8 (ns+2nv)] GEMM the caller performs), the per-edge work is the
+ * combination with SH(1) and the gate.  Table / gradient rows: [dst half | src half], each [ns+2nv channels][4] =
+ * (P, U_x, U_y, U_z), norms and 1/sqrt(3) folded in.  Weight layout: wz = weights_l0e [(2ns+2+2nv), ns+nv],
+ * wv = weights_l1o [(2ns+2+2nv), nv], rows in the reference's concatenation order (L1TP:81-88); nz / nvn = norm_l0e /
+ * norm_l1o or NULL. */
+int se3_msg1_supported(int32_t ns, int32_t nv, int32_t n_extra); /* 1 if instantiated */
+int se3_msg1_max_parts(void);                                   /* rows of gwe_part the backward may write */
+int se3_msg1_expand(int32_t ns, int32_t nv, const float* wz, const float* wv, const float* nz, const float* nvn,
+                    float* wbig /*[ns+3nv, 8(ns+2nv)]*/, float* we /*[2, ns+2nv]*/, void* stream);
+/* one warp per destination node: rowptr [n_dst+1] = CSR of the edges by destination, src [E] (may point into the
+ * halo rows of the table), y [E,4] = SH(1), extra [E,2]; writes pre [E, ns+4nv] (pre-activation, kept for backward)
+ * and post [E, ns+3nv] (gated message). */
+int se3_msg1_edge_forward(int32_t ns, int32_t nv, int64_t n_dst, const int64_t* rowptr, const int32_t* src,
+                          const float* table /*[n_all, 8(ns+2nv)]*/, const float* we, const float* y,
+                          const float* extra, float gate_cs, float gate_cg, float* pre, float* post, void* stream);
+/* gate VJP + transposed SH combine + segment sums, no atomics: G [n_all, 8(ns+2nv)] is overwritten (dst half of the
+ * rows >= n_dst: zero); tptr [n_all+1] / perm [E] = the edges in stable order by source (se3_graph_transpose);
+ * gpre [E, ns+4nv] scratch; gwe_part [se3_msg1_max_parts(), 2, ns+2nv] per-block partials, *nparts rows written. */
+int se3_msg1_edge_backward(int32_t ns, int32_t nv, int64_t n_dst, int64_t n_all, const int64_t* rowptr,
+                           const int64_t* tptr, const int32_t* perm, const float* y, const float* extra,
+                           const float* pre, const float* gpost, float gate_cs, float gate_cg, float* gpre, float* G,
+                           float* gwe_part, int32_t* nparts, void* stream);
+/* gwz / gwv (overwritten) from gwbig = x^T . G and the extras' partials */
+int se3_msg1_contract(int32_t ns, int32_t nv, const float* gwbig, const float* gwe_part, int32_t nparts,
+                      const float* nz, const float* nvn, float* gwz, float* gwv, void* stream);
+/* rowptr [n+1] of an ascending index (rowptr[k] = first position with idx >= k) */
+int se3_rowptr_from_sorted(int64_t e, int64_t n, const int32_t* idx_sorted, int64_t* rowptr, void* stream);
+/* stable counting sort of the edges by source: tptr [n_src+1], perm [e] (edge ids, ascending inside a segment) */
+int se3_graph_transpose_work_bytes(int64_t n_src, size_t* bytes);
+int se3_graph_transpose(int64_t e, int64_t n_src, const int32_t* src, int64_t* tptr, int32_t* perm, void* work,
+                        size_t work_bytes, void* stream);
+
 /* ---------------------------------------------------------------- o3tp ---- */
 /* Fully connected O(3) tensor product for 0 <= l <= 2 (BASELINE configs[2]): the generalisation of
  * L1TensorProduct the reference excludes (L1TP:13-14 asserts lmax == 1), same conventions: paths enumerated

@@ -19,7 +19,9 @@ from typing import Optional
 import torch
 from torch import nn
 
-from se3gnn_b200 import capi
+import os
+
+from se3gnn_b200 import capi, msg
 from se3gnn_b200.gate import SIGMOID_CST, SILU_CST
 from se3gnn_b200.irreps import Irreps
 from se3gnn_b200.tp import TPConfig, get_plan, tp_layer
@@ -79,24 +81,35 @@ class SEGNN(nn.Module):
         return TPConfig(plan=plan, widths=widths, **kw)
 
     # -------------------------------------------------------------- forward
-    def forward(self, x_in, node_attr, edge_attr, edge_extra, dst, src, halo=None):
+    def forward(self, x_in, node_attr, edge_attr, edge_extra, dst, src, halo=None, rowptr=None):
         """x_in [Nn,8], node_attr [Nn,4], edge_attr [E,4], edge_extra [E,2], dst/src [E] int32 (sorted by dst).
         Returns the per-node output [Nn, out_dim].
 
         Domain-decomposed run (``se3gnn_b200.domain``): the node arrays hold the rank's OWNED nodes, ``dst`` are owned
         local ids, ``src`` may point past Nn into the halo, and ``halo(x) -> [Nn + n_halo, d]`` appends the halo rows
-        fetched from their owners (one NCCL all-to-all-v per layer, differentiable)."""
+        fetched from their owners (one NCCL all-to-all-v per layer, differentiable).  ``rowptr`` [Nn+1] int64: CSR row
+        pointers of ``dst`` if the caller has them (the graph builder does); derived from ``dst`` otherwise."""
         if not x_in.is_cuda:
             raise RuntimeError("se3gnn_b200.SEGNN runs on CUDA (sm_100a) only; there is no CPU fallback")
         nn_, e, d = x_in.shape[0], edge_attr.shape[0], self.d
         ws, ns = self._wn(self.embed)
         x = tp_layer(self._cfg(self.embed, (self.in_irreps.dim,), False, "embed"), nn_, [x_in], [None], node_attr, ws, ns)
+        # msg1 by linearity (node tables + per-edge SH combine, se3gnn_b200.msg) unless SE3_MSG1=tp asks for the
+        # per-edge tensor-product kernel (kept for A/B measurements and for hidden sizes that are not instantiated)
+        lin = e > 0 and os.environ.get("SE3_MSG1", "table") != "tp" and msg.supported(self.ns, self.nv, edge_extra.shape[1])
+        ei = None
         for l in range(self.num_layers):
             ws, ns = self._wn(self.msg1[l])
-            cfg = self._cfg(self.msg1[l], (d, d, edge_extra.shape[1]), True, "msg1",
-                            grad_modes=(capi.GRAD_SORTED, capi.GRAD_ATOMIC, capi.GRAD_NONE), share_grad={1: 0})
             xe = x if halo is None else halo(x)
-            m1 = tp_layer(cfg, e, [xe, xe, edge_extra], [dst, src, None], edge_attr, ws, ns)
+            if lin:
+                if ei is None:
+                    ei = msg.build_edge_index(dst, src, nn_, xe.shape[0], rowptr)
+                m1 = msg.msg1(xe, ws[0], ws[3], ns[0], ns[3], edge_attr, edge_extra, ei, self.ns, self.nv,
+                              SILU_CST, SIGMOID_CST)
+            else:
+                cfg = self._cfg(self.msg1[l], (d, d, edge_extra.shape[1]), True, "msg1",
+                                grad_modes=(capi.GRAD_SORTED, capi.GRAD_ATOMIC, capi.GRAD_NONE), share_grad={1: 0})
+                m1 = tp_layer(cfg, e, [xe, xe, edge_extra], [dst, src, None], edge_attr, ws, ns)
             ws, ns = self._wn(self.msg2[l])
             cfg = self._cfg(self.msg2[l], (d,), True, "msg2", num_segments=nn_)
             agg = tp_layer(cfg, e, [m1], [None], edge_attr, ws, ns, seg_idx=dst)
@@ -111,4 +124,4 @@ class SEGNN(nn.Module):
 
     def forward_graph(self, g):
         """Convenience: run on an ``OctreeGraph`` from ``se3gnn_b200.octree.build_octree_graph``."""
-        return self.forward(g.x_in, g.node_attr, g.edge_attr, g.edge_extra, g.dst, g.col)
+        return self.forward(g.x_in, g.node_attr, g.edge_attr, g.edge_extra, g.dst, g.col, rowptr=g.rowptr)

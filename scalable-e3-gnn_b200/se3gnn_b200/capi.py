@@ -88,6 +88,21 @@ EXPORTS = [
     ("se3_l1tp_plan_info", C.c_int, [C.c_void_p, _i32p, _i32p, _i32p, _i32p]),
     ("se3_l1tp_forward", C.c_int, [C.c_void_p, C.POINTER(L1tpFwdArgs), C.c_void_p]),
     ("se3_l1tp_backward", C.c_int, [C.c_void_p, C.POINTER(L1tpBwdArgs), C.c_void_p]),
+    ("se3_msg1_supported", C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
+    ("se3_msg1_max_parts", C.c_int, []),
+    ("se3_msg1_expand", C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p]),
+    ("se3_msg1_edge_forward", C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("se3_msg1_edge_backward", C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, _i32p, C.c_void_p]),
+    ("se3_msg1_contract", C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("se3_rowptr_from_sorted", C.c_int, [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("se3_graph_transpose_work_bytes", C.c_int, [C.c_int64, C.POINTER(C.c_size_t)]),
+    ("se3_graph_transpose", C.c_int, [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                      C.c_void_p]),
     ("se3_o3tp_plan_create", C.c_int, [C.POINTER(O3tpDesc), C.POINTER(C.c_void_p)]),
     ("se3_o3tp_plan_destroy", None, [C.c_void_p]),
     ("se3_o3tp_plan_info", C.c_int, [C.c_void_p, _i32p]),

@@ -1,0 +1,121 @@
+"""Host side of the SEGNN message layer's first tensor product by linearity (csrc/msg_table.cu).
+
+``TP(cat(x[dst], x[src], extra), Y)`` is linear in its first input, so the weight contraction runs once per NODE
+(``T = x . wbig``, a dense GEMM over irrep channels with ~17x fewer rows than there are edges) and the per-edge work
+is the combination with SH(1) plus the gate.  The backward is the exact transpose: gate VJP and segment sums per edge
+(no atomics: CSR rows by destination, stable transposed order by source), then node-level GEMMs for the input and
+weight gradients.  The reference op chain this replaces: ``L1TensorProduct.forward`` (L1TP:242-297) on the
+concatenated row, followed by the public-SEGNN swish gate.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import capi
+
+
+@dataclass
+class EdgeIndex:
+    """CSR views of one (local) edge list that the message kernels need, built once per graph."""
+    n_dst: int                 # destination (owned) nodes
+    n_all: int                 # rows of the node-feature matrix the sources index (owned + halo)
+    e: int
+    rowptr: torch.Tensor       # [n_dst + 1] int64, edges sorted by destination
+    src: torch.Tensor          # [e] int32
+    dst: torch.Tensor          # [e] int32
+    tptr: torch.Tensor         # [n_all + 1] int64, edges in stable order by source
+    perm: torch.Tensor         # [e] int32
+
+
+def build_edge_index(dst: torch.Tensor, src: torch.Tensor, n_dst: int, n_all: int,
+                     rowptr: Optional[torch.Tensor] = None) -> EdgeIndex:
+    lib = capi.lib()
+    dev = dst.device
+    e = int(dst.numel())
+    st = capi.current_stream_ptr()
+    if rowptr is None or rowptr.numel() != n_dst + 1:
+        rowptr = torch.empty(n_dst + 1, device=dev, dtype=torch.int64)
+        capi.check(lib.se3_rowptr_from_sorted(e, n_dst, capi.ptr(dst), rowptr.data_ptr(), st), "se3_rowptr_from_sorted")
+    nb = C.c_size_t()
+    capi.check(lib.se3_graph_transpose_work_bytes(n_all, C.byref(nb)))
+    work = torch.empty(nb.value, device=dev, dtype=torch.uint8)
+    tptr = torch.empty(n_all + 1, device=dev, dtype=torch.int64)
+    perm = torch.empty(max(e, 1), device=dev, dtype=torch.int32)
+    with capi.mark("graph.transpose", 4.0 * e * 4 + 16.0 * n_all):
+        capi.check(lib.se3_graph_transpose(e, n_all, capi.ptr(src), tptr.data_ptr(), perm.data_ptr(), work.data_ptr(),
+                                           nb.value, st), "se3_graph_transpose")
+    return EdgeIndex(n_dst=n_dst, n_all=n_all, e=e, rowptr=rowptr, src=src, dst=dst, tptr=tptr, perm=perm)
+
+
+def supported(ns: int, nv: int, n_extra: int) -> bool:
+    return bool(capi.lib().se3_msg1_supported(ns, nv, n_extra))
+
+
+class Msg1Fn(torch.autograd.Function):
+    """(xe [n_all, d], wz, wv, nz, nv_norm, y [E,4], extra [E,2], ei, ns, nv, cs, cg) -> gated message [E, ns + 3 nv]."""
+
+    @staticmethod
+    def forward(ctx, xe, wz, wv, nz, nvn, y, extra, ei: EdgeIndex, ns: int, nv: int, cs: float, cg: float):
+        lib = capi.lib()
+        dev = xe.device
+        st = capi.current_stream_ptr()
+        ch, d = ns + 2 * nv, ns + 3 * nv
+        assert xe.shape == (ei.n_all, d) and xe.is_contiguous() and xe.dtype == torch.float32
+        wbig = torch.empty((d, 8 * ch), device=dev, dtype=torch.float32)
+        we = torch.empty((2, ch), device=dev, dtype=torch.float32)
+        capi.check(lib.se3_msg1_expand(ns, nv, wz.data_ptr(), wv.data_ptr(), capi.ptr(nz), capi.ptr(nvn), wbig.data_ptr(),
+                                       we.data_ptr(), st), "se3_msg1_expand")
+        with capi.mark("msg1.table", 4.0 * ei.n_all * (d + 8 * ch), 2.0 * ei.n_all * d * 2 * ch):
+            table = torch.mm(xe, wbig)
+        pre = torch.empty((ei.e, ns + 4 * nv), device=dev, dtype=torch.float32)
+        post = torch.empty((ei.e, d), device=dev, dtype=torch.float32)
+        with capi.mark("msg1.edge_fwd", 4.0 * (ei.e * (4 + 2 + 1 + ns + 4 * nv + d) + (ei.n_all + ei.n_dst) * 4 * ch)):
+            capi.check(lib.se3_msg1_edge_forward(ns, nv, ei.n_dst, ei.rowptr.data_ptr(), ei.src.data_ptr(), table.data_ptr(),
+                                                 we.data_ptr(), y.data_ptr(), extra.data_ptr(), cs, cg, pre.data_ptr(),
+                                                 post.data_ptr(), st), "se3_msg1_edge_forward")
+        ctx.ei, ctx.dims = ei, (ns, nv, cs, cg)
+        ctx.save_for_backward(xe, wbig, pre, y, extra, nz, nvn, wz, wv)
+        return post
+
+    @staticmethod
+    def backward(ctx, gpost):
+        lib = capi.lib()
+        xe, wbig, pre, y, extra, nz, nvn, wz, wv = ctx.saved_tensors
+        ei: EdgeIndex = ctx.ei
+        ns, nv, cs, cg = ctx.dims
+        dev = xe.device
+        st = capi.current_stream_ptr()
+        ch, d = ns + 2 * nv, ns + 3 * nv
+        gpost = gpost.contiguous()
+        gpre = torch.empty_like(pre)
+        G = torch.empty((ei.n_all, 8 * ch), device=dev, dtype=torch.float32)
+        parts = torch.empty((int(lib.se3_msg1_max_parts()), 2, ch), device=dev, dtype=torch.float32)
+        nparts = C.c_int32()
+        with capi.mark("msg1.edge_bwd", 4.0 * (ei.e * (2 * 4 + 2 + 1 + d + 3 * (ns + 4 * nv)) + 2 * ei.n_all * 4 * ch)):
+            capi.check(lib.se3_msg1_edge_backward(ns, nv, ei.n_dst, ei.n_all, ei.rowptr.data_ptr(), ei.tptr.data_ptr(),
+                                                  ei.perm.data_ptr(), y.data_ptr(), extra.data_ptr(), pre.data_ptr(),
+                                                  gpost.data_ptr(), cs, cg, gpre.data_ptr(), G.data_ptr(), parts.data_ptr(),
+                                                  C.byref(nparts), st), "se3_msg1_edge_backward")
+        gx = gwz = gwv = None
+        with capi.mark("msg1.node_bwd", 4.0 * ei.n_all * (2 * d + 2 * 8 * ch), 2.0 * 2 * ei.n_all * d * 2 * ch):
+            if ctx.needs_input_grad[0]:
+                gx = torch.mm(G, wbig.t())
+            if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+                gwbig = torch.mm(xe.t(), G)
+                gwz, gwv = torch.empty_like(wz), torch.empty_like(wv)
+                capi.check(lib.se3_msg1_contract(ns, nv, gwbig.data_ptr(), parts.data_ptr(), nparts.value, capi.ptr(nz),
+                                                 capi.ptr(nvn), gwz.data_ptr(), gwv.data_ptr(), st), "se3_msg1_contract")
+        return gx, gwz, gwv, None, None, None, None, None, None, None, None, None
+
+
+def msg1(xe, wz, wv, nz, nvn, y, extra, ei: EdgeIndex, ns: int, nv: int, cs: float, cg: float) -> torch.Tensor:
+    for name, t in (("x", xe), ("weights_l0e", wz), ("weights_l1o", wv), ("edge_attr", y), ("edge_extra", extra)):
+        if not t.is_cuda:
+            raise RuntimeError(f"se3gnn_b200.msg1: {name} must be a CUDA tensor (there is no CPU fallback)")
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise TypeError(f"se3gnn_b200.msg1: {name} must be contiguous float32")
+    return Msg1Fn.apply(xe, wz, wv, nz, nvn, y, extra, ei, ns, nv, cs, cg)

@@ -58,8 +58,12 @@ def test_segnn_forward_backward_vs_oracle(n, layers):
     print(f"n={n} layers={layers}: out rel err {e_out:.2e}, worst grad rel err {worst:.2e}")
 
 
-def _model_vs_oracle(pos, vel, mass, target, layers, tol_out=1e-5, tol_grad=5e-5):
-    """GPU octree bit-exact vs the CPU specification, then model outputs / loss / weight gradients vs the fp64 oracle."""
+def _model_vs_oracle(pos, vel, mass, target, layers, tol_out=1e-5, tol_grad=5e-5, fp32_reference=False):
+    """GPU octree bit-exact vs the CPU specification, then model outputs / loss / weight gradients vs the fp64 oracle.
+
+    Weight gradients are fp32 sums over every edge of every layer with heavy cancellation; at 1.8M edges the op
+    sequence of the reference itself, run in fp32 on the CPU, sits 1e-4 .. 1e-3 away from fp64.  ``fp32_reference``:
+    the tolerance per parameter is max(tol_grad, 2 x that error) — "as accurate as the reference's own arithmetic"."""
     from models.segnn.segnn import SEGNN
     from se3gnn_b200.octree import build_octree_graph
     n = len(pos)
@@ -85,8 +89,24 @@ def _model_vs_oracle(pos, vel, mass, target, layers, tol_out=1e-5, tol_grad=5e-5
     assert e_out <= tol_out, f"node outputs rel err {e_out:.2e}"
     assert abs(loss.item() - l_ref.item()) <= 1e-5 * abs(l_ref.item())
     pr = dict(oracle.named_parameters())
-    worst = max(_relerr(p.grad, pr[k].grad) for k, p in model.named_parameters())
-    assert worst <= tol_grad, f"weight grads rel err {worst:.2e}"
+    ref32 = {}
+    if fp32_reference:
+        o32 = SEGNNOracle(num_layers=layers).float()
+        o32.load_state_dict({k: v.detach().cpu().float() for k, v in model.state_dict().items()})
+        f32 = lambda t: t.detach().cpu().float()
+        out32 = o32(f32(g.x_in), f32(g.node_attr), f32(g.edge_attr), f32(g.edge_extra), g.dst.cpu(), g.col.cpu())
+        (out32[:n] - f32(tgt)).square().mean().backward()
+        ref32 = {k: _relerr(p.grad, pr[k].grad) for k, p in o32.named_parameters()}
+    worst, bad = 0.0, []
+    for k, p in model.named_parameters():
+        err = _relerr(p.grad, pr[k].grad)
+        lim = max(tol_grad, 2.0 * ref32.get(k, 0.0))
+        worst = max(worst, err)
+        if err > lim:
+            bad.append(f"{k}: {err:.2e} > {lim:.2e} (fp32 reference {ref32.get(k, float('nan')):.2e})")
+    if fp32_reference:
+        print("fp32 reference op sequence, worst grad rel err vs fp64: %.2e; CUDA worst: %.2e" % (max(ref32.values()), worst))
+    assert not bad, "weight grads: " + "; ".join(bad)
     return g, e_out, worst
 
 
@@ -95,7 +115,7 @@ def test_bench_size_parity_100k_plummer():
     tile tails, persistent-CTA scheduling, segment-sum boundaries, > 2^31-byte per-edge tensors)."""
     from se3gnn_b200.pipeline import synthetic_cloud
     pos, vel, mass, target = synthetic_cloud(100_000, "plummer", 1)
-    g, e_out, worst = _model_vs_oracle(pos, vel, mass, target, 4)
+    g, e_out, worst = _model_vs_oracle(pos, vel, mass, target, 4, fp32_reference=True)
     assert g.e > 1_500_000
     print(f"100k plummer: {g.e} edges, out rel err {e_out:.2e}, worst grad rel err {worst:.2e}")
 

@@ -152,6 +152,16 @@ int se3_msg1_edge_backward(int32_t ns, int32_t nv, int64_t n_dst, int64_t n_all,
 /* gwz / gwv (overwritten) from gwbig = x^T . G and the extras' partials */
 int se3_msg1_contract(int32_t ns, int32_t nv, const float* gwbig, const float* gwe_part, int32_t nparts,
                       const float* nz, const float* nvn, float* gwz, float* gwv, void* stream);
+/* The whole message layer forward in ONE launch (csrc/msg_fused_fwd.cu, tcgen05): node tables of message 1 -> SH
+ * combine + gate -> weight contraction of message 2 on the tensor cores (3xTF32) -> SH combine + gate -> sorted-segment
+ * sum over dst.  dst [rows] ascending; table / we as above (message 1); wz2 / wv2 / nz2 / nv2: weights_l0e
+ * [(ns+nv), ns+nv], weights_l1o [(ns+nv), nv] and norms of message 2.  Writes pre1 [rows, ns+4nv], m1 [rows, ns+3nv],
+ * pre2 [rows, ns+4nv] (what the backward reads) and agg [n_dst, ns+3nv] (+=: zero on entry). */
+int se3_msg_fused_supported(int32_t ns, int32_t nv, int32_t n_extra);
+int se3_msg_fused_forward(int32_t ns, int32_t nv, int64_t rows, const int32_t* dst, const int32_t* src,
+                          const float* table, const float* we, const float* y, const float* extra, const float* wz2,
+                          const float* wv2, const float* nz2, const float* nv2, float gate_cs, float gate_cg,
+                          float* pre1, float* m1, float* pre2, float* agg, void* stream);
 /* rowptr [n+1] of an ascending index (rowptr[k] = first position with idx >= k) */
 int se3_rowptr_from_sorted(int64_t e, int64_t n, const int32_t* idx_sorted, int64_t* rowptr, void* stream);
 /* stable counting sort of the edges by source: tptr [n_src+1], perm [e] (edge ids, ascending inside a segment) */

@@ -96,23 +96,33 @@ class SEGNN(nn.Module):
         x = tp_layer(self._cfg(self.embed, (self.in_irreps.dim,), False, "embed"), nn_, [x_in], [None], node_attr, ws, ns)
         # msg1 by linearity (node tables + per-edge SH combine, se3gnn_b200.msg) unless SE3_MSG1=tp asks for the
         # per-edge tensor-product kernel (kept for A/B measurements and for hidden sizes that are not instantiated)
-        lin = e > 0 and os.environ.get("SE3_MSG1", "table") != "tp" and msg.supported(self.ns, self.nv, edge_extra.shape[1])
+        mode = os.environ.get("SE3_MSG", "fused")    # fused | table | tp
+        ne = edge_extra.shape[1]
+        lin = e > 0 and mode != "tp" and msg.supported(self.ns, self.nv, ne)
+        fused = lin and mode == "fused" and msg.fused_supported(self.ns, self.nv, ne)
         ei = None
         for l in range(self.num_layers):
             ws, ns = self._wn(self.msg1[l])
             xe = x if halo is None else halo(x)
-            if lin:
-                if ei is None:
-                    ei = msg.build_edge_index(dst, src, nn_, xe.shape[0], rowptr)
+            if lin and ei is None:
+                ei = msg.build_edge_index(dst, src, nn_, xe.shape[0], rowptr)
+            if fused:
+                # the whole message layer: node tables -> ONE tcgen05 kernel (message 1, gate, message 2, gate, segment sum)
+                w2, n2 = self._wn(self.msg2[l])
+                agg = msg.message_layer(xe, (ws[0], ws[3]), (ns[0], ns[3]), (w2[0], w2[3]), (n2[0], n2[3]), edge_attr,
+                                        edge_extra, ei, self.ns, self.nv, SILU_CST, SIGMOID_CST,
+                                        get_plan(self.msg2[l].iri1, self.msg2[l].iro))
+            elif lin:
                 m1 = msg.msg1(xe, ws[0], ws[3], ns[0], ns[3], edge_attr, edge_extra, ei, self.ns, self.nv,
                               SILU_CST, SIGMOID_CST)
             else:
                 cfg = self._cfg(self.msg1[l], (d, d, edge_extra.shape[1]), True, "msg1",
                                 grad_modes=(capi.GRAD_SORTED, capi.GRAD_ATOMIC, capi.GRAD_NONE), share_grad={1: 0})
                 m1 = tp_layer(cfg, e, [xe, xe, edge_extra], [dst, src, None], edge_attr, ws, ns)
-            ws, ns = self._wn(self.msg2[l])
-            cfg = self._cfg(self.msg2[l], (d,), True, "msg2", num_segments=nn_)
-            agg = tp_layer(cfg, e, [m1], [None], edge_attr, ws, ns, seg_idx=dst)
+            if not fused:
+                ws, ns = self._wn(self.msg2[l])
+                cfg = self._cfg(self.msg2[l], (d,), True, "msg2", num_segments=nn_)
+                agg = tp_layer(cfg, e, [m1], [None], edge_attr, ws, ns, seg_idx=dst)
             ws, ns = self._wn(self.upd1[l])
             u1 = tp_layer(self._cfg(self.upd1[l], (d, d), True, "upd1"), nn_, [x, agg], [None, None], node_attr, ws, ns)
             ws, ns = self._wn(self.upd2[l])

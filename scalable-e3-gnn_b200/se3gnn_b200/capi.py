@@ -99,6 +99,9 @@ EXPORTS = [
                                          C.c_void_p, C.c_void_p, C.c_void_p, _i32p, C.c_void_p]),
     ("se3_msg1_contract", C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("se3_msg_fused_supported", C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
+    ("se3_msg_fused_forward", C.c_int, [C.c_int32, C.c_int32, C.c_int64] + [C.c_void_p] * 10 + [C.c_float, C.c_float]
+     + [C.c_void_p] * 5),
     ("se3_rowptr_from_sorted", C.c_int, [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("se3_graph_transpose_work_bytes", C.c_int, [C.c_int64, C.POINTER(C.c_size_t)]),
     ("se3_graph_transpose", C.c_int, [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,

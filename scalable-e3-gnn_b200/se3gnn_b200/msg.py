@@ -119,3 +119,110 @@ def msg1(xe, wz, wv, nz, nvn, y, extra, ei: EdgeIndex, ns: int, nv: int, cs: flo
         if t.dtype != torch.float32 or not t.is_contiguous():
             raise TypeError(f"se3gnn_b200.msg1: {name} must be contiguous float32")
     return Msg1Fn.apply(xe, wz, wv, nz, nvn, y, extra, ei, ns, nv, cs, cg)
+
+
+# ------------------------------------------------------------------------------------------------ fused message layer
+def fused_supported(ns: int, nv: int, n_extra: int) -> bool:
+    return bool(capi.lib().se3_msg_fused_supported(ns, nv, n_extra)) and supported(ns, nv, n_extra)
+
+
+class MsgLayerFn(torch.autograd.Function):
+    """The whole message layer: (xe, message-1 weights, message-2 weights, SH, extras, edge index) -> agg [n_dst, d].
+
+    Forward: node-table GEMM + ONE fused tcgen05 kernel (csrc/msg_fused_fwd.cu).  Backward: message 2 through the
+    tensor-product backward kernels (input gradient written per edge, weight gradients), message 1 through the
+    segment-sum kernels of csrc/msg_table.cu and the node-level GEMMs."""
+
+    @staticmethod
+    def forward(ctx, xe, wz1, wv1, nz1, nv1, wz2, wv2, nz2, nv2, y, extra, ei: EdgeIndex, ns, nv, cs, cg, plan2):
+        lib = capi.lib()
+        dev = xe.device
+        st = capi.current_stream_ptr()
+        ch, d, dpre = ns + 2 * nv, ns + 3 * nv, ns + 4 * nv
+        assert xe.shape == (ei.n_all, d) and xe.is_contiguous() and xe.dtype == torch.float32
+        wbig = torch.empty((d, 8 * ch), device=dev, dtype=torch.float32)
+        we = torch.empty((2, ch), device=dev, dtype=torch.float32)
+        capi.check(lib.se3_msg1_expand(ns, nv, wz1.data_ptr(), wv1.data_ptr(), capi.ptr(nz1), capi.ptr(nv1),
+                                       wbig.data_ptr(), we.data_ptr(), st), "se3_msg1_expand")
+        with capi.mark("msg.table", 4.0 * ei.n_all * (d + 8 * ch), 2.0 * ei.n_all * d * 2 * ch):
+            table = torch.mm(xe, wbig)
+        pre1 = torch.empty((ei.e, dpre), device=dev, dtype=torch.float32)
+        m1 = torch.empty((ei.e, d), device=dev, dtype=torch.float32)
+        pre2 = torch.empty((ei.e, dpre), device=dev, dtype=torch.float32)
+        agg = torch.zeros((ei.n_dst, d), device=dev, dtype=torch.float32)
+        # algorithmic bytes: SH + extras + both indices, the three per-edge tensors the backward reads, the node tables
+        # (each row once) and the aggregate
+        nbytes = 4.0 * (ei.e * (4 + 2 + 2 + 2 * dpre + d) + (ei.n_all + ei.n_dst) * 4 * ch + ei.n_dst * d)
+        flops = 2.0 * ei.e * ((ns + nv) * (ns + nv) + ns * nv + 3 * nv * nv + 3 * nv * (ns + nv))
+        with capi.mark("msg.fused_fwd", nbytes, flops):
+            capi.check(lib.se3_msg_fused_forward(ns, nv, ei.e, ei.dst.data_ptr(), ei.src.data_ptr(), table.data_ptr(),
+                                                 we.data_ptr(), y.data_ptr(), extra.data_ptr(), wz2.data_ptr(),
+                                                 wv2.data_ptr(), capi.ptr(nz2), capi.ptr(nv2), cs, cg, pre1.data_ptr(),
+                                                 m1.data_ptr(), pre2.data_ptr(), agg.data_ptr(), st), "se3_msg_fused_forward")
+        ctx.ei, ctx.dims, ctx.plan2 = ei, (ns, nv, cs, cg), plan2
+        ctx.save_for_backward(xe, wbig, pre1, m1, pre2, y, extra, nz1, nv1, wz1, wv1, wz2, wv2, nz2, nv2)
+        return agg
+
+    @staticmethod
+    def backward(ctx, gagg):
+        lib = capi.lib()
+        xe, wbig, pre1, m1, pre2, y, extra, nz1, nv1, wz1, wv1, wz2, wv2, nz2, nv2 = ctx.saved_tensors
+        ei: EdgeIndex = ctx.ei
+        ns, nv, cs, cg = ctx.dims
+        dev = xe.device
+        st = capi.current_stream_ptr()
+        ch, d, dpre = ns + 2 * nv, ns + 3 * nv, ns + 4 * nv
+        gagg = gagg.contiguous()
+        # ---- message 2: gate VJP + tensor-product backward on the tensor cores (csrc/l1tp_tc2_bwd*.cu)
+        a = capi.L1tpBwdArgs()
+        a.rows, a.nseg = ei.e, 1
+        a.seg[0].base, a.seg[0].idx, a.seg[0].width, a.seg[0].ld = m1.data_ptr(), None, d, d
+        a.in2 = y.data_ptr()
+        a.w[0], a.w[3] = wz2.data_ptr(), wv2.data_ptr()
+        a.norm[0], a.norm[3] = capi.ptr(nz2), capi.ptr(nv2)
+        a.epilogue, a.gate_ns, a.gate_cs, a.gate_cg = capi.EPI_GATE, ns, cs, cg
+        a.raw, a.gout, a.gout_idx = pre2.data_ptr(), gagg.data_ptr(), ei.dst.data_ptr()
+        gm1 = torch.empty_like(m1)
+        gwz2, gwv2 = torch.empty_like(wz2), torch.empty_like(wv2)
+        rowb = 4.0 * (4 + 1 + dpre)
+        if capi._prof is None:
+            a.gseg[0], a.gseg_mode[0] = gm1.data_ptr(), capi.GRAD_STORE
+            a.gw[0], a.gw[3] = gwz2.data_ptr(), gwv2.data_ptr()
+            capi.check(lib.se3_l1tp_backward(ctx.plan2.handle, C.byref(a), st), "se3_l1tp_backward")
+        else:   # per-kernel table: the weight-gradient and input-gradient kernels timed separately (same kernels)
+            a.gw[0], a.gw[3] = gwz2.data_ptr(), gwv2.data_ptr()
+            with capi.mark("msg2.bwdw", ei.e * (rowb + 4.0 * d) + 4.0 * ei.n_dst * d):
+                capi.check(lib.se3_l1tp_backward(ctx.plan2.handle, C.byref(a), st), "se3_l1tp_backward")
+            a.gw[0], a.gw[3] = None, None
+            a.gseg[0], a.gseg_mode[0] = gm1.data_ptr(), capi.GRAD_STORE
+            with capi.mark("msg2.bwdi", ei.e * (rowb + 4.0 * d) + 4.0 * ei.n_dst * d):
+                capi.check(lib.se3_l1tp_backward(ctx.plan2.handle, C.byref(a), st), "se3_l1tp_backward")
+        # ---- message 1: gate VJP + transposed SH combine + segment sums, then the node-level GEMMs
+        gpre = torch.empty_like(pre1)
+        G = torch.empty((ei.n_all, 8 * ch), device=dev, dtype=torch.float32)
+        parts = torch.empty((int(lib.se3_msg1_max_parts()), 2, ch), device=dev, dtype=torch.float32)
+        nparts = C.c_int32()
+        with capi.mark("msg1.edge_bwd", 4.0 * (ei.e * (2 * 4 + 2 + 1 + d + 3 * dpre) + 2 * ei.n_all * 4 * ch)):
+            capi.check(lib.se3_msg1_edge_backward(ns, nv, ei.n_dst, ei.n_all, ei.rowptr.data_ptr(), ei.tptr.data_ptr(),
+                                                  ei.perm.data_ptr(), y.data_ptr(), extra.data_ptr(), pre1.data_ptr(),
+                                                  gm1.data_ptr(), cs, cg, gpre.data_ptr(), G.data_ptr(), parts.data_ptr(),
+                                                  C.byref(nparts), st), "se3_msg1_edge_backward")
+        gx = gwz1 = gwv1 = None
+        with capi.mark("msg1.node_bwd", 4.0 * ei.n_all * (2 * d + 2 * 8 * ch), 2.0 * 2 * ei.n_all * d * 2 * ch):
+            if ctx.needs_input_grad[0]:
+                gx = torch.mm(G, wbig.t())
+            gwbig = torch.mm(xe.t(), G)
+            gwz1, gwv1 = torch.empty_like(wz1), torch.empty_like(wv1)
+            capi.check(lib.se3_msg1_contract(ns, nv, gwbig.data_ptr(), parts.data_ptr(), nparts.value, capi.ptr(nz1),
+                                             capi.ptr(nv1), gwz1.data_ptr(), gwv1.data_ptr(), st), "se3_msg1_contract")
+        return (gx, gwz1, gwv1, None, None, gwz2, gwv2, None, None) + (None,) * 8
+
+
+def message_layer(xe, w1, n1, w2, n2, y, extra, ei: EdgeIndex, ns: int, nv: int, cs: float, cg: float, plan2) -> torch.Tensor:
+    """w1 / w2 = (weights_l0e, weights_l1o), n1 / n2 = (norm_l0e, norm_l1o) of the two message tensor products."""
+    for name, t in (("x", xe), ("edge_attr", y), ("edge_extra", extra), *[(f"weight{i}", w) for i, w in enumerate(w1 + w2)]):
+        if not t.is_cuda:
+            raise RuntimeError(f"se3gnn_b200.message_layer: {name} must be a CUDA tensor (there is no CPU fallback)")
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise TypeError(f"se3gnn_b200.message_layer: {name} must be contiguous float32")
+    return MsgLayerFn.apply(xe, w1[0], w1[1], n1[0], n1[1], w2[0], w2[1], n2[0], n2[1], y, extra, ei, ns, nv, cs, cg, plan2)

@@ -162,6 +162,16 @@ int se3_msg_fused_forward(int32_t ns, int32_t nv, int64_t rows, const int32_t* d
                           const float* table, const float* we, const float* y, const float* extra, const float* wz2,
                           const float* wv2, const float* nz2, const float* nv2, float gate_cs, float gate_cg,
                           float* pre1, float* m1, float* pre2, float* agg, void* stream);
+/* The node-level contraction itself, block-sparse and in exact fp32 (csrc/msg_node.cu): table = x . W (forward),
+ * gx = G . W^T and gwz / gwv = x^T . G (+ the extras' rows from gwe_part) straight from / into the parameters' layout;
+ * se3_msg1_expand(wbig = NULL) then only produces `we`.  part: scratch of max_parts x part_floats floats
+ * (se3_msg1_node_parts).  gx, or gwz and gwv together, may be NULL (skipped). */
+int se3_msg1_node_parts(int32_t ns, int32_t nv, int32_t* max_parts, int32_t* part_floats);
+int se3_msg1_node_table(int32_t ns, int32_t nv, int64_t n, const float* x, const float* wz, const float* wv,
+                        const float* nz, const float* nvn, float* table, void* stream);
+int se3_msg1_node_backward(int32_t ns, int32_t nv, int64_t n, const float* x, const float* G, const float* wz,
+                           const float* wv, const float* nz, const float* nvn, const float* gwe_part, int32_t neparts,
+                           float* gx, float* gwz, float* gwv, float* part, int32_t max_parts, void* stream);
 /* rowptr [n+1] of an ascending index (rowptr[k] = first position with idx >= k) */
 int se3_rowptr_from_sorted(int64_t e, int64_t n, const int32_t* idx_sorted, int64_t* rowptr, void* stream);
 /* stable counting sort of the edges by source: tptr [n_src+1], perm [e] (edge ids, ascending inside a segment) */

@@ -44,10 +44,12 @@ struct FusedDims {
     static constexpr int NU = SQ + (RS4 ? 1 : 0) + NP;
     static constexpr int OSTR = DPRE;                              // pre-activation tile: exact image of the global rows
     static constexpr int PSTR = ((D + 3) & ~3) + 4;                // message tile stride (stride % 8 == 4)
+    static constexpr int STGB = ((HALF * 4 - 112 + 127) / 128) * 128 + 112;  // bytes per staged row: >= HALF floats, 28 (mod 32) words
     static constexpr int halfS = FTM * K1 * 4, halfV = FTM * K2 * 4, HALFB = halfS + 3 * halfV, ABYTES = 2 * HALFB;
     static_assert(NS % 2 == 0 && NV % 2 == 0, "even channel counts (8-byte stores)");
     static_assert(2 * RP + RS <= 8 && NBLK <= 8, "output columns do not fit 64 accumulator columns");
     static_assert(NU <= 16, "at most two rounds of units per warp pair");
+    static_assert(STGB >= HALF * 4 && STGB % 16 == 0 && (HALF * 4) % 16 == 0, "staged rows are 16-byte multiples");
     static_assert((DPRE & 3) == 2 || (DPRE & 3) == 0, "pre-activation tile copy");
 };
 
@@ -96,8 +98,18 @@ struct FusedSmem {
     static constexpr int o_bar = o_we + ((2 * F::CH * 4 + 15) & ~15);
     static constexpr int o_sseg = o_bar + 8 * 8 + 16;
     static constexpr int o_hs = o_sseg + 68 * 4;
-    static constexpr int total = o_hs + 8 * F::D * 16;
+    static constexpr int o_stg = (o_hs + 8 * F::D * 16 + 127) & ~127;   // src table rows of the next tile (cp.async.bulk)
+    static constexpr int total = o_stg + FTM * F::STGB;
 };
+
+__device__ __forceinline__ void fbulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fmbar_arrive_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(bar), "r"(bytes) : "memory");
+}
 
 template <int NS, int NV>
 __global__ void __launch_bounds__(F_THREADS, 1) msg_fused_fwd_kernel(const __grid_constant__ FusedFwdArgs A) {
@@ -108,7 +120,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) msg_fused_fwd_kernel(const __gri
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + SM::o_bar);
     const uint32_t bar0 = smem_u32(bars);
-    // barriers: 0,1 operand set full | 2,3 accumulator full | 4,5 accumulator empty
+    // barriers: 0,1 operand set full | 2,3 accumulator full | 4,5 accumulator empty | 6 staged src rows landed
     auto BAR = [&](int i) { return bar0 + 8u * i; };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
     float* we_s = reinterpret_cast<float*>(smraw + SM::o_we);
@@ -121,6 +133,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) msg_fused_fwd_kernel(const __gri
             mbar_init(BAR(2 + i), 1);
             mbar_init(BAR(4 + i), FW);
         }
+        mbar_init(BAR(6), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     {   // zero both operand sets (K padding is never written again)
@@ -226,7 +239,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) msg_fused_fwd_kernel(const __gri
         const int rowoffS = (((wrow >> 3) * KQ1) << 7) + ((wrow & 7) << 4);
         const int rowoffV = (((wrow >> 3) * KQ2) << 7) + ((wrow & 7) << 4);
         // row data of the tile being built, fetched one tile ahead
-        int n_dst = 0, n_src = 0;
+        int n_dst = 0;
         float4 n_y = make_float4(0.f, 0.f, 0.f, 0.f);
         float2 n_ex = make_float2(0.f, 0.f);
         auto load_row = [&](int it) {
@@ -234,9 +247,27 @@ __global__ void __launch_bounds__(F_THREADS, 1) msg_fused_fwd_kernel(const __gri
             long long gr = row0 + wrow;
             if (gr > R - 1) gr = R - 1;
             n_dst = ldgi_v(A.dst + gr);
-            n_src = ldgi_v(A.src + gr);
             n_y = ldg4_v(A.y + 4 * gr);
             n_ex = ldg2_v(A.extra + 2 * gr);
+        };
+        // src halves of the table rows of the NEXT tile: one cp.async.bulk (TMA, no tensor map) per row, issued by
+        // warp 0 as soon as every worker has finished reading the staged rows of the current tile; they land during the
+        // epilogue of the previous tile, so the build never waits on a gathered load
+        const uint32_t stg_u32 = smem_u32(smraw + SM::o_stg);
+        int pf_src0 = 0, pf_src1 = 0;
+        auto load_pf = [&](int it) {
+            const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * FTM;
+            long long g0 = row0 + lane, g1 = g0 + 32;
+            if (g0 > R - 1) g0 = R - 1;
+            if (g1 > R - 1) g1 = R - 1;
+            pf_src0 = ldgi_v(A.src + g0);
+            pf_src1 = ldgi_v(A.src + g1);
+        };
+        auto issue_pf = [&]() {
+            if (lane == 0) fmbar_arrive_tx(BAR(6), FTM * F::HALF * 4);
+            __syncwarp();
+            fbulk_g2s(stg_u32 + lane * F::STGB, A.table + (long long)pf_src0 * F::LDT + F::HALF, F::HALF * 4, BAR(6));
+            fbulk_g2s(stg_u32 + (lane + 32) * F::STGB, A.table + (long long)pf_src1 * F::LDT + F::HALF, F::HALF * 4, BAR(6));
         };
         auto st_hl4 = [&](unsigned char* p, float a, float b, float c, float d) {   // 16-byte operand piece, hi and lo
             float4 h, l;
@@ -263,7 +294,9 @@ __global__ void __launch_bounds__(F_THREADS, 1) msg_fused_fwd_kernel(const __gri
             const float4 y = n_y;
             const float2 ex = n_ex;
             const float* td = A.table + (long long)n_dst * F::LDT;
-            const float* ts = A.table + (long long)n_src * F::LDT + F::HALF;
+            const float* ts = reinterpret_cast<const float*>(smraw + SM::o_stg + wrow * F::STGB);   // staged src half
+            auto lds4 = [&](const float* q) { return *reinterpret_cast<const float4*>(q); };
+            mbar_wait(BAR(6), (uint32_t)(it & 1));
             float* pre = A.pre1 + gr * F::DPRE;
             float* m1 = A.m1 + gr * F::D;
 #pragma unroll
@@ -274,7 +307,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) msg_fused_fwd_kernel(const __gri
                     // four scalar channels 4u .. 4u+3
                     float4 a[4], b[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) { a[j] = ldg4_v(td + 16 * u + 4 * j); b[j] = ldg4_v(ts + 16 * u + 4 * j); }
+                    for (int j = 0; j < 4; ++j) { a[j] = ldg4_v(td + 16 * u + 4 * j); b[j] = lds4(ts + 16 * u + 4 * j); }
                     float x[4], m[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) { x[j] = zval(a[j], b[j], 4 * u + j, y, ex); m[j] = A.cs * x[j] * sigm(x[j]); }
@@ -286,8 +319,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) msg_fused_fwd_kernel(const __gri
                     st_hl4(aset + rowoffS + (u << 7), m[0], m[1], m[2], m[3]);
                 } else if (F::RS4 && u == F::SQ) {
                     // the last RS4 (= 2) scalar channels
-                    const float4 a0 = ldg4_v(td + 16 * u), b0 = ldg4_v(ts + 16 * u);
-                    const float4 a1 = ldg4_v(td + 16 * u + 4), b1 = ldg4_v(ts + 16 * u + 4);
+                    const float4 a0 = ldg4_v(td + 16 * u), b0 = lds4(ts + 16 * u);
+                    const float4 a1 = ldg4_v(td + 16 * u + 4), b1 = lds4(ts + 16 * u + 4);
                     const float x0 = zval(a0, b0, 4 * u, y, ex), x1 = zval(a1, b1, 4 * u + 1, y, ex);
                     const float m0 = A.cs * x0 * sigm(x0), mm1 = A.cs * x1 * sigm(x1);
                     if (valid) {
@@ -299,10 +332,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) msg_fused_fwd_kernel(const __gri
                     // pair unit i: gates NS + 2i, NS + 2i + 1 and the vector channels they gate
                     const int i = u - F::SQ - (F::RS4 ? 1 : 0);
                     const int cg0 = NS + 2 * i, cv0 = MZ + 2 * i;
-                    const float4 ga0 = ldg4_v(td + 4 * cg0), gb0 = ldg4_v(ts + 4 * cg0);
-                    const float4 ga1 = ldg4_v(td + 4 * cg0 + 4), gb1 = ldg4_v(ts + 4 * cg0 + 4);
-                    const float4 va0 = ldg4_v(td + 4 * cv0), vb0 = ldg4_v(ts + 4 * cv0);
-                    const float4 va1 = ldg4_v(td + 4 * cv0 + 4), vb1 = ldg4_v(ts + 4 * cv0 + 4);
+                    const float4 ga0 = ldg4_v(td + 4 * cg0), gb0 = lds4(ts + 4 * cg0);
+                    const float4 ga1 = ldg4_v(td + 4 * cg0 + 4), gb1 = lds4(ts + 4 * cg0 + 4);
+                    const float4 va0 = ldg4_v(td + 4 * cv0), vb0 = lds4(ts + 4 * cv0);
+                    const float4 va1 = ldg4_v(td + 4 * cv0 + 4), vb1 = lds4(ts + 4 * cv0 + 4);
                     const float xg0 = zval(ga0, gb0, cg0, y, ex), xg1 = zval(ga1, gb1, cg0 + 1, y, ex);
                     const float P0 = va0.x + vb0.x + fmaf(ex.x, we_s[cv0], ex.y * we_s[CH + cv0]);
                     const float P1 = va1.x + vb1.x + fmaf(ex.x, we_s[cv0 + 1], ex.y * we_s[CH + cv0 + 1]);
@@ -440,15 +473,26 @@ __global__ void __launch_bounds__(F_THREADS, 1) msg_fused_fwd_kernel(const __gri
             sorted_segment_sum_tile<FWT>(ptile, F::PSTR, F::D, nvalid, sseg, A.agg, F::D, hsm, tid, 3);
         };
 
-        if (nt > 0) load_row(0);
+        if (nt > 0) {
+            load_row(0);
+            if (warp == 0) {
+                load_pf(0);
+                issue_pf();
+                if (nt > 1) load_pf(1);
+            }
+        }
         for (int it = 0; it < nt; ++it) {
             build(it);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(it & 1));
             if (it + 1 < nt) load_row(it + 1);
+            named_bar(2, FWT);             // every worker is done with the staged rows of tile it and the tiles of tile it-2
+            if (warp == 0 && it + 1 < nt) {
+                issue_pf();
+                if (it + 2 < nt) load_pf(it + 2);
+            }
             if (it >= 1) {
-                named_bar(2, FWT);         // every worker is done reading the tiles of tile it-2
                 drain(it - 1);
                 named_bar(1, FWT);
                 finish(it - 1);

@@ -135,110 +135,110 @@ __global__ void __launch_bounds__(256) msg1_edge_fwd_kernel(const Msg1Fwd A) {
     }
 }
 
-// SRC = false: rows of the CSR by destination; computes the gate VJP from (pre, gpost), writes gpre and the dst half
-//              of G, accumulates the extras' weight gradient.
-// SRC = true : segments of the transposed order; reads gpre through perm, writes the src half of G.
-template <int NS, int NV, bool SRC>
+// Backward segment sums, one warp per node, ONE EDGE PER WARP STEP with every lane busy: lanes [0, MZ/2) own two 0e
+// channels each (scalars or gates), lanes [MZ/2, MZ/2 + NV) one vector channel each (34x0e+10x1o: 22 + 10 = 32 lanes).
+// A lane keeps the (P, U_x, U_y, U_z) sums of its channels in registers for the whole CSR row and writes them once.
+//   MODE 0: rows of the CSR by destination; gate VJP from (pre, gpost) -> gpre (kept for the src pass), dst half of G,
+//           extras' weight gradient
+//   MODE 1: segments of the transposed (by source) order; reads gpre through perm, src half of G
+//   MODE 2: as MODE 0 but gpre is an input (the gate VJP was done by the producer of gpre)
+template <int NS, int NV, int MODE>
 __global__ void __launch_bounds__(256) msg1_edge_bwd_kernel(const Msg1Bwd A) {
     using Dm = MsgDims<NS, NV>;
-    constexpr int MZ = Dm::MZ, CH = Dm::CH, NG = Dm::NG;
-    const int lane = threadIdx.x & 31, half = lane >> 4, l16 = lane & 15, warp = threadIdx.x >> 5;
+    constexpr int MZ = Dm::MZ, CH = Dm::CH, ZL = MZ / 2;
+    static_assert(MZ % 2 == 0 && NS % 2 == 0 && ZL + NV <= 32, "lane mapping: two 0e channels or one vector channel per lane");
+    constexpr bool SRC = MODE == 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long w0 = (long long)blockIdx.x * 8 + warp, wstride = (long long)gridDim.x * 8;
-    float gw0[NG], gw1[NG], gv0[NG], gv1[NG];
-#pragma unroll
-    for (int g = 0; g < NG; ++g) gw0[g] = gw1[g] = gv0[g] = gv1[g] = 0.0f;
+    const bool zl = lane < ZL, vl = lane >= ZL && lane < ZL + NV;
+    const bool gl = zl && 2 * lane >= NS;                 // gate lane: gates v0 = 2 lane - NS, v0 + 1
+    const int v = lane - ZL;                              // vector lanes: channel v
+    const int c0 = 2 * lane;                              // z lanes: channels c0, c0 + 1
+    const int gsrc = vl ? (NS + v) >> 1 : 0, gsel = vl ? (NS + v) & 1 : 0;     // lane / element holding the gate of v
+    const int d0 = gl ? ZL + (c0 - NS) : 0;               // gate lanes: vector lanes of their two gates (d0, d0 + 1)
+    float ge[4] = {0.f, 0.f, 0.f, 0.f};                   // extras' gradient: z lanes [j][c0 + i] -> ge[2 j + i]; vector lanes ge[j]
     const long long* ptr = SRC ? A.tptr : A.rowptr;
     const long long nseg = SRC ? A.n_all : A.n_dst;
     for (long long n = w0; n < A.n_all; n += wstride) {
         long long e0 = 0, e1 = 0;
         if (n < nseg) { e0 = __ldg(ptr + n); e1 = __ldg(ptr + n + 1); }
-        float4 acc[NG], av[NG];
-#pragma unroll
-        for (int g = 0; g < NG; ++g) acc[g] = av[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (long long k = e0 + half; k < e1; k += 2) {
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;       // z lanes: channels c0, c0 + 1; vector lanes: a0 only
+        for (long long k = e0; k < e1; ++k) {
             const long long e = SRC ? (long long)__ldg(A.perm + k) : k;
             const float4 y = ld4(A.y + 4 * e);
             float2 ex = make_float2(0.f, 0.f);
             if (!SRC) ex = ld2(A.extra + 2 * e);
-            const float* pre = A.pre + e * Dm::DPRE;
-            const float* gm = A.gpost + e * Dm::DPOST;
             float* gp = A.gpre + e * Dm::DPRE;
-#pragma unroll
-            for (int g = 0; g < NG; ++g) {
-                const int ch = g * 16 + l16;
-                if (ch < MZ) {
-                    float gx;
-                    float q0 = 0.f, q1 = 0.f, q2 = 0.f;
-                    const bool isv = ch >= NS;
-                    if (SRC) {
-                        gx = __ldg(gp + ch);
-                        if (isv) { const float* qv = gp + MZ + 3 * (ch - NS); q0 = __ldg(qv); q1 = __ldg(qv + 1); q2 = __ldg(qv + 2); }
-                    } else {
-                        const float x = __ldg(pre + ch);
-                        const float sg = sigm(x);
-                        if (!isv) {
-                            gx = A.cs * __ldg(gm + ch) * sg * fmaf(x, 1.0f - sg, 1.0f);
-                        } else {
-                            const int v = ch - NS;
-                            const float* gv = gm + NS + 3 * v;
-                            const float* pv = pre + MZ + 3 * v;
-                            const float g0 = __ldg(gv), g1 = __ldg(gv + 1), g2 = __ldg(gv + 2);
-                            const float dot = fmaf(g0, __ldg(pv), fmaf(g1, __ldg(pv + 1), g2 * __ldg(pv + 2)));
-                            const float gs = A.cg * sg;
-                            gx = gs * (1.0f - sg) * dot;
-                            q0 = gs * g0; q1 = gs * g1; q2 = gs * g2;
-                            float* qo = gp + MZ + 3 * v;
-                            qo[0] = q0; qo[1] = q1; qo[2] = q2;
-                        }
-                        gp[ch] = gx;
-                    }
-                    const float px = y.x * gx;
-                    acc[g].x += px;
-                    acc[g].y = fmaf(y.y, gx, acc[g].y);
-                    acc[g].z = fmaf(y.z, gx, acc[g].z);
-                    acc[g].w = fmaf(y.w, gx, acc[g].w);
-                    if (!SRC) { gw0[g] = fmaf(ex.x, px, gw0[g]); gw1[g] = fmaf(ex.y, px, gw1[g]); }
-                    if (isv) {
-                        const float d = fmaf(y.y, q0, fmaf(y.z, q1, y.w * q2));
-                        av[g].x += d;
-                        av[g].y = fmaf(y.x, q0, av[g].y);
-                        av[g].z = fmaf(y.x, q1, av[g].z);
-                        av[g].w = fmaf(y.x, q2, av[g].w);
-                        if (!SRC) { gv0[g] = fmaf(ex.x, d, gv0[g]); gv1[g] = fmaf(ex.y, d, gv1[g]); }
-                    }
+            float gx0 = 0.f, gx1 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f;
+            if (MODE == 0) {
+                const float* pre = A.pre + e * Dm::DPRE;
+                const float* gm = A.gpost + e * Dm::D;
+                float x0 = 0.f, x1 = 0.f, sg0 = 0.f, sg1 = 0.f, dot = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f;
+                if (zl) {
+                    const float2 x = ld2(pre + c0);
+                    x0 = x.x; x1 = x.y;
+                    sg0 = sigm(x0); sg1 = sigm(x1);
                 }
+                if (vl) {
+                    const float* gv = gm + NS + 3 * v;
+                    const float* pv = pre + MZ + 3 * v;
+                    g0 = __ldg(gv); g1 = __ldg(gv + 1); g2 = __ldg(gv + 2);
+                    dot = fmaf(g0, __ldg(pv), fmaf(g1, __ldg(pv + 1), g2 * __ldg(pv + 2)));
+                }
+                // gate sigmoid -> vector lanes; vector dots -> gate lanes
+                const float s_a = __shfl_sync(0xffffffffu, sg0, gsrc), s_b = __shfl_sync(0xffffffffu, sg1, gsrc);
+                const float dt0 = __shfl_sync(0xffffffffu, dot, d0), dt1 = __shfl_sync(0xffffffffu, dot, d0 + 1);
+                if (zl) {
+                    if (!gl) {
+                        const float2 g = ld2(gm + c0);
+                        gx0 = A.cs * g.x * sg0 * fmaf(x0, 1.0f - sg0, 1.0f);
+                        gx1 = A.cs * g.y * sg1 * fmaf(x1, 1.0f - sg1, 1.0f);
+                    } else {
+                        gx0 = A.cg * sg0 * (1.0f - sg0) * dt0;
+                        gx1 = A.cg * sg1 * (1.0f - sg1) * dt1;
+                    }
+                    *reinterpret_cast<float2*>(gp + c0) = make_float2(gx0, gx1);
+                }
+                if (vl) {
+                    const float gs = A.cg * (gsel ? s_b : s_a);
+                    q0 = gs * g0; q1 = gs * g1; q2 = gs * g2;
+                    float* qo = gp + MZ + 3 * v;
+                    qo[0] = q0; qo[1] = q1; qo[2] = q2;
+                }
+            } else {
+                if (zl) { const float2 g = ld2(gp + c0); gx0 = g.x; gx1 = g.y; }
+                if (vl) { const float* qv = gp + MZ + 3 * v; q0 = __ldg(qv); q1 = __ldg(qv + 1); q2 = __ldg(qv + 2); }
+            }
+            if (zl) {
+                const float p0 = y.x * gx0, p1 = y.x * gx1;
+                a0.x += p0; a0.y = fmaf(y.y, gx0, a0.y); a0.z = fmaf(y.z, gx0, a0.z); a0.w = fmaf(y.w, gx0, a0.w);
+                a1.x += p1; a1.y = fmaf(y.y, gx1, a1.y); a1.z = fmaf(y.z, gx1, a1.z); a1.w = fmaf(y.w, gx1, a1.w);
+                if (!SRC) {
+                    ge[0] = fmaf(ex.x, p0, ge[0]); ge[1] = fmaf(ex.x, p1, ge[1]);
+                    ge[2] = fmaf(ex.y, p0, ge[2]); ge[3] = fmaf(ex.y, p1, ge[3]);
+                }
+            } else if (vl) {
+                const float d = fmaf(y.y, q0, fmaf(y.z, q1, y.w * q2));
+                a0.x += d; a0.y = fmaf(y.x, q0, a0.y); a0.z = fmaf(y.x, q1, a0.z); a0.w = fmaf(y.x, q2, a0.w);
+                if (!SRC) { ge[0] = fmaf(ex.x, d, ge[0]); ge[1] = fmaf(ex.y, d, ge[1]); }
             }
         }
         float* gn = A.G + n * Dm::LDT + (SRC ? Dm::HALF : 0);
-#pragma unroll
-        for (int g = 0; g < NG; ++g) {
-            const int ch = g * 16 + l16;
-            float4 a = acc[g], b = av[g];
-            a.x += __shfl_xor_sync(0xffffffffu, a.x, 16); a.y += __shfl_xor_sync(0xffffffffu, a.y, 16);
-            a.z += __shfl_xor_sync(0xffffffffu, a.z, 16); a.w += __shfl_xor_sync(0xffffffffu, a.w, 16);
-            if (g * 16 + 15 >= NS && g * 16 < MZ) {
-                b.x += __shfl_xor_sync(0xffffffffu, b.x, 16); b.y += __shfl_xor_sync(0xffffffffu, b.y, 16);
-                b.z += __shfl_xor_sync(0xffffffffu, b.z, 16); b.w += __shfl_xor_sync(0xffffffffu, b.w, 16);
-            }
-            if (half == 0 && ch < MZ) {
-                *reinterpret_cast<float4*>(gn + 4 * ch) = a;
-                if (ch >= NS) *reinterpret_cast<float4*>(gn + 4 * (MZ + ch - NS)) = b;
-            }
+        if (zl) {
+            *reinterpret_cast<float4*>(gn + 4 * c0) = a0;
+            *reinterpret_cast<float4*>(gn + 4 * c0 + 4) = a1;
+        } else if (vl) {
+            *reinterpret_cast<float4*>(gn + 4 * (MZ + v)) = a0;
         }
     }
     if (!SRC) {
         // extras' weight gradient of this block: [2][CH] partial (summed deterministically by msg1_contract)
         __shared__ float sgw[8][2][CH];
-#pragma unroll
-        for (int g = 0; g < NG; ++g) {
-            const int ch = g * 16 + l16;
-            float a0 = gw0[g], a1 = gw1[g], b0 = gv0[g], b1 = gv1[g];
-            a0 += __shfl_xor_sync(0xffffffffu, a0, 16); a1 += __shfl_xor_sync(0xffffffffu, a1, 16);
-            b0 += __shfl_xor_sync(0xffffffffu, b0, 16); b1 += __shfl_xor_sync(0xffffffffu, b1, 16);
-            if (half == 0 && ch < MZ) {
-                sgw[warp][0][ch] = a0; sgw[warp][1][ch] = a1;
-                if (ch >= NS) { sgw[warp][0][MZ + ch - NS] = b0; sgw[warp][1][MZ + ch - NS] = b1; }
-            }
+        if (zl) {
+            sgw[warp][0][c0] = ge[0]; sgw[warp][0][c0 + 1] = ge[1];
+            sgw[warp][1][c0] = ge[2]; sgw[warp][1][c0 + 1] = ge[3];
+        } else if (vl) {
+            sgw[warp][0][MZ + v] = ge[0]; sgw[warp][1][MZ + v] = ge[1];
         }
         __syncthreads();
         for (int t = threadIdx.x; t < 2 * CH; t += 256) {
@@ -281,7 +281,7 @@ __global__ void msg1_expand_kernel(const float* __restrict__ wz, const float* __
             if (ch < MZ) val = f * (nz ? nz[ch] : 1.0f) * wz[row * MZ + ch];
             else val = C3f * (nvn ? nvn[3 * (ch - MZ)] : 1.0f) * wv[row * NV + ch - MZ];
         }
-        wbig[t] = val;
+        if (wbig) wbig[t] = val;
     }
 }
 
@@ -374,9 +374,10 @@ static int msg1_launch_fwd(const Msg1Fwd& A, cudaStream_t st) {
 }
 template <int NS, int NV>
 static int msg1_launch_bwd(const Msg1Bwd& A, int grid, cudaStream_t st) {
-    msg1_edge_bwd_kernel<NS, NV, false><<<grid, 256, 0, st>>>(A);
+    if (A.pre) msg1_edge_bwd_kernel<NS, NV, 0><<<grid, 256, 0, st>>>(A);
+    else msg1_edge_bwd_kernel<NS, NV, 2><<<grid, 256, 0, st>>>(A);    // gpre given: the gate VJP was done by its producer
     SE3_LAUNCHED();
-    msg1_edge_bwd_kernel<NS, NV, true><<<grid, 256, 0, st>>>(A);
+    msg1_edge_bwd_kernel<NS, NV, 1><<<grid, 256, 0, st>>>(A);
     SE3_LAUNCHED();
     return SE3_OK;
 }
@@ -388,18 +389,18 @@ using namespace se3;
 #define SE3_MSG1_DISPATCH(ns, nv, CALL)                                      \
     if ((ns) == 34 && (nv) == 10) { CALL(34, 10) }                           \
     else if ((ns) == 16 && (nv) == 8) { CALL(16, 8) }                        \
-    else if ((ns) == 6 && (nv) == 3) { CALL(6, 3) }                          \
+    else if ((ns) == 8 && (nv) == 4) { CALL(8, 4) }                          \
     else { set_error("msg1: hidden irreps %dx0e+%dx1o are not instantiated", (int)(ns), (int)(nv)); return SE3_ERR_INVALID; }
 
 extern "C" int se3_msg1_supported(int32_t ns, int32_t nv, int32_t ne) {
-    return ne == 2 && ((ns == 34 && nv == 10) || (ns == 16 && nv == 8) || (ns == 6 && nv == 3)) ? 1 : 0;
+    return ne == 2 && ((ns == 34 && nv == 10) || (ns == 16 && nv == 8) || (ns == 8 && nv == 4)) ? 1 : 0;
 }
 
 extern "C" int se3_msg1_max_parts(void) { return num_sms() * 8; }
 
 extern "C" int se3_msg1_expand(int32_t ns, int32_t nv, const float* wz, const float* wv, const float* nz, const float* nvn,
                                float* wbig, float* we, void* stream) {
-    if (!wz || !wv || !wbig || !we) { set_error("msg1_expand: null argument"); return SE3_ERR_INVALID; }
+    if (!wz || !wv || !we) { set_error("msg1_expand: null argument"); return SE3_ERR_INVALID; }   // wbig may be NULL
 #define CALL(a, b) msg1_expand_kernel<a, b><<<64, 256, 0, (cudaStream_t)stream>>>(wz, wv, nz, nvn, wbig, we);
     SE3_MSG1_DISPATCH(ns, nv, CALL)
 #undef CALL
@@ -438,7 +439,7 @@ extern "C" int se3_msg1_edge_backward(int32_t ns, int32_t nv, int64_t n_dst, int
     if (n_dst < 0 || n_all < n_dst || !nparts) { set_error("msg1_edge_backward: bad argument"); return SE3_ERR_INVALID; }
     *nparts = 0;
     if (n_all == 0) return SE3_OK;
-    if (!rowptr || !tptr || !perm || !y || !extra || !pre || !gpost || !gpre || !G || !gwe_part) {
+    if (!rowptr || !tptr || !perm || !y || !extra || !gpre || !G || !gwe_part || (pre && !gpost)) {
         set_error("msg1_edge_backward: null argument");
         return SE3_ERR_INVALID;
     }

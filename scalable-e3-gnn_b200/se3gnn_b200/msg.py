@@ -51,6 +51,40 @@ def build_edge_index(dst: torch.Tensor, src: torch.Tensor, n_dst: int, n_all: in
     return EdgeIndex(n_dst=n_dst, n_all=n_all, e=e, rowptr=rowptr, src=src, dst=dst, tptr=tptr, perm=perm)
 
 
+def _node_forward(xe, wz, wv, nz, nvn, ns, nv, n_all, tag):
+    """node tables T = x . W (csrc/msg_node.cu) and the extras' folded weights `we`"""
+    lib = capi.lib()
+    dev = xe.device
+    st = capi.current_stream_ptr()
+    ch, d = ns + 2 * nv, ns + 3 * nv
+    we = torch.empty((2, ch), device=dev, dtype=torch.float32)
+    capi.check(lib.se3_msg1_expand(ns, nv, wz.data_ptr(), wv.data_ptr(), capi.ptr(nz), capi.ptr(nvn), None, we.data_ptr(), st),
+               "se3_msg1_expand")
+    table = torch.empty((n_all, 8 * ch), device=dev, dtype=torch.float32)
+    with capi.mark(tag, 4.0 * n_all * (d + 8 * ch), 2.0 * n_all * 2 * ch * d):
+        capi.check(lib.se3_msg1_node_table(ns, nv, n_all, xe.data_ptr(), wz.data_ptr(), wv.data_ptr(), capi.ptr(nz),
+                                           capi.ptr(nvn), table.data_ptr(), st), "se3_msg1_node_table")
+    return table, we
+
+
+def _node_backward(xe, G, wz, wv, nz, nvn, parts, nparts, ns, nv, n_all, need_gx, tag):
+    """gx = G . W^T, gwz / gwv = x^T . G (+ extras' rows), straight into the parameters' layout"""
+    lib = capi.lib()
+    dev = xe.device
+    ch, d = ns + 2 * nv, ns + 3 * nv
+    mp, pf = C.c_int32(), C.c_int32()
+    capi.check(lib.se3_msg1_node_parts(ns, nv, C.byref(mp), C.byref(pf)))
+    scratch = torch.empty((mp.value, pf.value), device=dev, dtype=torch.float32)
+    gx = torch.empty_like(xe) if need_gx else None
+    gwz, gwv = torch.empty_like(wz), torch.empty_like(wv)
+    with capi.mark(tag, 4.0 * n_all * (2 * d + 2 * 8 * ch), 2.0 * 2 * n_all * 2 * ch * d):
+        capi.check(lib.se3_msg1_node_backward(ns, nv, n_all, xe.data_ptr(), G.data_ptr(), wz.data_ptr(), wv.data_ptr(),
+                                              capi.ptr(nz), capi.ptr(nvn), parts.data_ptr(), nparts, capi.ptr(gx),
+                                              gwz.data_ptr(), gwv.data_ptr(), scratch.data_ptr(), mp.value,
+                                              capi.current_stream_ptr()), "se3_msg1_node_backward")
+    return gx, gwz, gwv
+
+
 def supported(ns: int, nv: int, n_extra: int) -> bool:
     return bool(capi.lib().se3_msg1_supported(ns, nv, n_extra))
 
@@ -65,12 +99,7 @@ class Msg1Fn(torch.autograd.Function):
         st = capi.current_stream_ptr()
         ch, d = ns + 2 * nv, ns + 3 * nv
         assert xe.shape == (ei.n_all, d) and xe.is_contiguous() and xe.dtype == torch.float32
-        wbig = torch.empty((d, 8 * ch), device=dev, dtype=torch.float32)
-        we = torch.empty((2, ch), device=dev, dtype=torch.float32)
-        capi.check(lib.se3_msg1_expand(ns, nv, wz.data_ptr(), wv.data_ptr(), capi.ptr(nz), capi.ptr(nvn), wbig.data_ptr(),
-                                       we.data_ptr(), st), "se3_msg1_expand")
-        with capi.mark("msg1.table", 4.0 * ei.n_all * (d + 8 * ch), 2.0 * ei.n_all * d * 2 * ch):
-            table = torch.mm(xe, wbig)
+        table, we = _node_forward(xe, wz, wv, nz, nvn, ns, nv, ei.n_all, "msg.table")
         pre = torch.empty((ei.e, ns + 4 * nv), device=dev, dtype=torch.float32)
         post = torch.empty((ei.e, d), device=dev, dtype=torch.float32)
         with capi.mark("msg1.edge_fwd", 4.0 * (ei.e * (4 + 2 + 1 + ns + 4 * nv + d) + (ei.n_all + ei.n_dst) * 4 * ch)):
@@ -78,13 +107,13 @@ class Msg1Fn(torch.autograd.Function):
                                                  we.data_ptr(), y.data_ptr(), extra.data_ptr(), cs, cg, pre.data_ptr(),
                                                  post.data_ptr(), st), "se3_msg1_edge_forward")
         ctx.ei, ctx.dims = ei, (ns, nv, cs, cg)
-        ctx.save_for_backward(xe, wbig, pre, y, extra, nz, nvn, wz, wv)
+        ctx.save_for_backward(xe, pre, y, extra, nz, nvn, wz, wv)
         return post
 
     @staticmethod
     def backward(ctx, gpost):
         lib = capi.lib()
-        xe, wbig, pre, y, extra, nz, nvn, wz, wv = ctx.saved_tensors
+        xe, pre, y, extra, nz, nvn, wz, wv = ctx.saved_tensors
         ei: EdgeIndex = ctx.ei
         ns, nv, cs, cg = ctx.dims
         dev = xe.device
@@ -100,15 +129,8 @@ class Msg1Fn(torch.autograd.Function):
                                                   ei.perm.data_ptr(), y.data_ptr(), extra.data_ptr(), pre.data_ptr(),
                                                   gpost.data_ptr(), cs, cg, gpre.data_ptr(), G.data_ptr(), parts.data_ptr(),
                                                   C.byref(nparts), st), "se3_msg1_edge_backward")
-        gx = gwz = gwv = None
-        with capi.mark("msg1.node_bwd", 4.0 * ei.n_all * (2 * d + 2 * 8 * ch), 2.0 * 2 * ei.n_all * d * 2 * ch):
-            if ctx.needs_input_grad[0]:
-                gx = torch.mm(G, wbig.t())
-            if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
-                gwbig = torch.mm(xe.t(), G)
-                gwz, gwv = torch.empty_like(wz), torch.empty_like(wv)
-                capi.check(lib.se3_msg1_contract(ns, nv, gwbig.data_ptr(), parts.data_ptr(), nparts.value, capi.ptr(nz),
-                                                 capi.ptr(nvn), gwz.data_ptr(), gwv.data_ptr(), st), "se3_msg1_contract")
+        gx, gwz, gwv = _node_backward(xe, G, wz, wv, nz, nvn, parts, nparts.value, ns, nv, ei.n_all,
+                                      ctx.needs_input_grad[0], "msg.node_bwd")
         return gx, gwz, gwv, None, None, None, None, None, None, None, None, None
 
 
@@ -140,12 +162,7 @@ class MsgLayerFn(torch.autograd.Function):
         st = capi.current_stream_ptr()
         ch, d, dpre = ns + 2 * nv, ns + 3 * nv, ns + 4 * nv
         assert xe.shape == (ei.n_all, d) and xe.is_contiguous() and xe.dtype == torch.float32
-        wbig = torch.empty((d, 8 * ch), device=dev, dtype=torch.float32)
-        we = torch.empty((2, ch), device=dev, dtype=torch.float32)
-        capi.check(lib.se3_msg1_expand(ns, nv, wz1.data_ptr(), wv1.data_ptr(), capi.ptr(nz1), capi.ptr(nv1),
-                                       wbig.data_ptr(), we.data_ptr(), st), "se3_msg1_expand")
-        with capi.mark("msg.table", 4.0 * ei.n_all * (d + 8 * ch), 2.0 * ei.n_all * d * 2 * ch):
-            table = torch.mm(xe, wbig)
+        table, we = _node_forward(xe, wz1, wv1, nz1, nv1, ns, nv, ei.n_all, "msg.table")
         pre1 = torch.empty((ei.e, dpre), device=dev, dtype=torch.float32)
         m1 = torch.empty((ei.e, d), device=dev, dtype=torch.float32)
         pre2 = torch.empty((ei.e, dpre), device=dev, dtype=torch.float32)
@@ -160,13 +177,13 @@ class MsgLayerFn(torch.autograd.Function):
                                                  wv2.data_ptr(), capi.ptr(nz2), capi.ptr(nv2), cs, cg, pre1.data_ptr(),
                                                  m1.data_ptr(), pre2.data_ptr(), agg.data_ptr(), st), "se3_msg_fused_forward")
         ctx.ei, ctx.dims, ctx.plan2 = ei, (ns, nv, cs, cg), plan2
-        ctx.save_for_backward(xe, wbig, pre1, m1, pre2, y, extra, nz1, nv1, wz1, wv1, wz2, wv2, nz2, nv2)
+        ctx.save_for_backward(xe, pre1, m1, pre2, y, extra, nz1, nv1, wz1, wv1, wz2, wv2, nz2, nv2)
         return agg
 
     @staticmethod
     def backward(ctx, gagg):
         lib = capi.lib()
-        xe, wbig, pre1, m1, pre2, y, extra, nz1, nv1, wz1, wv1, wz2, wv2, nz2, nv2 = ctx.saved_tensors
+        xe, pre1, m1, pre2, y, extra, nz1, nv1, wz1, wv1, wz2, wv2, nz2, nv2 = ctx.saved_tensors
         ei: EdgeIndex = ctx.ei
         ns, nv, cs, cg = ctx.dims
         dev = xe.device
@@ -207,14 +224,8 @@ class MsgLayerFn(torch.autograd.Function):
                                                   ei.perm.data_ptr(), y.data_ptr(), extra.data_ptr(), pre1.data_ptr(),
                                                   gm1.data_ptr(), cs, cg, gpre.data_ptr(), G.data_ptr(), parts.data_ptr(),
                                                   C.byref(nparts), st), "se3_msg1_edge_backward")
-        gx = gwz1 = gwv1 = None
-        with capi.mark("msg1.node_bwd", 4.0 * ei.n_all * (2 * d + 2 * 8 * ch), 2.0 * 2 * ei.n_all * d * 2 * ch):
-            if ctx.needs_input_grad[0]:
-                gx = torch.mm(G, wbig.t())
-            gwbig = torch.mm(xe.t(), G)
-            gwz1, gwv1 = torch.empty_like(wz1), torch.empty_like(wv1)
-            capi.check(lib.se3_msg1_contract(ns, nv, gwbig.data_ptr(), parts.data_ptr(), nparts.value, capi.ptr(nz1),
-                                             capi.ptr(nv1), gwz1.data_ptr(), gwv1.data_ptr(), st), "se3_msg1_contract")
+        gx, gwz1, gwv1 = _node_backward(xe, G, wz1, wv1, nz1, nv1, parts, nparts.value, ns, nv, ei.n_all,
+                                        ctx.needs_input_grad[0], "msg.node_bwd")
         return (gx, gwz1, gwv1, None, None, gwz2, gwv2, None, None) + (None,) * 8
 
 

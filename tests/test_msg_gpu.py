@@ -32,7 +32,7 @@ def test_edge_index_bit_exact(n_dst, n_all, e):
         np.testing.assert_array_equal(ei.perm.cpu().numpy()[:e], np.argsort(src, kind="stable"))
 
 
-@pytest.mark.parametrize("ns,nv,n_dst,n_all,e", [(34, 10, 300, 300, 5003), (34, 10, 2000, 2100, 40000), (6, 3, 64, 80, 999),
+@pytest.mark.parametrize("ns,nv,n_dst,n_all,e", [(34, 10, 300, 300, 5003), (34, 10, 2000, 2100, 40000), (8, 4, 64, 80, 999),
                                                  (16, 8, 500, 500, 7000), (34, 10, 10, 10, 1)])
 def test_msg1_kernels_vs_restatement(ns, nv, n_dst, n_all, e):
     from se3gnn_b200 import msg

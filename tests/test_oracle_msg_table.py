@@ -9,7 +9,7 @@ from oracle.l1tp_port import L1TPPort
 from oracle.segnn_oracle import SIGMOID_CST, SILU_CST
 
 
-@pytest.mark.parametrize("ns,nv", [(34, 10), (6, 3), (16, 8)])
+@pytest.mark.parametrize("ns,nv", [(34, 10), (8, 4), (16, 8)])
 def test_table_formulation_equals_port(ns, nv):
     torch.manual_seed(ns)
     rng = np.random.default_rng(nv)

@@ -144,7 +144,8 @@ int se3_msg1_edge_forward(int32_t ns, int32_t nv, int64_t n_dst, const int64_t* 
                           const float* extra, float gate_cs, float gate_cg, float* pre, float* post, void* stream);
 /* gate VJP + transposed SH combine + segment sums, no atomics: G [n_all, 8(ns+2nv)] is overwritten (dst half of the
  * rows >= n_dst: zero); tptr [n_all+1] / perm [E] = the edges in stable order by source (se3_graph_transpose);
- * gpre [E, ns+4nv] scratch; gwe_part [se3_msg1_max_parts(), 2, ns+2nv] per-block partials, *nparts rows written. */
+ * gpre [E, ns+4nv] scratch (pre == NULL: gpre is an INPUT, the gate VJP was done by its producer and gpost is unused);
+ * gwe_part [se3_msg1_max_parts(), 2, ns+2nv] per-block partials, *nparts rows written. */
 int se3_msg1_edge_backward(int32_t ns, int32_t nv, int64_t n_dst, int64_t n_all, const int64_t* rowptr,
                            const int64_t* tptr, const int32_t* perm, const float* y, const float* extra,
                            const float* pre, const float* gpost, float gate_cs, float gate_cg, float* gpre, float* G,
@@ -162,6 +163,18 @@ int se3_msg_fused_forward(int32_t ns, int32_t nv, int64_t rows, const int32_t* d
                           const float* table, const float* we, const float* y, const float* extra, const float* wz2,
                           const float* wv2, const float* nz2, const float* nv2, float gate_cs, float gate_cg,
                           float* pre1, float* m1, float* pre2, float* agg, void* stream);
+/* the same with cycle counters of the kernel's phases (diagnostics; dbg = NULL or [148][2][8] int64) */
+int se3_msg_fused_forward_dbg(int32_t ns, int32_t nv, int64_t rows, const int32_t* dst, const int32_t* src,
+                              const float* table, const float* we, const float* y, const float* extra, const float* wz2,
+                              const float* wv2, const float* nz2, const float* nv2, float gate_cs, float gate_cg,
+                              float* pre1, float* m1, float* pre2, float* agg, int64_t* dbg, void* stream);
+/* Input-gradient side of the message layer in one launch (csrc/msg_fused_bwd.cu, tcgen05): cotangent of the aggregate
+ * gagg [n_dst, ns+3nv] gathered through dst -> gate VJP of message 2 (pre2) -> contraction with W2^T (3xTF32) -> gate VJP
+ * of message 1 (pre1) -> gpre1 [rows, ns+4nv], the input of se3_msg1_edge_backward(pre = NULL).  gpre2 (may be NULL)
+ * receives the cotangent of message 2's pre-activation. */
+int se3_msg_fused_backward(int32_t ns, int32_t nv, int64_t rows, const int32_t* dst, const float* y, const float* pre1,
+                           const float* pre2, const float* gagg, const float* wz2, const float* wv2, const float* nz2,
+                           const float* nv2, float gate_cs, float gate_cg, float* gpre1, float* gpre2, void* stream);
 /* The node-level contraction itself, block-sparse and in exact fp32 (csrc/msg_node.cu): table = x . W (forward),
  * gx = G . W^T and gwz / gwv = x^T . G (+ the extras' rows from gwe_part) straight from / into the parameters' layout;
  * se3_msg1_expand(wbig = NULL) then only produces `we`.  part: scratch of max_parts x part_floats floats

@@ -1101,18 +1101,6 @@ int se3_l1tp_tc2_try_backward_w(const int n[4], const int m[4], const int t_in[4
                                 const int* h_tab, const se3_l1tp_bwd_args* a, const se3::RowSrc& src, const se3::EpiL& epi,
                                 float* partials, int wtot, int gw_z_off, int gw_v_off, int max_grid, cudaStream_t st,
                                 int* grid_out, bool* launched);
-int se3_l1tp_tc_try_backward_w(const int n[4], const int m[4], const int t_in[4], const int t_out[4], int ntab,
-                               const int* d_tab, const se3_l1tp_bwd_args* a, const se3::RowSrc& src, const se3::EpiL& epi,
-                               float* partials, int wtot, int gw_z_off, int gw_v_off, int max_grid, cudaStream_t st,
-                               int* grid_out, bool* launched);
-int se3_l1tp_tc_try_backward_in(const int n[4], const int m[4], const int t_in[4], const int t_out[4], int ntab,
-                                const int* d_tab, const se3_l1tp_bwd_args* a, const se3::RowSrc& src, const se3::EpiL& epi,
-                                float* const gseg[SE3_MAX_SEG], const int gmode[SE3_MAX_SEG], cudaStream_t st,
-                                bool* launched);
-int se3_l1tp_tc_try_forward(const int n[4], const int m[4], const int t_in[4], const int t_out[4], int ntab,
-                            const int* d_tab, const se3_l1tp_fwd_args* a, const se3::RowSrc& src, const se3::EpiL& epi,
-                            cudaStream_t st, bool* launched);
-
 extern "C" int se3_l1tp_plan_create(const se3_l1tp_desc* d, se3_l1tp_plan** out) {
     if (!d || !out) { set_error("null argument"); return SE3_ERR_INVALID; }
     *out = nullptr;
@@ -1322,10 +1310,6 @@ extern "C" int se3_l1tp_forward(se3_l1tp_plan* p, const se3_l1tp_fwd_args* a, vo
                                       (cudaStream_t)stream, &launched);
         if (rc) return rc;
         if (launched) return SE3_OK;
-        rc = se3_l1tp_tc_try_forward(p->n, p->m, p->t_in, p->t_out, p->L.ntab, p->d_tab, a, K.src, K.epi,
-                                     (cudaStream_t)stream, &launched);
-        if (rc) return rc;
-        if (launched) return SE3_OK;
     }
     const long long ntiles = (a->rows + p->L.TR - 1) / p->L.TR;
     const int grid = (int)std::min<long long>(ntiles, (long long)num_sms() * p->occ_fwd);
@@ -1388,11 +1372,6 @@ extern "C" int se3_l1tp_backward(se3_l1tp_plan* p, const se3_l1tp_bwd_args* a, v
                                          p->d_partials, p->L.wtot, p->w_off[0], p->w_off[3],
                                          grid_cap ? std::min(grid_cap, num_sms()) : num_sms(), st, &tc_grid, &tcw);
         if (rc) return rc;
-        if (!tcw)
-        rc = se3_l1tp_tc_try_backward_w(p->n, p->m, p->t_in, p->t_out, p->L.ntab, p->d_tab, a, K.src, K.epi,
-                                        p->d_partials, p->L.wtot, p->w_off[0], p->w_off[3],
-                                        grid_cap ? std::min(grid_cap, num_sms()) : num_sms(), st, &tc_grid, &tcw);
-        if (rc) return rc;
         if (tcw) red_blocks = tc_grid;
         else K.partials = p->d_partials;
     }
@@ -1402,10 +1381,6 @@ extern "C" int se3_l1tp_backward(se3_l1tp_plan* p, const se3_l1tp_bwd_args* a, v
         bool tci = false;
         rc = se3_l1tp_tc2_try_backward_in(p->n, p->m, p->t_in, p->t_out, p->L.ntab, p->h_tab.data(), p->d_tab, a, K.src,
                                           K.epi, K.gseg, K.gmode, st, &tci);
-        if (rc) return rc;
-        if (!tci)
-        rc = se3_l1tp_tc_try_backward_in(p->n, p->m, p->t_in, p->t_out, p->L.ntab, p->d_tab, a, K.src, K.epi, K.gseg,
-                                         K.gmode, st, &tci);
         if (rc) return rc;
         if (tci) {
             need_in = false;

@@ -525,7 +525,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) l1tp_tc2_fwd_kernel(const __gri
 using namespace se3;
 
 // Launches the second-generation forward when the configuration is eligible (launched=false otherwise: the caller
-// falls through to the first-generation tcgen05 kernel or the generic fp32 kernel).
+// falls through to the generic fp32 kernel).
 int se3_l1tp_tc2_try_forward(const int n[4], const int m[4], const int t_in[4], const int t_out[4], int ntab,
                              const int* h_tab, const int* d_tab, const se3_l1tp_fwd_args* a, const RowSrc& src,
                              const EpiL& epi, cudaStream_t st, bool* launched) {

@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) l1tp_tc2_bwdw_kernel(const __gr
 using namespace se3;
 
 // weight gradients, second generation; launched=false when the configuration is not eligible (the caller falls back
-// to the first-generation kernel)
+// to the generic fp32 kernel)
 int se3_l1tp_tc2_try_backward_w(const int n[4], const int m[4], const int t_in[4], const int t_out[4], int ntab,
                                 const int* h_tab, const se3_l1tp_bwd_args* a, const RowSrc& src, const EpiL& epi,
                                 float* partials, int wtot, int gw_z_off, int gw_v_off, int max_grid, cudaStream_t st,

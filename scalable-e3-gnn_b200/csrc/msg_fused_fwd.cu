@@ -31,6 +31,7 @@ static constexpr int FW = 16;                  // worker warps
 static constexpr int F_THREADS = (FW + 1) * 32;
 static constexpr int FWT = FW * 32;
 static constexpr int FTM = 64;                 // rows per tile
+static constexpr int NDMAX = 16;               // staged distinct destination rows per tile (more: read from global)
 
 template <int NS, int NV>
 struct FusedDims {
@@ -47,8 +48,9 @@ struct FusedDims {
     static constexpr int STGB = ((HALF * 4 - 112 + 127) / 128) * 128 + 112;  // bytes per staged row: >= HALF floats, 28 (mod 32) words
     static constexpr int halfS = FTM * K1 * 4, halfV = FTM * K2 * 4, HALFB = halfS + 3 * halfV, ABYTES = 2 * HALFB;
     static_assert(NS % 2 == 0 && NV % 2 == 0, "even channel counts (8-byte stores)");
+    static_assert(D <= 64, "segment sum: one thread per column and run slot");
     static_assert(2 * RP + RS <= 8 && NBLK <= 8, "output columns do not fit 64 accumulator columns");
-    static_assert(NU <= 16, "at most two rounds of units per warp pair");
+    static_assert(SQ <= 8 && NP + (RS4 ? 1 : 0) <= 8, "one round of scalar quads and one of pairs per warp pair");
     static_assert(STGB >= HALF * 4 && STGB % 16 == 0 && (HALF * 4) % 16 == 0, "staged rows are 16-byte multiples");
     static_assert((DPRE & 3) == 2 || (DPRE & 3) == 0, "pre-activation tile copy");
 };
@@ -67,6 +69,29 @@ __host__ __device__ constexpr int fused_colch(int n) {
     return -1;
 }
 
+// drain tasks: the used 8-column accumulator blocks spread over the four task slots jq (two blocks each at most) by
+// longest-processing-time-first on their costs (tail block > gate/vector block > scalar block)
+template <int NS, int NV>
+struct DrainMap {
+    int blk[4][2];
+    constexpr DrainMap() : blk{{-1, -1}, {-1, -1}, {-1, -1}, {-1, -1}} {
+        using F = FusedDims<NS, NV>;
+        int load[4] = {0, 0, 0, 0}, cnt[4] = {0, 0, 0, 0};
+        // blocks in decreasing cost: tail, pair blocks, scalar blocks
+        int order[8] = {0, 0, 0, 0, 0, 0, 0, 0}, cost[8] = {0, 0, 0, 0, 0, 0, 0, 0}, n = 0;
+        if (F::NBLK > F::FB + F::PBF) { order[n] = F::FB + F::PBF; cost[n] = 22; ++n; }
+        for (int b = F::FB; b < F::FB + F::PBF; ++b) { order[n] = b; cost[n] = 16; ++n; }
+        for (int b = 0; b < F::FB; ++b) { order[n] = b; cost[n] = 10; ++n; }
+        for (int i = 0; i < n; ++i) {
+            int best = -1;
+            for (int q = 0; q < 4; ++q)
+                if (cnt[q] < 2 && (best < 0 || load[q] < load[best])) best = q;
+            blk[best][cnt[best]++] = order[i];
+            load[best] += cost[i];
+        }
+    }
+};
+
 struct FusedFwdArgs {
     long long rows;            // edges
     const int* dst;            // [E] ascending
@@ -84,6 +109,7 @@ struct FusedFwdArgs {
     float* pre2;               // [E, DPRE]
     float* agg;                // [n_dst, D], zero on entry
     float cs, cg;
+    long long* dbg;            // NULL, or [grid][2][8] cycle counters of the phases (diagnostics: SE3_DBG_TIMING)
 };
 
 template <int NS, int NV>
@@ -92,14 +118,16 @@ struct FusedSmem {
     static constexpr int o_b1 = 0;
     static constexpr int o_b2 = o_b1 + 2 * F::N * F::K1 * 4;
     static constexpr int o_a = (o_b2 + 2 * F::N * F::K2 * 4 + 1023) & ~1023;
-    static constexpr int o_out = o_a + 2 * F::ABYTES;
+    static constexpr int o_out = o_a + F::ABYTES;            // ONE operand set: the MMAs of tile t are long complete when tile t+1 is built
     static constexpr int o_post = o_out + ((FTM * F::OSTR * 4 + 15) & ~15);
     static constexpr int o_we = o_post + FTM * F::PSTR * 4;
     static constexpr int o_bar = o_we + ((2 * F::CH * 4 + 15) & ~15);
     static constexpr int o_sseg = o_bar + 8 * 8 + 16;
     static constexpr int o_hs = o_sseg + 68 * 4;
-    static constexpr int o_stg = (o_hs + 8 * F::D * 16 + 127) & ~127;   // src table rows of the next tile (cp.async.bulk)
-    static constexpr int total = o_stg + FTM * F::STGB;
+    static constexpr int o_stg = (o_hs + 127) & ~127;   // src table rows of the next tile (cp.async.bulk)
+    static constexpr int o_dstg = o_stg + FTM * F::STGB;                // its distinct dst table rows (first NDMAX)
+    static constexpr int o_slot = o_dstg + NDMAX * F::STGB;             // row -> dst slot
+    static constexpr int total = o_slot + FTM * 4;
 };
 
 __device__ __forceinline__ void fbulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -138,7 +166,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) msg_fused_fwd_kernel(const __gri
     }
     {   // zero both operand sets (K padding is never written again)
         float4* z = reinterpret_cast<float4*>(smraw + SM::o_a);
-        for (int t = tid; t < (2 * F::ABYTES) >> 4; t += F_THREADS) z[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int t = tid; t < F::ABYTES >> 4; t += F_THREADS) z[t] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     {   // message-2 weights -> canonical K-major B tiles (hi | lo), norms and c3 folded, columns permuted
         unsigned char* b1 = smraw + SM::o_b1;
@@ -203,7 +231,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) msg_fused_fwd_kernel(const __gri
             tc_fence_after();
             if (lane == 0) {
                 const uint32_t acc = tmem_base + (uint32_t)b * ACC;
-                const uint32_t aS = sb + SM::o_a + (uint32_t)b * F::ABYTES;
+                const uint32_t aS = sb + SM::o_a;
                 const uint64_t dSh = make_desc(aS, sboS), dSl = make_desc(aS + F::HALFB, sboS);
 #pragma unroll
                 for (int j = 0; j < K1 / 8; ++j) {
@@ -254,7 +282,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) msg_fused_fwd_kernel(const __gri
         // warp 0 as soon as every worker has finished reading the staged rows of the current tile; they land during the
         // epilogue of the previous tile, so the build never waits on a gathered load
         const uint32_t stg_u32 = smem_u32(smraw + SM::o_stg);
-        int pf_src0 = 0, pf_src1 = 0;
+        int pf_src0 = 0, pf_src1 = 0, pf_dst0 = 0, pf_dst1 = 0;
+        int* sslot = reinterpret_cast<int*>(smraw + SM::o_slot);
         auto load_pf = [&](int it) {
             const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * FTM;
             long long g0 = row0 + lane, g1 = g0 + 32;
@@ -262,12 +291,29 @@ __global__ void __launch_bounds__(F_THREADS, 1) msg_fused_fwd_kernel(const __gri
             if (g1 > R - 1) g1 = R - 1;
             pf_src0 = ldgi_v(A.src + g0);
             pf_src1 = ldgi_v(A.src + g1);
+            pf_dst0 = ldgi_v(A.dst + g0);
+            pf_dst1 = ldgi_v(A.dst + g1);
         };
         auto issue_pf = [&]() {
-            if (lane == 0) fmbar_arrive_tx(BAR(6), FTM * F::HALF * 4);
+            // dst is ascending: slot of a row = number of changes of dst up to it; the first row of a slot copies the
+            // dst half of that node's table row (once per node and tile instead of once per edge)
+            const int up0 = __shfl_up_sync(0xffffffffu, pf_dst0, 1), last0 = __shfl_sync(0xffffffffu, pf_dst0, 31);
+            const int up1 = __shfl_up_sync(0xffffffffu, pf_dst1, 1);
+            const bool f0 = lane > 0 && pf_dst0 != up0;
+            const bool f1 = pf_dst1 != (lane == 0 ? last0 : up1);
+            const unsigned b0 = __ballot_sync(0xffffffffu, f0), b1 = __ballot_sync(0xffffffffu, f1);
+            const unsigned le = 0xffffffffu >> (31 - lane);
+            const int s0 = __popc(b0 & le), s1 = __popc(b0) + __popc(b1 & le);
+            sslot[lane] = s0;
+            sslot[lane + 32] = s1;
+            const int ncopy = min(__popc(b0) + __popc(b1) + 1, NDMAX);
+            if (lane == 0) fmbar_arrive_tx(BAR(6), (FTM + ncopy) * F::HALF * 4);
             __syncwarp();
             fbulk_g2s(stg_u32 + lane * F::STGB, A.table + (long long)pf_src0 * F::LDT + F::HALF, F::HALF * 4, BAR(6));
             fbulk_g2s(stg_u32 + (lane + 32) * F::STGB, A.table + (long long)pf_src1 * F::LDT + F::HALF, F::HALF * 4, BAR(6));
+            const uint32_t dstg_u32 = stg_u32 + (SM::o_dstg - SM::o_stg);
+            if ((lane == 0 || f0) && s0 < NDMAX) fbulk_g2s(dstg_u32 + s0 * F::STGB, A.table + (long long)pf_dst0 * F::LDT, F::HALF * 4, BAR(6));
+            if (f1 && s1 < NDMAX) fbulk_g2s(dstg_u32 + s1 * F::STGB, A.table + (long long)pf_dst1 * F::LDT, F::HALF * 4, BAR(6));
         };
         auto st_hl4 = [&](unsigned char* p, float a, float b, float c, float d) {   // 16-byte operand piece, hi and lo
             float4 h, l;
@@ -287,27 +333,36 @@ __global__ void __launch_bounds__(F_THREADS, 1) msg_fused_fwd_kernel(const __gri
             return fmaf(y.x, P, fmaf(y.y, a.y + b.y, fmaf(y.z, a.z + b.z, y.w * (a.w + b.w))));
         };
         auto build = [&](int it) {
-            unsigned char* aset = smraw + SM::o_a + (it & 1) * F::ABYTES;
+            unsigned char* aset = smraw + SM::o_a;
             const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * FTM;
             const long long gr = row0 + wrow;
             const bool valid = gr < R;
             const float4 y = n_y;
             const float2 ex = n_ex;
-            const float* td = A.table + (long long)n_dst * F::LDT;
             const float* ts = reinterpret_cast<const float*>(smraw + SM::o_stg + wrow * F::STGB);   // staged src half
             auto lds4 = [&](const float* q) { return *reinterpret_cast<const float4*>(q); };
             mbar_wait(BAR(6), (uint32_t)(it & 1));
+            if (it >= 1) mbar_wait(BAR(2 + ((it - 1) & 1)), (uint32_t)(((it - 1) >> 1) & 1));   // MMAs of tile it-1 have read the set
+            const int slot = sslot[wrow];
+            // staged dst half (generic pointer: shared memory, or global for the rare tile with > NDMAX destinations)
+            const float* td = slot < NDMAX ? reinterpret_cast<const float*>(smraw + SM::o_dstg + slot * F::STGB)
+                                           : A.table + (long long)n_dst * F::LDT;
             float* pre = A.pre1 + gr * F::DPRE;
             float* m1 = A.m1 + gr * F::D;
 #pragma unroll
             for (int round = 0; round < 2; ++round) {
-                const int u = 8 * sub + 4 * round + cq;
+                // round 0: scalar quads 4 sub + cq; round 1: pairs 4 sub + cq, then the partial quad (the heavy pair
+                // units are spread over all warps: a warp's round costs the sum of the unit kinds its lanes hold)
+                const int t = 4 * sub + cq;
+                int u;
+                if (round == 0) u = t < F::SQ ? t : F::NU;
+                else u = t < F::NP ? F::SQ + (F::RS4 ? 1 : 0) + t : ((F::RS4 && t == F::NP) ? F::SQ : F::NU);
                 if (u >= F::NU) continue;
                 if (u < F::SQ) {
                     // four scalar channels 4u .. 4u+3
                     float4 a[4], b[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) { a[j] = ldg4_v(td + 16 * u + 4 * j); b[j] = lds4(ts + 16 * u + 4 * j); }
+                    for (int j = 0; j < 4; ++j) { a[j] = lds4(td + 16 * u + 4 * j); b[j] = lds4(ts + 16 * u + 4 * j); }
                     float x[4], m[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) { x[j] = zval(a[j], b[j], 4 * u + j, y, ex); m[j] = A.cs * x[j] * sigm(x[j]); }
@@ -319,8 +374,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) msg_fused_fwd_kernel(const __gri
                     st_hl4(aset + rowoffS + (u << 7), m[0], m[1], m[2], m[3]);
                 } else if (F::RS4 && u == F::SQ) {
                     // the last RS4 (= 2) scalar channels
-                    const float4 a0 = ldg4_v(td + 16 * u), b0 = lds4(ts + 16 * u);
-                    const float4 a1 = ldg4_v(td + 16 * u + 4), b1 = lds4(ts + 16 * u + 4);
+                    const float4 a0 = lds4(td + 16 * u), b0 = lds4(ts + 16 * u);
+                    const float4 a1 = lds4(td + 16 * u + 4), b1 = lds4(ts + 16 * u + 4);
                     const float x0 = zval(a0, b0, 4 * u, y, ex), x1 = zval(a1, b1, 4 * u + 1, y, ex);
                     const float m0 = A.cs * x0 * sigm(x0), mm1 = A.cs * x1 * sigm(x1);
                     if (valid) {
@@ -332,10 +387,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) msg_fused_fwd_kernel(const __gri
                     // pair unit i: gates NS + 2i, NS + 2i + 1 and the vector channels they gate
                     const int i = u - F::SQ - (F::RS4 ? 1 : 0);
                     const int cg0 = NS + 2 * i, cv0 = MZ + 2 * i;
-                    const float4 ga0 = ldg4_v(td + 4 * cg0), gb0 = lds4(ts + 4 * cg0);
-                    const float4 ga1 = ldg4_v(td + 4 * cg0 + 4), gb1 = lds4(ts + 4 * cg0 + 4);
-                    const float4 va0 = ldg4_v(td + 4 * cv0), vb0 = lds4(ts + 4 * cv0);
-                    const float4 va1 = ldg4_v(td + 4 * cv0 + 4), vb1 = lds4(ts + 4 * cv0 + 4);
+                    const float4 ga0 = lds4(td + 4 * cg0), gb0 = lds4(ts + 4 * cg0);
+                    const float4 ga1 = lds4(td + 4 * cg0 + 4), gb1 = lds4(ts + 4 * cg0 + 4);
+                    const float4 va0 = lds4(td + 4 * cv0), vb0 = lds4(ts + 4 * cv0);
+                    const float4 va1 = lds4(td + 4 * cv0 + 4), vb1 = lds4(ts + 4 * cv0 + 4);
                     const float xg0 = zval(ga0, gb0, cg0, y, ex), xg1 = zval(ga1, gb1, cg0 + 1, y, ex);
                     const float P0 = va0.x + vb0.x + fmaf(ex.x, we_s[cv0], ex.y * we_s[CH + cv0]);
                     const float P1 = va1.x + vb1.x + fmaf(ex.x, we_s[cv0 + 1], ex.y * we_s[CH + cv0 + 1]);
@@ -373,7 +428,6 @@ __global__ void __launch_bounds__(F_THREADS, 1) msg_fused_fwd_kernel(const __gri
         float4 ypre = make_float4(0.f, 0.f, 0.f, 0.f), ypre2 = ypre;
         int segpre = -1;
         int* sseg = reinterpret_cast<int*>(smraw + SM::o_sseg);
-        float4* hsm = reinterpret_cast<float4*>(smraw + SM::o_hs);
         auto prefetch_y = [&](int it) {   // SH rows (and segment ids) of this thread's epilogue rows of tile `it`
             const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * FTM;
             long long ga = row0 + 16 * e + fg, gb = ga + 8;
@@ -422,8 +476,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) msg_fused_fwd_kernel(const __gri
             float* pb = pa + 8 * F::PSTR;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const int blk = jq + (FW / 4) * h;
-                if (blk < F::NBLK) {
+                constexpr DrainMap<NS, NV> DM{};
+                const int blk = h == 0 ? (jq == 0 ? DM.blk[0][0] : (jq == 1 ? DM.blk[1][0] : (jq == 2 ? DM.blk[2][0] : DM.blk[3][0])))
+                                       : (jq == 0 ? DM.blk[0][1] : (jq == 1 ? DM.blk[1][1] : (jq == 2 ? DM.blk[2][1] : DM.blk[3][1])));
+                if (blk >= 0) {
                     float p[4], ux[4], uy[4], uz[4];
                     const int cb = 8 * blk;
                     tc_ld_16x256(acc + cb, p);
@@ -464,13 +520,41 @@ __global__ void __launch_bounds__(F_THREADS, 1) msg_fused_fwd_kernel(const __gri
         auto finish = [&](int it) {
             const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * FTM;
             const int nvalid = (int)min((long long)FTM, R - row0);
-            {   // pre-activation of message 2: the tile is the exact image of the global rows
+            if (warp >= FW / 2) {
+                // upper half of the workers: pre-activation of message 2 (the tile is the exact image of the global rows)
                 float* dstp = A.pre2 + row0 * F::DPRE;
                 const int total = nvalid * F::DPRE, n4 = total >> 2;
-                for (int t = tid; t < n4; t += FWT) reinterpret_cast<float4*>(dstp)[t] = reinterpret_cast<const float4*>(otile)[t];
-                for (int t = (n4 << 2) + tid; t < total; t += FWT) dstp[t] = otile[t];
+                for (int t = tid - FWT / 2; t < n4; t += FWT / 2) reinterpret_cast<float4*>(dstp)[t] = reinterpret_cast<const float4*>(otile)[t];
+                for (int t = (n4 << 2) + tid - FWT / 2; t < total; t += FWT / 2) dstp[t] = otile[t];
+            } else {
+                // lower half: sorted-segment sum (north-star kernel 5), run based: the rows are sorted by destination, so a
+                // tile is a handful of runs; every warp derives the run starts with two ballots, thread = (column, run
+                // slot) sums whole runs, one writer per (node, column): plain store, except for the (at most two) runs
+                // that continue in the neighbouring tiles, which use red.add.  No barrier, no merge pass.
+                const int c = tid & 63, slot = tid >> 6;
+                const bool s0 = lane < nvalid && (lane == 0 || sseg[1 + lane] != sseg[lane]);
+                const bool s1 = 32 + lane < nvalid && sseg[33 + lane] != sseg[32 + lane];
+                unsigned long long mask = (unsigned long long)__ballot_sync(0xffffffffu, s0) |
+                                          ((unsigned long long)__ballot_sync(0xffffffffu, s1) << 32);
+                const int prevseg = sseg[0], nextseg = sseg[65];
+                int j = 0;
+                while (mask) {
+                    const int start = __ffsll((long long)mask) - 1;
+                    mask &= mask - 1;
+                    const int end = mask ? __ffsll((long long)mask) - 1 : nvalid;
+                    if ((j & (FWT / 128 - 1)) == slot && c < F::D) {
+                        const float* col = ptile + c;
+                        float acc = 0.0f;
+#pragma unroll 4
+                        for (int r = start; r < end; ++r) acc += col[r * F::PSTR];
+                        const int seg = sseg[1 + start];
+                        float* o = A.agg + (long long)seg * F::D + c;
+                        if ((start == 0 && seg == prevseg) || (end == nvalid && seg == nextseg)) atomicAdd(o, acc);
+                        else *o = acc;
+                    }
+                    ++j;
+                }
             }
-            sorted_segment_sum_tile<FWT>(ptile, F::PSTR, F::D, nvalid, sseg, A.agg, F::D, hsm, tid, 3);
         };
 
         if (nt > 0) {
@@ -481,23 +565,39 @@ __global__ void __launch_bounds__(F_THREADS, 1) msg_fused_fwd_kernel(const __gri
                 if (nt > 1) load_pf(1);
             }
         }
+        long long tacc[6] = {0, 0, 0, 0, 0, 0};
+        const bool timing = A.dbg != nullptr && lane == 0 && (warp == 0 || warp == 9);
         for (int it = 0; it < nt; ++it) {
+            long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0;
+            if (timing) t0 = clock64();
             build(it);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(it & 1));
             if (it + 1 < nt) load_row(it + 1);
+            if (timing) t1 = clock64();
             named_bar(2, FWT);             // every worker is done with the staged rows of tile it and the tiles of tile it-2
+            if (timing) t2 = clock64();
             if (warp == 0 && it + 1 < nt) {
                 issue_pf();
                 if (it + 2 < nt) load_pf(it + 2);
             }
             if (it >= 1) {
                 drain(it - 1);
+                if (timing) t3 = clock64();
                 named_bar(1, FWT);
+                if (timing) t4 = clock64();
                 finish(it - 1);
             }
             prefetch_y(it);
+            if (timing && it >= 1) {
+                t5 = clock64();
+                tacc[0] += t1 - t0; tacc[1] += t2 - t1; tacc[2] += t3 - t2; tacc[3] += t4 - t3; tacc[4] += t5 - t4; tacc[5] += 1;
+            }
+        }
+        if (timing) {
+            long long* o = A.dbg + ((long long)blockIdx.x * 2 + (warp == 0 ? 0 : 1)) * 8;
+            for (int i = 0; i < 6; ++i) o[i] = tacc[i];
         }
         if (nt > 0) {
             named_bar(2, FWT);
@@ -540,6 +640,12 @@ static int msg_fused_fwd_launch(const FusedFwdArgs& A, cudaStream_t st) {
 
 using namespace se3;
 
+extern "C" int se3_msg_fused_forward_dbg(int32_t ns, int32_t nv, int64_t rows, const int32_t* dst, const int32_t* src,
+                                         const float* table, const float* we, const float* y, const float* extra,
+                                         const float* wz2, const float* wv2, const float* nz2, const float* nv2,
+                                         float gate_cs, float gate_cg, float* pre1, float* m1, float* pre2, float* agg,
+                                         int64_t* dbg, void* stream);
+
 extern "C" int se3_msg_fused_supported(int32_t ns, int32_t nv, int32_t ne) {
     return ne == 2 && ((ns == 34 && nv == 10) || (ns == 16 && nv == 8)) ? 1 : 0;
 }
@@ -548,6 +654,16 @@ extern "C" int se3_msg_fused_forward(int32_t ns, int32_t nv, int64_t rows, const
                                      const float* table, const float* we, const float* y, const float* extra,
                                      const float* wz2, const float* wv2, const float* nz2, const float* nv2, float gate_cs,
                                      float gate_cg, float* pre1, float* m1, float* pre2, float* agg, void* stream) {
+    return se3_msg_fused_forward_dbg(ns, nv, rows, dst, src, table, we, y, extra, wz2, wv2, nz2, nv2, gate_cs, gate_cg, pre1, m1,
+                                     pre2, agg, nullptr, stream);
+}
+
+// diagnostics: dbg = NULL or [148][2][8] int64 receiving the accumulated clock64() cycles of the phases of two warps
+extern "C" int se3_msg_fused_forward_dbg(int32_t ns, int32_t nv, int64_t rows, const int32_t* dst, const int32_t* src,
+                                         const float* table, const float* we, const float* y, const float* extra,
+                                         const float* wz2, const float* wv2, const float* nz2, const float* nv2,
+                                         float gate_cs, float gate_cg, float* pre1, float* m1, float* pre2, float* agg,
+                                         int64_t* dbg, void* stream) {
     if (rows < 0 || rows >= (1ll << 31) - FTM) { set_error("msg_fused_forward: bad row count"); return SE3_ERR_INVALID; }
     if (rows == 0) return SE3_OK;
     if (!dst || !src || !table || !we || !y || !extra || !wz2 || !wv2 || !pre1 || !m1 || !pre2 || !agg) {
@@ -558,6 +674,7 @@ extern "C" int se3_msg_fused_forward(int32_t ns, int32_t nv, int64_t rows, const
     FusedFwdArgs A;
     A.rows = rows; A.dst = dst; A.src = src; A.table = table; A.we = we; A.y = y; A.extra = extra; A.wz2 = wz2; A.wv2 = wv2;
     A.nz2 = nz2; A.nv2 = nv2; A.pre1 = pre1; A.m1 = m1; A.pre2 = pre2; A.agg = agg; A.cs = gate_cs; A.cg = gate_cg;
+    A.dbg = (long long*)dbg;
     if (ns == 34 && nv == 10) return msg_fused_fwd_launch<34, 10>(A, (cudaStream_t)stream);
     if (ns == 16 && nv == 8) return msg_fused_fwd_launch<16, 8>(A, (cudaStream_t)stream);
     set_error("msg_fused_forward: hidden irreps %dx0e+%dx1o are not instantiated", (int)ns, (int)nv);

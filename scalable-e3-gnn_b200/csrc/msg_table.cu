@@ -163,6 +163,47 @@ __global__ void __launch_bounds__(256) msg1_edge_bwd_kernel(const Msg1Bwd A) {
         long long e0 = 0, e1 = 0;
         if (n < nseg) { e0 = __ldg(ptr + n); e1 = __ldg(ptr + n + 1); }
         float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;       // z lanes: channels c0, c0 + 1; vector lanes: a0 only
+        if (MODE != 0) {
+            // gpre is an input: four edges per step, all loads issued before the first use (the loop is latency-bound)
+            for (long long k = e0; k < e1; k += 4) {
+                long long ee[4];
+                float4 yy[4];
+                float2 xx[4], gz[4];
+                float qa[4], qb[4], qc[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const long long kk = k + j < e1 ? k + j : e1 - 1;
+                    ee[j] = SRC ? (long long)__ldg(A.perm + kk) : kk;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    yy[j] = ld4(A.y + 4 * ee[j]);
+                    xx[j] = SRC ? make_float2(0.f, 0.f) : ld2(A.extra + 2 * ee[j]);
+                    const float* gp = A.gpre + ee[j] * Dm::DPRE;
+                    gz[j] = zl ? ld2(gp + c0) : make_float2(0.f, 0.f);
+                    const float* qv = gp + MZ + 3 * (vl ? v : 0);
+                    qa[j] = vl ? __ldg(qv) : 0.f; qb[j] = vl ? __ldg(qv + 1) : 0.f; qc[j] = vl ? __ldg(qv + 2) : 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (k + j >= e1) break;
+                    const float4 y = yy[j];
+                    if (zl) {
+                        const float p0 = y.x * gz[j].x, p1 = y.x * gz[j].y;
+                        a0.x += p0; a0.y = fmaf(y.y, gz[j].x, a0.y); a0.z = fmaf(y.z, gz[j].x, a0.z); a0.w = fmaf(y.w, gz[j].x, a0.w);
+                        a1.x += p1; a1.y = fmaf(y.y, gz[j].y, a1.y); a1.z = fmaf(y.z, gz[j].y, a1.z); a1.w = fmaf(y.w, gz[j].y, a1.w);
+                        if (!SRC) {
+                            ge[0] = fmaf(xx[j].x, p0, ge[0]); ge[1] = fmaf(xx[j].x, p1, ge[1]);
+                            ge[2] = fmaf(xx[j].y, p0, ge[2]); ge[3] = fmaf(xx[j].y, p1, ge[3]);
+                        }
+                    } else if (vl) {
+                        const float d = fmaf(y.y, qa[j], fmaf(y.z, qb[j], y.w * qc[j]));
+                        a0.x += d; a0.y = fmaf(y.x, qa[j], a0.y); a0.z = fmaf(y.x, qb[j], a0.z); a0.w = fmaf(y.x, qc[j], a0.w);
+                        if (!SRC) { ge[0] = fmaf(xx[j].x, d, ge[0]); ge[1] = fmaf(xx[j].y, d, ge[1]); }
+                    }
+                }
+            }
+        } else
         for (long long k = e0; k < e1; ++k) {
             const long long e = SRC ? (long long)__ldg(A.perm + k) : k;
             const float4 y = ld4(A.y + 4 * e);

@@ -106,6 +106,10 @@ EXPORTS = [
     ("se3_msg1_node_table", C.c_int, [C.c_int32, C.c_int32, C.c_int64] + [C.c_void_p] * 7),
     ("se3_msg1_node_backward", C.c_int, [C.c_int32, C.c_int32, C.c_int64] + [C.c_void_p] * 7 + [C.c_int32]
      + [C.c_void_p] * 4 + [C.c_int32, C.c_void_p]),
+    ("se3_msg_fused_forward_dbg", C.c_int, [C.c_int32, C.c_int32, C.c_int64] + [C.c_void_p] * 10 + [C.c_float, C.c_float]
+     + [C.c_void_p] * 6),
+    ("se3_msg_fused_backward", C.c_int, [C.c_int32, C.c_int32, C.c_int64] + [C.c_void_p] * 9 + [C.c_float, C.c_float]
+     + [C.c_void_p] * 3),
     ("se3_rowptr_from_sorted", C.c_int, [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("se3_graph_transpose_work_bytes", C.c_int, [C.c_int64, C.POINTER(C.c_size_t)]),
     ("se3_graph_transpose", C.c_int, [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,

@@ -144,6 +144,7 @@ def msg1(xe, wz, wv, nz, nvn, y, extra, ei: EdgeIndex, ns: int, nv: int, cs: flo
 
 
 # ------------------------------------------------------------------------------------------------ fused message layer
+DBG_TIMING = None   # tools/bench_msg.py --timing sets this to a list: receives the phase cycle counters of every forward
 def fused_supported(ns: int, nv: int, n_extra: int) -> bool:
     return bool(capi.lib().se3_msg_fused_supported(ns, nv, n_extra)) and supported(ns, nv, n_extra)
 
@@ -163,19 +164,26 @@ class MsgLayerFn(torch.autograd.Function):
         ch, d, dpre = ns + 2 * nv, ns + 3 * nv, ns + 4 * nv
         assert xe.shape == (ei.n_all, d) and xe.is_contiguous() and xe.dtype == torch.float32
         table, we = _node_forward(xe, wz1, wv1, nz1, nv1, ns, nv, ei.n_all, "msg.table")
-        pre1 = torch.empty((ei.e, dpre), device=dev, dtype=torch.float32)
+        # the backward kernel stages whole 64-row blocks of the pre-activations with cp.async.bulk: rows rounded up
+        epad = (ei.e + 63) // 64 * 64
+        pre1 = torch.empty((epad, dpre), device=dev, dtype=torch.float32)[:ei.e]
         m1 = torch.empty((ei.e, d), device=dev, dtype=torch.float32)
-        pre2 = torch.empty((ei.e, dpre), device=dev, dtype=torch.float32)
+        pre2 = torch.empty((epad, dpre), device=dev, dtype=torch.float32)[:ei.e]
         agg = torch.zeros((ei.n_dst, d), device=dev, dtype=torch.float32)
         # algorithmic bytes: SH + extras + both indices, the three per-edge tensors the backward reads, the node tables
         # (each row once) and the aggregate
         nbytes = 4.0 * (ei.e * (4 + 2 + 2 + 2 * dpre + d) + (ei.n_all + ei.n_dst) * 4 * ch + ei.n_dst * d)
         flops = 2.0 * ei.e * ((ns + nv) * (ns + nv) + ns * nv + 3 * nv * nv + 3 * nv * (ns + nv))
+        dbg = None
+        if DBG_TIMING is not None:
+            dbg = torch.zeros((148, 2, 8), device=dev, dtype=torch.int64)
+            DBG_TIMING.append(dbg)
         with capi.mark("msg.fused_fwd", nbytes, flops):
-            capi.check(lib.se3_msg_fused_forward(ns, nv, ei.e, ei.dst.data_ptr(), ei.src.data_ptr(), table.data_ptr(),
-                                                 we.data_ptr(), y.data_ptr(), extra.data_ptr(), wz2.data_ptr(),
-                                                 wv2.data_ptr(), capi.ptr(nz2), capi.ptr(nv2), cs, cg, pre1.data_ptr(),
-                                                 m1.data_ptr(), pre2.data_ptr(), agg.data_ptr(), st), "se3_msg_fused_forward")
+            capi.check(lib.se3_msg_fused_forward_dbg(ns, nv, ei.e, ei.dst.data_ptr(), ei.src.data_ptr(), table.data_ptr(),
+                                                     we.data_ptr(), y.data_ptr(), extra.data_ptr(), wz2.data_ptr(),
+                                                     wv2.data_ptr(), capi.ptr(nz2), capi.ptr(nv2), cs, cg, pre1.data_ptr(),
+                                                     m1.data_ptr(), pre2.data_ptr(), agg.data_ptr(), capi.ptr(dbg), st),
+                       "se3_msg_fused_forward")
         ctx.ei, ctx.dims, ctx.plan2 = ei, (ns, nv, cs, cg), plan2
         ctx.save_for_backward(xe, pre1, m1, pre2, y, extra, nz1, nv1, wz1, wv1, wz2, wv2, nz2, nv2)
         return agg
@@ -190,7 +198,16 @@ class MsgLayerFn(torch.autograd.Function):
         st = capi.current_stream_ptr()
         ch, d, dpre = ns + 2 * nv, ns + 3 * nv, ns + 4 * nv
         gagg = gagg.contiguous()
-        # ---- message 2: gate VJP + tensor-product backward on the tensor cores (csrc/l1tp_tc2_bwd*.cu)
+        # ---- input-gradient side in ONE tcgen05 kernel: gate VJP (message 2) -> W2^T -> gate VJP (message 1)
+        gpre1 = torch.empty_like(pre1)
+        rowb = 4.0 * (4 + 1 + dpre)
+        with capi.mark("msg.fused_bwd", ei.e * (rowb + 4.0 * 2 * dpre) + 4.0 * ei.n_dst * d,
+                       2.0 * ei.e * ((ns + nv) * (ns + nv) + ns * nv + 3 * nv * nv + 3 * nv * (ns + nv))):
+            capi.check(lib.se3_msg_fused_backward(ns, nv, ei.e, ei.dst.data_ptr(), y.data_ptr(), pre1.data_ptr(),
+                                                  pre2.data_ptr(), gagg.data_ptr(), wz2.data_ptr(), wv2.data_ptr(),
+                                                  capi.ptr(nz2), capi.ptr(nv2), cs, cg, gpre1.data_ptr(), None, st),
+                       "se3_msg_fused_backward")
+        # ---- weight gradient of message 2 (csrc/l1tp_tc2_bwdw.cu: MN-major tcgen05, accumulators resident in TMEM)
         a = capi.L1tpBwdArgs()
         a.rows, a.nseg = ei.e, 1
         a.seg[0].base, a.seg[0].idx, a.seg[0].width, a.seg[0].ld = m1.data_ptr(), None, d, d
@@ -199,31 +216,19 @@ class MsgLayerFn(torch.autograd.Function):
         a.norm[0], a.norm[3] = capi.ptr(nz2), capi.ptr(nv2)
         a.epilogue, a.gate_ns, a.gate_cs, a.gate_cg = capi.EPI_GATE, ns, cs, cg
         a.raw, a.gout, a.gout_idx = pre2.data_ptr(), gagg.data_ptr(), ei.dst.data_ptr()
-        gm1 = torch.empty_like(m1)
         gwz2, gwv2 = torch.empty_like(wz2), torch.empty_like(wv2)
-        rowb = 4.0 * (4 + 1 + dpre)
-        if capi._prof is None:
-            a.gseg[0], a.gseg_mode[0] = gm1.data_ptr(), capi.GRAD_STORE
-            a.gw[0], a.gw[3] = gwz2.data_ptr(), gwv2.data_ptr()
+        a.gw[0], a.gw[3] = gwz2.data_ptr(), gwv2.data_ptr()
+        with capi.mark("msg2.bwdw", ei.e * (rowb + 4.0 * d) + 4.0 * ei.n_dst * d):
             capi.check(lib.se3_l1tp_backward(ctx.plan2.handle, C.byref(a), st), "se3_l1tp_backward")
-        else:   # per-kernel table: the weight-gradient and input-gradient kernels timed separately (same kernels)
-            a.gw[0], a.gw[3] = gwz2.data_ptr(), gwv2.data_ptr()
-            with capi.mark("msg2.bwdw", ei.e * (rowb + 4.0 * d) + 4.0 * ei.n_dst * d):
-                capi.check(lib.se3_l1tp_backward(ctx.plan2.handle, C.byref(a), st), "se3_l1tp_backward")
-            a.gw[0], a.gw[3] = None, None
-            a.gseg[0], a.gseg_mode[0] = gm1.data_ptr(), capi.GRAD_STORE
-            with capi.mark("msg2.bwdi", ei.e * (rowb + 4.0 * d) + 4.0 * ei.n_dst * d):
-                capi.check(lib.se3_l1tp_backward(ctx.plan2.handle, C.byref(a), st), "se3_l1tp_backward")
-        # ---- message 1: gate VJP + transposed SH combine + segment sums, then the node-level GEMMs
-        gpre = torch.empty_like(pre1)
+        # ---- message 1: transposed SH combine + segment sums (dst rows, then the transposed order), node-level kernels
         G = torch.empty((ei.n_all, 8 * ch), device=dev, dtype=torch.float32)
         parts = torch.empty((int(lib.se3_msg1_max_parts()), 2, ch), device=dev, dtype=torch.float32)
         nparts = C.c_int32()
-        with capi.mark("msg1.edge_bwd", 4.0 * (ei.e * (2 * 4 + 2 + 1 + d + 3 * dpre) + 2 * ei.n_all * 4 * ch)):
+        with capi.mark("msg1.edge_bwd", 4.0 * (ei.e * (2 * 4 + 2 + 1 + 2 * dpre) + 2 * ei.n_all * 4 * ch)):
             capi.check(lib.se3_msg1_edge_backward(ns, nv, ei.n_dst, ei.n_all, ei.rowptr.data_ptr(), ei.tptr.data_ptr(),
-                                                  ei.perm.data_ptr(), y.data_ptr(), extra.data_ptr(), pre1.data_ptr(),
-                                                  gm1.data_ptr(), cs, cg, gpre.data_ptr(), G.data_ptr(), parts.data_ptr(),
-                                                  C.byref(nparts), st), "se3_msg1_edge_backward")
+                                                  ei.perm.data_ptr(), y.data_ptr(), extra.data_ptr(), None, None, cs, cg,
+                                                  gpre1.data_ptr(), G.data_ptr(), parts.data_ptr(), C.byref(nparts), st),
+                       "se3_msg1_edge_backward")
         gx, gwz1, gwv1 = _node_backward(xe, G, wz1, wv1, nz1, nv1, parts, nparts.value, ns, nv, ei.n_all,
                                         ctx.needs_input_grad[0], "msg.node_bwd")
         return (gx, gwz1, gwv1, None, None, gwz2, gwv2, None, None) + (None,) * 8

@@ -18,6 +18,7 @@ ap.add_argument("--particles", type=int, default=100_000)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--kind", default="plummer")
 ap.add_argument("--mode", default="fused")
+ap.add_argument("--timing", action="store_true", help="print the phase cycle counters of the fused forward kernel")
 a = ap.parse_args()
 os.environ["SE3_MSG"] = a.mode
 
@@ -50,6 +51,18 @@ for tag, ms, nb, fl in prof:
     r[0] += ms
     r[1] += nb
     r[2] += 1
+if a.timing:
+    from se3gnn_b200 import msg as _msg
+    _msg.DBG_TIMING = []
+    step()
+    torch.cuda.synchronize()
+    t = _msg.DBG_TIMING[0].double()            # [148][2][8]
+    names = ["build", "bar2 wait", "drain(+issue)", "bar1 wait", "finish+prefetch", "tiles"]
+    for w, wn in enumerate(("warp 0 (sub 0, seg-sum)", "warp 9 (sub 1, copy-out)")):
+        tiles = t[:, w, 5].clamp_min(1)
+        print(wn, {n: round(float((t[:, w, i] / tiles).mean()), 1) for i, n in enumerate(names[:5])}, "tiles/CTA", float(tiles.mean()),
+              file=sys.stderr)
+    _msg.DBG_TIMING = None
 print(json.dumps({"edges": g.e, "nodes": g.n + g.m, "mode": a.mode,
                   "kernels": {k: {"ms": v[0] / v[2], "GBps": v[1] / max(v[0], 1e-9) / 1e6} for k, v in
                               sorted(agg.items(), key=lambda kv: -kv[1][0]) if k.startswith(("msg", "graph.tr"))}}))

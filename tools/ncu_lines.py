@@ -32,13 +32,25 @@ for r in rows:
         smp = int(r[hdr["# Samples"] + off] or 0)
     except ValueError:
         continue
-    lines.append((ins, smp, cur_file, int(r[0]), r[1].strip()[:110]))
+    def col(name):
+        try:
+            return int(r[hdr[name] + off] or 0)
+        except (ValueError, KeyError, IndexError):
+            return 0
+    st = {k: col(k) for k in ("stall_long_sb", "stall_short_sb", "stall_barrier", "stall_wait", "stall_sleep", "stall_lg", "stall_mio", "stall_math")}
+    lines.append((ins, smp, cur_file, int(r[0]), r[1].strip()[:100], st))
     tot_i += ins
     tot_s += smp
 print(f"total warp instructions {tot_i}, stall samples {tot_s}")
 print("by instructions:")
-for ins, smp, f, ln, src in sorted(lines, reverse=True)[:top]:
+for ins, smp, f, ln, src, st in sorted(lines, key=lambda t: -t[0])[:top]:
     print(f"{100.0 * ins / max(tot_i, 1):5.1f}% inst {100.0 * smp / max(tot_s, 1):5.1f}% smp  {f}:{ln}  {src}")
 print("by stall samples:")
-for ins, smp, f, ln, src in sorted(lines, key=lambda t: -t[1])[:top // 2]:
-    print(f"{100.0 * ins / max(tot_i, 1):5.1f}% inst {100.0 * smp / max(tot_s, 1):5.1f}% smp  {f}:{ln}  {src}")
+for ins, smp, f, ln, src, st in sorted(lines, key=lambda t: -t[1])[:top // 2]:
+    why = " ".join(f"{k[6:]}={v}" for k, v in sorted(st.items(), key=lambda kv: -kv[1])[:3] if v)
+    print(f"{100.0 * ins / max(tot_i, 1):5.1f}% inst {100.0 * smp / max(tot_s, 1):5.1f}% smp  {f}:{ln}  {src[:70]}  [{why}]")
+tot = {}
+for *_, st in lines:
+    for k, v in st.items():
+        tot[k] = tot.get(k, 0) + v
+print("stall totals:", {k[6:]: v for k, v in sorted(tot.items(), key=lambda kv: -kv[1])})

@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--leaf", type=int, default=32)
     ap.add_argument("--cpu-sample", type=int, default=100_000, help="upper bound of the CPU arm's particles per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="skip BASELINE configs[2..4] (measured after the headline region into `other_configs`)")
     ap.add_argument("--no-parity", action="store_true", help="skip the step-0 loss check against the CPU oracle")
     ap.add_argument("--dump", default=None, help="write the per-kernel table (JSON) here")
     ap.add_argument("--parallel", default="dd", choices=["dd", "dp"],
@@ -166,6 +168,115 @@ def step0_parity(a, model, devt, dev):
     return {"loss_step0": loss, "loss_ref": l_ref, "loss_rel_err": abs(loss - l_ref) / max(abs(l_ref), 1e-300),
             "out_rel_err": err, "tolerance": 1e-5, "oracle": "oracle/segnn_oracle.py fp64 (CPU), same graph and weights",
             "seconds": time.perf_counter() - t0}
+
+
+def other_configs(a, world, rank, dev, model, ts, budget_s=150.0):
+    """BASELINE configs[2..4], measured in the same run after the headline region so that the driver's record carries
+    them (each a few steps, CUDA events, inputs resident in HBM; failures are recorded, never fatal).
+      N = 1: configs[2] (SEGNN l_max = 2, 1M particles) and configs[4] (octree build only, 1M / 10M / 100M Plummer points)
+      N > 1: configs[3] (ONE 10M-particle cloud, Morton-range decomposition over the N ranks)"""
+    import torch
+    import torch.distributed as dist
+    out, t_start = {}, time.perf_counter()
+    left = lambda: budget_s - (time.perf_counter() - t_start)
+
+    def timed(fn, steps, warm=1):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            r = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps, r
+
+    if world == 1:
+        try:   # ---- configs[4]: graph construction only
+            from se3gnn_b200.octree import build_octree_graph
+            peak = 6550.1
+            try:
+                peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+            except Exception:
+                pass
+            rows = []
+            for n in (1_000_000, 10_000_000, 100_000_000):
+                if left() < 40:
+                    break
+                g = torch.Generator(device=dev)
+                g.manual_seed(1)
+                d = torch.randn((n, 3), device=dev, generator=g)
+                d /= d.norm(dim=1, keepdim=True)
+                u = torch.rand(n, device=dev, generator=g).clamp_min(1e-12)
+                pos = ((1.0 / torch.sqrt(u ** (-2.0 / 3.0) - 1.0)).clamp_max(10.0)[:, None] * d).contiguous()
+                del d, u
+                ms, gr = timed(lambda: build_octree_graph(pos, leaf_size=a.leaf, features=False), 3)
+                nb = 24.0 * n + 8 * 32.0 * n + 8.0 * gr.e     # keys + 8 radix passes + CSR emission (DESIGN 4.5)
+                rows.append({"points": n, "edges": int(gr.e), "cells": int(gr.m), "ms": ms, "edges_per_s": gr.e / (ms * 1e-3),
+                             "algorithmic_GBps": nb / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": nb / (ms * 1e-3) / 1e9 / peak})
+                del gr, pos
+                torch.cuda.empty_cache()
+            out["configs[4] octree graph construction only (Plummer, leaf 32, 1 GPU)"] = rows
+        except Exception as e:  # pragma: no cover
+            out["configs[4]"] = {"error": repr(e)[:300]}
+        try:   # ---- configs[2]: l_max = 2 at 1M particles
+            if left() > 60:
+                from models.segnn.segnn_l2 import SEGNNL2
+                from se3gnn_b200.octree import build_octree_graph, sh2_attributes
+                from se3gnn_b200.pipeline import synthetic_cloud
+                n = 1_000_000
+                pos, vel, mass, target = (torch.from_numpy(x).to(dev) for x in synthetic_cloud(n, "plummer", 1))
+                torch.manual_seed(0)
+                m2 = SEGNNL2("23x0e+7x1o+4x2e", 4).to(dev)
+                opt = torch.optim.Adam(m2.parameters(), lr=1e-3, fused=True)
+
+                def step2():
+                    g = build_octree_graph(pos, vel, mass, leaf_size=a.leaf)
+                    o = m2.forward_graph(g, sh2_attributes(g))
+                    loss = (o[:n] - target.index_select(0, g.order.long())).square().mean()
+                    opt.zero_grad(set_to_none=True)
+                    loss.backward()
+                    opt.step()
+                    return g
+                ms, g = timed(step2, 2)
+                out["configs[2] SEGNN l_max=2, 1M particles, 1 GPU"] = {
+                    "ms_per_step": ms, "particles_per_s": n / (ms * 1e-3), "edges": int(g.e), "hidden": "23x0e+7x1o+4x2e",
+                    "contraction": "fp32 SIMT (csrc/o3tp.cu); the bf16 tensor-core contraction configs[2] names is not built",
+                    "peak_mem_GB": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)}
+                del m2, opt, g, pos, vel, mass, target
+                torch.cuda.empty_cache()
+        except Exception as e:  # pragma: no cover
+            out["configs[2]"] = {"error": repr(e)[:300]}
+    else:
+        try:   # ---- configs[3]: ONE 10M-particle cloud over the N ranks
+            from se3gnn_b200.pipeline import synthetic_cloud
+            n = 10_000_000
+            cloud = [torch.from_numpy(x).to(dev) for x in synthetic_cloud(n, "plummer", 1)]
+            torch.cuda.synchronize()
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ts.step_device_dd(*cloud)
+            torch.cuda.synchronize()
+            dist.barrier()
+            steps = 3
+            e0.record()
+            for _ in range(steps):
+                loss = ts.step_device_dd(*cloud)
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            out["configs[3] SEGNN l_max=1, ONE 10M-particle cloud, Morton-range decomposition"] = {
+                "n_gpus": world, "ms_per_step": ms, "particles_per_s": n / (ms * 1e-3), "edges_total": int(ts.last_graph.e),
+                "loss": float(loss.item()), "scaling": "strong (the cloud is fixed, the ranks split it)"}
+            del cloud
+            torch.cuda.empty_cache()
+        except Exception as e:  # pragma: no cover
+            out["configs[3]"] = {"error": repr(e)[:300]}
+    out["seconds"] = round(time.perf_counter() - t_start, 1)
+    return out
 
 
 def run_b200(a):
@@ -308,22 +419,30 @@ def run_b200(a):
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     tr = top[1]
     ach = tr["bytes"] / (tr["ms"] * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_source = None, None
     try:
         if a.particles == 100_000 and a.layers == 4 and a.kind == "plummer":   # the workload the ncu capture was taken on
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(top[0])
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            traffic = tj.get(top[0])
+            if traffic is not None:
+                traffic_source = tj.get("_source", "ncu --set full capture committed under profiles/ (a constant of that "
+                                                   "build, not a measurement of this run)")
     except Exception:
         pass
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
     roofline = {"kernel": top[0], "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": traffic, "peak_source": peak_src,
+                "traffic": traffic, "traffic_source": traffic_source, "peak_source": peak_src,
                 "bytes_per_launch": tr["bytes"] / tr["launches"], "ms_per_launch": tr["ms"] / tr["launches"],
                 "share_of_step": tr["ms"] / tot_ms,
                 "fp32_tflops": tr["flops"] / (tr["ms"] * 1e-3) / 1e12,
                 "fp32_peak_tflops_at_clock": fp32_peak,
-                "note": "tcgen05 3xTF32 kernel (fp32 parity 1e-5); bound by SIMT issue of the operand build / epilogue around "
-                        "the MMAs, not by HBM or the tensor pipe: see DESIGN.md section 4 and profiles/"}
+                "note": ("dominant library call by CUDA-event time: %s, %.3f ms per launch x %d per step = %.0f %% of the step's "
+                         "kernel time; %.0f GB/s of algorithmic bytes = %.2f of the measured HBM peak, %.1f TFLOP/s of "
+                         "fp32-equivalent contraction flops (3xTF32 on tcgen05 where the call is a tensor-core kernel); "
+                         "issue / stall counters of the same kernel: profiles/ (ncu captures named per round)"
+                         % (top[0], tr["ms"] / tr["launches"], tr["launches"] // 2, 100.0 * tr["ms"] / tot_ms, ach, ach / peak,
+                            tr["flops"] / (tr["ms"] * 1e-3) / 1e12))}
     table = {k: {"ms_per_step": v["ms"] / 2, "GBps": v["bytes"] / max(v["ms"], 1e-9) / 1e6,
                  "TFLOPs": v["flops"] / max(v["ms"], 1e-9) / 1e9, "launches_per_step": v["launches"] // 2}
              for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
@@ -331,6 +450,9 @@ def run_b200(a):
         os.makedirs(os.path.dirname(os.path.abspath(a.dump)), exist_ok=True)
         json.dump({"kernels": table, "edges": edges, "cells": cells, "particles": n}, open(a.dump, "w"), indent=1)
 
+    others = None
+    if not a.no_other_configs and a.particles == 100_000 and (world == 1 or dd):
+        others = other_configs(a, world, rank, dev, model, ts)
     if world > 1:
         dist.barrier()
     if rank != 0:
@@ -362,7 +484,7 @@ def run_b200(a):
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": cfg, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cb, "edges_per_s": tot_edges * K / (ms * 1e-3),
-            "loss": float(loss.item()), "parity": parity, "kernels": table}
+            "loss": float(loss.item()), "parity": parity, "other_configs": others, "kernels": table}
     if parity is not None:
         line["loss_ref"], line["loss_rel_err"] = parity["loss_ref"], parity["loss_rel_err"]
     _emit(json.dumps(line))

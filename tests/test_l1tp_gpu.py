@@ -101,7 +101,10 @@ def test_plain_vs_oracle_large(in1, out, rows):
     if "0o" not in in1 and "1e" not in in1 and out != "1x1o" and "96x0e" not in in1 and din % 4 == 0:
         # a x0e + b x1o -> c x0e + d x1o: forward, weight-gradient and input-gradient all run on the tensor cores
         # (the weight-gradient kernel stages the cotangent rows with 16-byte cp.async: it declines dout % 4 != 0 here)
-        assert capi.tc_launch_count() - tc0 == (3 if dout % 4 == 0 else 2), "tcgen05 kernels did not launch"
+        # (the 8-column embedding input is declined by the tcgen05 weight-gradient kernel: generic fp32 kernel; the
+        # first-generation tcgen05 kernel that used to take it was retired in round 2)
+        want = (3 if dout % 4 == 0 else 2) - (1 if in1 == "2x1o+2x0e" else 0)
+        assert capi.tc_launch_count() - tc0 == want, "tcgen05 kernels did not launch"
     w64 = {k: v.astype(np.float64) for k, v in w.items()}
     ref = O.forward(x.astype(np.float64), y.astype(np.float64), w64, nrm, in1, out)
     gx, gy, gw = O.backward(x.astype(np.float64), y.astype(np.float64), go.astype(np.float64), w64, nrm, in1, out)

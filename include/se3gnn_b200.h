@@ -175,6 +175,14 @@ int se3_msg_fused_forward_dbg(int32_t ns, int32_t nv, int64_t rows, const int32_
 int se3_msg_fused_backward(int32_t ns, int32_t nv, int64_t rows, const int32_t* dst, const float* y, const float* pre1,
                            const float* pre2, const float* gagg, const float* wz2, const float* wv2, const float* nz2,
                            const float* nv2, float gate_cs, float gate_cg, float* gpre1, float* gpre2, void* stream);
+/* Weight gradient of message 2 (csrc/msg_fused_bwdw.cu, tcgen05 MN-major, accumulators resident in TMEM): gwz2
+ * [(ns+nv), ns+nv] and gwv2 [(ns+nv), nv] (overwritten) from the saved gated message 1 and gpre2 of
+ * se3_msg_fused_backward; m1 / gpre2 must be allocated with the row count rounded up to 32 (whole tiles are copied by
+ * cp.async.bulk; the extra rows may hold anything).  partials: max_parts x part_floats floats of scratch. */
+int se3_msg_fused_bwdw_parts(int32_t ns, int32_t nv, int32_t* max_parts, int32_t* part_floats);
+int se3_msg_fused_backward_w(int32_t ns, int32_t nv, int64_t rows, const float* y, const float* m1, const float* gpre2,
+                             const float* nz2, const float* nv2, float* gwz2, float* gwv2, float* partials,
+                             int32_t max_parts, void* stream);
 /* The node-level contraction itself, block-sparse and in exact fp32 (csrc/msg_node.cu): table = x . W (forward),
  * gx = G . W^T and gwz / gwv = x^T . G (+ the extras' rows from gwe_part) straight from / into the parameters' layout;
  * se3_msg1_expand(wbig = NULL) then only produces `we`.  part: scratch of max_parts x part_floats floats
@@ -185,6 +193,27 @@ int se3_msg1_node_table(int32_t ns, int32_t nv, int64_t n, const float* x, const
 int se3_msg1_node_backward(int32_t ns, int32_t nv, int64_t n, const float* x, const float* G, const float* wz,
                            const float* wv, const float* nz, const float* nvn, const float* gwe_part, int32_t neparts,
                            float* gx, float* gwz, float* gwv, float* part, int32_t max_parts, void* stream);
+/* -------------------------------------------------------------- domain ---- */
+/* Morton-range domain decomposition of the replicated global graph (csrc/domain.cu; builder-defined, the reference
+ * has no distributed code).  bounds [world+1] int64: particle-rank slab boundaries (device).  A cell belongs to the
+ * owner of its first particle.
+ * se3_domain_mark: pos [n+m] = local id of the nodes `rank` owns (-1 otherwise; owned particles first, then owned cells,
+ *   both in global order), loc_rowptr [n_own+1] (capacity n+m+1) = CSR row pointers of the owned rows,
+ *   counts [4+world] int64 (device): [0] owned particles, [1] owned nodes, [2] local edges.
+ * se3_domain_edges (after reading counts[0..2]): own_ids [n_own], dst_loc / src_loc [e_loc] local ids in the global
+ *   (dst, src) order (sources this rank does not own: n_own + position in halo_ids), the rank's rows of edge_attr
+ *   [E,4] / edge_extra [E,2] (either may be NULL), halo_ids (capacity n+m; ascending global id inside each owner,
+ *   grouped by owner), counts[3] = n_halo, counts[4+r] = halo nodes owned by rank r.
+ * work: se3_domain_work_bytes(n+m); hpos [n+m], scratch [2 (n+m)] int32. */
+int se3_domain_work_bytes(int64_t nn, size_t* bytes);
+int se3_domain_mark(int64_t n, int64_t m, int32_t rank, int32_t world, const int64_t* bounds, const int32_t* cell_start,
+                    const int64_t* rowptr, int32_t* pos, int64_t* loc_rowptr, int64_t* counts, void* work,
+                    size_t work_bytes, void* stream);
+int se3_domain_edges(int64_t n, int64_t m, int32_t world, const int64_t* bounds, const int32_t* cell_start,
+                     const int32_t* pos, const int64_t* loc_rowptr, const int64_t* rowptr, const int32_t* col,
+                     const float* edge_attr, const float* edge_extra, int64_t n_own, int64_t e_loc, int32_t* own_ids,
+                     int32_t* dst_loc, int32_t* src_loc, float* attr_loc, float* extra_loc, int32_t* halo_ids,
+                     int32_t* hpos, int32_t* scratch, int64_t* counts, void* work, size_t work_bytes, void* stream);
 /* rowptr [n+1] of an ascending index (rowptr[k] = first position with idx >= k) */
 int se3_rowptr_from_sorted(int64_t e, int64_t n, const int32_t* idx_sorted, int64_t* rowptr, void* stream);
 /* stable counting sort of the edges by source: tptr [n_src+1], perm [e] (edge ids, ascending inside a segment) */

@@ -12,7 +12,8 @@
 //
 // Math (norms and 1/sqrt(3) folded into the B tiles; g0 / g1 = scalar / vector part of g_pre2, S / V = message 1):
 //     HZ = g0 [mz],  HG[m] = sum_c Y1c g1[m][c],  HVc[m] = g1[m][c]
-//     GS1 = HZ . BZs,  GS2 = HG . BVs,  GD = HZ . BZd,  GTc = HVc . BVv          (60 MMAs M=64 per tile)
+//     GS1 = HZ . BZs,  GS2 = HG . BVs,  GD = HZ . BZd,  GTc = HVc . BVv          (42 MMAs M=64 per tile: [GS1 | GD] is
+//     one product, the two B tiles share the operand HZ)
 //     gS_k = Y0 GS1[k] + GS2[k]          gV_kc = Y1c GD[k] + Y0 GTc[k]
 // Same skeleton as msg_fused_fwd.cu: persistent CTA per SM, 16 worker warps + 1 MMA warp, 64-row tiles, operand sets
 // and accumulators double buffered.  Build = streaming loads (the cotangent rows are gathered through the SORTED dst
@@ -36,7 +37,8 @@ struct BwdDims {
     static constexpr int KZ = (MZ + 7) & ~7, KV = (NV + 7) & ~7, K1T = KZ + KV;      // T1 = [HZ | HG]
     static constexpr int KQ1 = K1T / 4, KQ3 = KV / 4, KQZ = KZ / 4;
     static constexpr int NSP = (NS + 7) & ~7, NDP = (NV + 7) & ~7;                   // accumulator widths
-    static constexpr int cS1 = 0, cS2 = NSP, cD = 2 * NSP, cT = 2 * NSP + NDP, ACC = 256;
+    // accumulator columns: [GS1 | GD] is ONE product (the two B tiles share the A operand HZ: a single N = NSP + NDP tile)
+    static constexpr int cS1 = 0, cD = NSP, cS2 = NSP + NDP, cT = 2 * NSP + NDP, ACC = 256;
     static constexpr int SB = NSP / 8, VB = NDP / 8;                                 // 8-column blocks
     static constexpr int SQ = NS / 4, RS4 = NS % 4, NP = NV / 2, NU = SQ + (RS4 ? 1 : 0) + NP;
     static constexpr int halfT1 = BTM * K1T * 4, halfT3 = BTM * KV * 4, HALFB = halfT1 + 3 * halfT3, TBYTES = 2 * HALFB;
@@ -64,10 +66,9 @@ struct FusedBwdArgs {
 template <int NS, int NV>
 struct BwdSmem {
     using F = BwdDims<NS, NV>;
-    static constexpr int o_bs1 = 0;                                         // [NSP][KZ]  hi | lo
-    static constexpr int o_bs2 = o_bs1 + 2 * F::NSP * F::KZ * 4;            // [NSP][KV]
-    static constexpr int o_bd = o_bs2 + 2 * F::NSP * F::KV * 4;             // [NDP][KZ]
-    static constexpr int o_bt = o_bd + 2 * F::NDP * F::KZ * 4;              // [NDP][KV]
+    static constexpr int o_bs1 = 0;                                         // [NSP + NDP][KZ]  hi | lo   (BZs rows, then BZd rows)
+    static constexpr int o_bs2 = o_bs1 + 2 * (F::NSP + F::NDP) * F::KZ * 4; // [NSP][KV]
+    static constexpr int o_bt = o_bs2 + 2 * F::NSP * F::KV * 4;             // [NDP][KV]
     static constexpr int o_t = (o_bt + 2 * F::NDP * F::KV * 4 + 1023) & ~1023;
     static constexpr int o_out = o_t + F::TBYTES;           // ONE operand set (see msg_fused_fwd.cu)
     static constexpr int TILEB = (BTM * F::DPRE * 4 + 127) & ~127;
@@ -118,24 +119,25 @@ __global__ void __launch_bounds__(B_THREADS, 1) msg_fused_bwd_kernel(const __gri
         for (int t = tid; t < F::TBYTES >> 4; t += B_THREADS) z[t] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     {   // transposed weights -> canonical K-major B tiles (hi | lo): row n = input channel of message 2, K = its output
-        auto fill = [&](int off, int NN, int KK, int nvalid, int kvalid, auto value) {
+        // rows [n0, n0 + NN) of a tile of NT rows
+        auto fill = [&](int off, int NT, int n0, int NN, int KK, int nvalid, int kvalid, auto value) {
             unsigned char* b = smraw + off;
             for (int t = tid; t < NN * KK; t += B_THREADS) {
                 const int n = t / KK, k = t - n * KK;
                 const float x = (n < nvalid && k < kvalid) ? value(n, k) : 0.0f;
                 float hi, lo;
                 split_tf32(x, hi, lo);
-                const int o = canon_off(n, k, KK >> 2);
+                const int o = canon_off(n0 + n, k, KK >> 2);
                 *reinterpret_cast<float*>(b + o) = hi;
-                *reinterpret_cast<float*>(b + NN * KK * 4 + o) = lo;
+                *reinterpret_cast<float*>(b + NT * KK * 4 + o) = lo;
             }
         };
         auto nz = [&](int m) { return A.nz2 ? __ldg(A.nz2 + m) : 1.0f; };
         auto nv = [&](int m) { return A.nv2 ? __ldg(A.nv2 + 3 * m) : 1.0f; };
-        fill(SM::o_bs1, NSP, KZ, NS, MZ, [&](int k, int m) { return nz(m) * __ldg(A.wz2 + k * MZ + m); });
-        fill(SM::o_bs2, NSP, KV, NS, NV, [&](int k, int m) { return nv(m) * C3f * __ldg(A.wv2 + k * NV + m); });
-        fill(SM::o_bd, NDP, KZ, NV, MZ, [&](int k, int m) { return nz(m) * C3f * __ldg(A.wz2 + (NS + k) * MZ + m); });
-        fill(SM::o_bt, NDP, KV, NV, NV, [&](int k, int m) { return nv(m) * C3f * __ldg(A.wv2 + (NS + k) * NV + m); });
+        fill(SM::o_bs1, NSP + NDP, 0, NSP, KZ, NS, MZ, [&](int k, int m) { return nz(m) * __ldg(A.wz2 + k * MZ + m); });
+        fill(SM::o_bs1, NSP + NDP, NSP, NDP, KZ, NV, MZ, [&](int k, int m) { return nz(m) * C3f * __ldg(A.wz2 + (NS + k) * MZ + m); });
+        fill(SM::o_bs2, NSP, 0, NSP, KV, NS, NV, [&](int k, int m) { return nv(m) * C3f * __ldg(A.wv2 + k * NV + m); });
+        fill(SM::o_bt, NDP, 0, NDP, KV, NV, NV, [&](int k, int m) { return nv(m) * C3f * __ldg(A.wv2 + (NS + k) * NV + m); });
     }
     fence_proxy_async();
     if (warp == BWK) {
@@ -154,71 +156,13 @@ __global__ void __launch_bounds__(B_THREADS, 1) msg_fused_bwd_kernel(const __gri
     if (warp == BWK) {
         // ================= MMA issuer
         const uint32_t sb = smem_u32(smraw);
-        const uint32_t idS = make_idesc(NSP), idD = make_idesc(NDP);
+        const uint32_t idS = make_idesc(NSP), idD = make_idesc(NDP), idSD = make_idesc(NSP + NDP);
         constexpr uint32_t sboT1 = KQ1 * 128, sboT3 = KQ3 * 128, sboZ = KQZ * 128, sboG = KQ3 * 128;
-        const uint64_t bS1h = make_desc(sb + SM::o_bs1, sboZ), bS1l = make_desc(sb + SM::o_bs1 + NSP * KZ * 4, sboZ);
+        const uint64_t bS1h = make_desc(sb + SM::o_bs1, sboZ), bS1l = make_desc(sb + SM::o_bs1 + (NSP + NDP) * KZ * 4, sboZ);
         const uint64_t bS2h = make_desc(sb + SM::o_bs2, sboG), bS2l = make_desc(sb + SM::o_bs2 + NSP * KV * 4, sboG);
-        const uint64_t bDh = make_desc(sb + SM::o_bd, sboZ), bDl = make_desc(sb + SM::o_bd + NDP * KZ * 4, sboZ);
         const uint64_t bTh = make_desc(sb + SM::o_bt, sboT3), bTl = make_desc(sb + SM::o_bt + NDP * KV * 4, sboT3);
         constexpr uint64_t v3 = (uint64_t)(F::halfT3 >> 4);
-        for (int it = 0; it < nt; ++it) {
-            const int b = it & 1;
-            const uint32_t ph = (it >> 1) & 1;
-            mbar_wait(BAR(b), ph);
-            mbar_wait(BAR(4 + b), ph ^ 1);
-            tc_fence_after();
-            if (lane == 0) {
-                const uint32_t acc = tmem_base + (uint32_t)b * F::ACC;
-                const uint32_t t1 = sb + SM::o_t;
-                const uint64_t a1h = make_desc(t1, sboT1), a1l = make_desc(t1 + F::HALFB, sboT1);
-#pragma unroll
-                for (int j = 0; j < KZ / 8; ++j) {
-                    const uint64_t o = (uint64_t)(j * 16);
-                    tc_mma_tf32(acc + F::cS1, a1h + o, bS1h + o, idS, j ? 1u : 0u);
-                    tc_mma_tf32(acc + F::cS1, a1h + o, bS1l + o, idS, 1u);
-                    tc_mma_tf32(acc + F::cS1, a1l + o, bS1h + o, idS, 1u);
-                    tc_mma_tf32(acc + F::cD, a1h + o, bDh + o, idD, j ? 1u : 0u);
-                    tc_mma_tf32(acc + F::cD, a1h + o, bDl + o, idD, 1u);
-                    tc_mma_tf32(acc + F::cD, a1l + o, bDh + o, idD, 1u);
-                }
-#pragma unroll
-                for (int j = 0; j < KV / 8; ++j) {
-                    const uint64_t o = (uint64_t)(j * 16), oa = (uint64_t)((KZ / 8 + j) * 16);
-                    tc_mma_tf32(acc + F::cS2, a1h + oa, bS2h + o, idS, j ? 1u : 0u);
-                    tc_mma_tf32(acc + F::cS2, a1h + oa, bS2l + o, idS, 1u);
-                    tc_mma_tf32(acc + F::cS2, a1l + oa, bS2h + o, idS, 1u);
-                }
-                const uint64_t a3h = make_desc(t1 + F::halfT1, sboT3), a3l = make_desc(t1 + F::halfT1 + F::HALFB, sboT3);
-#pragma unroll
-                for (int c = 0; c < 3; ++c)
-#pragma unroll
-                    for (int j = 0; j < KV / 8; ++j) {
-                        const uint64_t o = (uint64_t)(j * 16), oa = o + (uint64_t)c * v3;
-                        tc_mma_tf32(acc + F::cT + c * NDP, a3h + oa, bTh + o, idD, j ? 1u : 0u);
-                        tc_mma_tf32(acc + F::cT + c * NDP, a3h + oa, bTl + o, idD, 1u);
-                        tc_mma_tf32(acc + F::cT + c * NDP, a3l + oa, bTh + o, idD, 1u);
-                    }
-                tc_commit(BAR(2 + b));
-            }
-            __syncwarp();
-        }
-    } else {
-        // ================= workers
-        const int r8 = lane & 7, cq = lane >> 3;
-        const int wrow = (warp & 7) * 8 + r8;
-        const int sub = warp >> 3;
-        const int rp1 = (((wrow >> 3) * KQ1) << 7) + ((wrow & 7) << 4);
-        const int rp3 = (((wrow >> 3) * KQ3) << 7) + ((wrow & 7) << 4);
-        int n_dst = 0;
-        float4 n_y = make_float4(0.f, 0.f, 0.f, 0.f);
-        auto load_row = [&](int it) {
-            const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * BTM;
-            long long gr = row0 + wrow;
-            if (gr > R - 1) gr = R - 1;
-            n_dst = ldgi_v(A.dst + gr);
-            n_y = ldg4_v(A.y + 4 * gr);
-        };
-        // TMA staging (warp 0, a tile ahead): the tile's pre-activation blocks are contiguous in HBM (ONE cp.async.bulk each),
+        // TMA staging (this otherwise idle warp, a tile ahead): the tile's pre-activation blocks are contiguous in HBM (ONE cp.async.bulk each),
         // the cotangent rows are gathered once per distinct destination of the tile (dst is ascending)
         int pf_dst0 = 0, pf_dst1 = 0;
         int* sslot = reinterpret_cast<int*>(smraw + SM::o_slot);
@@ -261,6 +205,71 @@ __global__ void __launch_bounds__(B_THREADS, 1) msg_fused_bwd_kernel(const __gri
                 bmbar_arrive_tx(BAR(7 + (it & 1)), blk);
                 bbulk_g2s(sm_u32 + SM::o_p1 + (it & 1) * SM::TILEB, A.pre1 + row0 * F::DPRE, blk, BAR(7 + (it & 1)));
             }
+        };
+        if (nt > 0) {
+            load_pf(0);
+            issue_pf(0);
+            if (nt > 1) load_pf(1);
+        }
+        for (int it = 0; it < nt; ++it) {
+            const int b = it & 1;
+            const uint32_t ph = (it >> 1) & 1;
+            mbar_wait(BAR(b), ph);
+            if (it + 1 < nt) {                 // the build staging is free: every worker arrived from build(it).  Issued BEFORE
+                issue_pf(it + 1);              // the MMAs (their issue takes ~3k cycles of this thread; the copies are needed first)
+                if (it + 2 < nt) load_pf(it + 2);
+            }
+            mbar_wait(BAR(4 + b), ph ^ 1);     // drain(it - 2) done: accumulator b AND staging buffer b of message 1 are free
+            issue_p1(it);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t acc = tmem_base + (uint32_t)b * F::ACC;
+                const uint32_t t1 = sb + SM::o_t;
+                const uint64_t a1h = make_desc(t1, sboT1), a1l = make_desc(t1 + F::HALFB, sboT1);
+#pragma unroll
+                for (int j = 0; j < KZ / 8; ++j) {
+                    const uint64_t o = (uint64_t)(j * 16);
+                    tc_mma_tf32(acc + F::cS1, a1h + o, bS1h + o, idSD, j ? 1u : 0u);     // [GS1 | GD]
+                    tc_mma_tf32(acc + F::cS1, a1h + o, bS1l + o, idSD, 1u);
+                    tc_mma_tf32(acc + F::cS1, a1l + o, bS1h + o, idSD, 1u);
+                }
+#pragma unroll
+                for (int j = 0; j < KV / 8; ++j) {
+                    const uint64_t o = (uint64_t)(j * 16), oa = (uint64_t)((KZ / 8 + j) * 16);
+                    tc_mma_tf32(acc + F::cS2, a1h + oa, bS2h + o, idS, j ? 1u : 0u);
+                    tc_mma_tf32(acc + F::cS2, a1h + oa, bS2l + o, idS, 1u);
+                    tc_mma_tf32(acc + F::cS2, a1l + oa, bS2h + o, idS, 1u);
+                }
+                const uint64_t a3h = make_desc(t1 + F::halfT1, sboT3), a3l = make_desc(t1 + F::halfT1 + F::HALFB, sboT3);
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int j = 0; j < KV / 8; ++j) {
+                        const uint64_t o = (uint64_t)(j * 16), oa = o + (uint64_t)c * v3;
+                        tc_mma_tf32(acc + F::cT + c * NDP, a3h + oa, bTh + o, idD, j ? 1u : 0u);
+                        tc_mma_tf32(acc + F::cT + c * NDP, a3h + oa, bTl + o, idD, 1u);
+                        tc_mma_tf32(acc + F::cT + c * NDP, a3l + oa, bTh + o, idD, 1u);
+                    }
+                tc_commit(BAR(2 + b));
+            }
+            __syncwarp();
+        }
+    } else {
+        // ================= workers
+        const int* sslot = reinterpret_cast<const int*>(smraw + SM::o_slot);
+        const int r8 = lane & 7, cq = lane >> 3;
+        const int wrow = (warp & 7) * 8 + r8;
+        const int sub = warp >> 3;
+        const int rp1 = (((wrow >> 3) * KQ1) << 7) + ((wrow & 7) << 4);
+        const int rp3 = (((wrow >> 3) * KQ3) << 7) + ((wrow & 7) << 4);
+        int n_dst = 0;
+        float4 n_y = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto load_row = [&](int it) {
+            const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * BTM;
+            long long gr = row0 + wrow;
+            if (gr > R - 1) gr = R - 1;
+            n_dst = ldgi_v(A.dst + gr);
+            n_y = ldg4_v(A.y + 4 * gr);
         };
         auto st_hl4 = [&](unsigned char* p, float a, float b, float c, float d) {
             float4 h, l;
@@ -432,15 +441,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) msg_fused_bwd_kernel(const __gri
             for (int t = (n4 << 2) + tid; t < total; t += BWT) dstp[t] = otile[t];
         };
 
-        if (nt > 0) {
-            load_row(0);
-            if (warp == 0) {
-                load_pf(0);
-                issue_pf(0);
-                issue_p1(0);
-                if (nt > 1) { load_pf(1); issue_p1(1); }
-            }
-        }
+        if (nt > 0) load_row(0);
         for (int it = 0; it < nt; ++it) {
             build(it);
             fence_proxy_async();
@@ -448,14 +449,9 @@ __global__ void __launch_bounds__(B_THREADS, 1) msg_fused_bwd_kernel(const __gri
             if (lane == 0) mbar_arrive(BAR(it & 1));
             if (it + 1 < nt) load_row(it + 1);
             named_bar(2, BWT);             // every worker is done with the staged rows of tile it and the result tile of tile it-2
-            if (warp == 0 && it + 1 < nt) {
-                issue_pf(it + 1);
-                if (it + 2 < nt) load_pf(it + 2);
-            }
             if (it >= 1) {
                 drain(it - 1);
                 named_bar(1, BWT);
-                if (warp == 0 && it + 1 < nt) issue_p1(it + 1);    // buffer (it + 1) & 1 was read by drain(it - 1)
                 finish(it - 1);
             }
             prefetch_x(it);

@@ -9,9 +9,12 @@
 // applied once, in the final reduction):
 //     M side:  T1 = [Y0 g0 | sum_c Y1c g1[.][c]]   HZ = g0           HVc = Y0 g1[.][c]
 //     N side:  S                                   D  = <V_k, Y1>    Vc
-//     A1 [T1 x S]  += T1^T S      A2 [HZ x D] += HZ^T D      A3c [HVc x Vc] += HVc^T Vc      (15 MMAs per 8 rows)
-// The output-channel side is the MMA M dimension (64 lanes, 54 / 44 / 3 x 10 used) and the input-channel side is N
-// (40 / 16 / 16 columns): M = 64 costs the same tensor time as M = 128, so the wide side goes to M.
+//     A1 [T1 x S]  += T1^T S      A2 [HZ x D] += HZ^T D      A3c [HVc x Vc] += HVc^T Vc
+// issued as TWO products per 8 rows: [T1 | HZ]^T [S | D] (M = 128, N = 64: the two wanted blocks of a 2 x 2 block
+// accumulator) and [HVx | HVy | HVz]^T [Vx | Vy | Vz] (M = 64, N = 48: the three diagonal blocks); the cross blocks are
+// simply not read.  That is 6 tcgen05.mma per 8 rows instead of 15: the kernel is bound by the single issuing thread
+// (the first version with one product per block took as long as the kernel it replaces, 0.76 ms per 1.78M rows).
+// The output-channel side is the MMA M dimension and the input-channel side is N.
 // Feeding: the tile's rows of message 1 and of g_pre2 are contiguous in HBM: TWO cp.async.bulk (TMA) copies per
 // 32-row tile into a double-buffered staging area, issued a tile ahead; the 16 worker warps only rescale by the SH,
 // split into tf32 hi / lo and store 16-byte pieces (lane = (piece, row of a 4-row atom): conflict-free).
@@ -33,15 +36,16 @@ static constexpr int WHALF = WNCHK * WCH, WSET = 2 * WHALF;
 template <int NS, int NV>
 struct WDims {
     static constexpr int MZ = NS + NV, DPRE = NS + 4 * NV, D = NS + 3 * NV;
-    static constexpr int N1 = (NS + 7) & ~7;                       // columns of A1 (S slots)
-    static constexpr int cA1 = 0, cA2 = N1, cA3 = N1 + 16, NCOL = N1 + 16 + 48;
+    static constexpr int N1 = (NS + 7) & ~7;                       // S slots (D sits at slot 48 of the same N = 64 operand)
+    static constexpr int cA12 = 0, cA3 = 64, NCOL = 64 + 48;       // TMEM columns: [T1 | HZ] x [S | D], then HV x V
+    static constexpr int ROWS = 128 + 64;                          // rows of a partial: 128 lanes of A12, 64 slots of A3
     static constexpr int GP = (MZ + 3) / 4, HP = (NV + 3) / 4, SP = (NS + 3) / 4, VP = (NV + 3) / 4;   // 16-byte pieces
-    static constexpr int PART = 64 * NCOL;                         // floats of one CTA's partial
+    static constexpr int PART = 128 * 64 + 64 * 48;                // floats of one CTA's partial: A12 [128][64] | A3 [64][48]
     static_assert(MZ + NV <= 64 && MZ % 4 == 0, "T1 = [Y0 g0 | HG] fits 64 slots, HG starts on a piece boundary");
     static_assert(NV <= 16 && NS + 8 <= 48 && N1 <= 40, "vector operands use 16 slots; D sits at slot 16 of S's second chunk");
     static_assert(NS % 2 == 0 && NV % 2 == 0 && DPRE % 2 == 0, "8-byte aligned rows");
     static_assert(GP + HP <= 16 && SP + VP <= 16, "two rounds of eight tasks per warp pair");
-    static_assert(NCOL <= 128, "TMEM columns");
+    static_assert(NCOL <= 128 && N1 <= 48, "TMEM columns; S and D share one N = 64 operand");
 };
 
 struct FusedBwdWArgs {
@@ -121,37 +125,28 @@ __global__ void __launch_bounds__(W_THREADS, 1) msg_fused_bwdw_kernel(const __gr
     if (warp == WW) {
         // ================= MMA issuer
         const uint32_t sb = smem_u32(smraw) + SM::o_set;
-        const uint32_t id1 = make_idesc_ex(64, F::N1, 1, 1), id2 = make_idesc_ex(64, 16, 1, 1);
+        const uint32_t id1 = make_idesc_ex(128, 64, 1, 1), id2 = make_idesc_ex(64, 48, 1, 1);
         for (int it = 0; it < nt; ++it) {
             const int b = it & 1;
             mbar_wait(BAR(b), (it >> 1) & 1);
             tc_fence_after();
             if (lane == 0) {
                 const uint32_t s0 = sb + (uint32_t)b * WSET;
-                const uint64_t dT1 = wmk_desc_mn(s0 + kT1 * WCH), dHZ = wmk_desc_mn(s0 + kHZ * WCH), dHV = wmk_desc_mn(s0 + kHV * WCH);
-                const uint64_t dS = wmk_desc_mn(s0 + kS * WCH), dV = wmk_desc_mn(s0 + kV * WCH);
-                const uint64_t dD = dS + (uint64_t)(WCH >> 4) + 4ull;        // second chunk of S, slot 16 (+64 bytes)
-                const uint64_t lo = (uint64_t)(WHALF >> 4), chs = (uint64_t)(WCH >> 4);
+                // M = 128 operand [T1 | HZ] = chunks kT1 .. kT1 + 3; N = 64 operand [S | - | D | -] = chunks kS, kS + 1
+                // M = 64 operand [HVx | HVy | HVz | -] = chunks kHV, kHV + 1; N = 48 operand [Vx | Vy | Vz] = chunks kV, kV + 1
+                const uint64_t dT = wmk_desc_mn(s0 + kT1 * WCH), dS = wmk_desc_mn(s0 + kS * WCH);
+                const uint64_t dHV = wmk_desc_mn(s0 + kHV * WCH), dV = wmk_desc_mn(s0 + kV * WCH);
+                const uint64_t lo = (uint64_t)(WHALF >> 4);
 #pragma unroll
                 for (int ks = 0; ks < WTW / 8; ++ks) {
                     const uint32_t acc0 = (it == 0 && ks == 0) ? 0u : 1u;
                     const uint64_t ko = (uint64_t)(ks * 64);   // 8 rows x 128 B, in 16-byte units
-                    tc_mma_tf32(tmem_base + F::cA1, dT1 + ko, dS + ko, id1, acc0);
-                    tc_mma_tf32(tmem_base + F::cA1, dT1 + ko, dS + ko + lo, id1, 1u);
-                    tc_mma_tf32(tmem_base + F::cA1, dT1 + ko + lo, dS + ko, id1, 1u);
-                    tc_mma_tf32(tmem_base + F::cA2, dHZ + ko, dD + ko, id2, acc0);
-                    tc_mma_tf32(tmem_base + F::cA2, dHZ + ko, dD + ko + lo, id2, 1u);
-                    tc_mma_tf32(tmem_base + F::cA2, dHZ + ko + lo, dD + ko, id2, 1u);
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        // M side [HVx | HVy | HVz | -] (one M = 64 operand, the block of component c is rows 16c..16c+15);
-                        // N side Vx: chunk kV slots 0..15, Vy: slots 16..31 (+64 B), Vz: next chunk slots 0..15
-                        const uint64_t ob = ko + (c == 1 ? 4ull : (c == 2 ? chs : 0ull));
-                        const uint32_t acc = tmem_base + F::cA3 + 16 * c;
-                        tc_mma_tf32(acc, dHV + ko, dV + ob, id2, acc0);
-                        tc_mma_tf32(acc, dHV + ko, dV + ob + lo, id2, 1u);
-                        tc_mma_tf32(acc, dHV + ko + lo, dV + ob, id2, 1u);
-                    }
+                    tc_mma_tf32(tmem_base + F::cA12, dT + ko, dS + ko, id1, acc0);
+                    tc_mma_tf32(tmem_base + F::cA12, dT + ko, dS + ko + lo, id1, 1u);
+                    tc_mma_tf32(tmem_base + F::cA12, dT + ko + lo, dS + ko, id1, 1u);
+                    tc_mma_tf32(tmem_base + F::cA3, dHV + ko, dV + ko, id2, acc0);
+                    tc_mma_tf32(tmem_base + F::cA3, dHV + ko, dV + ko + lo, id2, 1u);
+                    tc_mma_tf32(tmem_base + F::cA3, dHV + ko + lo, dV + ko, id2, 1u);
                 }
                 tc_commit(BAR(2 + b));
             }
@@ -268,21 +263,32 @@ __global__ void __launch_bounds__(W_THREADS, 1) msg_fused_bwdw_kernel(const __gr
             named_bar(1, WWT);                                   // every worker is done with staging buffer b
             if (warp == 0 && lane == 0 && it + 2 < nt) issue_pf(it + 2);
         }
-        // ---------------- final epilogue (warps 0-3): TMEM accumulators -> this CTA's partial [64][NCOL]
+        // ---------------- final epilogue (warps 0-3): TMEM accumulators -> this CTA's partial: A12 [128][64] | A3 [64][48]
         if (warp < 4) {
             mbar_wait(BAR(6), 0);
             tc_fence_after();
             float* part = A.partials + (long long)blockIdx.x * F::PART;
             const uint32_t tq = tmem_base + ((uint32_t)(32 * warp) << 16);
-            const int slot = 16 * warp + (lane & 15);              // M = 64: slot 16 q + i lives in TMEM lane 32 q + i
-            for (int c0 = 0; c0 < F::NCOL; c0 += 8) {
-                float a[8];
-                tc_ld8(tq + c0, a);
-                tc_wait_ld();
-                if (lane < 16) {
-                    float4* o = reinterpret_cast<float4*>(part + slot * F::NCOL + c0);
-                    o[0] = make_float4(a[0], a[1], a[2], a[3]);
-                    o[1] = make_float4(a[4], a[5], a[6], a[7]);
+            {   // M = 128: TMEM lane = row of [T1 | HZ]
+                float4* o = reinterpret_cast<float4*>(part + (32 * warp + lane) * 64);
+                for (int c0 = 0; c0 < 64; c0 += 8) {
+                    float a[8];
+                    tc_ld8(tq + F::cA12 + c0, a);
+                    tc_wait_ld();
+                    o[c0 / 4] = make_float4(a[0], a[1], a[2], a[3]);
+                    o[c0 / 4 + 1] = make_float4(a[4], a[5], a[6], a[7]);
+                }
+            }
+            {   // M = 64: slot 16 q + i lives in TMEM lane 32 q + i
+                float4* o = reinterpret_cast<float4*>(part + 128 * 64 + (16 * warp + (lane & 15)) * 48);
+                for (int c0 = 0; c0 < 48; c0 += 8) {
+                    float a[8];
+                    tc_ld8(tq + F::cA3 + c0, a);
+                    tc_wait_ld();
+                    if (lane < 16) {
+                        o[c0 / 4] = make_float4(a[0], a[1], a[2], a[3]);
+                        o[c0 / 4 + 1] = make_float4(a[4], a[5], a[6], a[7]);
+                    }
                 }
             }
         }
@@ -305,15 +311,15 @@ __global__ void msg_fused_bwdw_reduce_kernel(const float* __restrict__ part, int
         const int k = t / CH, ch = t - k * CH;          // k: input channel (scalars, then vectors); ch: output channel
         float g = 0.0f;
         if (k < NS) {
-            const float* p = part + ch * F::NCOL + F::cA1 + k;                     // A1[T1 slot ch][S slot k]
+            const float* p = part + ch * 64 + k;                                   // A12[T1 slot ch][S slot k]
             for (int q = 0; q < nparts; ++q) g += p[(long long)q * F::PART];
         } else if (ch < MZ) {
-            const float* p = part + ch * F::NCOL + F::cA2 + (k - NS);              // A2[HZ slot ch][D slot]
+            const float* p = part + (64 + ch) * 64 + 48 + (k - NS);                // A12[HZ slot ch][D slot]
             for (int q = 0; q < nparts; ++q) g += p[(long long)q * F::PART];
             g *= C3f;
         } else {
-            for (int c = 0; c < 3; ++c) {                                          // A3c[16 c + m][V slot]
-                const float* p = part + (16 * c + ch - MZ) * F::NCOL + F::cA3 + 16 * c + (k - NS);
+            for (int c = 0; c < 3; ++c) {                                          // A3[HVc slot][Vc slot]: diagonal block c
+                const float* p = part + 128 * 64 + (16 * c + ch - MZ) * 48 + 16 * c + (k - NS);
                 for (int q = 0; q < nparts; ++q) g += p[(long long)q * F::PART];
             }
         }
@@ -352,7 +358,7 @@ using namespace se3;
 extern "C" int se3_msg_fused_bwdw_parts(int32_t ns, int32_t nv, int32_t* max_parts, int32_t* part_floats) {
     if (!max_parts || !part_floats) { set_error("msg_fused_bwdw_parts: null argument"); return SE3_ERR_INVALID; }
     *max_parts = num_sms();
-    *part_floats = 64 * (((ns + 7) & ~7) + 64);
+    *part_floats = 128 * 64 + 64 * 48;
     return SE3_OK;
 }
 

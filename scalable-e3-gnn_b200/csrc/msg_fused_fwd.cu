@@ -148,7 +148,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) msg_fused_fwd_kernel(const __gri
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + SM::o_bar);
     const uint32_t bar0 = smem_u32(bars);
-    // barriers: 0,1 operand set full | 2,3 accumulator full | 4,5 accumulator empty | 6 staged src rows landed
+    // barriers: 0,1 operand set full | 2,3 accumulator full | 4,5 accumulator empty | 6 staged src rows landed (cp.async
+    //           of every worker thread) | 7 staged dst rows landed (TMA)
     auto BAR = [&](int i) { return bar0 + 8u * i; };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
     float* we_s = reinterpret_cast<float*>(smraw + SM::o_we);
@@ -161,7 +162,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) msg_fused_fwd_kernel(const __gri
             mbar_init(BAR(2 + i), 1);
             mbar_init(BAR(4 + i), FW);
         }
-        mbar_init(BAR(6), 1);
+        mbar_init(BAR(6), FWT);          // one cp.async.mbarrier.arrive.noinc per worker thread
+        mbar_init(BAR(7), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     {   // zero both operand sets (K padding is never written again)
@@ -223,10 +225,53 @@ __global__ void __launch_bounds__(F_THREADS, 1) msg_fused_fwd_kernel(const __gri
         const uint64_t dB1h = make_desc(sb + SM::o_b1, sboS), dB1l = make_desc(sb + SM::o_b1 + N * K1 * 4, sboS);
         const uint64_t dB2h = make_desc(sb + SM::o_b2, sboV), dB2l = make_desc(sb + SM::o_b2 + N * K2 * 4, sboV);
         constexpr uint32_t vstep = ((uint32_t)F::halfV) >> 4;
+        // dst halves of the table rows of the NEXT tile: one cp.async.bulk (TMA, no tensor map) per DISTINCT destination,
+        // issued by this (otherwise idle) warp as soon as every worker has arrived from the build of the current tile, i.e.
+        // has finished reading the staged rows.  (The 64 src rows are gathered by the workers with 16-byte cp.async: a
+        // bulk request per 864-byte row was measured at ~100 cycles each, longer than the epilogue they should hide in.)
+        const uint32_t stg_u32 = smem_u32(smraw + SM::o_stg);
+        int pf_dst0 = 0, pf_dst1 = 0;
+        int* sslot = reinterpret_cast<int*>(smraw + SM::o_slot);
+        auto load_pf = [&](int it) {
+            const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * FTM;
+            long long g0 = row0 + lane, g1 = g0 + 32;
+            if (g0 > R - 1) g0 = R - 1;
+            if (g1 > R - 1) g1 = R - 1;
+            pf_dst0 = ldgi_v(A.dst + g0);
+            pf_dst1 = ldgi_v(A.dst + g1);
+        };
+        auto issue_pf = [&]() {
+            // dst is ascending: slot of a row = number of changes of dst up to it; the first row of a slot copies the
+            // dst half of that node's table row (once per node and tile instead of once per edge)
+            const int up0 = __shfl_up_sync(0xffffffffu, pf_dst0, 1), last0 = __shfl_sync(0xffffffffu, pf_dst0, 31);
+            const int up1 = __shfl_up_sync(0xffffffffu, pf_dst1, 1);
+            const bool f0 = lane > 0 && pf_dst0 != up0;
+            const bool f1 = pf_dst1 != (lane == 0 ? last0 : up1);
+            const unsigned b0 = __ballot_sync(0xffffffffu, f0), b1 = __ballot_sync(0xffffffffu, f1);
+            const unsigned le = 0xffffffffu >> (31 - lane);
+            const int s0 = __popc(b0 & le), s1 = __popc(b0) + __popc(b1 & le);
+            sslot[lane] = s0;
+            sslot[lane + 32] = s1;
+            const int ncopy = min(__popc(b0) + __popc(b1) + 1, NDMAX);
+            if (lane == 0) fmbar_arrive_tx(BAR(7), ncopy * F::HALF * 4);
+            __syncwarp();
+            const uint32_t dstg_u32 = stg_u32 + (SM::o_dstg - SM::o_stg);
+            if ((lane == 0 || f0) && s0 < NDMAX) fbulk_g2s(dstg_u32 + s0 * F::STGB, A.table + (long long)pf_dst0 * F::LDT, F::HALF * 4, BAR(7));
+            if (f1 && s1 < NDMAX) fbulk_g2s(dstg_u32 + s1 * F::STGB, A.table + (long long)pf_dst1 * F::LDT, F::HALF * 4, BAR(7));
+        };
+        if (nt > 0) {
+            load_pf(0);
+            issue_pf();
+            if (nt > 1) load_pf(1);
+        }
         for (int it = 0; it < nt; ++it) {
             const int b = it & 1;
             const uint32_t ph = (it >> 1) & 1;
             mbar_wait(BAR(b), ph);
+            if (it + 1 < nt) {             // staging is free: every worker arrived from build(it); copies first, MMAs after
+                issue_pf();
+                if (it + 2 < nt) load_pf(it + 2);
+            }
             mbar_wait(BAR(4 + b), ph ^ 1);
             tc_fence_after();
             if (lane == 0) {
@@ -259,6 +304,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) msg_fused_fwd_kernel(const __gri
         }
     } else {
         // ================= workers
+        const int* sslot = reinterpret_cast<const int*>(smraw + SM::o_slot);
         // build mapping: warp w owns row group rb = w & 7 (rows 8 rb + (lane & 7)); its lanes' units are
         // u = 8 (w >> 3) + 4 round + (lane >> 3), round = 0, 1
         const int r8 = lane & 7, cq = lane >> 3;
@@ -278,42 +324,25 @@ __global__ void __launch_bounds__(F_THREADS, 1) msg_fused_fwd_kernel(const __gri
             n_y = ldg4_v(A.y + 4 * gr);
             n_ex = ldg2_v(A.extra + 2 * gr);
         };
-        // src halves of the table rows of the NEXT tile: one cp.async.bulk (TMA, no tensor map) per row, issued by
-        // warp 0 as soon as every worker has finished reading the staged rows of the current tile; they land during the
-        // epilogue of the previous tile, so the build never waits on a gathered load
-        const uint32_t stg_u32 = smem_u32(smraw + SM::o_stg);
-        int pf_src0 = 0, pf_src1 = 0, pf_dst0 = 0, pf_dst1 = 0;
-        int* sslot = reinterpret_cast<int*>(smraw + SM::o_slot);
-        auto load_pf = [&](int it) {
+        // src halves of the table rows of tile `it` -> staging, 16 bytes per cp.async: eight threads per row (its index
+        // is fetched a whole build ahead into ONE register), each thread copies every eighth piece -> 128 contiguous
+        // bytes per row and step; completion on BAR(6) (every worker thread arrives once per tile)
+        constexpr int PCS = F::HALF / 4;                         // 16-byte pieces per row
+        static_assert(FWT == 8 * FTM, "eight gather threads per row");
+        int g_src = 0;
+        auto load_gsrc = [&](int it) {
             const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * FTM;
-            long long g0 = row0 + lane, g1 = g0 + 32;
-            if (g0 > R - 1) g0 = R - 1;
-            if (g1 > R - 1) g1 = R - 1;
-            pf_src0 = ldgi_v(A.src + g0);
-            pf_src1 = ldgi_v(A.src + g1);
-            pf_dst0 = ldgi_v(A.dst + g0);
-            pf_dst1 = ldgi_v(A.dst + g1);
+            long long gr = row0 + (tid >> 3);
+            if (gr > R - 1) gr = R - 1;
+            g_src = ldgi_v(A.src + gr);
         };
-        auto issue_pf = [&]() {
-            // dst is ascending: slot of a row = number of changes of dst up to it; the first row of a slot copies the
-            // dst half of that node's table row (once per node and tile instead of once per edge)
-            const int up0 = __shfl_up_sync(0xffffffffu, pf_dst0, 1), last0 = __shfl_sync(0xffffffffu, pf_dst0, 31);
-            const int up1 = __shfl_up_sync(0xffffffffu, pf_dst1, 1);
-            const bool f0 = lane > 0 && pf_dst0 != up0;
-            const bool f1 = pf_dst1 != (lane == 0 ? last0 : up1);
-            const unsigned b0 = __ballot_sync(0xffffffffu, f0), b1 = __ballot_sync(0xffffffffu, f1);
-            const unsigned le = 0xffffffffu >> (31 - lane);
-            const int s0 = __popc(b0 & le), s1 = __popc(b0) + __popc(b1 & le);
-            sslot[lane] = s0;
-            sslot[lane + 32] = s1;
-            const int ncopy = min(__popc(b0) + __popc(b1) + 1, NDMAX);
-            if (lane == 0) fmbar_arrive_tx(BAR(6), (FTM + ncopy) * F::HALF * 4);
-            __syncwarp();
-            fbulk_g2s(stg_u32 + lane * F::STGB, A.table + (long long)pf_src0 * F::LDT + F::HALF, F::HALF * 4, BAR(6));
-            fbulk_g2s(stg_u32 + (lane + 32) * F::STGB, A.table + (long long)pf_src1 * F::LDT + F::HALF, F::HALF * 4, BAR(6));
-            const uint32_t dstg_u32 = stg_u32 + (SM::o_dstg - SM::o_stg);
-            if ((lane == 0 || f0) && s0 < NDMAX) fbulk_g2s(dstg_u32 + s0 * F::STGB, A.table + (long long)pf_dst0 * F::LDT, F::HALF * 4, BAR(6));
-            if (f1 && s1 < NDMAX) fbulk_g2s(dstg_u32 + s1 * F::STGB, A.table + (long long)pf_dst1 * F::LDT, F::HALF * 4, BAR(6));
+        auto gather_src = [&]() {
+            const uint32_t dstp = smem_u32(smraw + SM::o_stg) + (tid >> 3) * F::STGB + 16 * (tid & 7);
+            const float* srcp = A.table + (long long)g_src * F::LDT + F::HALF + 4 * (tid & 7);
+#pragma unroll
+            for (int j = 0; j < (PCS + 7) / 8; ++j)
+                if (8 * j + (tid & 7) < PCS) cp_async16(dstp + 128 * j, srcp + 32 * j, true);
+            cp_async_mbar_arrive_noinc(BAR(6));
         };
         auto st_hl4 = [&](unsigned char* p, float a, float b, float c, float d) {   // 16-byte operand piece, hi and lo
             float4 h, l;
@@ -342,6 +371,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) msg_fused_fwd_kernel(const __gri
             const float* ts = reinterpret_cast<const float*>(smraw + SM::o_stg + wrow * F::STGB);   // staged src half
             auto lds4 = [&](const float* q) { return *reinterpret_cast<const float4*>(q); };
             mbar_wait(BAR(6), (uint32_t)(it & 1));
+            mbar_wait(BAR(7), (uint32_t)(it & 1));
             if (it >= 1) mbar_wait(BAR(2 + ((it - 1) & 1)), (uint32_t)(((it - 1) >> 1) & 1));   // MMAs of tile it-1 have read the set
             const int slot = sslot[wrow];
             // staged dst half (generic pointer: shared memory, or global for the rare tile with > NDMAX destinations)
@@ -559,17 +589,15 @@ __global__ void __launch_bounds__(F_THREADS, 1) msg_fused_fwd_kernel(const __gri
 
         if (nt > 0) {
             load_row(0);
-            if (warp == 0) {
-                load_pf(0);
-                issue_pf();
-                if (nt > 1) load_pf(1);
-            }
+            load_gsrc(0);
+            gather_src();
         }
         long long tacc[6] = {0, 0, 0, 0, 0, 0};
         const bool timing = A.dbg != nullptr && lane == 0 && (warp == 0 || warp == 9);
         for (int it = 0; it < nt; ++it) {
             long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0;
             if (timing) t0 = clock64();
+            if (it + 1 < nt) load_gsrc(it + 1);     // consumed after the build, by gather_src
             build(it);
             fence_proxy_async();
             __syncwarp();
@@ -577,11 +605,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) msg_fused_fwd_kernel(const __gri
             if (it + 1 < nt) load_row(it + 1);
             if (timing) t1 = clock64();
             named_bar(2, FWT);             // every worker is done with the staged rows of tile it and the tiles of tile it-2
+            if (it + 1 < nt) gather_src();
             if (timing) t2 = clock64();
-            if (warp == 0 && it + 1 < nt) {
-                issue_pf();
-                if (it + 2 < nt) load_pf(it + 2);
-            }
             if (it >= 1) {
                 drain(it - 1);
                 if (timing) t3 = clock64();

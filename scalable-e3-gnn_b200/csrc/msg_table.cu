@@ -393,16 +393,36 @@ __global__ void tr_fill_kernel(const int* __restrict__ src, long long e, unsigne
     if (i < e) perm[atomicAdd(cursor + src[i], 1ull)] = (int)i;
 }
 // the fill order inside a segment is arbitrary: sort every segment ascending by edge id (= stable by source: the
-// summation order of the src pass, and with it the result, is run-to-run deterministic)
-__global__ void tr_sort_kernel(const long long* __restrict__ ptr, long long n, int* __restrict__ perm) {
-    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+// summation order of the src pass, and with it the result, is run-to-run deterministic).  One warp per segment:
+// segments of up to 64 edges (every node of the octree graph: <= 32 + 26 + 8 + 1 neighbours) by rank counting with
+// shuffles (coalesced load, rank = number of smaller ids, scattered store), longer ones by a serial insertion sort.
+__global__ void __launch_bounds__(256) tr_sort_kernel(const long long* __restrict__ ptr, long long n, int* __restrict__ perm) {
+    const int lane = threadIdx.x & 31;
+    const long long j = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (j >= n) return;
     const long long a = ptr[j], b = ptr[j + 1];
-    for (long long i = a + 1; i < b; ++i) {
-        const int v = perm[i];
-        long long k = i;
-        while (k > a && perm[k - 1] > v) { perm[k] = perm[k - 1]; --k; }
-        perm[k] = v;
+    const int len = (int)(b - a);
+    if (len <= 1) return;
+    if (len <= 64) {
+        const int v0 = lane < len ? perm[a + lane] : 0x7fffffff;
+        const int v1 = 32 + lane < len ? perm[a + 32 + lane] : 0x7fffffff;
+        int r0 = 0, r1 = 0;
+#pragma unroll 8
+        for (int l = 0; l < 32; ++l) {
+            const int u0 = __shfl_sync(0xffffffffu, v0, l), u1 = __shfl_sync(0xffffffffu, v1, l);
+            r0 += (u0 < v0) + (u1 < v0);
+            r1 += (u0 < v1) + (u1 < v1);
+        }
+        __syncwarp();
+        if (lane < len) perm[a + r0] = v0;          // edge ids are distinct: ranks are a permutation
+        if (32 + lane < len) perm[a + r1] = v1;
+    } else if (lane == 0) {
+        for (long long i = a + 1; i < b; ++i) {
+            const int v = perm[i];
+            long long k = i;
+            while (k > a && perm[k - 1] > v) { perm[k] = perm[k - 1]; --k; }
+            perm[k] = v;
+        }
     }
 }
 
@@ -523,7 +543,7 @@ extern "C" int se3_graph_transpose(int64_t e, int64_t n_src, const int32_t* src,
     tr_scan_kernel<<<1, 1024, 0, st>>>(cnt, n_src, (long long*)tptr, cursor); SE3_LAUNCHED();
     if (e > 0) {
         tr_fill_kernel<<<(unsigned)((e + 255) / 256), 256, 0, st>>>(src, e, cursor, perm); SE3_LAUNCHED();
-        tr_sort_kernel<<<(unsigned)((n_src + 127) / 128), 128, 0, st>>>((const long long*)tptr, n_src, perm); SE3_LAUNCHED();
+        tr_sort_kernel<<<(unsigned)((n_src + 7) / 8), 256, 0, st>>>((const long long*)tptr, n_src, perm); SE3_LAUNCHED();
     }
     return SE3_OK;
 }

@@ -102,6 +102,8 @@ EXPORTS = [
     ("se3_msg_fused_supported", C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
     ("se3_msg_fused_forward", C.c_int, [C.c_int32, C.c_int32, C.c_int64] + [C.c_void_p] * 10 + [C.c_float, C.c_float]
      + [C.c_void_p] * 5),
+    ("se3_msg_fused_bwdw_parts", C.c_int, [C.c_int32, C.c_int32, _i32p, _i32p]),
+    ("se3_msg_fused_backward_w", C.c_int, [C.c_int32, C.c_int32, C.c_int64] + [C.c_void_p] * 8 + [C.c_int32, C.c_void_p]),
     ("se3_msg1_node_parts", C.c_int, [C.c_int32, C.c_int32, _i32p, _i32p]),
     ("se3_msg1_node_table", C.c_int, [C.c_int32, C.c_int32, C.c_int64] + [C.c_void_p] * 7),
     ("se3_msg1_node_backward", C.c_int, [C.c_int32, C.c_int32, C.c_int64] + [C.c_void_p] * 7 + [C.c_int32]
@@ -110,6 +112,10 @@ EXPORTS = [
      + [C.c_void_p] * 6),
     ("se3_msg_fused_backward", C.c_int, [C.c_int32, C.c_int32, C.c_int64] + [C.c_void_p] * 9 + [C.c_float, C.c_float]
      + [C.c_void_p] * 3),
+    ("se3_domain_work_bytes", C.c_int, [C.c_int64, C.POINTER(C.c_size_t)]),
+    ("se3_domain_mark", C.c_int, [C.c_int64, C.c_int64, C.c_int32, C.c_int32] + [C.c_void_p] * 7 + [C.c_size_t, C.c_void_p]),
+    ("se3_domain_edges", C.c_int, [C.c_int64, C.c_int64, C.c_int32] + [C.c_void_p] * 8 + [C.c_int64, C.c_int64]
+     + [C.c_void_p] * 10 + [C.c_size_t, C.c_void_p]),
     ("se3_rowptr_from_sorted", C.c_int, [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("se3_graph_transpose_work_bytes", C.c_int, [C.c_int64, C.POINTER(C.c_size_t)]),
     ("se3_graph_transpose", C.c_int, [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,

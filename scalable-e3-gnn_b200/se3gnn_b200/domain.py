@@ -64,6 +64,11 @@ class LocalGraph:
     send_counts: List[int] = field(default_factory=list)   # rows sent to each rank
     send_idx: Optional[torch.Tensor] = None                # [sum(send_counts)] int64 local owned ids, grouped by rank
     edge_runs: Optional[list] = None                       # [(a, b)] ranges of the global edge arrays (CSR rows of owned nodes)
+    rowptr: Optional[torch.Tensor] = None                  # [n_own + 1] int64 CSR row pointers of dst (CUDA path)
+    edge_attr: Optional[torch.Tensor] = None               # [e_loc, 4] the rank's rows of the per-edge arrays (CUDA path)
+    edge_extra: Optional[torch.Tensor] = None              # [e_loc, 2]
+    pos: Optional[torch.Tensor] = None                     # [nn] int32 global node -> local id of owned nodes, -1 otherwise
+    counts: Optional[torch.Tensor] = None                  # device int64 [4 + world] (CUDA path, before finish_halo)
 
     @property
     def e(self) -> int:
@@ -138,6 +143,85 @@ def local_graph(rank: int, world: int, n: int, cell_start: torch.Tensor, leaf_of
                     part_lo=lo, own_ids=own_ids, halo_ids=halo_ids, dst=g2l[dg].to(torch.int32),
                     src=g2l[sg].to(torch.int32), edge_ids=e_ids, recv_counts=[int(c) for c in recv_counts])
     lg.edge_runs = runs
+    return lg
+
+
+def local_graph_cuda(rank: int, world: int, g, bounds: Optional[torch.Tensor] = None) -> LocalGraph:
+    """``local_graph`` for an ``OctreeGraph`` on the GPU (csrc/domain.cu): three kernels' worth of passes, ONE small D2H
+    read (the sizes of the local arrays); the halo counts stay on the device for ``finish_halo``.  Same result as the
+    torch version above (which remains the host-logic twin the CPU gloo tests run)."""
+    import ctypes as C
+    from . import capi
+    lib = capi.lib()
+    dev = g.dst.device
+    n, m = g.n, g.m
+    nn = n + m
+    if bounds is None:
+        bounds = slab_bounds(n, world, g.leaf_of_rank, g.cell_start)
+    bounds = bounds.to(torch.int64).contiguous()
+    st = capi.current_stream_ptr()
+    wb = C.c_size_t()
+    capi.check(lib.se3_domain_work_bytes(nn, C.byref(wb)))
+    work = torch.empty(wb.value, device=dev, dtype=torch.uint8)
+    pos = torch.empty(nn, device=dev, dtype=torch.int32)
+    lrp = torch.empty(nn + 1, device=dev, dtype=torch.int64)
+    counts = torch.empty(4 + world, device=dev, dtype=torch.int64)
+    cs = g.cell_start.contiguous()
+    with capi.mark("domain.mark", 8.0 * 3 * nn):
+        capi.check(lib.se3_domain_mark(n, m, rank, world, bounds.data_ptr(), capi.ptr(cs), g.rowptr.data_ptr(), pos.data_ptr(),
+                                       lrp.data_ptr(), counts.data_ptr(), work.data_ptr(), wb.value, st), "se3_domain_mark")
+    n_part, n_own, e_loc, part_lo = (int(v) for v in torch.cat([counts[:3], bounds[rank:rank + 1]]).tolist())   # the one blocking read
+    i32 = dict(device=dev, dtype=torch.int32)
+    own_ids = torch.empty(n_own, **i32)
+    dst_l, src_l = torch.empty(e_loc, **i32), torch.empty(e_loc, **i32)
+    ea = torch.empty((e_loc, 4), device=dev, dtype=torch.float32) if g.edge_attr is not None else None
+    ex = torch.empty((e_loc, 2), device=dev, dtype=torch.float32) if g.edge_extra is not None else None
+    halo_ids = torch.empty(nn, **i32)
+    hpos = torch.empty(nn, **i32)
+    scratch = torch.empty(2 * nn, **i32)
+    with capi.mark("domain.edges", 4.0 * (e_loc * (3 + 6 * 2) + 4 * nn)):
+        capi.check(lib.se3_domain_edges(n, m, world, bounds.data_ptr(), capi.ptr(cs), pos.data_ptr(), lrp.data_ptr(),
+                                        g.rowptr.data_ptr(), g.col.data_ptr(), capi.ptr(g.edge_attr), capi.ptr(g.edge_extra),
+                                        n_own, e_loc, capi.ptr(own_ids), capi.ptr(dst_l), capi.ptr(src_l), capi.ptr(ea),
+                                        capi.ptr(ex), halo_ids.data_ptr(), hpos.data_ptr(), scratch.data_ptr(),
+                                        counts.data_ptr(), work.data_ptr(), wb.value, st), "se3_domain_edges")
+    lg = LocalGraph(rank=rank, world=world, n_global=n, nn_global=nn, n_part=n_part, n_own=n_own, n_halo=-1,
+                    part_lo=part_lo, own_ids=own_ids, halo_ids=halo_ids, dst=dst_l, src=src_l, edge_ids=None,
+                    recv_counts=[])
+    lg.rowptr, lg.edge_attr, lg.edge_extra, lg.pos, lg.counts = lrp[:n_own + 1], ea, ex, pos, counts
+    lg.bounds = bounds
+    return lg
+
+
+def finish_halo(lg: LocalGraph, group=None) -> LocalGraph:
+    """Second half of the CUDA path: per-owner halo counts -> every owner learns what it must send.  One all-gather of
+    the count vectors, ONE blocking read (n_halo, receive and send counts together), one all-to-all-v of the ids."""
+    dev = lg.own_ids.device
+    world = lg.world
+    rc_dev = lg.counts[4:4 + world]
+    live = world > 1 and dist.is_available() and dist.is_initialized()
+    if live:
+        if dist.get_backend(group) == "nccl":
+            mat = torch.empty((world, world), device=dev, dtype=torch.int64)
+            dist.all_gather_into_tensor(mat, rc_dev.contiguous(), group=group)
+        else:   # gloo (single-GPU emulation in the tests): staged through the host
+            parts = [torch.empty(world, dtype=torch.int64) for _ in range(world)]
+            dist.all_gather(parts, rc_dev.cpu(), group=group)
+            mat = torch.stack(parts).to(dev)
+        packed = torch.cat([lg.counts[3:4], rc_dev, mat[:, lg.rank]])
+    else:
+        packed = torch.cat([lg.counts[3:4], rc_dev, rc_dev])
+    vals = [int(v) for v in packed.tolist()]
+    lg.n_halo = vals[0]
+    lg.recv_counts = vals[1:1 + world]
+    lg.send_counts = vals[1 + world:1 + 2 * world]
+    lg.halo_ids = lg.halo_ids[:lg.n_halo]
+    if live:
+        want = torch.empty(sum(lg.send_counts), dtype=torch.int32, device=dev)
+        _a2a(want, lg.halo_ids, lg.send_counts, lg.recv_counts, group)
+        lg.send_idx = lg.pos.index_select(0, want.long()).long()
+    else:
+        lg.send_idx = torch.empty(0, dtype=torch.int64, device=dev)
     return lg
 
 

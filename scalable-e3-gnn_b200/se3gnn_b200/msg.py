@@ -167,7 +167,7 @@ class MsgLayerFn(torch.autograd.Function):
         # the backward kernel stages whole 64-row blocks of the pre-activations with cp.async.bulk: rows rounded up
         epad = (ei.e + 63) // 64 * 64
         pre1 = torch.empty((epad, dpre), device=dev, dtype=torch.float32)[:ei.e]
-        m1 = torch.empty((ei.e, d), device=dev, dtype=torch.float32)
+        m1 = torch.empty((epad, d), device=dev, dtype=torch.float32)[:ei.e]
         pre2 = torch.empty((epad, dpre), device=dev, dtype=torch.float32)[:ei.e]
         agg = torch.zeros((ei.n_dst, d), device=dev, dtype=torch.float32)
         # algorithmic bytes: SH + extras + both indices, the three per-edge tensors the backward reads, the node tables
@@ -200,26 +200,25 @@ class MsgLayerFn(torch.autograd.Function):
         gagg = gagg.contiguous()
         # ---- input-gradient side in ONE tcgen05 kernel: gate VJP (message 2) -> W2^T -> gate VJP (message 1)
         gpre1 = torch.empty_like(pre1)
+        epad = (ei.e + 63) // 64 * 64
+        gpre2 = torch.empty((epad, dpre), device=dev, dtype=torch.float32)[:ei.e]
         rowb = 4.0 * (4 + 1 + dpre)
-        with capi.mark("msg.fused_bwd", ei.e * (rowb + 4.0 * 2 * dpre) + 4.0 * ei.n_dst * d,
+        with capi.mark("msg.fused_bwd", ei.e * (rowb + 4.0 * 3 * dpre) + 4.0 * ei.n_dst * d,
                        2.0 * ei.e * ((ns + nv) * (ns + nv) + ns * nv + 3 * nv * nv + 3 * nv * (ns + nv))):
             capi.check(lib.se3_msg_fused_backward(ns, nv, ei.e, ei.dst.data_ptr(), y.data_ptr(), pre1.data_ptr(),
                                                   pre2.data_ptr(), gagg.data_ptr(), wz2.data_ptr(), wv2.data_ptr(),
-                                                  capi.ptr(nz2), capi.ptr(nv2), cs, cg, gpre1.data_ptr(), None, st),
+                                                  capi.ptr(nz2), capi.ptr(nv2), cs, cg, gpre1.data_ptr(), gpre2.data_ptr(), st),
                        "se3_msg_fused_backward")
-        # ---- weight gradient of message 2 (csrc/l1tp_tc2_bwdw.cu: MN-major tcgen05, accumulators resident in TMEM)
-        a = capi.L1tpBwdArgs()
-        a.rows, a.nseg = ei.e, 1
-        a.seg[0].base, a.seg[0].idx, a.seg[0].width, a.seg[0].ld = m1.data_ptr(), None, d, d
-        a.in2 = y.data_ptr()
-        a.w[0], a.w[3] = wz2.data_ptr(), wv2.data_ptr()
-        a.norm[0], a.norm[3] = capi.ptr(nz2), capi.ptr(nv2)
-        a.epilogue, a.gate_ns, a.gate_cs, a.gate_cg = capi.EPI_GATE, ns, cs, cg
-        a.raw, a.gout, a.gout_idx = pre2.data_ptr(), gagg.data_ptr(), ei.dst.data_ptr()
+        # ---- weight gradient of message 2 (csrc/msg_fused_bwdw.cu: MN-major tcgen05, accumulators resident in TMEM)
         gwz2, gwv2 = torch.empty_like(wz2), torch.empty_like(wv2)
-        a.gw[0], a.gw[3] = gwz2.data_ptr(), gwv2.data_ptr()
-        with capi.mark("msg2.bwdw", ei.e * (rowb + 4.0 * d) + 4.0 * ei.n_dst * d):
-            capi.check(lib.se3_l1tp_backward(ctx.plan2.handle, C.byref(a), st), "se3_l1tp_backward")
+        mp, pf = C.c_int32(), C.c_int32()
+        capi.check(lib.se3_msg_fused_bwdw_parts(ns, nv, C.byref(mp), C.byref(pf)))
+        wparts = torch.empty((mp.value, pf.value), device=dev, dtype=torch.float32)
+        with capi.mark("msg.fused_bwdw", 4.0 * ei.e * (4 + d + dpre),
+                       2.0 * ei.e * ((ns + nv) * (ns + nv) + ns * nv + 3 * nv * nv + 3 * nv * (ns + nv))):
+            capi.check(lib.se3_msg_fused_backward_w(ns, nv, ei.e, y.data_ptr(), m1.data_ptr(), gpre2.data_ptr(),
+                                                    capi.ptr(nz2), capi.ptr(nv2), gwz2.data_ptr(), gwv2.data_ptr(),
+                                                    wparts.data_ptr(), mp.value, st), "se3_msg_fused_backward_w")
         # ---- message 1: transposed SH combine + segment sums (dst rows, then the transposed order), node-level kernels
         G = torch.empty((ei.n_all, 8 * ch), device=dev, dtype=torch.float32)
         parts = torch.empty((int(lib.se3_msg1_max_parts()), 2, ch), device=dev, dtype=torch.float32)

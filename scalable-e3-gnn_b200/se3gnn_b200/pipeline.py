@@ -99,15 +99,14 @@ class TrainStep:
         self.flat_grad.zero_()
         g = build_octree_graph(pos, vel, mass, leaf_size=self.leaf_size)
         self.last_graph = g
-        # (the CSR-row-range variant, rowptr=g.rowptr, measured slower inside the step: ~40 tiny host-bound launches)
-        lg = domain.local_graph(rank, world, g.n, g.cell_start, g.leaf_of_rank, g.dst, g.col)
-        if world > 1:
-            domain.exchange_halo_lists(lg, self.group)
+        # ownership, local CSR, the rank's rows of the per-edge arrays and the halo lists: csrc/domain.cu, two small D2H reads
+        lg = domain.local_graph_cuda(rank, world, g)
+        domain.finish_halo(lg, self.group)
         self.last_local = lg
         halo = (lambda x: domain.halo_exchange(x, lg, self.group)) if world > 1 else None
-        out = self.model(g.x_in.index_select(0, lg.own_ids), domain.gather_rows(g.node_attr, lg.own_ids),
-                         domain.take_edges(lg, g.edge_attr), domain.take_edges(lg, g.edge_extra),
-                         lg.dst, lg.src, halo=halo)
+        own = lg.own_ids.long()
+        out = self.model(g.x_in.index_select(0, own), domain.gather_rows(g.node_attr, own), lg.edge_attr, lg.edge_extra,
+                         lg.dst, lg.src, halo=halo, rowptr=lg.rowptr)
         own_part = g.order[lg.part_lo:lg.part_lo + lg.n_part].long()
         tgt = target.index_select(0, own_part)
         loss = (out[:lg.n_part] - tgt).square().sum() / (3.0 * n)

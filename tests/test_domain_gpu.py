@@ -62,3 +62,34 @@ def test_two_rank_decomposition_matches_single_rank(n, layers):
     for r in res:
         assert abs(r[1] - loss) <= 2e-5 * abs(loss)
         assert np.abs(r[2] - ref).max() <= 1e-4 * scale
+
+
+@pytest.mark.parametrize("n,world", [(20000, 2), (30011, 3), (50000, 8), (300, 8)])
+def test_cuda_local_graph_equals_torch_twin(n, world):
+    """csrc/domain.cu (ownership, local CSR, halo lists grouped by owner) against the torch implementation that the CPU
+    gloo tests run: every array identical, for every rank of the decomposition (no collectives needed: the global graph
+    is replicated)."""
+    from se3gnn_b200 import domain
+    from se3gnn_b200.octree import build_octree_graph
+    from se3gnn_b200.pipeline import synthetic_cloud
+    pos, vel, mass, _ = (torch.from_numpy(a).cuda() for a in synthetic_cloud(n, "plummer", seed=3))
+    g = build_octree_graph(pos, vel, mass)
+    tot_own = tot_e = 0
+    for rank in range(world):
+        ref = domain.local_graph(rank, world, g.n, g.cell_start, g.leaf_of_rank, g.dst, g.col)
+        lg = domain.local_graph_cuda(rank, world, g)
+        domain.finish_halo(lg)          # world > 1 without a process group: only the local part
+        eq = lambda a, b: torch.testing.assert_close(a.long().cpu(), b.long().cpu(), rtol=0, atol=0)
+        assert (lg.n_part, lg.n_own, lg.e, lg.n_halo, lg.part_lo) == (ref.n_part, ref.n_own, ref.e, ref.n_halo, ref.part_lo)
+        eq(lg.own_ids, ref.own_ids)
+        eq(lg.halo_ids, ref.halo_ids)
+        eq(lg.dst, ref.dst)
+        eq(lg.src, ref.src)
+        assert lg.recv_counts == ref.recv_counts
+        torch.testing.assert_close(lg.edge_attr, domain.take_edges(ref, g.edge_attr), rtol=0, atol=0)
+        torch.testing.assert_close(lg.edge_extra, domain.take_edges(ref, g.edge_extra), rtol=0, atol=0)
+        rp = torch.searchsorted(lg.dst.long().contiguous(), torch.arange(lg.n_own + 1, device="cuda"))
+        eq(lg.rowptr, rp)
+        tot_own += lg.n_own
+        tot_e += lg.e
+    assert tot_own == g.n + g.m and tot_e == g.e

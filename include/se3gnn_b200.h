@@ -157,7 +157,9 @@ int se3_msg1_contract(int32_t ns, int32_t nv, const float* gwbig, const float* g
  * combine + gate -> weight contraction of message 2 on the tensor cores (3xTF32) -> SH combine + gate -> sorted-segment
  * sum over dst.  dst [rows] ascending; table / we as above (message 1); wz2 / wv2 / nz2 / nv2: weights_l0e
  * [(ns+nv), ns+nv], weights_l1o [(ns+nv), nv] and norms of message 2.  Writes pre1 [rows, ns+4nv], m1 [rows, ns+3nv],
- * pre2 [rows, ns+4nv] (what the backward reads) and agg [n_dst, ns+3nv] (+=: zero on entry). */
+ * pre2 [rows, ns+4nv] (what the backward reads) and agg [n_dst, ns+3nv] (+=: zero on entry).  pre1 / m1 / pre2 must be
+ * ALLOCATED with the row count rounded up to a multiple of 64: whole 64-row tiles are written with cp.async.bulk (the
+ * rows past `rows` receive unspecified values), and the backward kernels read whole tiles the same way. */
 int se3_msg_fused_supported(int32_t ns, int32_t nv, int32_t n_extra);
 int se3_msg_fused_forward(int32_t ns, int32_t nv, int64_t rows, const int32_t* dst, const int32_t* src,
                           const float* table, const float* we, const float* y, const float* extra, const float* wz2,
@@ -171,7 +173,8 @@ int se3_msg_fused_forward_dbg(int32_t ns, int32_t nv, int64_t rows, const int32_
 /* Input-gradient side of the message layer in one launch (csrc/msg_fused_bwd.cu, tcgen05): cotangent of the aggregate
  * gagg [n_dst, ns+3nv] gathered through dst -> gate VJP of message 2 (pre2) -> contraction with W2^T (3xTF32) -> gate VJP
  * of message 1 (pre1) -> gpre1 [rows, ns+4nv], the input of se3_msg1_edge_backward(pre = NULL).  gpre2 (may be NULL)
- * receives the cotangent of message 2's pre-activation. */
+ * receives the cotangent of message 2's pre-activation.  pre1 / pre2 / gpre1 / gpre2 must be ALLOCATED with the row
+ * count rounded up to a multiple of 64 (whole tiles travel by cp.async.bulk in both directions). */
 int se3_msg_fused_backward(int32_t ns, int32_t nv, int64_t rows, const int32_t* dst, const float* y, const float* pre1,
                            const float* pre2, const float* gagg, const float* wz2, const float* wv2, const float* nz2,
                            const float* nv2, float gate_cs, float gate_cg, float* gpre1, float* gpre2, void* stream);

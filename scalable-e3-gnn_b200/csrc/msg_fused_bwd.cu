@@ -58,8 +58,8 @@ struct FusedBwdArgs {
     const float* wv2;          // [(NS + NV), NV]
     const float* nz2;
     const float* nv2;
-    float* gpre1;              // [E, DPRE]
-    float* gpre2;              // [E, DPRE] or NULL
+    float* gpre1;              // [E rounded up to 64 rows, DPRE]: whole tiles are written by cp.async.bulk
+    float* gpre2;              // [E rounded up to 64 rows, DPRE] or NULL
     float cs, cg;
 };
 
@@ -76,7 +76,8 @@ struct BwdSmem {
     static constexpr int o_p1 = o_p2 + TILEB;                              // staged pre-activation of message 1, two tiles
     static constexpr int o_ga = o_p1 + 2 * TILEB;                          // staged cotangent rows of the distinct destinations
     static constexpr int o_slot = o_ga + BNDMAX * F::D * 4;
-    static constexpr int o_bar = o_slot + BTM * 4;
+    static constexpr int o_g2t = (o_slot + BTM * 4 + 127) & ~127;            // cotangent of message 2's pre-activation (bulk-stored)
+    static constexpr int o_bar = o_g2t + TILEB;
     static constexpr int total = o_bar + 12 * 8 + 16;
 };
 
@@ -89,6 +90,13 @@ __device__ __forceinline__ void bmbar_arrive_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(bar), "r"(bytes) : "memory");
 }
 
+__device__ __forceinline__ void bbulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bbulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bbulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bbulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 template <int NS, int NV>
 __global__ void __launch_bounds__(B_THREADS, 1) msg_fused_bwd_kernel(const __grid_constant__ FusedBwdArgs A) {
     using F = BwdDims<NS, NV>;
@@ -99,7 +107,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) msg_fused_bwd_kernel(const __gri
     uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + SM::o_bar);
     const uint32_t bar0 = smem_u32(bars);
     // barriers: 0,1 operand set full | 2,3 accumulator full | 4,5 accumulator empty | 6 staged rows of the build landed |
-    //           7,8 staged pre-activation of message 1 landed (even / odd tiles)
+    //           7,8 staged pre-activation of message 1 landed (even / odd tiles) | 9 result tile stored (free)
     auto BAR = [&](int i) { return bar0 + 8u * i; };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
@@ -112,6 +120,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) msg_fused_bwd_kernel(const __gri
         mbar_init(BAR(6), 1);
         mbar_init(BAR(7), 1);
         mbar_init(BAR(8), 1);
+        mbar_init(BAR(9), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     {
@@ -215,6 +224,13 @@ __global__ void __launch_bounds__(B_THREADS, 1) msg_fused_bwd_kernel(const __gri
             const int b = it & 1;
             const uint32_t ph = (it >> 1) & 1;
             mbar_wait(BAR(b), ph);
+            if (lane == 0 && A.gpre2) {        // cotangent of message 2's pre-activation of this tile: one bulk store; the prefetch
+                const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * BTM;   // below waits for its reads
+                bbulk_s2g(A.gpre2 + row0 * F::DPRE, sb + SM::o_g2t, BTM * F::DPRE * 4);
+                bbulk_commit();
+                bbulk_wait_read0();
+            }
+            __syncwarp();
             if (it + 1 < nt) {                 // the build staging is free: every worker arrived from build(it).  Issued BEFORE
                 issue_pf(it + 1);              // the MMAs (their issue takes ~3k cycles of this thread; the copies are needed first)
                 if (it + 2 < nt) load_pf(it + 2);
@@ -251,6 +267,27 @@ __global__ void __launch_bounds__(B_THREADS, 1) msg_fused_bwd_kernel(const __gri
                         tc_mma_tf32(acc + F::cT + c * NDP, a3l + oa, bTh + o, idD, 1u);
                     }
                 tc_commit(BAR(2 + b));
+            }
+            __syncwarp();
+            if (it >= 1) {                     // result tile (g_pre1) of tile it-1: stored as soon as its drain is complete
+                mbar_wait(BAR(4 + ((it - 1) & 1)), (uint32_t)(((it - 1) >> 1) & 1));
+                if (lane == 0) {
+                    const long long row0 = ((long long)blockIdx.x + (long long)(it - 1) * gridDim.x) * BTM;
+                    bbulk_s2g(A.gpre1 + row0 * F::DPRE, sb + SM::o_out, BTM * F::DPRE * 4);
+                    bbulk_commit();
+                    bbulk_wait_read0();
+                    mbar_arrive(BAR(9));
+                }
+                __syncwarp();
+            }
+        }
+        if (nt > 0) {
+            mbar_wait(BAR(4 + ((nt - 1) & 1)), (uint32_t)(((nt - 1) >> 1) & 1));
+            if (lane == 0) {
+                const long long row0 = ((long long)blockIdx.x + (long long)(nt - 1) * gridDim.x) * BTM;
+                bbulk_s2g(A.gpre1 + row0 * F::DPRE, sb + SM::o_out, BTM * F::DPRE * 4);
+                bbulk_commit();
+                bbulk_wait0();
             }
             __syncwarp();
         }
@@ -297,8 +334,8 @@ __global__ void __launch_bounds__(B_THREADS, 1) msg_fused_bwd_kernel(const __gri
             const int slot = sslot[wrow];
             const float* gm = slot < BNDMAX ? reinterpret_cast<const float*>(smraw + SM::o_ga) + slot * F::D
                                             : A.gagg + (long long)n_dst * F::D;
-            float* go = A.gpre2 ? A.gpre2 + gr * F::DPRE : nullptr;
-            const bool wr = valid && go != nullptr;
+            float* go = reinterpret_cast<float*>(smraw + SM::o_g2t) + wrow * F::DPRE;   // tile rows, bulk-stored by the MMA warp
+            const bool wr = A.gpre2 != nullptr;
             auto ld2s = [&](const float* q) { return *reinterpret_cast<const float2*>(q); };
             auto ld4s = [&](const float* q) { return *reinterpret_cast<const float4*>(q); };
 #pragma unroll
@@ -386,6 +423,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) msg_fused_bwd_kernel(const __gri
             const float4 ya = ypre, yb = ypre2;
             mbar_wait(BAR(2 + b), (it >> 1) & 1);
             mbar_wait(BAR(7 + (it & 1)), (uint32_t)((it >> 1) & 1));
+            if (it >= 1) mbar_wait(BAR(9), (uint32_t)((it - 1) & 1));     // the result tile of tile it-1 has been stored
             tc_fence_after();
             const uint32_t acc = tmem_base + (uint32_t)b * F::ACC + ((uint32_t)(32 * e) << 16);
             float* oa = otile + (16 * e + fg) * F::DPRE;
@@ -429,18 +467,10 @@ __global__ void __launch_bounds__(B_THREADS, 1) msg_fused_bwd_kernel(const __gri
                 }
             }
             tc_fence_before();
+            fence_proxy_async();               // the result tile is read by a bulk store (async proxy)
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(4 + b));
         };
-        auto finish = [&](int it) {
-            const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * BTM;
-            const int nvalid = (int)min((long long)BTM, R - row0);
-            float* dstp = A.gpre1 + row0 * F::DPRE;
-            const int total = nvalid * F::DPRE, n4 = total >> 2;
-            for (int t = tid; t < n4; t += BWT) reinterpret_cast<float4*>(dstp)[t] = reinterpret_cast<const float4*>(otile)[t];
-            for (int t = (n4 << 2) + tid; t < total; t += BWT) dstp[t] = otile[t];
-        };
-
         if (nt > 0) load_row(0);
         for (int it = 0; it < nt; ++it) {
             build(it);
@@ -448,20 +478,12 @@ __global__ void __launch_bounds__(B_THREADS, 1) msg_fused_bwd_kernel(const __gri
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(it & 1));
             if (it + 1 < nt) load_row(it + 1);
-            named_bar(2, BWT);             // every worker is done with the staged rows of tile it and the result tile of tile it-2
-            if (it >= 1) {
-                drain(it - 1);
-                named_bar(1, BWT);
-                finish(it - 1);
-            }
+            // no CTA-wide barrier: every hand-off is an mbarrier (staged rows and slots: issued by the MMA warp once all
+            // workers arrived from the build; operand set: MMAs of the previous tile; result tile: its bulk store)
+            if (it >= 1) drain(it - 1);
             prefetch_x(it);
         }
-        if (nt > 0) {
-            named_bar(2, BWT);
-            drain(nt - 1);
-            named_bar(1, BWT);
-            finish(nt - 1);
-        }
+        if (nt > 0) drain(nt - 1);
     }
     tc_fence_before();
     __syncthreads();

@@ -199,8 +199,8 @@ class MsgLayerFn(torch.autograd.Function):
         ch, d, dpre = ns + 2 * nv, ns + 3 * nv, ns + 4 * nv
         gagg = gagg.contiguous()
         # ---- input-gradient side in ONE tcgen05 kernel: gate VJP (message 2) -> W2^T -> gate VJP (message 1)
-        gpre1 = torch.empty_like(pre1)
         epad = (ei.e + 63) // 64 * 64
+        gpre1 = torch.empty((epad, dpre), device=dev, dtype=torch.float32)[:ei.e]
         gpre2 = torch.empty((epad, dpre), device=dev, dtype=torch.float32)[:ei.e]
         rowb = 4.0 * (4 + 1 + dpre)
         with capi.mark("msg.fused_bwd", ei.e * (rowb + 4.0 * 3 * dpre) + 4.0 * ei.n_dst * d,

@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--leaf", type=int, default=32)
     ap.add_argument("--cpu-sample", type=int, default=100_000, help="upper bound of the CPU arm's particles per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--force-dd", action="store_true",
+                    help="diagnostics: run the domain-decomposed code path on one GPU (world 1: no halo, no collectives)")
     ap.add_argument("--no-other-configs", action="store_true",
                     help="skip BASELINE configs[2..4] (measured after the headline region into `other_configs`)")
     ap.add_argument("--no-parity", action="store_true", help="skip the step-0 loss check against the CPU oracle")
@@ -317,7 +319,7 @@ def run_b200(a):
 
     torch.manual_seed(0)
     model = SEGNN(num_layers=a.layers).to(dev)
-    dd = world > 1 and a.parallel == "dd"
+    dd = (world > 1 or a.force_dd) and a.parallel == "dd"
     ts = TrainStep(model, leaf_size=a.leaf, distributed=world > 1 and not dd, decompose=dd)
     n = a.particles
     if dd:

@@ -10,6 +10,7 @@ concatenated row, followed by the public-SEGNN swish gate.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -145,6 +146,19 @@ def msg1(xe, wz, wv, nz, nvn, y, extra, ei: EdgeIndex, ns: int, nv: int, cs: flo
 
 # ------------------------------------------------------------------------------------------------ fused message layer
 DBG_TIMING = None   # tools/bench_msg.py --timing sets this to a list: receives the phase cycle counters of every forward
+# weight-gradient kernel of message 2 on a side stream: OFF.  Measured (gpurun c3): no gain end to end (16.61 vs 16.44 ms
+# per step) and a slower device-timed loop; the kernel's one CTA per SM (196 KB of shared memory) leaves no room for the
+# kernels it was meant to overlap with.  SE3_OVERLAP=1 re-enables it for experiments.
+OVERLAP_BWDW = os.environ.get("SE3_OVERLAP", "0") == "1"
+_SIDE = {}
+
+
+def _side_stream(dev):
+    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    s = _SIDE.get(key)
+    if s is None:
+        s = _SIDE[key] = torch.cuda.Stream(device=dev)
+    return s
 def fused_supported(ns: int, nv: int, n_extra: int) -> bool:
     return bool(capi.lib().se3_msg_fused_supported(ns, nv, n_extra)) and supported(ns, nv, n_extra)
 
@@ -214,11 +228,18 @@ class MsgLayerFn(torch.autograd.Function):
         mp, pf = C.c_int32(), C.c_int32()
         capi.check(lib.se3_msg_fused_bwdw_parts(ns, nv, C.byref(mp), C.byref(pf)))
         wparts = torch.empty((mp.value, pf.value), device=dev, dtype=torch.float32)
+        # It depends only on g_pre2 and nothing below depends on it; optionally (SE3_OVERLAP=1, see OVERLAP_BWDW) on a side
+        # stream, joined before this function returns.
+        side = _side_stream(dev) if (capi._prof is None and OVERLAP_BWDW) else None
+        main = torch.cuda.current_stream(dev)
+        if side is not None:
+            side.wait_stream(main)
         with capi.mark("msg.fused_bwdw", 4.0 * ei.e * (4 + d + dpre),
                        2.0 * ei.e * ((ns + nv) * (ns + nv) + ns * nv + 3 * nv * nv + 3 * nv * (ns + nv))):
             capi.check(lib.se3_msg_fused_backward_w(ns, nv, ei.e, y.data_ptr(), m1.data_ptr(), gpre2.data_ptr(),
                                                     capi.ptr(nz2), capi.ptr(nv2), gwz2.data_ptr(), gwv2.data_ptr(),
-                                                    wparts.data_ptr(), mp.value, st), "se3_msg_fused_backward_w")
+                                                    wparts.data_ptr(), mp.value, side.cuda_stream if side is not None else st),
+                       "se3_msg_fused_backward_w")
         # ---- message 1: transposed SH combine + segment sums (dst rows, then the transposed order), node-level kernels
         G = torch.empty((ei.n_all, 8 * ch), device=dev, dtype=torch.float32)
         parts = torch.empty((int(lib.se3_msg1_max_parts()), 2, ch), device=dev, dtype=torch.float32)
@@ -230,6 +251,8 @@ class MsgLayerFn(torch.autograd.Function):
                        "se3_msg1_edge_backward")
         gx, gwz1, gwv1 = _node_backward(xe, G, wz1, wv1, nz1, nv1, parts, nparts.value, ns, nv, ei.n_all,
                                         ctx.needs_input_grad[0], "msg.node_bwd")
+        if side is not None:
+            main.wait_stream(side)      # gwz2 / gwv2 (and the scratch they were built from) are complete from here on
         return (gx, gwz1, gwv1, None, None, gwz2, gwv2, None, None) + (None,) * 8
 
 

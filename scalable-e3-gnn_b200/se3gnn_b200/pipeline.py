@@ -112,9 +112,11 @@ class TrainStep:
         loss = (out[:lg.n_part] - tgt).square().sum() / (3.0 * n)
         loss.backward()
         lossd = loss.detach().clone()
-        if world > 1:
-            dist.all_reduce(self.flat_grad, group=self.group)
-            dist.all_reduce(lossd, group=self.group)
+        if world > 1:   # ONE collective for the weight gradients and the loss
+            buf = torch.cat([self.flat_grad, lossd.reshape(1)])
+            dist.all_reduce(buf, group=self.group)
+            self.flat_grad.copy_(buf[:-1])
+            lossd = buf[-1].clone()
         self.opt.step()
         return lossd
 

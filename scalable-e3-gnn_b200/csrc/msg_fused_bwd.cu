@@ -20,6 +20,7 @@
 // index: L1 hits) + gate VJP in registers + tf32 hi/lo K-major operand stores; drain = tcgen05.ld 16x256b, SH combine,
 // gate VJP with the prefetched pre-activation of message 1, result tile in shared memory; finish = coalesced copy-out.
 #include <algorithm>
+#include <type_traits>
 
 #include "tc_common.cuh"
 
@@ -72,13 +73,14 @@ struct BwdSmem {
     static constexpr int o_t = (o_bt + 2 * F::NDP * F::KV * 4 + 1023) & ~1023;
     static constexpr int o_out = o_t + F::TBYTES;           // ONE operand set (see msg_fused_fwd.cu)
     static constexpr int TILEB = (BTM * F::DPRE * 4 + 127) & ~127;
-    static constexpr int o_p2 = (o_out + TILEB + 127) & ~127;              // staged pre-activation of message 2 (this tile)
-    static constexpr int o_p1 = o_p2 + TILEB;                              // staged pre-activation of message 1, two tiles
-    static constexpr int o_ga = o_p1 + 2 * TILEB;                          // staged cotangent rows of the distinct destinations
-    static constexpr int o_slot = o_ga + BNDMAX * F::D * 4;
-    static constexpr int o_g2t = (o_slot + BTM * 4 + 127) & ~127;            // cotangent of message 2's pre-activation (bulk-stored)
+    static constexpr int o_p2 = (o_out + TILEB + 127) & ~127;              // staged pre-activation of message 2, two tiles
+    static constexpr int o_p1 = o_p2 + 2 * TILEB;                          // staged pre-activation of message 1, two tiles
+    static constexpr int GAB = BNDMAX * F::D * 4;
+    static constexpr int o_ga = o_p1 + 2 * TILEB;                          // staged cotangent rows of the distinct destinations, two tiles
+    static constexpr int o_slot = o_ga + 2 * GAB;                          // row -> slot, two tiles
+    static constexpr int o_g2t = (o_slot + 2 * (BTM + 4) * 4 + 127) & ~127;        // cotangent of message 2's pre-activation (bulk-stored)
     static constexpr int o_bar = o_g2t + TILEB;
-    static constexpr int total = o_bar + 12 * 8 + 16;
+    static constexpr int total = o_bar + 14 * 8 + 16;
 };
 
 __device__ __forceinline__ void bbulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -106,10 +108,12 @@ __global__ void __launch_bounds__(B_THREADS, 1) msg_fused_bwd_kernel(const __gri
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + SM::o_bar);
     const uint32_t bar0 = smem_u32(bars);
-    // barriers: 0,1 operand set full | 2,3 accumulator full | 4,5 accumulator empty | 6 staged rows of the build landed |
-    //           7,8 staged pre-activation of message 1 landed (even / odd tiles) | 9 result tile stored (free)
+    // barriers: 0,1 operand set full | 2,3 accumulator full | 4,5 accumulator empty | 6,10 staged rows of the build landed
+    //           (even / odd tiles: the staging is double buffered, the copies are issued TWO tiles ahead) |
+    //           7,8 staged pre-activation of message 1 landed (even / odd tiles) | 9 result tile stored (free) |
+    //           11 g_pre2 tile stored (free)
     auto BAR = [&](int i) { return bar0 + 8u * i; };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
@@ -118,6 +122,8 @@ __global__ void __launch_bounds__(B_THREADS, 1) msg_fused_bwd_kernel(const __gri
             mbar_init(BAR(4 + i), BWK);
         }
         mbar_init(BAR(6), 1);
+        mbar_init(BAR(10), 1);
+        mbar_init(BAR(11), 1);
         mbar_init(BAR(7), 1);
         mbar_init(BAR(8), 1);
         mbar_init(BAR(9), 1);
@@ -193,17 +199,21 @@ __global__ void __launch_bounds__(B_THREADS, 1) msg_fused_bwd_kernel(const __gri
             const unsigned b0 = __ballot_sync(0xffffffffu, f0), b1 = __ballot_sync(0xffffffffu, f1);
             const unsigned le = 0xffffffffu >> (31 - lane);
             const int s0 = __popc(b0 & le), s1 = __popc(b0) + __popc(b1 & le);
-            sslot[lane] = s0;
-            sslot[lane + 32] = s1;
-            const int ncopy = min(__popc(b0) + __popc(b1) + 1, BNDMAX);
+            const int pb = it & 1;
+            const uint32_t pbar = pb ? BAR(10) : BAR(6);
+            sslot[pb * (BTM + 4) + lane] = s0;
+            sslot[pb * (BTM + 4) + lane + 32] = s1;
+            const int ndist = __popc(b0) + __popc(b1) + 1;
+            const int ncopy = min(ndist, BNDMAX);
+            if (lane == 0) sslot[pb * (BTM + 4) + BTM] = ndist > BNDMAX ? 1 : 0;
             constexpr uint32_t blk = BTM * F::DPRE * 4;
             if (lane == 0) {
-                bmbar_arrive_tx(BAR(6), blk + ncopy * F::D * 4);
-                bbulk_g2s(sm_u32 + SM::o_p2, A.pre2 + row0 * F::DPRE, blk, BAR(6));
+                bmbar_arrive_tx(pbar, blk + ncopy * F::D * 4);
+                bbulk_g2s(sm_u32 + SM::o_p2 + pb * SM::TILEB, A.pre2 + row0 * F::DPRE, blk, pbar);
             }
             __syncwarp();
-            if ((lane == 0 || f0) && s0 < BNDMAX) bbulk_g2s(sm_u32 + SM::o_ga + s0 * F::D * 4, A.gagg + (long long)pf_dst0 * F::D, F::D * 4, BAR(6));
-            if (f1 && s1 < BNDMAX) bbulk_g2s(sm_u32 + SM::o_ga + s1 * F::D * 4, A.gagg + (long long)pf_dst1 * F::D, F::D * 4, BAR(6));
+            if ((lane == 0 || f0) && s0 < BNDMAX) bbulk_g2s(sm_u32 + SM::o_ga + pb * SM::GAB + s0 * F::D * 4, A.gagg + (long long)pf_dst0 * F::D, F::D * 4, pbar);
+            if (f1 && s1 < BNDMAX) bbulk_g2s(sm_u32 + SM::o_ga + pb * SM::GAB + s1 * F::D * 4, A.gagg + (long long)pf_dst1 * F::D, F::D * 4, pbar);
         };
         // pre-activation of message 1 of tile `it` -> buffer it & 1 (read by drain(it), two iterations after this is issued:
         // the buffer is free once drain(it - 2) is complete, i.e. after the named barrier that follows it)
@@ -218,7 +228,8 @@ __global__ void __launch_bounds__(B_THREADS, 1) msg_fused_bwd_kernel(const __gri
         if (nt > 0) {
             load_pf(0);
             issue_pf(0);
-            if (nt > 1) load_pf(1);
+            if (nt > 1) { load_pf(1); issue_pf(1); }
+            if (nt > 2) load_pf(2);
         }
         for (int it = 0; it < nt; ++it) {
             const int b = it & 1;
@@ -229,11 +240,12 @@ __global__ void __launch_bounds__(B_THREADS, 1) msg_fused_bwd_kernel(const __gri
                 bbulk_s2g(A.gpre2 + row0 * F::DPRE, sb + SM::o_g2t, BTM * F::DPRE * 4);
                 bbulk_commit();
                 bbulk_wait_read0();
+                mbar_arrive(BAR(11));          // the next build may overwrite the tile
             }
             __syncwarp();
-            if (it + 1 < nt) {                 // the build staging is free: every worker arrived from build(it).  Issued BEFORE
-                issue_pf(it + 1);              // the MMAs (their issue takes ~3k cycles of this thread; the copies are needed first)
-                if (it + 2 < nt) load_pf(it + 2);
+            if (it + 2 < nt) {                 // staging buffer it & 1 is free: every worker arrived from build(it).  Issued BEFORE
+                issue_pf(it + 2);              // the MMAs (their issue takes ~3k cycles of this thread), TWO tiles ahead: a bulk
+                if (it + 3 < nt) load_pf(it + 3);   // copy needs longer to land than the drain of one tile takes
             }
             mbar_wait(BAR(4 + b), ph ^ 1);     // drain(it - 2) done: accumulator b AND staging buffer b of message 1 are free
             issue_p1(it);
@@ -321,19 +333,20 @@ __global__ void __launch_bounds__(B_THREADS, 1) msg_fused_bwd_kernel(const __gri
             *reinterpret_cast<float2*>(p + F::HALFB) = l;
         };
         auto swish_vjp = [&](float g, float x) { const float s = sigm(x); return A.cs * g * s * fmaf(x, 1.0f - s, 1.0f); };
-        auto build = [&](int it) {
+        // OVF: the tile has more than BNDMAX distinct destinations (rare): the cotangent rows past the staged slots come from
+        // global memory through a generic pointer; in the common case every load of the build is an LDS
+        auto build_body = [&](int it, auto OVF) {
             unsigned char* tset = smraw + SM::o_t;
             const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * BTM;
             long long gr = row0 + wrow;
             const bool valid = gr < R;
             if (!valid) gr = R - 1;
             const float4 y = n_y;
-            mbar_wait(BAR(6), (uint32_t)(it & 1));
-            if (it >= 1) mbar_wait(BAR(2 + ((it - 1) & 1)), (uint32_t)(((it - 1) >> 1) & 1));   // MMAs of tile it-1 have read the set
-            const float* pre = reinterpret_cast<const float*>(smraw + SM::o_p2) + wrow * F::DPRE;
-            const int slot = sslot[wrow];
-            const float* gm = slot < BNDMAX ? reinterpret_cast<const float*>(smraw + SM::o_ga) + slot * F::D
-                                            : A.gagg + (long long)n_dst * F::D;
+            const int pb = it & 1;
+            const float* pre = reinterpret_cast<const float*>(smraw + SM::o_p2 + pb * SM::TILEB) + wrow * F::DPRE;
+            const int slot = sslot[pb * (BTM + 4) + wrow];
+            const float* gms = reinterpret_cast<const float*>(smraw + SM::o_ga + pb * SM::GAB) + (slot < BNDMAX ? slot : 0) * F::D;
+            const float* gm = (decltype(OVF)::value && slot >= BNDMAX) ? A.gagg + (long long)n_dst * F::D : gms;
             float* go = reinterpret_cast<float*>(smraw + SM::o_g2t) + wrow * F::DPRE;   // tile rows, bulk-stored by the MMA warp
             const bool wr = A.gpre2 != nullptr;
             auto ld2s = [&](const float* q) { return *reinterpret_cast<const float2*>(q); };
@@ -387,6 +400,14 @@ __global__ void __launch_bounds__(B_THREADS, 1) msg_fused_bwd_kernel(const __gri
                     st_hl2(t3 + 2 * F::halfT3, q02, q12);
                 }
             }
+        };
+        auto build = [&](int it) {
+            const int pb = it & 1;
+            mbar_wait(pb ? BAR(10) : BAR(6), (uint32_t)((it >> 1) & 1));
+            if (it >= 1 && A.gpre2) mbar_wait(BAR(11), (uint32_t)((it - 1) & 1));    // the g_pre2 tile of tile it-1 has been stored
+            if (it >= 1) mbar_wait(BAR(2 + ((it - 1) & 1)), (uint32_t)(((it - 1) >> 1) & 1));   // MMAs of tile it-1 have read the set
+            if (sslot[pb * (BTM + 4) + BTM] == 0) build_body(it, std::false_type{});
+            else build_body(it, std::true_type{});
         };
         // ---- epilogue: warp = (lane quarter e, task pair jq): tasks jq and jq + 4 of [SB scalar blocks | VB vector blocks]
         const int e = warp & 3, jq = warp >> 2;

@@ -303,28 +303,34 @@ __global__ void __launch_bounds__(W_THREADS, 1) msg_fused_bwdw_kernel(const __gr
 
 // gwz [(NS + NV), MZ], gwv [(NS + NV), NV] (overwritten): fixed-order sum of the per-CTA partials, norms and 1/sqrt(3)
 template <int NS, int NV>
-__global__ void msg_fused_bwdw_reduce_kernel(const float* __restrict__ part, int nparts, const float* nz, const float* nvn,
-                                             float* __restrict__ gwz, float* __restrict__ gwv) {
+__global__ void __launch_bounds__(256) msg_fused_bwdw_reduce_kernel(const float* __restrict__ part, int nparts, const float* nz,
+                                                                    const float* nvn, float* __restrict__ gwz, float* __restrict__ gwv) {
     using F = WDims<NS, NV>;
     constexpr int MZ = F::MZ, CH = MZ + NV, ROWS = NS + NV;
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ROWS * CH; t += gridDim.x * blockDim.x) {
+    // one warp per output element: lane l sums partials l, l + 32, ... (fixed order), then a shuffle tree
+    const int lane = threadIdx.x & 31;
+    for (int t = blockIdx.x * 8 + (threadIdx.x >> 5); t < ROWS * CH; t += gridDim.x * 8) {
         const int k = t / CH, ch = t - k * CH;          // k: input channel (scalars, then vectors); ch: output channel
         float g = 0.0f;
         if (k < NS) {
             const float* p = part + ch * 64 + k;                                   // A12[T1 slot ch][S slot k]
-            for (int q = 0; q < nparts; ++q) g += p[(long long)q * F::PART];
+            for (int q = lane; q < nparts; q += 32) g += p[(long long)q * F::PART];
         } else if (ch < MZ) {
             const float* p = part + (64 + ch) * 64 + 48 + (k - NS);                // A12[HZ slot ch][D slot]
-            for (int q = 0; q < nparts; ++q) g += p[(long long)q * F::PART];
+            for (int q = lane; q < nparts; q += 32) g += p[(long long)q * F::PART];
             g *= C3f;
         } else {
             for (int c = 0; c < 3; ++c) {                                          // A3[HVc slot][Vc slot]: diagonal block c
                 const float* p = part + 128 * 64 + (16 * c + ch - MZ) * 48 + 16 * c + (k - NS);
-                for (int q = 0; q < nparts; ++q) g += p[(long long)q * F::PART];
+                for (int q = lane; q < nparts; q += 32) g += p[(long long)q * F::PART];
             }
         }
-        if (ch < MZ) gwz[k * MZ + ch] = g * (nz ? nz[ch] : 1.0f);
-        else gwv[k * NV + ch - MZ] = g * C3f * (nvn ? nvn[3 * (ch - MZ)] : 1.0f);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+        if (lane == 0) {
+            if (ch < MZ) gwz[k * MZ + ch] = g * (nz ? nz[ch] : 1.0f);
+            else gwv[k * NV + ch - MZ] = g * C3f * (nvn ? nvn[3 * (ch - MZ)] : 1.0f);
+        }
     }
 }
 
@@ -346,7 +352,7 @@ static int msg_fused_bwdw_launch(const FusedBwdWArgs& A0, const float* nz, const
     msg_fused_bwdw_kernel<NS, NV><<<grid, W_THREADS, std::max(SM::total, 120 * 1024), st>>>(A0);
     SE3_LAUNCHED();
     g_tc_launches.fetch_add(1, std::memory_order_relaxed);
-    msg_fused_bwdw_reduce_kernel<NS, NV><<<16, 256, 0, st>>>(A0.partials, grid, nz, nvn, gwz, gwv);
+    msg_fused_bwdw_reduce_kernel<NS, NV><<<num_sms(), 256, 0, st>>>(A0.partials, grid, nz, nvn, gwz, gwv);
     SE3_LAUNCHED();
     return SE3_OK;
 }

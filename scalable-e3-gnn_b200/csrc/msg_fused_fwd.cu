@@ -22,6 +22,7 @@
 //   * drain: tcgen05.ld 16x256b -> 4 FMAs per channel with the SH -> gate in registers -> pre-activation tile and
 //     message tile in shared memory;  finish: coalesced copy of the pre-activation, sorted-segment sum of the messages.
 #include <algorithm>
+#include <type_traits>
 
 #include "tc_common.cuh"
 
@@ -127,7 +128,7 @@ struct FusedSmem {
     static constexpr int o_stg = (o_hs + 127) & ~127;   // src table rows of the next tile (cp.async.bulk)
     static constexpr int o_dstg = o_stg + FTM * F::STGB;                // its distinct dst table rows (first NDMAX)
     static constexpr int o_slot = o_dstg + NDMAX * F::STGB;             // row -> dst slot
-    static constexpr int total = o_slot + FTM * 4;
+    static constexpr int total = o_slot + FTM * 4 + 16;                 // + the overflow flag
 };
 
 __device__ __forceinline__ void fbulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -252,7 +253,9 @@ __global__ void __launch_bounds__(F_THREADS, 1) msg_fused_fwd_kernel(const __gri
             const int s0 = __popc(b0 & le), s1 = __popc(b0) + __popc(b1 & le);
             sslot[lane] = s0;
             sslot[lane + 32] = s1;
-            const int ncopy = min(__popc(b0) + __popc(b1) + 1, NDMAX);
+            const int ndist = __popc(b0) + __popc(b1) + 1;
+            const int ncopy = min(ndist, NDMAX);
+            if (lane == 0) sslot[FTM] = ndist > NDMAX ? 1 : 0;
             if (lane == 0) fmbar_arrive_tx(BAR(7), ncopy * F::HALF * 4);
             __syncwarp();
             const uint32_t dstg_u32 = stg_u32 + (SM::o_dstg - SM::o_stg);
@@ -361,7 +364,9 @@ __global__ void __launch_bounds__(F_THREADS, 1) msg_fused_fwd_kernel(const __gri
             const float P = a.x + b.x + fmaf(ex.x, we_s[ch], ex.y * we_s[CH + ch]);
             return fmaf(y.x, P, fmaf(y.y, a.y + b.y, fmaf(y.z, a.z + b.z, y.w * (a.w + b.w))));
         };
-        auto build = [&](int it) {
+        // OVF: the tile has more than NDMAX distinct destinations (rare): the dst halves of the rows past the staged slots
+        // come straight from global memory through a generic pointer; in the common case every table load is an LDS
+        auto build_body = [&](int it, auto OVF) {
             unsigned char* aset = smraw + SM::o_a;
             const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * FTM;
             const long long gr = row0 + wrow;
@@ -370,13 +375,9 @@ __global__ void __launch_bounds__(F_THREADS, 1) msg_fused_fwd_kernel(const __gri
             const float2 ex = n_ex;
             const float* ts = reinterpret_cast<const float*>(smraw + SM::o_stg + wrow * F::STGB);   // staged src half
             auto lds4 = [&](const float* q) { return *reinterpret_cast<const float4*>(q); };
-            mbar_wait(BAR(6), (uint32_t)(it & 1));
-            mbar_wait(BAR(7), (uint32_t)(it & 1));
-            if (it >= 1) mbar_wait(BAR(2 + ((it - 1) & 1)), (uint32_t)(((it - 1) >> 1) & 1));   // MMAs of tile it-1 have read the set
             const int slot = sslot[wrow];
-            // staged dst half (generic pointer: shared memory, or global for the rare tile with > NDMAX destinations)
-            const float* td = slot < NDMAX ? reinterpret_cast<const float*>(smraw + SM::o_dstg + slot * F::STGB)
-                                           : A.table + (long long)n_dst * F::LDT;
+            const float* tds = reinterpret_cast<const float*>(smraw + SM::o_dstg + (slot < NDMAX ? slot : 0) * F::STGB);
+            const float* td = (decltype(OVF)::value && slot >= NDMAX) ? A.table + (long long)n_dst * F::LDT : tds;
             float* pre = A.pre1 + gr * F::DPRE;
             float* m1 = A.m1 + gr * F::D;
 #pragma unroll
@@ -447,6 +448,13 @@ __global__ void __launch_bounds__(F_THREADS, 1) msg_fused_fwd_kernel(const __gri
                     st_hl2(v0 + 2 * F::halfV, q02, q12);
                 }
             }
+        };
+        auto build = [&](int it) {
+            mbar_wait(BAR(6), (uint32_t)(it & 1));
+            mbar_wait(BAR(7), (uint32_t)(it & 1));
+            if (it >= 1) mbar_wait(BAR(2 + ((it - 1) & 1)), (uint32_t)(((it - 1) >> 1) & 1));   // MMAs of tile it-1 have read the set
+            if (sslot[FTM] == 0) build_body(it, std::false_type{});
+            else build_body(it, std::true_type{});
         };
         // ---- epilogue
         const int e = warp & 3, jq = warp >> 2;

@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(448) msg1_node_gw_kernel(const float* __restri
         if (grp < 3) {
 #pragma unroll 4
             for (int r = 0; r < GW_TILE; ++r) {
-                const float g = gs[r * LDT + 4 * pc];
+                const float g = reinterpret_cast<const float4*>(gs + r * LDT + 4 * pc)->x;   // 16-byte load: conflict-free
                 const float* xr = xs + r * D + kbeg;
 #pragma unroll
                 for (int i = 0; i < Gm::MAXA; ++i)
@@ -210,27 +210,33 @@ __global__ void __launch_bounds__(448) msg1_node_gw_kernel(const float* __restri
 // gwz [(2NS+2+2NV), MZ], gwv [(same), NV] overwritten: sum of the per-block partials (fixed order) with the folded
 // factors, plus the extras' rows from the per-block partials of the edge kernel
 template <int NS, int NV>
-__global__ void msg1_node_gw_reduce_kernel(const float* __restrict__ part, int nparts, const float* __restrict__ gwe_part,
-                                           int neparts, const float* nz, const float* nvn, float* __restrict__ gwz,
-                                           float* __restrict__ gwv) {
+__global__ void __launch_bounds__(256) msg1_node_gw_reduce_kernel(const float* __restrict__ part, int nparts,
+                                                                  const float* __restrict__ gwe_part, int neparts, const float* nz,
+                                                                  const float* nvn, float* __restrict__ gwz, float* __restrict__ gwv) {
     using Nd = NodeDims<NS, NV>;
     constexpr int MZ = Nd::MZ, CH = Nd::CH, KR = Nd::KR, NSC = Nd::NSC, ROWS = NSC + 2 * NV;
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ROWS * CH; t += gridDim.x * blockDim.x) {
+    // one warp per output element: lane l sums partials l, l + 32, ... (fixed order), then a shuffle tree
+    const int lane = threadIdx.x & 31;
+    for (int t = blockIdx.x * 8 + (threadIdx.x >> 5); t < ROWS * CH; t += gridDim.x * 8) {
         const int row = t / CH, ch = t - row * CH;
         float g = 0.0f;
         bool vec = false;
         if (row >= 2 * NS && row < NSC) {
             const int j = row - 2 * NS;
-            for (int q = 0; q < neparts; ++q) g += gwe_part[((long long)q * 2 + j) * CH + ch];
+            for (int q = lane; q < neparts; q += 32) g += gwe_part[((long long)q * 2 + j) * CH + ch];
         } else {
             int p, k;
             if (row < 2 * NS) { p = row / NS; k = row - p * NS; }
             else { const int r = row - NSC; p = r / NV; k = NS + r - p * NV; vec = true; }
             const float* src = part + (p * KR + k) * CH + ch;
-            for (int q = 0; q < nparts; ++q) g += src[(long long)q * Nd::WF];
+            for (int q = lane; q < nparts; q += 32) g += src[(long long)q * Nd::WF];
         }
-        if (ch < MZ) gwz[row * MZ + ch] = g * (vec ? C3f : 1.0f) * (nz ? nz[ch] : 1.0f);
-        else gwv[row * NV + ch - MZ] = g * C3f * (nvn ? nvn[3 * (ch - MZ)] : 1.0f);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+        if (lane == 0) {
+            if (ch < MZ) gwz[row * MZ + ch] = g * (vec ? C3f : 1.0f) * (nz ? nz[ch] : 1.0f);
+            else gwv[row * NV + ch - MZ] = g * C3f * (nvn ? nvn[3 * (ch - MZ)] : 1.0f);
+        }
     }
 }
 
@@ -260,10 +266,10 @@ static int node_backward(const float* x, const float* G, long long n, const floa
         const int smem = GW_TILE * (Nd::D + Nd::LDT) * 4;
         static bool attr = false;
         if (!attr) { SE3_CUDA_TRY(cudaFuncSetAttribute(msg1_node_gw_kernel<NS, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
-        const int grid = (int)std::max<long long>(1, std::min<long long>((n + GW_TILE - 1) / GW_TILE, std::min<long long>(max_parts, (long long)num_sms() * 2)));
+        const int grid = (int)std::max<long long>(1, std::min<long long>((n + GW_TILE - 1) / GW_TILE, std::min<long long>(max_parts, (long long)num_sms() * 4)));
         msg1_node_gw_kernel<NS, NV><<<grid, 448, smem, st>>>(x, G, n, part);
         SE3_LAUNCHED();
-        msg1_node_gw_reduce_kernel<NS, NV><<<32, 256, 0, st>>>(part, grid, gwe_part, neparts, nz, nvn, gwz, gwv);
+        msg1_node_gw_reduce_kernel<NS, NV><<<num_sms() * 2, 256, 0, st>>>(part, grid, gwe_part, neparts, nz, nvn, gwz, gwv);
         SE3_LAUNCHED();
     }
     return SE3_OK;
@@ -281,7 +287,7 @@ using namespace se3;
 
 extern "C" int se3_msg1_node_parts(int32_t ns, int32_t nv, int32_t* max_parts, int32_t* part_floats) {
     if (!max_parts || !part_floats) { set_error("msg1_node_parts: null argument"); return SE3_ERR_INVALID; }
-    *max_parts = num_sms() * 2;
+    *max_parts = num_sms() * 4;
     *part_floats = 2 * (ns + nv) * (ns + 2 * nv);
     return SE3_OK;
 }

@@ -368,25 +368,34 @@ __global__ void tr_count_kernel(const int* __restrict__ src, long long e, int* _
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < e) atomicAdd(cnt + src[i], 1);
 }
-// single-block exclusive scan of int counts into int64 pointers (n + 1 entries); also seeds the fill cursors
+// single-block exclusive scan of int counts into int64 pointers (n + 1 entries); also seeds the fill cursors.
+// Chunks of 1024 consecutive elements (coalesced), warp-shuffle scan per chunk, running carry.
 __global__ void __launch_bounds__(1024) tr_scan_kernel(const int* __restrict__ cnt, long long n, long long* __restrict__ ptr,
                                                         unsigned long long* __restrict__ cursor) {
-    __shared__ long long part[1024];
-    const int t = threadIdx.x;
-    const long long per = (n + 1023) / 1024, a = min(n, (long long)t * per), b = min(n, a + per);
-    long long s = 0;
-    for (long long i = a; i < b; ++i) s += cnt[i];
-    part[t] = s;
+    __shared__ long long wsum[32];
+    __shared__ long long carry_s;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t == 0) carry_s = 0;
     __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-        const long long v = t >= o ? part[t - o] : 0;
+    for (long long base = 0; base < n; base += 1024) {
+        const long long i = base + t;
+        const long long v = i < n ? (long long)cnt[i] : 0;
+        long long inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        if (lane == 31) wsum[warp] = inc;
         __syncthreads();
-        part[t] += v;
+        long long off = carry_s;
+        for (int w = 0; w < warp; ++w) off += wsum[w];
+        if (i < n) { const long long ex = off + inc - v; ptr[i] = ex; cursor[i] = (unsigned long long)ex; }
+        __syncthreads();
+        if (t == 1023) carry_s = off + inc;
         __syncthreads();
     }
-    long long run = part[t] - s;
-    for (long long i = a; i < b; ++i) { ptr[i] = run; cursor[i] = (unsigned long long)run; run += cnt[i]; }
-    if (t == 1023) ptr[n] = part[1023];
+    if (t == 0) ptr[n] = carry_s;
 }
 __global__ void tr_fill_kernel(const int* __restrict__ src, long long e, unsigned long long* __restrict__ cursor, int* __restrict__ perm) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -407,11 +416,16 @@ __global__ void __launch_bounds__(256) tr_sort_kernel(const long long* __restric
         const int v0 = lane < len ? perm[a + lane] : 0x7fffffff;
         const int v1 = 32 + lane < len ? perm[a + 32 + lane] : 0x7fffffff;
         int r0 = 0, r1 = 0;
+        const int l0 = len < 32 ? len : 32;
+        if (len <= 32) {
+            for (int l = 0; l < l0; ++l) r0 += __shfl_sync(0xffffffffu, v0, l) < v0;
+        } else {
 #pragma unroll 8
-        for (int l = 0; l < 32; ++l) {
-            const int u0 = __shfl_sync(0xffffffffu, v0, l), u1 = __shfl_sync(0xffffffffu, v1, l);
-            r0 += (u0 < v0) + (u1 < v0);
-            r1 += (u0 < v1) + (u1 < v1);
+            for (int l = 0; l < 32; ++l) {
+                const int u0 = __shfl_sync(0xffffffffu, v0, l), u1 = __shfl_sync(0xffffffffu, v1, l);
+                r0 += (u0 < v0) + (u1 < v0);
+                r1 += (u0 < v1) + (u1 < v1);
+            }
         }
         __syncwarp();
         if (lane < len) perm[a + r0] = v0;          // edge ids are distinct: ranks are a permutation

@@ -270,6 +270,37 @@ int se3_o3tp_backward_seg(se3_o3tp_plan* plan, int64_t rows, int32_t nseg, const
                           const float* w, const float* gout, float* const* gseg, const int32_t* gseg_mode, float* gin2,
                           float* gw, void* stream);
 
+/* ---------------------------------------------------------------- o3msg ---- */
+/* First tensor product of the l <= 2 SEGNN message layer by linearity (the op chain it replaces: the tensor product
+ * above applied to cat(x[dst], x[src], extra), i.e. L1TP:242-297 generalised to l = 2; l <= 1 counterpart: se3_msg1_*).
+ * The weight contraction runs once per node into per-role tables (made with se3_o3tp_forward on a scalar second input,
+ * see se3gnn_b200/o3msg.py); per edge: pre[e][off + w (2l+1) + c] = a sum_paths sum_i M_p(Y_e)[i][c] (tdst[dst e] +
+ * tsrc[src e])[tbase_p + w (2 l1 + 1) + i] + the scalar extras' paths (weights read from the flat buffer w).
+ * One descriptor per output irrep; <= 4 table paths and <= 2 extras paths each. */
+#define SE3_O3MSG_MAXP 4
+#define SE3_O3MSG_MAXX 2
+typedef struct se3_o3msg_io {
+    int32_t l, mul, off;                    /* degree, multiplicity, first column of the output irrep in a pre row  */
+    float a;                                /* normalisation factor of the output irrep (se3_o3tp_plan_paths)       */
+    int32_t np;                             /* table paths into this irrep                                           */
+    int32_t p_l1[SE3_O3MSG_MAXP], p_l2[SE3_O3MSG_MAXP], p_yoff[SE3_O3MSG_MAXP], p_tbase[SE3_O3MSG_MAXP];
+    int32_t nx;                             /* extras paths (scalar extras x Y_l -> l)                               */
+    int32_t x_l2[SE3_O3MSG_MAXX], x_yoff[SE3_O3MSG_MAXX], x_woff[SE3_O3MSG_MAXX] /* [x_mul, mul] block in w */,
+        x_off[SE3_O3MSG_MAXX] /* first column in an extras row */, x_mul[SE3_O3MSG_MAXX];
+    int32_t gx_off, gx_slots;               /* backward: gex[n][gx_off + w gx_slots + s], gx_slots = sum x_mul (<= 4) */
+} se3_o3msg_io;
+/* dst/src [edges] int32; tdst [*, ldt], tsrc [*, ldt]; y [edges, ldy]; extra [edges, ldx]; pre [edges, ldo] */
+int se3_o3msg_edge_forward(const se3_o3msg_io* io, int32_t nio, int64_t edges, const int32_t* dst, const int32_t* src,
+                           const float* tdst, const float* tsrc, int32_t ldt, const float* y, int32_t ldy,
+                           const float* extra, int32_t ldx, const float* w, float* pre, int32_t ldo, void* stream);
+/* Transpose: gdst [n_dst, ldt] = sums over the CSR rows (rowptr, edges sorted by destination), gsrc [n_all, ldt] = sums
+ * over the transposed order (tptr, perm: se3_graph_transpose); every table entry is written (no zero-init, no atomics).
+ * gex [n_dst, ldg]: per-destination partial sums of the extras' weight gradients (the caller adds the rows up). */
+int se3_o3msg_edge_backward(const se3_o3msg_io* io, int32_t nio, int64_t n_dst, int64_t n_all, const int64_t* rowptr,
+                            const int64_t* tptr, const int32_t* perm, const float* y, int32_t ldy, const float* extra,
+                            int32_t ldx, const float* gpre, int32_t ldo, float* gdst, float* gsrc, int32_t ldt, float* gex,
+                            int32_t ldg, void* stream);
+
 /* ---------------------------------------------------------------- gate ---- */
 /* Gated non-linearity on flat rows (public SEGNN O3TensorProductSwishGate's Gate; the reference mount has no source for
  * it): raw = [ns scalars | ng gate scalars | block b: cnt[b] channels x dim[b] components ...], ng = sum cnt;

@@ -13,66 +13,117 @@ struct GateL {
     float cs, cg;
 };
 
-__device__ __forceinline__ float sigmoidf(float z) { return 1.0f / (1.0f + expf(-z)); }
+// sigmoid with two MUFU ops (ex2.approx, rcp.approx: ~1e-7 relative, far inside the 1e-5 parity budget)
+__device__ __forceinline__ float sigmoidf(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return r;
+}
 
-// gate index and nothing else: column j (>= 0) of the gated part
-__device__ __forceinline__ int gate_of(const GateL& L, int j) {
-    int g0 = 0;
+constexpr int GATE_NT = 256;
+constexpr int GATE_MAXD = 512;   // widest raw row the column tables in shared memory cover
+
+// Column tables (shared memory, built once per block from the layout):
+//   forward, output column j:   src[j] = raw column of the value, gate[j] = raw column of its gate scalar (-1: silu)
+//   backward, raw column j:     scalar: (j, -1, 0) | gate scalar: (first gated raw column, first gout column, dim) |
+//                               gated value: (gout column, gate raw column, -1)
+// A block walks chunks of whole rows, thread = element, so global reads and writes are coalesced and the only
+// division is a 32-bit multiply-high by a per-launch constant.
+struct GateTab {
+    short a[GATE_MAXD], b[GATE_MAXD], c[GATE_MAXD];
+};
+
+__device__ __forceinline__ void gate_tables(const GateL& L, GateTab& T, bool bwd) {
+    for (int j = threadIdx.x; j < (bwd ? L.d_raw : L.d_out); j += blockDim.x) {
+        short a = (short)j, b = -1, c = 0;
+        if (!bwd) {
+            if (j >= L.ns) {
+                int jj = j - L.ns, g0 = 0;
+                a = (short)(L.ns + L.ng + jj);
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-        if (b < L.nblk) {
-            const int w = L.cnt[b] * L.dim[b];
-            if (j < L.off[b] + w) return g0 + (j - L.off[b]) / L.dim[b];
-            g0 += L.cnt[b];
+                for (int k = 0; k < 4; ++k)
+                    if (k < L.nblk) {
+                        if (jj >= L.off[k] && jj < L.off[k] + L.cnt[k] * L.dim[k]) b = (short)(L.ns + g0 + (jj - L.off[k]) / L.dim[k]);
+                        g0 += L.cnt[k];
+                    }
+            }
+        } else if (j >= L.ns && j < L.ns + L.ng) {
+            int k0 = j - L.ns, g0 = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (k < L.nblk) {
+                    if (k0 >= g0 && k0 < g0 + L.cnt[k]) {
+                        const int col = L.off[k] + (k0 - g0) * L.dim[k];
+                        a = (short)(L.ns + L.ng + col); b = (short)(L.ns + col); c = (short)L.dim[k];
+                    }
+                    g0 += L.cnt[k];
+                }
+        } else if (j >= L.ns + L.ng) {
+            int jj = j - L.ns - L.ng, g0 = 0;
+            a = (short)(L.ns + jj); c = -1;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (k < L.nblk) {
+                    if (jj >= L.off[k] && jj < L.off[k] + L.cnt[k] * L.dim[k]) b = (short)(L.ns + g0 + (jj - L.off[k]) / L.dim[k]);
+                    g0 += L.cnt[k];
+                }
         }
+        T.a[j] = a; T.b[j] = b; T.c[j] = c;
     }
-    return 0;
+    __syncthreads();
 }
 
-__global__ void gate_fwd_kernel(GateL L, long long rows, const float* __restrict__ raw, float* __restrict__ out) {
-    const long long total = rows * L.d_out;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long r = i / L.d_out;
-        const int j = (int)(i - r * L.d_out);
-        const float* x = raw + r * L.d_raw;
-        float v;
-        if (j < L.ns) {
-            const float s = x[j];
-            v = L.cs * s * sigmoidf(s);
-        } else {
-            const int jj = j - L.ns;
-            v = x[L.ns + L.ng + jj] * (L.cg * sigmoidf(x[L.ns + gate_of(L, jj)]));
+__global__ void __launch_bounds__(GATE_NT) gate_fwd_kernel(const __grid_constant__ GateL L, long long rows, int chunk,
+                                                           unsigned magic, const float* __restrict__ raw,
+                                                           float* __restrict__ out) {
+    __shared__ GateTab T;
+    gate_tables(L, T, false);
+    const int d = L.d_out;
+    for (long long r0 = (long long)blockIdx.x * chunk; r0 < rows; r0 += (long long)gridDim.x * chunk) {
+        const int nr = (int)min((long long)chunk, rows - r0);
+        const float* x0 = raw + r0 * L.d_raw;
+        float* o0 = out + r0 * d;
+        for (int i = threadIdx.x; i < nr * d; i += GATE_NT) {
+            const int r = (int)__umulhi((unsigned)i, magic), j = i - r * d;
+            const float* x = x0 + r * L.d_raw;
+            const float v = x[T.a[j]];
+            const int gc = T.b[j];
+            o0[i] = gc < 0 ? L.cs * v * sigmoidf(v) : v * (L.cg * sigmoidf(x[gc]));
         }
-        out[i] = v;
     }
 }
 
-__global__ void gate_bwd_kernel(GateL L, long long rows, const float* __restrict__ raw, const float* __restrict__ gout,
-                                float* __restrict__ graw) {
-    const long long total = rows * L.d_raw;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long r = i / L.d_raw;
-        const int j = (int)(i - r * L.d_raw);
-        const float* x = raw + r * L.d_raw;
-        const float* g = gout + r * L.d_out;
-        float v;
-        if (j < L.ns) {
-            const float s = x[j], sg = sigmoidf(s);
-            v = g[j] * L.cs * (sg + s * sg * (1.f - sg));
-        } else if (j < L.ns + L.ng) {
-            // gate scalar k: sum over the components of its channel
-            int k = j - L.ns, b = 0, g0 = 0;
-            while (b + 1 < L.nblk && k >= g0 + L.cnt[b]) { g0 += L.cnt[b]; ++b; }
-            const int col = L.off[b] + (k - g0) * L.dim[b];
-            float acc = 0.f;
-            for (int c = 0; c < L.dim[b]; ++c) acc += g[L.ns + col + c] * x[L.ns + L.ng + col + c];
-            const float sg = sigmoidf(x[j]);
-            v = acc * L.cg * sg * (1.f - sg);
-        } else {
-            const int jj = j - L.ns - L.ng;
-            v = g[L.ns + jj] * (L.cg * sigmoidf(x[L.ns + gate_of(L, jj)]));
+__global__ void __launch_bounds__(GATE_NT) gate_bwd_kernel(const __grid_constant__ GateL L, long long rows, int chunk,
+                                                           unsigned magic, const float* __restrict__ raw,
+                                                           const float* __restrict__ gout, float* __restrict__ graw) {
+    __shared__ GateTab T;
+    gate_tables(L, T, true);
+    const int d = L.d_raw;
+    for (long long r0 = (long long)blockIdx.x * chunk; r0 < rows; r0 += (long long)gridDim.x * chunk) {
+        const int nr = (int)min((long long)chunk, rows - r0);
+        const float* x0 = raw + r0 * d;
+        const float* g0 = gout + r0 * L.d_out;
+        float* o0 = graw + r0 * d;
+        for (int i = threadIdx.x; i < nr * d; i += GATE_NT) {
+            const int r = (int)__umulhi((unsigned)i, magic), j = i - r * d;
+            const float* x = x0 + r * d;
+            const float* g = g0 + r * L.d_out;
+            const int a = T.a[j], b = T.b[j], c = T.c[j];
+            float v;
+            if (c == 0) {                       // scalar: silu'
+                const float s = x[j], sg = sigmoidf(s);
+                v = g[j] * L.cs * (sg + s * sg * (1.f - sg));
+            } else if (c < 0) {                 // gated value
+                v = g[a] * (L.cg * sigmoidf(x[b]));
+            } else {                            // gate scalar: sum over the components of its channel
+                float acc = 0.f;
+                for (int k = 0; k < c; ++k) acc = fmaf(g[b + k], x[a + k], acc);
+                const float sg = sigmoidf(x[j]);
+                v = acc * L.cg * sg * (1.f - sg);
+            }
+            o0[i] = v;
         }
-        graw[i] = v;
     }
 }
 
@@ -90,7 +141,14 @@ int make_layout(GateL& L, int ns, int nblk, const int32_t* cnt, const int32_t* d
     }
     L.d_out = ns + off;
     L.d_raw = ns + L.ng + off;
-    return L.d_out > 0 ? SE3_OK : SE3_ERR_INVALID;
+    return L.d_out > 0 && L.d_raw <= GATE_MAXD ? SE3_OK : SE3_ERR_INVALID;
+}
+
+// rows per block iteration: ~16 elements per thread, whole rows; the element index inside a chunk stays far below 2^31,
+// and floor(i / d) == umulhi(i, ceil(2^32 / d)) holds for i < 2^16 * ... (checked for the chunk sizes used: i < 8192)
+void gate_chunk(int d, int* chunk, unsigned* magic) {
+    *chunk = std::max(1, (16 * GATE_NT) / d);
+    *magic = (unsigned)((0x100000000ull + (unsigned long long)d - 1) / (unsigned long long)d);
 }
 
 }  // namespace
@@ -103,9 +161,11 @@ extern "C" int se3_gate_forward(int64_t rows, int32_t ns, int32_t nblk, const in
         return SE3_ERR_INVALID;
     }
     if (rows == 0) return SE3_OK;
-    const long long total = rows * L.d_out;
-    const int grid = (int)std::min<long long>((total + 255) / 256, (long long)se3::num_sms() * 16);
-    gate_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(L, rows, raw, out);
+    int chunk;
+    unsigned magic;
+    gate_chunk(L.d_out, &chunk, &magic);
+    const int grid = (int)std::min<long long>((rows + chunk - 1) / chunk, (long long)se3::num_sms() * 8);
+    gate_fwd_kernel<<<grid, GATE_NT, 0, (cudaStream_t)stream>>>(L, rows, chunk, magic, raw, out);
     SE3_LAUNCHED();
     return SE3_OK;
 }
@@ -118,9 +178,11 @@ extern "C" int se3_gate_backward(int64_t rows, int32_t ns, int32_t nblk, const i
         return SE3_ERR_INVALID;
     }
     if (rows == 0) return SE3_OK;
-    const long long total = rows * L.d_raw;
-    const int grid = (int)std::min<long long>((total + 255) / 256, (long long)se3::num_sms() * 16);
-    gate_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(L, rows, raw, gout, graw);
+    int chunk;
+    unsigned magic;
+    gate_chunk(L.d_raw, &chunk, &magic);
+    const int grid = (int)std::min<long long>((rows + chunk - 1) / chunk, (long long)se3::num_sms() * 8);
+    gate_bwd_kernel<<<grid, GATE_NT, 0, (cudaStream_t)stream>>>(L, rows, chunk, magic, raw, gout, graw);
     SE3_LAUNCHED();
     return SE3_OK;
 }

@@ -10,12 +10,16 @@ attributes of ``octree.sh2_attributes(g)`` (edge_attr9 [E,9], node_attr9 [Nn,9])
 """
 from __future__ import annotations
 
+import os
+
 import torch
 from torch import nn
 
 from se3gnn_b200.gate import irreps_gate
 from se3gnn_b200.irreps import Irreps
 from se3gnn_b200.o3tp import O3TensorProduct
+from se3gnn_b200 import o3msg
+from se3gnn_b200.msg import build_edge_index
 
 INPUT_IRREPS = "2x1o+2x0e"   # (pos - centroid, vel, |vel|, mass)
 EXTRA_IRREPS = "2x0e"        # (|rel|, m_i m_j)
@@ -66,10 +70,20 @@ class SEGNNL2(nn.Module):
         if not x_in.is_cuda:
             raise RuntimeError("SEGNNL2 runs on CUDA (sm_100a) only; there is no CPU fallback")
         x = self.embed(x_in, node_attr)
+        # message 1: "table" = weight contraction once per node by linearity (se3gnn_b200/o3msg.py), "tp" = the tensor
+        # product on the concatenated row read in place (the A/B path)
+        table = os.environ.get("SE3_L2_MSG", "table") == "table" and o3msg.supported(self.msg1[0], self.hidden, EXTRA_IRREPS)
+        ei = None
         for l in range(self.num_layers):
-            # cat(x[dst], x[src], edge_extra) is read in place by the kernel; its gradient is scattered by the backward
             xe = x if halo is None else halo(x)
-            m = self.gate(self.msg1[l].forward_cat([(xe, dst, True), (xe, src), (edge_extra, None)], edge_attr))
+            if table:
+                if ei is None:   # CSR rows by destination and the transposed order by source: once per graph
+                    ei = build_edge_index(dst, src, x.shape[0], xe.shape[0])
+                pre = o3msg.tables_for(self.msg1[l], self.hidden, EXTRA_IRREPS)(self.msg1[l].weight, xe, edge_attr, edge_extra, ei)
+            else:
+                # cat(x[dst], x[src], edge_extra) is read in place by the kernel; its gradient is scattered by the backward
+                pre = self.msg1[l].forward_cat([(xe, dst, True), (xe, src), (edge_extra, None)], edge_attr)
+            m = self.gate(pre)
             m = self.gate(self.msg2[l](m, edge_attr))
             agg = torch.zeros_like(x).index_add_(0, dst, m)
             u = self.gate(self.upd1[l].forward_cat([(x, None), (agg, None)], node_attr))

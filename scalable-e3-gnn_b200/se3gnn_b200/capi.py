@@ -33,6 +33,21 @@ class RowSeg(C.Structure):
     _fields_ = [("base", C.c_void_p), ("idx", C.c_void_p), ("width", C.c_int32), ("ld", C.c_int32)]
 
 
+O3MSG_MAXP, O3MSG_MAXX = 4, 2
+
+
+class O3MsgIO(C.Structure):
+    """``se3_o3msg_io``: one output irrep of the message product by linearity (csrc/o3msg.cu)."""
+    _fields_ = [
+        ("l", C.c_int32), ("mul", C.c_int32), ("off", C.c_int32), ("a", C.c_float), ("np", C.c_int32),
+        ("p_l1", C.c_int32 * O3MSG_MAXP), ("p_l2", C.c_int32 * O3MSG_MAXP), ("p_yoff", C.c_int32 * O3MSG_MAXP),
+        ("p_tbase", C.c_int32 * O3MSG_MAXP), ("nx", C.c_int32),
+        ("x_l2", C.c_int32 * O3MSG_MAXX), ("x_yoff", C.c_int32 * O3MSG_MAXX), ("x_woff", C.c_int32 * O3MSG_MAXX),
+        ("x_off", C.c_int32 * O3MSG_MAXX), ("x_mul", C.c_int32 * O3MSG_MAXX),
+        ("gx_off", C.c_int32), ("gx_slots", C.c_int32),
+    ]
+
+
 class L1tpFwdArgs(C.Structure):
     _fields_ = [
         ("rows", C.c_int64), ("nseg", C.c_int32), ("seg", RowSeg * MAX_SEG),
@@ -132,6 +147,12 @@ EXPORTS = [
                                        C.c_void_p, C.c_void_p]),
     ("se3_o3tp_backward_seg", C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(RowSeg), C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.POINTER(C.c_void_p), _i32p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("se3_o3msg_edge_forward", C.c_int, [C.POINTER(O3MsgIO), C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
+                                         C.c_void_p, C.c_int32, C.c_void_p]),
+    ("se3_o3msg_edge_backward", C.c_int, [C.POINTER(O3MsgIO), C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
+                                          C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
     ("se3_gate_forward", C.c_int, [C.c_int64, C.c_int32, C.c_int32, _i32p, _i32p, C.c_float, C.c_float, C.c_void_p,
                                    C.c_void_p, C.c_void_p]),
     ("se3_gate_backward", C.c_int, [C.c_int64, C.c_int32, C.c_int32, _i32p, _i32p, C.c_float, C.c_float, C.c_void_p,

@@ -63,14 +63,27 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.steps
+    nl = (capi.launch_count() - n0) / a.steps
+    # one more step with CUDA events around every library call: where the time goes (outside the timed region)
+    capi.profile_begin()
+    step()
+    agg = {}
+    for tag, t, _, _ in capi.profile_end():
+        k = agg.setdefault(tag, [0.0, 0])
+        k[0] += t
+        k[1] += 1
+    kernels = {k: {"ms_per_step": round(v[0], 3), "calls": v[1]} for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])}
+    mode = os.environ.get("SE3_L2_MSG", "table")
     print(json.dumps({
         "workload": f"SEGNN l_max=2, 4 layers, hidden {a.hidden}, {n} particles (plummer), fp32, octree leaf size 32 "
                     + ("[BASELINE configs[2], fp32 contraction]" if n == 1_000_000 else "[BASELINE configs[2] at a different size]"),
         "ms_per_step": round(ms, 3), "particles_per_s": n / ms * 1e3, "edges": int(g.e), "cells": int(g.m),
-        "gpu_launches_per_step": (capi.launch_count() - n0) / a.steps, "loss": float(loss.detach()),
+        "gpu_launches_per_step": nl, "loss": float(loss.detach()), "message1": mode,
         "peak_mem_GB": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2),
-        "note": "tensor products csrc/o3tp.cu (fp32 SIMT, gathered inputs read in place), gates csrc/gate.cu; "
-                "aggregation (index_add) and residual are torch ops",
+        "kernels": kernels,
+        "note": "tensor products csrc/o3tp.cu (fp32 SIMT, gathered inputs read in place), message 1 "
+                + ("by linearity (node tables + per-edge coupling, csrc/o3msg.cu)" if mode == "table" else "as a tensor product on the concatenated row")
+                + ", gates csrc/gate.cu; aggregation (index_add) and residual are torch ops",
     }), flush=True)
 
 

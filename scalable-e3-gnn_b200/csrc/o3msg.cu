@@ -106,6 +106,12 @@ __global__ void __launch_bounds__(NTH) o3msg_edge_fwd_kernel(const __grid_consta
     const int mul = A.io.mul;
     const int el = (int)((threadIdx.x * A.magic) >> 16), w = threadIdx.x - el * mul;
     if (el >= A.per_block) return;
+    float wx[SE3_O3MSG_MAXX][4];   // this thread's extras weights (its output channel is fixed): out of the edge loop
+#pragma unroll
+    for (int p = 0; p < SE3_O3MSG_MAXX; ++p)
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            wx[p][u] = (p < A.io.nx && u < A.io.x_mul[p]) ? __ldg(A.w + A.io.x_woff[p] + u * mul + w) : 0.f;
     for (long long e = (long long)blockIdx.x * A.per_block + el; e < A.E; e += (long long)gridDim.x * A.per_block) {
         const float* td = A.tdst + (long long)__ldg(A.dst + e) * A.ldt;
         const float* ts = A.tsrc + (long long)__ldg(A.src + e) * A.ldt;
@@ -132,9 +138,10 @@ __global__ void __launch_bounds__(NTH) o3msg_edge_fwd_kernel(const __grid_consta
         for (int p = 0; p < SE3_O3MSG_MAXX; ++p) {
             if (p < A.io.nx) {
                 float t = 0.f;
-                const float* wp = A.w + A.io.x_woff[p] + w;
                 const float* xp = A.ex + e * A.ldx + A.io.x_off[p];
-                for (int u = 0; u < A.io.x_mul[p]; ++u) t = fmaf(__ldg(wp + u * mul), __ldg(xp + u), t);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (u < A.io.x_mul[p]) t = fmaf(wx[p][u], __ldg(xp + u), t);
                 const float* yp = yr + A.io.x_yoff[p];
                 switch (A.io.x_l2[p]) {   // a scalar extra couples with Y_l into an output of the same degree
                     case 0: if constexpr (LO == 0) fwd_scalar<0, 0>(t, yp, acc); break;

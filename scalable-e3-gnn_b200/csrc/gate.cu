@@ -96,7 +96,8 @@ __global__ void __launch_bounds__(GATE_NT) gate_fwd_kernel(const __grid_constant
 
 __global__ void __launch_bounds__(GATE_NT) gate_bwd_kernel(const __grid_constant__ GateL L, long long rows, int chunk,
                                                            unsigned magic, const float* __restrict__ raw,
-                                                           const float* __restrict__ gout, float* __restrict__ graw) {
+                                                           const float* __restrict__ gout, const int32_t* __restrict__ gidx,
+                                                           float* __restrict__ graw) {
     __shared__ GateTab T;
     gate_tables(L, T, true);
     const int d = L.d_raw;
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(GATE_NT) gate_bwd_kernel(const __grid_constant
         for (int i = threadIdx.x; i < nr * d; i += GATE_NT) {
             const int r = (int)__umulhi((unsigned)i, magic), j = i - r * d;
             const float* x = x0 + r * d;
-            const float* g = g0 + r * L.d_out;
+            const float* g = gidx ? gout + (long long)__ldg(gidx + r0 + r) * L.d_out : g0 + r * L.d_out;
             const int a = T.a[j], b = T.b[j], c = T.c[j];
             float v;
             if (c == 0) {                       // scalar: silu'
@@ -123,6 +124,44 @@ __global__ void __launch_bounds__(GATE_NT) gate_bwd_kernel(const __grid_constant
                 v = acc * L.cg * sg * (1.f - sg);
             }
             o0[i] = v;
+        }
+    }
+}
+
+// out[n][:] = sum over the CSR row of node n of gate(raw[e][:]): the aggregation of the gated messages without the gated
+// [E, d_out] tensor and without atomics (one warp per node, lane = output column, run-to-run deterministic).
+__global__ void __launch_bounds__(GATE_NT) gate_segsum_kernel(const __grid_constant__ GateL L, long long n_seg,
+                                                              const long long* __restrict__ rowptr,
+                                                              const float* __restrict__ raw, float* __restrict__ out) {
+    __shared__ GateTab T;
+    gate_tables(L, T, false);
+    const int lane = threadIdx.x & 31;
+    const long long nwarp = (long long)gridDim.x * (GATE_NT / 32);
+    for (long long n = (long long)blockIdx.x * (GATE_NT / 32) + (threadIdx.x >> 5); n < n_seg; n += nwarp) {
+        const long long beg = __ldg(rowptr + n), end = __ldg(rowptr + n + 1);
+        for (int c0 = 0; c0 < L.d_out; c0 += 128) {
+            int aj[4], bj[4];
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int j = c0 + lane + 32 * k;
+                aj[k] = j < L.d_out ? T.a[j] : -1;
+                bj[k] = j < L.d_out ? T.b[j] : -1;
+            }
+#pragma unroll 2
+            for (long long e = beg; e < end; ++e) {
+                const float* x = raw + e * L.d_raw;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (aj[k] >= 0) {
+                        const float v = __ldg(x + aj[k]);
+                        acc[k] += bj[k] < 0 ? L.cs * v * sigmoidf(v) : v * (L.cg * sigmoidf(__ldg(x + bj[k])));
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (aj[k] >= 0) out[n * L.d_out + c0 + lane + 32 * k] = acc[k];
         }
     }
 }
@@ -182,7 +221,39 @@ extern "C" int se3_gate_backward(int64_t rows, int32_t ns, int32_t nblk, const i
     unsigned magic;
     gate_chunk(L.d_raw, &chunk, &magic);
     const int grid = (int)std::min<long long>((rows + chunk - 1) / chunk, (long long)se3::num_sms() * 8);
-    gate_bwd_kernel<<<grid, GATE_NT, 0, (cudaStream_t)stream>>>(L, rows, chunk, magic, raw, gout, graw);
+    gate_bwd_kernel<<<grid, GATE_NT, 0, (cudaStream_t)stream>>>(L, rows, chunk, magic, raw, gout, nullptr, graw);
+    SE3_LAUNCHED();
+    return SE3_OK;
+}
+
+extern "C" int se3_gate_segment_sum_forward(int64_t n_seg, const int64_t* rowptr, int32_t ns, int32_t nblk, const int32_t* cnt,
+                                            const int32_t* dim, float cs, float cg, const float* raw, float* out, void* stream) {
+    GateL L;
+    if (make_layout(L, ns, nblk, cnt, dim, cs, cg) || n_seg < 0 || (n_seg > 0 && (!rowptr || !out))) {
+        se3::set_error("se3_gate_segment_sum_forward: bad argument");
+        return SE3_ERR_INVALID;
+    }
+    if (n_seg == 0) return SE3_OK;
+    const int grid = (int)std::min<long long>((n_seg + GATE_NT / 32 - 1) / (GATE_NT / 32), (long long)se3::num_sms() * 32);
+    gate_segsum_kernel<<<grid, GATE_NT, 0, (cudaStream_t)stream>>>(L, n_seg, reinterpret_cast<const long long*>(rowptr), raw, out);
+    SE3_LAUNCHED();
+    return SE3_OK;
+}
+
+extern "C" int se3_gate_segment_sum_backward(int64_t rows, const int32_t* seg, int32_t ns, int32_t nblk, const int32_t* cnt,
+                                             const int32_t* dim, float cs, float cg, const float* raw, const float* gout,
+                                             float* graw, void* stream) {
+    GateL L;
+    if (make_layout(L, ns, nblk, cnt, dim, cs, cg) || rows < 0 || (rows > 0 && (!seg || !raw || !gout || !graw))) {
+        se3::set_error("se3_gate_segment_sum_backward: bad argument");
+        return SE3_ERR_INVALID;
+    }
+    if (rows == 0) return SE3_OK;
+    int chunk;
+    unsigned magic;
+    gate_chunk(L.d_raw, &chunk, &magic);
+    const int grid = (int)std::min<long long>((rows + chunk - 1) / chunk, (long long)se3::num_sms() * 8);
+    gate_bwd_kernel<<<grid, GATE_NT, 0, (cudaStream_t)stream>>>(L, rows, chunk, magic, raw, gout, seg, graw);
     SE3_LAUNCHED();
     return SE3_OK;
 }

@@ -15,7 +15,7 @@ import os
 import torch
 from torch import nn
 
-from se3gnn_b200.gate import irreps_gate
+from se3gnn_b200.gate import irreps_gate, irreps_gate_segment_sum
 from se3gnn_b200.irreps import Irreps
 from se3gnn_b200.o3tp import O3TensorProduct
 from se3gnn_b200 import o3msg
@@ -84,8 +84,11 @@ class SEGNNL2(nn.Module):
                 # cat(x[dst], x[src], edge_extra) is read in place by the kernel; its gradient is scattered by the backward
                 pre = self.msg1[l].forward_cat([(xe, dst, True), (xe, src), (edge_extra, None)], edge_attr)
             m = self.gate(pre)
-            m = self.gate(self.msg2[l](m, edge_attr))
-            agg = torch.zeros_like(x).index_add_(0, dst, m)
+            pre2 = self.msg2[l](m, edge_attr)
+            if ei is not None:   # gate + aggregation over the sorted destinations in one kernel, no atomics
+                agg = irreps_gate_segment_sum(pre2, self.ns, [(self.nv, 3), (self.nt, 5)], dst, ei.rowptr, x.shape[0])
+            else:
+                agg = torch.zeros_like(x).index_add_(0, dst, self.gate(pre2))
             u = self.gate(self.upd1[l].forward_cat([(x, None), (agg, None)], node_attr))
             x = x + self.upd2[l](u, node_attr)
         return self.pre2(self.gate(self.pre1(x, node_attr)), node_attr)

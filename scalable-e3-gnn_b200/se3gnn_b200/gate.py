@@ -63,3 +63,47 @@ def irreps_gate(raw, ns: int, blocks):
             return graw
 
     return _Gate.apply(raw)
+
+
+def irreps_gate_segment_sum(raw, ns: int, blocks, dst, rowptr, n_seg: int):
+    """sum over the incoming edges of gate(raw): raw [E, d_raw] with the edges sorted by destination `dst` (int32 [E]),
+    `rowptr` int64 [n_seg + 1] their CSR offsets -> [n_seg, d_out].  One kernel each way (`se3_gate_segment_sum_*`,
+    csrc/gate.cu): the gated per-edge tensor is never written and the aggregation uses no atomics.  Replaces
+    ``zeros.index_add_(0, dst, gate(raw))`` (public SEGNN: message 2's gate followed by the add-aggregation)."""
+    import torch
+
+    from . import capi
+
+    blocks = [(int(c), int(d)) for c, d in blocks if int(c) > 0]
+    cnt = (capi.C.c_int32 * 4)(*[c for c, _ in blocks])
+    dim = (capi.C.c_int32 * 4)(*[d for _, d in blocks])
+    d_out = ns + sum(c * d for c, d in blocks)
+    d_raw = d_out + sum(c for c, _ in blocks)
+
+    class _GateSum(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, raw):
+            raw = raw.contiguous()
+            if not raw.is_cuda or raw.dtype != torch.float32 or raw.dim() != 2 or raw.shape[1] != d_raw:
+                raise capi.Se3Error(f"irreps_gate_segment_sum: need a CUDA fp32 [rows, {d_raw}] tensor")
+            out = torch.empty((n_seg, d_out), device=raw.device, dtype=torch.float32)
+            with capi.mark("gate.segsum_fwd", 4.0 * (raw.shape[0] * d_raw + n_seg * d_out)):
+                capi.check(capi.lib().se3_gate_segment_sum_forward(n_seg, capi.ptr(rowptr), ns, len(blocks), cnt, dim, SILU_CST,
+                                                                   SIGMOID_CST, capi.ptr(raw), capi.ptr(out),
+                                                                   capi.current_stream_ptr()), "se3_gate_segment_sum_forward")
+            ctx.save_for_backward(raw)
+            return out
+
+        @staticmethod
+        def backward(ctx, gout):
+            (raw,) = ctx.saved_tensors
+            gout = gout.contiguous()
+            graw = torch.empty_like(raw)
+            with capi.mark("gate.segsum_bwd", 4.0 * (raw.shape[0] * 2 * d_raw + n_seg * d_out)):
+                capi.check(capi.lib().se3_gate_segment_sum_backward(raw.shape[0], capi.ptr(dst), ns, len(blocks), cnt, dim,
+                                                                    SILU_CST, SIGMOID_CST, capi.ptr(raw), capi.ptr(gout),
+                                                                    capi.ptr(graw), capi.current_stream_ptr()),
+                           "se3_gate_segment_sum_backward")
+            return graw
+
+    return _GateSum.apply(raw)

@@ -312,10 +312,12 @@ int se3_gate_backward(int64_t rows, int32_t ns, int32_t nblk, const int32_t* cnt
                       const float* raw, const float* gout, float* graw, void* stream);
 
 /* Gate followed by the aggregation over the destination (public SEGNN: message 2's gate, then scatter-add over dst), for
- * edges sorted by destination: out[n][:] = sum_{e in rowptr[n] .. rowptr[n+1]} gate(raw[e][:]) — no gated [E, d] tensor,
- * no atomics, out [n_seg, d_out] is overwritten.  Backward: graw[e] = gate VJP(raw[e], gout[seg[e]]). */
-int se3_gate_segment_sum_forward(int64_t n_seg, const int64_t* rowptr, int32_t ns, int32_t nblk, const int32_t* cnt,
-                                 const int32_t* dim, float cs, float cg, const float* raw, float* out, void* stream);
+ * edges sorted by destination seg [rows]: out[seg[e]][:] += gate(raw[e][:]) in tiles of 64 edges — no gated [E, d] tensor;
+ * runs inside a tile are written with plain stores, only tile-boundary runs use atomic adds; out [n_seg, d_out] is
+ * overwritten (zeroed first).  Backward: graw[e] = gate VJP(raw[e], gout[seg[e]]). */
+int se3_gate_segment_sum_forward(int64_t rows, const int32_t* seg, int64_t n_seg, int32_t ns, int32_t nblk,
+                                 const int32_t* cnt, const int32_t* dim, float cs, float cg, const float* raw, float* out,
+                                 void* stream);
 int se3_gate_segment_sum_backward(int64_t rows, const int32_t* seg, int32_t ns, int32_t nblk, const int32_t* cnt,
                                   const int32_t* dim, float cs, float cg, const float* raw, const float* gout /*[n_seg, d_out]*/,
                                   float* graw, void* stream);

@@ -3,7 +3,7 @@
 // l <= 1 tensor-product kernels does not cover (l = 2 blocks).  HBM-bound: every element is read / written once.
 //   raw  = [ ns scalars | ng gate scalars | block 0: cnt0 x dim0 | block 1: cnt1 x dim1 | ... ],  ng = sum cnt
 //   out  = [ cs silu(s) | block b, channel k, component c:  raw * cg sigmoid(gate[k_global]) ]
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace {
 
@@ -94,75 +94,101 @@ __global__ void __launch_bounds__(GATE_NT) gate_fwd_kernel(const __grid_constant
     }
 }
 
+// Backward, thread = (row, unit): a unit is one scalar or one gated channel with all its components, so the gate's
+// sigmoid is evaluated once per channel and the reduction over the components stays in registers (the element-wise
+// version spent 130 instructions per element, a fifth of them on the row pointers).  gidx: optional row index of the
+// cotangent (the fused gate + segment sum reads the cotangent of the destination node).
 __global__ void __launch_bounds__(GATE_NT) gate_bwd_kernel(const __grid_constant__ GateL L, long long rows, int chunk,
                                                            unsigned magic, const float* __restrict__ raw,
                                                            const float* __restrict__ gout, const int32_t* __restrict__ gidx,
                                                            float* __restrict__ graw) {
-    __shared__ GateTab T;
-    gate_tables(L, T, true);
-    const int d = L.d_raw;
+    __shared__ short ccol[GATE_MAXD], cdim[GATE_MAXD];
+    for (int k = threadIdx.x; k < L.ng; k += blockDim.x) {
+        int g0 = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+            if (b < L.nblk) {
+                if (k >= g0 && k < g0 + L.cnt[b]) { ccol[k] = (short)(L.off[b] + (k - g0) * L.dim[b]); cdim[k] = (short)L.dim[b]; }
+                g0 += L.cnt[b];
+            }
+    }
+    __syncthreads();
+    const int nu = L.ns + L.ng, d = L.d_raw, gbase = L.ns + L.ng;
     for (long long r0 = (long long)blockIdx.x * chunk; r0 < rows; r0 += (long long)gridDim.x * chunk) {
         const int nr = (int)min((long long)chunk, rows - r0);
         const float* x0 = raw + r0 * d;
-        const float* g0 = gout + r0 * L.d_out;
         float* o0 = graw + r0 * d;
-        for (int i = threadIdx.x; i < nr * d; i += GATE_NT) {
-            const int r = (int)__umulhi((unsigned)i, magic), j = i - r * d;
+        for (int i = threadIdx.x; i < nr * nu; i += GATE_NT) {
+            const int r = (int)__umulhi((unsigned)i, magic), u = i - r * nu;
             const float* x = x0 + r * d;
-            const float* g = gidx ? gout + (long long)__ldg(gidx + r0 + r) * L.d_out : g0 + r * L.d_out;
-            const int a = T.a[j], b = T.b[j], c = T.c[j];
-            float v;
-            if (c == 0) {                       // scalar: silu'
-                const float s = x[j], sg = sigmoidf(s);
-                v = g[j] * L.cs * (sg + s * sg * (1.f - sg));
-            } else if (c < 0) {                 // gated value
-                v = g[a] * (L.cg * sigmoidf(x[b]));
-            } else {                            // gate scalar: sum over the components of its channel
+            float* o = o0 + r * d;
+            const float* g = gout + (gidx ? (long long)__ldg(gidx + r0 + r) : r0 + r) * L.d_out;
+            if (u < L.ns) {                       // scalar: silu'
+                const float sv = x[u], sg = sigmoidf(sv);
+                o[u] = g[u] * L.cs * (sg + sv * sg * (1.f - sg));
+            } else {                              // gated channel: its components and its gate scalar
+                const int k = u - L.ns, col = ccol[k], dim = cdim[k];
+                const float sg = sigmoidf(x[u]), f = L.cg * sg;
+                const float* gv = g + L.ns + col;
+                const float* xv = x + gbase + col;
+                float* ov = o + gbase + col;
                 float acc = 0.f;
-                for (int k = 0; k < c; ++k) acc = fmaf(g[b + k], x[a + k], acc);
-                const float sg = sigmoidf(x[j]);
-                v = acc * L.cg * sg * (1.f - sg);
+                for (int c = 0; c < dim; ++c) {
+                    const float gc = gv[c];
+                    ov[c] = gc * f;
+                    acc = fmaf(gc, xv[c], acc);
+                }
+                o[u] = acc * f * (1.f - sg);
             }
-            o0[i] = v;
         }
     }
 }
 
-// out[n][:] = sum over the CSR row of node n of gate(raw[e][:]): the aggregation of the gated messages without the gated
-// [E, d_out] tensor and without atomics (one warp per node, lane = output column, run-to-run deterministic).
-__global__ void __launch_bounds__(GATE_NT) gate_segsum_kernel(const __grid_constant__ GateL L, long long n_seg,
-                                                              const long long* __restrict__ rowptr,
+// out[seg[e]][:] += gate(raw[e][:]) for edges sorted by segment: the aggregation of the gated messages without the gated
+// [E, d_out] tensor.  Tiles of 64 consecutive edges: the raw rows are one contiguous block (a linear 16-byte copy into
+// shared memory), the gate is applied element-wise into a second tile, and the runs of equal segment are summed by
+// sorted_segment_sum_tile (tc_common.cuh): plain stores for runs inside the tile, atomic adds only for the (at most two)
+// runs shared with the neighbouring tiles; out is zeroed by the host function.
+constexpr int GS_TM = 64;
+__global__ void __launch_bounds__(GATE_NT) gate_segsum_kernel(const __grid_constant__ GateL L, long long rows,
+                                                              const int32_t* __restrict__ seg,
                                                               const float* __restrict__ raw, float* __restrict__ out) {
+    extern __shared__ __align__(16) float gs_sm[];
     __shared__ GateTab T;
     gate_tables(L, T, false);
-    const int lane = threadIdx.x & 31;
-    const long long nwarp = (long long)gridDim.x * (GATE_NT / 32);
-    for (long long n = (long long)blockIdx.x * (GATE_NT / 32) + (threadIdx.x >> 5); n < n_seg; n += nwarp) {
-        const long long beg = __ldg(rowptr + n), end = __ldg(rowptr + n + 1);
-        for (int c0 = 0; c0 < L.d_out; c0 += 128) {
-            int aj[4], bj[4];
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int j = c0 + lane + 32 * k;
-                aj[k] = j < L.d_out ? T.a[j] : -1;
-                bj[k] = j < L.d_out ? T.b[j] : -1;
-            }
-#pragma unroll 2
-            for (long long e = beg; e < end; ++e) {
-                const float* x = raw + e * L.d_raw;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (aj[k] >= 0) {
-                        const float v = __ldg(x + aj[k]);
-                        acc[k] += bj[k] < 0 ? L.cs * v * sigmoidf(v) : v * (L.cg * sigmoidf(__ldg(x + bj[k])));
-                    }
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (aj[k] >= 0) out[n * L.d_out + c0 + lane + 32 * k] = acc[k];
+    float* rawt = gs_sm;                                     // [64][d_raw], exact image of the global rows
+    float* gt = rawt + ((GS_TM * L.d_raw + 3) & ~3);         // [64][d_out]
+    float4* hs = reinterpret_cast<float4*>(gt + GS_TM * L.d_out);
+    int* sseg = reinterpret_cast<int*>(hs + 8 * L.d_out);    // [66]
+    const int tid = threadIdx.x;
+    const long long ntiles = (rows + GS_TM - 1) / GS_TM;
+    const bool v4 = (reinterpret_cast<uintptr_t>(raw) & 15) == 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long r0 = tile * GS_TM;
+        const int nv = (int)min((long long)GS_TM, rows - r0), total = nv * L.d_raw;
+        const float* src = raw + r0 * L.d_raw;               // r0 * d_raw * 4 is a multiple of 256 bytes
+        if (v4) {
+            for (int i = tid; i < (total >> 2); i += GATE_NT)
+                reinterpret_cast<float4*>(rawt)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+            for (int i = (total & ~3) + tid; i < total; i += GATE_NT) rawt[i] = __ldg(src + i);
+        } else {
+            for (int i = tid; i < total; i += GATE_NT) rawt[i] = __ldg(src + i);
         }
+        if (tid < nv) sseg[1 + tid] = __ldg(seg + r0 + tid);
+        if (tid == GS_TM) sseg[0] = r0 > 0 ? __ldg(seg + r0 - 1) : -1;
+        if (tid == GS_TM + 1) sseg[GS_TM + 1] = r0 + GS_TM < rows ? __ldg(seg + r0 + GS_TM) : -1;
+        __syncthreads();
+        for (int r = tid >> 5; r < nv; r += GATE_NT / 32) {  // warp = row, lane = output column
+            const float* x = rawt + r * L.d_raw;
+            for (int j = tid & 31; j < L.d_out; j += 32) {
+                const float v = x[T.a[j]];
+                const int gc = T.b[j];
+                gt[r * L.d_out + j] = gc < 0 ? L.cs * v * sigmoidf(v) : v * (L.cg * sigmoidf(x[gc]));
+            }
+        }
+        __syncthreads();
+        se3::sorted_segment_sum_tile<GATE_NT>(gt, L.d_out, L.d_out, nv, sseg, out, L.d_out, hs, tid, 1);
+        __syncthreads();
     }
 }
 
@@ -219,23 +245,38 @@ extern "C" int se3_gate_backward(int64_t rows, int32_t ns, int32_t nblk, const i
     if (rows == 0) return SE3_OK;
     int chunk;
     unsigned magic;
-    gate_chunk(L.d_raw, &chunk, &magic);
+    gate_chunk(L.ns + L.ng, &chunk, &magic);
     const int grid = (int)std::min<long long>((rows + chunk - 1) / chunk, (long long)se3::num_sms() * 8);
     gate_bwd_kernel<<<grid, GATE_NT, 0, (cudaStream_t)stream>>>(L, rows, chunk, magic, raw, gout, nullptr, graw);
     SE3_LAUNCHED();
     return SE3_OK;
 }
 
-extern "C" int se3_gate_segment_sum_forward(int64_t n_seg, const int64_t* rowptr, int32_t ns, int32_t nblk, const int32_t* cnt,
-                                            const int32_t* dim, float cs, float cg, const float* raw, float* out, void* stream) {
+extern "C" int se3_gate_segment_sum_forward(int64_t rows, const int32_t* seg, int64_t n_seg, int32_t ns, int32_t nblk,
+                                            const int32_t* cnt, const int32_t* dim, float cs, float cg, const float* raw,
+                                            float* out, void* stream) {
     GateL L;
-    if (make_layout(L, ns, nblk, cnt, dim, cs, cg) || n_seg < 0 || (n_seg > 0 && (!rowptr || !out))) {
+    if (make_layout(L, ns, nblk, cnt, dim, cs, cg) || rows < 0 || n_seg < 0 || (n_seg > 0 && !out) || (rows > 0 && (!seg || !raw))) {
         se3::set_error("se3_gate_segment_sum_forward: bad argument");
         return SE3_ERR_INVALID;
     }
     if (n_seg == 0) return SE3_OK;
-    const int grid = (int)std::min<long long>((n_seg + GATE_NT / 32 - 1) / (GATE_NT / 32), (long long)se3::num_sms() * 32);
-    gate_segsum_kernel<<<grid, GATE_NT, 0, (cudaStream_t)stream>>>(L, n_seg, reinterpret_cast<const long long*>(rowptr), raw, out);
+    SE3_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)n_seg * L.d_out, (cudaStream_t)stream));
+    if (rows == 0) return SE3_OK;
+    const size_t smem = 4 * (((size_t)GS_TM * L.d_raw + 3) / 4 * 4 + (size_t)GS_TM * L.d_out + 4 * 8 * L.d_out + GS_TM + 2);
+    if (smem > 200 * 1024) {
+        se3::set_error("se3_gate_segment_sum_forward: rows too wide for the shared-memory tile");
+        return SE3_ERR_TOO_LARGE;
+    }
+    static size_t attr = 48 * 1024;
+    if (smem > attr) {
+        SE3_CUDA_TRY(cudaFuncSetAttribute(gate_segsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = smem;
+    }
+    const long long ntiles = (rows + GS_TM - 1) / GS_TM;
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(6, (200 * 1024) / smem));
+    const int grid = (int)std::min<long long>(ntiles, (long long)se3::num_sms() * per_sm);
+    gate_segsum_kernel<<<grid, GATE_NT, smem, (cudaStream_t)stream>>>(L, rows, seg, raw, out);
     SE3_LAUNCHED();
     return SE3_OK;
 }
@@ -251,7 +292,7 @@ extern "C" int se3_gate_segment_sum_backward(int64_t rows, const int32_t* seg, i
     if (rows == 0) return SE3_OK;
     int chunk;
     unsigned magic;
-    gate_chunk(L.d_raw, &chunk, &magic);
+    gate_chunk(L.ns + L.ng, &chunk, &magic);
     const int grid = (int)std::min<long long>((rows + chunk - 1) / chunk, (long long)se3::num_sms() * 8);
     gate_bwd_kernel<<<grid, GATE_NT, 0, (cudaStream_t)stream>>>(L, rows, chunk, magic, raw, gout, seg, graw);
     SE3_LAUNCHED();

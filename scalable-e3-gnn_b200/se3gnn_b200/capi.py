@@ -157,8 +157,8 @@ EXPORTS = [
                                    C.c_void_p, C.c_void_p]),
     ("se3_gate_backward", C.c_int, [C.c_int64, C.c_int32, C.c_int32, _i32p, _i32p, C.c_float, C.c_float, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
-    ("se3_gate_segment_sum_forward", C.c_int, [C.c_int64, C.c_void_p, C.c_int32, C.c_int32, _i32p, _i32p, C.c_float, C.c_float,
-                                               C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("se3_gate_segment_sum_forward", C.c_int, [C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, _i32p, _i32p, C.c_float,
+                                               C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("se3_gate_segment_sum_backward", C.c_int, [C.c_int64, C.c_void_p, C.c_int32, C.c_int32, _i32p, _i32p, C.c_float,
                                                 C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("se3_octree_work_bytes", C.c_int, [C.c_int64, C.c_int64, C.POINTER(C.c_size_t)]),

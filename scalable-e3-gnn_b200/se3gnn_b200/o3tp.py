@@ -23,7 +23,7 @@ class _O3tpFn(torch.autograd.Function):
         plan = mod._plan
         rows = in1.shape[0]
         out = torch.empty((rows, plan.d_out), device=in1.device, dtype=torch.float32)
-        with capi.mark("o3tp.fwd", mod.algo_bytes(rows, "fwd"), mod.flops(rows)):
+        with capi.mark(f"o3tp.fwd[{mod.in1_dim}x{mod.in2_dim}->{mod.iro.dim}]", mod.algo_bytes(rows, "fwd"), mod.flops(rows)):
             capi.check(capi.lib().se3_o3tp_forward(plan.handle, rows, capi.ptr(in1), capi.ptr(in2), capi.ptr(weight),
                                                    capi.ptr(out), capi.current_stream_ptr()), "se3_o3tp_forward")
         ctx.save_for_backward(in1, in2, weight)
@@ -40,7 +40,7 @@ class _O3tpFn(torch.autograd.Function):
         gin1 = torch.empty_like(in1)
         gin2 = torch.empty_like(in2) if ctx.needs_input_grad[1] else None
         gw = torch.empty_like(weight)
-        with capi.mark("o3tp.bwd", mod.algo_bytes(rows, "bwd"), 2 * mod.flops(rows)):
+        with capi.mark(f"o3tp.bwd[{mod.in1_dim}x{mod.in2_dim}->{mod.iro.dim}]", mod.algo_bytes(rows, "bwd"), 2 * mod.flops(rows)):
             capi.check(capi.lib().se3_o3tp_backward(plan.handle, rows, capi.ptr(in1), capi.ptr(in2), capi.ptr(weight),
                                                     capi.ptr(gout), capi.ptr(gin1), capi.ptr(gin2), capi.ptr(gw),
                                                     capi.current_stream_ptr()), "se3_o3tp_backward")
@@ -63,7 +63,7 @@ class _O3tpCatFn(torch.autograd.Function):
         plan = mod._plan
         rows = in2.shape[0]
         out = torch.empty((rows, plan.d_out), device=in2.device, dtype=torch.float32)
-        with capi.mark("o3tp.fwd", mod.algo_bytes(rows, "fwd"), mod.flops(rows)):
+        with capi.mark(f"o3tp.fwd[{mod.in1_dim}x{mod.in2_dim}->{mod.iro.dim}]", mod.algo_bytes(rows, "fwd"), mod.flops(rows)):
             capi.check(capi.lib().se3_o3tp_forward_seg(plan.handle, rows, len(tensors), _rowsegs(tensors, idxs), capi.ptr(in2),
                                                        capi.ptr(weight), capi.ptr(out), capi.current_stream_ptr()),
                        "se3_o3tp_forward_seg")
@@ -93,7 +93,7 @@ class _O3tpCatFn(torch.autograd.Function):
             modes[s] = capi.GRAD_STORE if ix is None else (capi.GRAD_SORTED if sorted_flags[s] else capi.GRAD_ATOMIC)
         gin2 = torch.empty_like(in2) if ctx.needs_input_grad[0] else None
         gw = torch.empty_like(weight)
-        with capi.mark("o3tp.bwd", mod.algo_bytes(rows, "bwd"), 2 * mod.flops(rows)):
+        with capi.mark(f"o3tp.bwd[{mod.in1_dim}x{mod.in2_dim}->{mod.iro.dim}]", mod.algo_bytes(rows, "bwd"), 2 * mod.flops(rows)):
             capi.check(capi.lib().se3_o3tp_backward_seg(plan.handle, rows, len(tensors), _rowsegs(tensors, idxs),
                                                         capi.ptr(in2), capi.ptr(weight), capi.ptr(gout), gptr, modes,
                                                         capi.ptr(gin2), capi.ptr(gw), capi.current_stream_ptr()),

@@ -8,6 +8,7 @@
 
 #include "common.cuh"
 #include "o3tp_tables.h"
+#include "o3tp_tc.h"
 
 namespace {
 
@@ -233,6 +234,8 @@ struct se3_o3tp_plan {
     size_t smem_gin = 0, smem_gw = 0;
     size_t smem_f = 0, smem_b = 0;
     int grid_f = 0, grid_b = 0;
+    O3TcGw* tcgw = nullptr;   // weight gradient on the tensor cores (o3tp_tc_gw.cu), nullptr if the plan is not covered
+    int gin_alone = 0;        // the input-gradient kernel can run next to it even when the SIMT pair is not used
 };
 
 static int pick_tile(const std::vector<int32_t>& blob, bool bwd, int* te, size_t* smem) {
@@ -319,6 +322,14 @@ extern "C" int se3_o3tp_plan_create(const se3_o3tp_desc* d, se3_o3tp_plan** out)
     }
     p->grid_f = bf * se3::num_sms();
     p->grid_b = bb * se3::num_sms();
+    p->tcgw = o3tp_tc_gw_create(p->P);
+    if (p->tcgw && !p->split && p->smem_gin <= SMEM_MAX) {
+        int b1 = 0;
+        cudaError_t e2 = cudaFuncSetAttribute(o3tp_gin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
+        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, o3tp_gin_kernel, O3_NT, p->smem_gin);
+        if (e2 == cudaSuccess && b1 >= 1) { p->gin_alone = 1; p->grid_gin = b1 * se3::num_sms(); }
+        else cudaGetLastError();
+    }
     *out = p;
     return SE3_OK;
 }
@@ -326,13 +337,15 @@ extern "C" int se3_o3tp_plan_create(const se3_o3tp_desc* d, se3_o3tp_plan** out)
 extern "C" void se3_o3tp_plan_destroy(se3_o3tp_plan* p) {
     if (!p) return;
     if (p->d_tab) cudaFree(p->d_tab);
+    o3tp_tc_gw_destroy(p->tcgw);
     delete p;
 }
 
 extern "C" int se3_o3tp_plan_info(const se3_o3tp_plan* p, int32_t dims[8]) {
     if (!p || !dims) { set_error("null argument"); return SE3_ERR_INVALID; }
     dims[0] = p->P.D1; dims[1] = p->P.D2; dims[2] = p->P.Dout; dims[3] = (int32_t)p->P.paths.size();
-    dims[4] = p->P.nW; dims[5] = p->te_f; dims[6] = p->te_b; dims[7] = (int32_t)(p->smem_b >> 10) | (p->gw_global << 16) | (p->dbuf_b << 17) | (p->split << 18);
+    dims[4] = p->P.nW; dims[5] = p->te_f; dims[6] = p->te_b; dims[7] = (int32_t)(p->smem_b >> 10) | (p->gw_global << 16) | (p->dbuf_b << 17) | (p->split << 18) |
+              ((p->tcgw && (p->split || p->gin_alone) ? 1 : 0) << 19);
     return SE3_OK;
 }
 
@@ -419,6 +432,34 @@ extern "C" int se3_o3tp_backward_seg(se3_o3tp_plan* p, int64_t rows, int32_t nse
     }
     SE3_CUDA_TRY(cudaMemsetAsync(gw, 0, sizeof(float) * p->P.nW, (cudaStream_t)stream));
     if (rows == 0) return SE3_OK;
+    // weight gradient on the tensor cores for the whole 32-row tiles of a dense in1 (o3tp_tc_gw.cu); the input gradients
+    // stay on the SIMT kernel, the (< 32) remaining rows add their weight gradient through the SIMT path
+    const long long rows_tc = rows & ~31ll;
+    if (p->tcgw && rows_tc > 0 && (p->split || p->gin_alone) && nseg == 1 && !X.idx[0] && X.ld[0] == p->P.D1 &&
+        o3tp_tc_gw_aligned(p->tcgw, X.base[0], in2, gout)) {
+        cudaStream_t st = (cudaStream_t)stream;
+        const long long t1 = (rows + o3::TE_GIN - 1) / o3::TE_GIN;
+        o3tp_gin_kernel<<<(int)std::min<long long>(t1, p->grid_gin), O3_NT, p->smem_gin, st>>>(p->d_tab, X, in2, w, gout, G, gin2, rows);
+        SE3_LAUNCHED();
+        const int rc = o3tp_tc_gw_run(p->tcgw, rows_tc, X.base[0], in2, gout, gw, st);
+        if (rc) return rc;
+        const long long tail = rows - rows_tc;
+        if (tail > 0) {
+            O3Rows Xt = X;
+            Xt.base[0] = X.base[0] + rows_tc * X.ld[0];
+            const float* in2t = in2 + rows_tc * p->P.D2;
+            const float* gt = gout + rows_tc * p->P.Dout;
+            if (p->split) {
+                o3tp_gw_kernel<<<1, O3_NT, p->smem_gw, st>>>(p->d_tab, Xt, in2t, gt, gw, tail);
+            } else {
+                O3GRows G0 = G;
+                for (int s = 0; s < 4; ++s) G0.mode[s] = 0;
+                o3tp_bwd_kernel<<<1, O3_NT, p->smem_b, st>>>(p->d_tab, Xt, in2t, w, gt, G0, nullptr, gw, tail, p->gw_global, p->dbuf_b);
+            }
+            SE3_LAUNCHED();
+        }
+        return SE3_OK;
+    }
     if (p->split) {
         const long long t1 = (rows + o3::TE_GIN - 1) / o3::TE_GIN, t2 = (rows + o3::TE_BWD - 1) / o3::TE_BWD;
         o3tp_gin_kernel<<<(int)std::min<long long>(t1, p->grid_gin), O3_NT, p->smem_gin, (cudaStream_t)stream>>>(

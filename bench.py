@@ -244,7 +244,10 @@ def other_configs(a, world, rank, dev, model, ts, budget_s=150.0):
                 ms, g = timed(step2, 2)
                 out["configs[2] SEGNN l_max=2, 1M particles, 1 GPU"] = {
                     "ms_per_step": ms, "particles_per_s": n / (ms * 1e-3), "edges": int(g.e), "hidden": "23x0e+7x1o+4x2e",
-                    "contraction": "fp32 SIMT (csrc/o3tp.cu); the bf16 tensor-core contraction configs[2] names is not built",
+                    "contraction": "message 1 by linearity (weight contraction once per node, csrc/o3msg.cu); weight gradients of "
+                                   "message 2 / update 2 / the node tables on the tensor cores (tcgen05 3xTF32, csrc/o3tp_tc_gw.cu); "
+                                   "forward and input gradients fp32 SIMT (csrc/o3tp.cu); gate + aggregation fused (csrc/gate.cu). "
+                                   "fp32 parity 1e-5 instead of the bf16 contraction configs[2] names",
                     "peak_mem_GB": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)}
                 del m2, opt, g, pos, vel, mass, target
                 torch.cuda.empty_cache()

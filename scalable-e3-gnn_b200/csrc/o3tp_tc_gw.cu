@@ -53,6 +53,7 @@ struct GwArgs {
     const float* g;
     float* partials;                               // [grid][64][32 nG]
     int o_x, o_g, o_y, xb, gb, yb, o_tab, o_bar, half;
+    int nstage;                                    // staging buffers (2; 1 when the cotangent rows are too wide for two)
 };
 
 __device__ __forceinline__ int tw_off(int chunk, int row, int slot) {   // byte offset inside the hi part of the set
@@ -191,9 +192,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) o3tp_tc_gw_kernel(const __grid_c
     } else {
         // ================= workers
         const uint32_t sm_u32 = smem_u32(smraw);
-        auto issue_pf = [&](int it) {      // warp 0, lane 0: the three contiguous blocks of tile `it` -> staging buffer it & 1
+        const int ns = A.nstage;
+        auto issue_pf = [&](int it) {      // warp 0, lane 0: the three contiguous blocks of tile `it` -> staging buffer it % ns
             const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * TW;
-            const int b = it & 1;
+            const int b = ns == 2 ? (it & 1) : 0;
             const uint32_t bx = TW * T.D1 * 4, bg = TW * T.Dout * 4, by = TW * T.D2 * 4;
             mbar_arrive_tx(BAR(2 + b), bx + bg + by);
             bulk_g2s(sm_u32 + A.o_x + b * A.xb, A.x + row0 * T.D1, bx, BAR(2 + b));
@@ -202,17 +204,17 @@ __global__ void __launch_bounds__(G_THREADS, 1) o3tp_tc_gw_kernel(const __grid_c
         };
         if (nt > 0 && warp == 0 && lane == 0) {
             issue_pf(0);
-            if (nt > 1) issue_pf(1);
+            if (nt > 1 && ns == 2) issue_pf(1);
         }
         const int xpieces = T.D1 >> 2;     // 16-byte pieces per x row
         for (int it = 0; it < nt; ++it) {
-            const int b = it & 1;
+            const int b = it & 1, sb = ns == 2 ? b : 0;
             if (tid == 0) ctr[b ^ 1] = 0;                        // the other counter: last used a tile ago, next used a tile ahead
-            mbar_wait(BAR(2 + b), (it >> 1) & 1);                // staged rows of this tile landed
+            mbar_wait(BAR(2 + sb), ns == 2 ? (it >> 1) & 1 : it & 1);   // staged rows of this tile landed
             if (it > 0) mbar_wait(BAR(1), (it - 1) & 1);         // the MMAs that read the set are done
-            const float* xs = reinterpret_cast<const float*>(smraw + A.o_x + b * A.xb);
-            const float* gs = reinterpret_cast<const float*>(smraw + A.o_g + b * A.gb);
-            const float* ys = reinterpret_cast<const float*>(smraw + A.o_y + b * A.yb);
+            const float* xs = reinterpret_cast<const float*>(smraw + A.o_x + sb * A.xb);
+            const float* gs = reinterpret_cast<const float*>(smraw + A.o_g + sb * A.gb);
+            const float* ys = reinterpret_cast<const float*>(smraw + A.o_y + sb * A.yb);
             // x rows -> M-side operand: task = (piece, row); a warp covers 8 pieces x 4 rows of one atom (conflict-free)
             for (int task = tid; task < TW * 8 * ((xpieces + 7) >> 3); task += GWT) {
                 const int pc = task & 7, r4 = (task >> 3) & 3, rq = (task >> 5) & 7, piece = (task >> 8) * 8 + pc, row = rq * 4 + r4;
@@ -241,8 +243,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) o3tp_tc_gw_kernel(const __grid_c
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(0));
-            named_bar(1, GWT);                                   // every worker is done with staging buffer b
-            if (warp == 0 && lane == 0 && it + 2 < nt) issue_pf(it + 2);
+            named_bar(1, GWT);                                   // every worker is done with this staging buffer
+            if (warp == 0 && lane == 0 && it + ns < nt) issue_pf(it + ns);
         }
         // ---------------- final epilogue (warps 0-3): TMEM -> this CTA's partial [64][32 nG]; M = 64: row 16 q + i lives in
         // TMEM lane 32 q + i
@@ -343,14 +345,18 @@ O3TcGw* o3tp_tc_gw_create(const o3::Plan& P) {
     A.half = (T.nX + T.nG) * CHB;
     auto r128 = [](int x) { return (x + 127) & ~127; };
     A.xb = r128(TW * T.D1 * 4); A.gb = r128(TW * T.Dout * 4); A.yb = r128(TW * T.D2 * 4);
-    A.o_x = 2 * A.half; A.o_g = A.o_x + 2 * A.xb; A.o_y = A.o_g + 2 * A.gb;
-    A.o_tab = A.o_y + 2 * A.yb; A.o_bar = A.o_tab + r128((int)sizeof(Tab));
-    S->smem = (size_t)A.o_bar + 128;
-    S->nw = P.nW;
     int dev = 0, maxsm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    if ((int)S->smem > maxsm) { delete S; return nullptr; }
+    for (A.nstage = 2; A.nstage >= 1; --A.nstage) {
+        const int n = A.nstage;
+        A.o_x = 2 * A.half; A.o_g = A.o_x + n * A.xb; A.o_y = A.o_g + n * A.gb;
+        A.o_tab = A.o_y + n * A.yb; A.o_bar = A.o_tab + r128((int)sizeof(Tab));
+        S->smem = (size_t)A.o_bar + 128;
+        if ((int)S->smem <= maxsm) break;
+    }
+    S->nw = P.nW;
+    if (A.nstage < 1) { delete S; return nullptr; }
     return S;
 }
 

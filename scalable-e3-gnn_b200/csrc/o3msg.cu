@@ -13,6 +13,7 @@
 // of the path + w, entry (col, i) at base_h + col (2 l1 + 1) + i; `tbase` of a path = base_h + first column * (2 l1 + 1).
 // Specification: oracle/lmax2_oracle.py (same couplings and normalisation as csrc/o3tp.cu: o3tp_cg_gen.inl).
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -42,6 +43,8 @@ struct EdgeArgs {
     int ldo;
     int per_block;      // edges (nodes) per block = NTH / mul
     unsigned magic;     // ceil(2^16 / mul): tid / mul = (tid * magic) >> 16 for tid < 256
+    int ny;             // in2 is SH-type with Y_l at column l^2 (checked by the host): the ny <= 9 values of a row are read
+                        // once into registers; 0: general offsets, every path reads its Y through the pointer
 };
 
 struct NodeArgs {
@@ -61,6 +64,7 @@ struct NodeArgs {
     int ldg;
     int per_block;
     unsigned magic;
+    int ny;
 };
 
 template <int L1, int L2, int LO>
@@ -100,7 +104,7 @@ O3_DEV void bwd_path(const float* __restrict__ yr, const float (&g)[2 * LO + 1],
 }
 
 // pre[e][off + w (2 LO + 1) + c] for one output irrep: thread = (edge, output channel w)
-template <int LO>
+template <int LO, bool SH>
 __global__ void __launch_bounds__(NTH) o3msg_edge_fwd_kernel(const __grid_constant__ EdgeArgs A) {
     constexpr int DO = 2 * LO + 1;
     const int mul = A.io.mul;
@@ -116,6 +120,11 @@ __global__ void __launch_bounds__(NTH) o3msg_edge_fwd_kernel(const __grid_consta
         const float* td = A.tdst + (long long)__ldg(A.dst + e) * A.ldt;
         const float* ts = A.tsrc + (long long)__ldg(A.src + e) * A.ldt;
         const float* yr = A.y + e * A.ldy;
+        float yreg[9];
+        if (SH) {
+#pragma unroll
+            for (int j = 0; j < 9; ++j) yreg[j] = j < A.ny ? __ldg(yr + j) : 0.f;
+        }
         float acc[DO];
 #pragma unroll
         for (int c = 0; c < DO; ++c) acc[c] = 0.f;
@@ -125,9 +134,9 @@ __global__ void __launch_bounds__(NTH) o3msg_edge_fwd_kernel(const __grid_consta
                 const int l1 = A.io.p_l1[p], o = A.io.p_tbase[p] + w * (2 * l1 + 1);
                 const float* yp = yr + A.io.p_yoff[p];
                 switch (l1 * 9 + A.io.p_l2[p] * 3 + LO) {
-#define O3M_CASE(a, b, c)                                                  \
-    case a * 9 + b * 3 + c:                                                \
-        if constexpr (c == LO) fwd_path<a, b, c>(td + o, ts + o, yp, acc); \
+#define O3M_CASE(a, b, c)                                                                         \
+    case a * 9 + b * 3 + c:                                                                       \
+        if constexpr (c == LO) fwd_path<a, b, c>(td + o, ts + o, SH ? yreg + b * b : yp, acc);    \
         break;
                     O3_TRIPLES(O3M_CASE)
 #undef O3M_CASE
@@ -144,9 +153,9 @@ __global__ void __launch_bounds__(NTH) o3msg_edge_fwd_kernel(const __grid_consta
                     if (u < A.io.x_mul[p]) t = fmaf(wx[p][u], __ldg(xp + u), t);
                 const float* yp = yr + A.io.x_yoff[p];
                 switch (A.io.x_l2[p]) {   // a scalar extra couples with Y_l into an output of the same degree
-                    case 0: if constexpr (LO == 0) fwd_scalar<0, 0>(t, yp, acc); break;
-                    case 1: if constexpr (LO == 1) fwd_scalar<1, 1>(t, yp, acc); break;
-                    case 2: if constexpr (LO == 2) fwd_scalar<2, 2>(t, yp, acc); break;
+                    case 0: if constexpr (LO == 0) fwd_scalar<0, 0>(t, SH ? yreg : yp, acc); break;
+                    case 1: if constexpr (LO == 1) fwd_scalar<1, 1>(t, SH ? yreg + 1 : yp, acc); break;
+                    case 2: if constexpr (LO == 2) fwd_scalar<2, 2>(t, SH ? yreg + 4 : yp, acc); break;
                 }
             }
         }
@@ -159,7 +168,7 @@ __global__ void __launch_bounds__(NTH) o3msg_edge_fwd_kernel(const __grid_consta
 // G[n][tbase_p + w (2 l1 + 1) + i] = sum over the edges of node n of coupling^T (a g): thread = (node, output channel w).
 // SRC = false: the CSR row of a destination (edges ptr[n] .. ptr[n+1]); also the extras' weight-gradient partials
 // gex[n][gx_off + w slots + s] = sum_e extra[e][s] q_e.  SRC = true: edges perm[ptr[n] .. ptr[n+1]) of a source.
-template <int LO, bool SRC>
+template <int LO, bool SRC, bool SH>
 __global__ void __launch_bounds__(NTH) o3msg_edge_bwd_kernel(const __grid_constant__ NodeArgs A) {
     constexpr int DO = 2 * LO + 1;
     const int mul = A.io.mul;
@@ -173,21 +182,47 @@ __global__ void __launch_bounds__(NTH) o3msg_edge_bwd_kernel(const __grid_consta
 #pragma unroll
         for (int i = 0; i < 5; ++i) gt[p][i] = 0.f;
     const long long beg = __ldg(A.ptr + n), end = __ldg(A.ptr + n + 1);
-    for (long long k = beg; k < end; ++k) {
-        const long long e = SRC ? (long long)__ldg(A.perm + k) : k;
-        const float* gp = A.gpre + e * A.ldo + A.io.off + w * DO;
-        const float* yr = A.y + e * A.ldy;
-        float g[DO];
+    // SH: the cotangent channel and the Y row of edge k + 1 are fetched while edge k is processed (the loop is serial per
+    // thread and was latency-bound: long scoreboard 70-77 % of the samples)
+    float gn[DO], yn[9];
+    long long en = 0;
+    auto fetch = [&](long long kk) {
+        en = SRC ? (long long)__ldg(A.perm + kk) : kk;
+        const float* gp = A.gpre + en * A.ldo + A.io.off + w * DO;
+        const float* yq = A.y + en * A.ldy;
 #pragma unroll
-        for (int c = 0; c < DO; ++c) g[c] = A.io.a * __ldg(gp + c);
+        for (int c = 0; c < DO; ++c) gn[c] = __ldg(gp + c);
+#pragma unroll
+        for (int j = 0; j < 9; ++j) yn[j] = j < A.ny ? __ldg(yq + j) : 0.f;
+    };
+    if (SH && beg < end) fetch(beg);
+    for (long long k = beg; k < end; ++k) {
+        long long e;
+        float yreg[9], g[DO];
+        const float* yr;
+        if (SH) {
+            e = en;
+#pragma unroll
+            for (int j = 0; j < 9; ++j) yreg[j] = yn[j];
+#pragma unroll
+            for (int c = 0; c < DO; ++c) g[c] = A.io.a * gn[c];
+            yr = A.y + e * A.ldy;
+            if (k + 1 < end) fetch(k + 1);
+        } else {
+            e = SRC ? (long long)__ldg(A.perm + k) : k;
+            const float* gp = A.gpre + e * A.ldo + A.io.off + w * DO;
+            yr = A.y + e * A.ldy;
+#pragma unroll
+            for (int c = 0; c < DO; ++c) g[c] = A.io.a * __ldg(gp + c);
+        }
 #pragma unroll
         for (int p = 0; p < SE3_O3MSG_MAXP; ++p) {
             if (p < A.io.np) {
                 const float* yp = yr + A.io.p_yoff[p];
                 switch (A.io.p_l1[p] * 9 + A.io.p_l2[p] * 3 + LO) {
-#define O3M_CASE(a, b, c)                                          \
-    case a * 9 + b * 3 + c:                                        \
-        if constexpr (c == LO) bwd_path<a, b, c>(yp, g, gt[p]);    \
+#define O3M_CASE(a, b, c)                                                              \
+    case a * 9 + b * 3 + c:                                                            \
+        if constexpr (c == LO) bwd_path<a, b, c>(SH ? yreg + b * b : yp, g, gt[p]);    \
         break;
                     O3_TRIPLES(O3M_CASE)
 #undef O3M_CASE
@@ -202,9 +237,9 @@ __global__ void __launch_bounds__(NTH) o3msg_edge_bwd_kernel(const __grid_consta
                     float q[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
                     const float* yp = yr + A.io.x_yoff[p];
                     switch (A.io.x_l2[p]) {
-                        case 0: if constexpr (LO == 0) bwd_path<0, 0, 0>(yp, g, q); break;
-                        case 1: if constexpr (LO == 1) bwd_path<0, 1, 1>(yp, g, q); break;
-                        case 2: if constexpr (LO == 2) bwd_path<0, 2, 2>(yp, g, q); break;
+                        case 0: if constexpr (LO == 0) bwd_path<0, 0, 0>(SH ? yreg : yp, g, q); break;
+                        case 1: if constexpr (LO == 1) bwd_path<0, 1, 1>(SH ? yreg + 1 : yp, g, q); break;
+                        case 2: if constexpr (LO == 2) bwd_path<0, 2, 2>(SH ? yreg + 4 : yp, g, q); break;
                     }
                     const float* xp = A.ex + e * A.ldx + A.io.x_off[p];
 #pragma unroll
@@ -232,6 +267,23 @@ __global__ void __launch_bounds__(NTH) o3msg_edge_bwd_kernel(const __grid_consta
         for (int s = 0; s < 4; ++s)
             if (s < A.io.gx_slots) o[s] = sx[s];
     }
+}
+
+// in2 of SH type: Y_l at column l^2 for every path, and the rows hold all of them
+int sh_width(const se3_o3msg_io* io, int nio, int ldy) {
+    int lmax = 0;
+    for (int k = 0; k < nio; ++k) {
+        for (int p = 0; p < io[k].np; ++p) {
+            if (io[k].p_yoff[p] != io[k].p_l2[p] * io[k].p_l2[p]) return 0;
+            lmax = std::max(lmax, io[k].p_l2[p]);
+        }
+        for (int p = 0; p < io[k].nx; ++p) {
+            if (io[k].x_yoff[p] != io[k].x_l2[p] * io[k].x_l2[p]) return 0;
+            lmax = std::max(lmax, io[k].x_l2[p]);
+        }
+    }
+    const int ny = (lmax + 1) * (lmax + 1);
+    return ny <= ldy ? ny : 0;
 }
 
 int check_io(const se3_o3msg_io* io, int nio) {
@@ -278,10 +330,21 @@ extern "C" int se3_o3msg_edge_forward(const se3_o3msg_io* io, int32_t nio, int64
         const long long blocks = (edges + A.per_block - 1) / A.per_block;
         const int grid = (int)std::min<long long>(blocks, (long long)se3::num_sms() * 64);
         cudaStream_t st = (cudaStream_t)stream;
-        switch (io[k].l) {
-            case 0: o3msg_edge_fwd_kernel<0><<<grid, NTH, 0, st>>>(A); break;
-            case 1: o3msg_edge_fwd_kernel<1><<<grid, NTH, 0, st>>>(A); break;
-            default: o3msg_edge_fwd_kernel<2><<<grid, NTH, 0, st>>>(A); break;
+        // measured: reading Y through the pointer per path is faster in the forward (49.7 vs 58.0 ms per step at 17.9M
+        // edges), the register copy wins in the backward (77 -> 64 ms), whose edge loop is serial per thread
+        A.ny = getenv("SE3_O3MSG_FWD_YREG") ? sh_width(io, nio, ldy) : 0;
+        if (A.ny) {
+            switch (io[k].l) {
+                case 0: o3msg_edge_fwd_kernel<0, true><<<grid, NTH, 0, st>>>(A); break;
+                case 1: o3msg_edge_fwd_kernel<1, true><<<grid, NTH, 0, st>>>(A); break;
+                default: o3msg_edge_fwd_kernel<2, true><<<grid, NTH, 0, st>>>(A); break;
+            }
+        } else {
+            switch (io[k].l) {
+                case 0: o3msg_edge_fwd_kernel<0, false><<<grid, NTH, 0, st>>>(A); break;
+                case 1: o3msg_edge_fwd_kernel<1, false><<<grid, NTH, 0, st>>>(A); break;
+                default: o3msg_edge_fwd_kernel<2, false><<<grid, NTH, 0, st>>>(A); break;
+            }
         }
         SE3_LAUNCHED();
     }
@@ -320,19 +383,26 @@ extern "C" int se3_o3msg_edge_backward(const se3_o3msg_io* io, int32_t nio, int6
             const long long blocks = (A.n + A.per_block - 1) / A.per_block;
             if (blocks > 0x7fffffffLL) { set_error("o3msg backward: too many nodes"); return SE3_ERR_TOO_LARGE; }
             const int grid = (int)blocks;
+            A.ny = sh_width(io, nio, ldy);
+#define O3M_LAUNCH(LO_, SRC_)                                                              \
+    do {                                                                                   \
+        if (A.ny) o3msg_edge_bwd_kernel<LO_, SRC_, true><<<grid, NTH, 0, st>>>(A);          \
+        else o3msg_edge_bwd_kernel<LO_, SRC_, false><<<grid, NTH, 0, st>>>(A);              \
+    } while (0)
             if (role == 0) {
                 switch (io[k].l) {
-                    case 0: o3msg_edge_bwd_kernel<0, false><<<grid, NTH, 0, st>>>(A); break;
-                    case 1: o3msg_edge_bwd_kernel<1, false><<<grid, NTH, 0, st>>>(A); break;
-                    default: o3msg_edge_bwd_kernel<2, false><<<grid, NTH, 0, st>>>(A); break;
+                    case 0: O3M_LAUNCH(0, false); break;
+                    case 1: O3M_LAUNCH(1, false); break;
+                    default: O3M_LAUNCH(2, false); break;
                 }
             } else {
                 switch (io[k].l) {
-                    case 0: o3msg_edge_bwd_kernel<0, true><<<grid, NTH, 0, st>>>(A); break;
-                    case 1: o3msg_edge_bwd_kernel<1, true><<<grid, NTH, 0, st>>>(A); break;
-                    default: o3msg_edge_bwd_kernel<2, true><<<grid, NTH, 0, st>>>(A); break;
+                    case 0: O3M_LAUNCH(0, true); break;
+                    case 1: O3M_LAUNCH(1, true); break;
+                    default: O3M_LAUNCH(2, true); break;
                 }
             }
+#undef O3M_LAUNCH
             SE3_LAUNCHED();
         }
     }

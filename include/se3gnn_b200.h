@@ -244,7 +244,7 @@ typedef struct se3_o3tp_plan se3_o3tp_plan; /* opaque */
 
 int se3_o3tp_plan_create(const se3_o3tp_desc* desc, se3_o3tp_plan** plan);
 void se3_o3tp_plan_destroy(se3_o3tp_plan* plan);
-/* dims[0..7] = d_in1, d_in2, d_out, n_paths, weight_floats, rows per tile forward, rows per tile backward, backward shared memory KiB | accumulators-in-global flag << 16 | double-buffer flag << 17 | split-backward flag << 18 | weight gradient on the tensor cores (dense in1, whole 32-row tiles) << 19 */
+/* dims[0..7] = d_in1, d_in2, d_out, n_paths, weight_floats, rows per tile forward, rows per tile backward, backward shared memory KiB | accumulators-in-global flag << 16 | double-buffer flag << 17 | split-backward flag << 18 | weight gradient on the tensor cores (dense in1, whole 32-row tiles) << 19 | scalar second input handled as per-irrep linear maps << 20 */
 int se3_o3tp_plan_info(const se3_o3tp_plan* plan, int32_t dims[8]);
 /* host arrays of n_paths entries each (any may be NULL); path_weight = the normalisation factor a_out */
 int se3_o3tp_plan_paths(const se3_o3tp_plan* plan, int32_t* i_in1, int32_t* i_in2, int32_t* i_out,

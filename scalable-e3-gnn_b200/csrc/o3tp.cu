@@ -8,6 +8,7 @@
 
 #include "common.cuh"
 #include "o3tp_tables.h"
+#include "o3tp_lin.h"
 #include "o3tp_tc.h"
 
 namespace {
@@ -236,6 +237,7 @@ struct se3_o3tp_plan {
     int grid_f = 0, grid_b = 0;
     O3TcGw* tcgw = nullptr;   // weight gradient on the tensor cores (o3tp_tc_gw.cu), nullptr if the plan is not covered
     int gin_alone = 0;        // the input-gradient kernel can run next to it even when the SIMT pair is not used
+    O3Lin* lin = nullptr;     // scalar second input: forward / input gradients as per-irrep linear maps (o3tp_lin.cu)
 };
 
 static int pick_tile(const std::vector<int32_t>& blob, bool bwd, int* te, size_t* smem) {
@@ -323,6 +325,7 @@ extern "C" int se3_o3tp_plan_create(const se3_o3tp_desc* d, se3_o3tp_plan** out)
     p->grid_f = bf * se3::num_sms();
     p->grid_b = bb * se3::num_sms();
     p->tcgw = o3tp_tc_gw_create(p->P);
+    p->lin = o3lin_create(p->P);
     if (p->tcgw && !p->split && p->smem_gin <= SMEM_MAX) {
         int b1 = 0;
         cudaError_t e2 = cudaFuncSetAttribute(o3tp_gin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
@@ -338,6 +341,7 @@ extern "C" void se3_o3tp_plan_destroy(se3_o3tp_plan* p) {
     if (!p) return;
     if (p->d_tab) cudaFree(p->d_tab);
     o3tp_tc_gw_destroy(p->tcgw);
+    o3lin_destroy(p->lin);
     delete p;
 }
 
@@ -345,7 +349,7 @@ extern "C" int se3_o3tp_plan_info(const se3_o3tp_plan* p, int32_t dims[8]) {
     if (!p || !dims) { set_error("null argument"); return SE3_ERR_INVALID; }
     dims[0] = p->P.D1; dims[1] = p->P.D2; dims[2] = p->P.Dout; dims[3] = (int32_t)p->P.paths.size();
     dims[4] = p->P.nW; dims[5] = p->te_f; dims[6] = p->te_b; dims[7] = (int32_t)(p->smem_b >> 10) | (p->gw_global << 16) | (p->dbuf_b << 17) | (p->split << 18) |
-              ((p->tcgw && (p->split || p->gin_alone) ? 1 : 0) << 19);
+              ((p->tcgw && (p->split || p->gin_alone || p->lin) ? 1 : 0) << 19) | ((p->lin ? 1 : 0) << 20);
     return SE3_OK;
 }
 
@@ -395,6 +399,10 @@ extern "C" int se3_o3tp_forward_seg(se3_o3tp_plan* p, int64_t rows, int32_t nseg
         return SE3_ERR_INVALID;
     }
     if (rows == 0) return SE3_OK;
+    // scalar second input: the linear-map forward (o3tp_lin.cu) was measured slower than this kernel (2.9 vs 1.06 ms for
+    // 1.1M rows of the node tables); its input-gradient kernel is used by the backward (3.2 vs 4.5 ms)
+    if (p->lin && nseg == 1 && !X.idx[0] && X.ld[0] == p->P.D1 && getenv("SE3_O3TP_LIN_FWD"))
+        return o3lin_forward(p->lin, rows, X.base[0], in2, w, out, (cudaStream_t)stream);
     const long long ntiles = (rows + p->te_f - 1) / p->te_f;
     const int grid = (int)std::min<long long>(ntiles, p->grid_f);
     o3tp_fwd_kernel<<<grid, O3_NT, p->smem_f, (cudaStream_t)stream>>>(p->d_tab, X, in2, w, out, rows, p->te_f);
@@ -435,12 +443,21 @@ extern "C" int se3_o3tp_backward_seg(se3_o3tp_plan* p, int64_t rows, int32_t nse
     // weight gradient on the tensor cores for the whole 32-row tiles of a dense in1 (o3tp_tc_gw.cu); the input gradients
     // stay on the SIMT kernel, the (< 32) remaining rows add their weight gradient through the SIMT path
     const long long rows_tc = rows & ~31ll;
-    if (p->tcgw && rows_tc > 0 && (p->split || p->gin_alone) && nseg == 1 && !X.idx[0] && X.ld[0] == p->P.D1 &&
+    const bool dense = nseg == 1 && !X.idx[0] && X.ld[0] == p->P.D1;
+    const bool lin_gin = p->lin && dense && !gin2 && ((G.mode[0] & 15) == 0 || (G.mode[0] & 15) == 1);
+    if (p->tcgw && rows_tc > 0 && (p->split || p->gin_alone || lin_gin) && dense &&
         o3tp_tc_gw_aligned(p->tcgw, X.base[0], in2, gout)) {
         cudaStream_t st = (cudaStream_t)stream;
-        const long long t1 = (rows + o3::TE_GIN - 1) / o3::TE_GIN;
-        o3tp_gin_kernel<<<(int)std::min<long long>(t1, p->grid_gin), O3_NT, p->smem_gin, st>>>(p->d_tab, X, in2, w, gout, G, gin2, rows);
-        SE3_LAUNCHED();
+        if (lin_gin) {
+            if ((G.mode[0] & 15) == 1) {
+                const int rc = o3lin_gin(p->lin, rows, gout, in2, w, G.base[0], st);
+                if (rc) return rc;
+            }
+        } else {
+            const long long t1 = (rows + o3::TE_GIN - 1) / o3::TE_GIN;
+            o3tp_gin_kernel<<<(int)std::min<long long>(t1, p->grid_gin), O3_NT, p->smem_gin, st>>>(p->d_tab, X, in2, w, gout, G, gin2, rows);
+            SE3_LAUNCHED();
+        }
         const int rc = o3tp_tc_gw_run(p->tcgw, rows_tc, X.base[0], in2, gout, gw, st);
         if (rc) return rc;
         const long long tail = rows - rows_tc;

@@ -325,6 +325,7 @@ class O3tpPlan:
         check(lib().se3_o3tp_plan_info(h, dims))
         self.d_in1, self.d_in2, self.d_out, self.n_paths, self.weight_floats, self.tile_fwd, self.tile_bwd = list(dims)[:7]
         self.split_backward = bool((dims[7] >> 18) & 1)   # input / weight gradients as two kernels
+        self.linear_maps = bool((dims[7] >> 20) & 1)      # scalar in2: forward / input gradients as linear maps (o3tp_lin.cu)
         self.tc_weight_grad = bool((dims[7] >> 19) & 1)   # weight gradient of a dense in1 on the tensor cores (tcgen05)
         n = max(1, self.n_paths)
         arrs = [(C.c_int32 * n)() for _ in range(4)]

@@ -13,8 +13,10 @@
 // layout of l1tp_tc2_bwdw.cu (128-byte column chunks of 32 slots, 4-row atoms, 32-byte units XOR-ed with row & 3).
 //
 // Feeding: the tile's rows of in1, of the cotangent and of in2 are contiguous in HBM: three cp.async.bulk copies per
-// 32-row tile into a double-buffered staging area, issued two tiles ahead.  One operand set (136 KB for the message
-// product): the workers rebuild it as soon as the MMAs of the previous tile have completed.
+// 32-row tile into a double-buffered staging area, issued two tiles ahead.  The GT operand (122 KB hi / lo for the
+// message product) exists once, so it is built and consumed in TWO phases (two groups of paths = two column ranges of
+// <= 256 columns, one MMA per K-step each): while the MMAs of phase A run the workers build phase B, and the MMAs of
+// phase B run under the next tile's phase A; the small x operand is double buffered.
 // Only whole 32-row tiles are taken; the caller runs the SIMT kernel on the remaining rows.
 #include <algorithm>
 #include <cstdlib>
@@ -42,7 +44,8 @@ struct Tab {
     int npath, nio, nitem, D1, D2, Dout, nX, nG;   // nX / nG: 32-slot chunks of the x / GT operand
     PathD path[MAXPATH];
     IoD io[MAXIO];
-    int item[MAXITEM];                             // path | first channel << 8, heaviest first
+    int item[MAXITEM];                             // path | first channel << 8, heaviest first inside a phase
+    int nphase, ph_chunk[3], ph_item[3];           // phase p: GT chunks [ph_chunk[p], ph_chunk[p+1]), items [ph_item[p], ph_item[p+1])
 };
 
 struct GwArgs {
@@ -52,7 +55,8 @@ struct GwArgs {
     const float* y;
     const float* g;
     float* partials;                               // [grid][64][32 nG]
-    int o_x, o_g, o_y, xb, gb, yb, o_tab, o_bar, half;
+    int o_x, o_g, o_y, xb, gb, yb, o_tab, o_bar;
+    int xhalf, xset, o_gt, ghalf;                  // bytes: hi part of an x set, one x set (hi | lo), GT hi offset, GT hi part
     int nstage;                                    // staging buffers (2; 1 when the cotangent rows are too wide for two)
 };
 
@@ -130,24 +134,22 @@ __global__ void __launch_bounds__(G_THREADS, 1) o3tp_tc_gw_kernel(const __grid_c
     Tab& T = *reinterpret_cast<Tab*>(smraw + A.o_tab);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + A.o_bar);
     const uint32_t bar0 = smem_u32(bars);
-    // barriers: 0 set full | 1 MMAs of the tile done (set free) | 2,3 staged rows landed | 4 accumulators final
+    // barriers: 0,1 phase operand full | 2,3 MMAs of the phase done (its GT columns free) | 4,5 staged rows landed | 6 final
     auto BAR = [&](int i) { return bar0 + 8u * i; };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
-    int* ctr = reinterpret_cast<int*>(bars + 7);   // two item counters
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    int* ctr = reinterpret_cast<int*>(bars + 9);   // item counters [phase][tile parity]
 
     for (int i = tid; i < (int)(sizeof(Tab) / 4); i += G_THREADS) reinterpret_cast<int*>(&T)[i] = reinterpret_cast<const int*>(&A.T)[i];
     if (tid == 0) {
         mbar_init(BAR(0), GW);
-        mbar_init(BAR(1), 1);
-        mbar_init(BAR(2), 1);
-        mbar_init(BAR(3), 1);
-        mbar_init(BAR(4), 1);
-        ctr[0] = 0; ctr[1] = 0;
+        mbar_init(BAR(1), GW);
+        for (int i = 2; i < 7; ++i) mbar_init(BAR(i), 1);
+        ctr[0] = ctr[1] = ctr[2] = ctr[3] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    {   // zero the operand set once: unused slots are never written again and must stay finite (0 * x)
+    {   // zero the operands once: unused slots are never written again and must stay finite (0 * x)
         float4* z = reinterpret_cast<float4*>(smraw);
-        for (int t = tid; t < (2 * A.half) >> 4; t += G_THREADS) z[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int t = tid; t < (2 * A.xset + 2 * A.ghalf) >> 4; t += G_THREADS) z[t] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     fence_proxy_async();
     if (warp == GW) {
@@ -160,34 +162,38 @@ __global__ void __launch_bounds__(G_THREADS, 1) o3tp_tc_gw_kernel(const __grid_c
     const uint32_t tmem_base = *tmem_slot;
     const long long ntiles = A.rows / TW;
     const int nt = (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
-    const int nX = A.T.nX, nG = A.T.nG;
+    const int nG = A.T.nG, nph = A.T.nphase;
 
     if (warp == GW) {
-        // ================= MMA issuer: P[64 x 32 nG] += X^T GT, N split into pieces of <= 256 columns
+        // ================= MMA issuer: P[64 x 32 nG] += X^T GT, one phase (column range) after the other
         const uint32_t sb = smem_u32(smraw);
-        const uint64_t dX = mk_desc_mn(sb), lo = (uint64_t)(A.half >> 4);
+        const uint64_t lox = (uint64_t)(A.xhalf >> 4), log = (uint64_t)(A.ghalf >> 4);
         for (int it = 0; it < nt; ++it) {
-            mbar_wait(BAR(0), it & 1);
-            tc_fence_after();
-            if (lane == 0) {
-                for (int ks = 0; ks < TW / 8; ++ks) {
-                    const uint32_t acc0 = (it == 0 && ks == 0) ? 0u : 1u;
-                    const uint64_t ko = (uint64_t)(ks * 64);   // 8 rows x 128 B, in 16-byte units
-                    for (int c0 = 0; c0 < nG; c0 += 8) {
-                        const int nc = min(8, nG - c0);
-                        const uint32_t id = make_idesc_ex(64, 32 * nc, 1, 1);
-                        const uint64_t dG = mk_desc_mn(sb + (uint32_t)(nX + c0) * CHB);
-                        const uint32_t d = tmem_base + 32u * c0;
-                        tc_mma_tf32(d, dX + ko, dG + ko, id, acc0);
-                        tc_mma_tf32(d, dX + ko, dG + ko + lo, id, 1u);
-                        tc_mma_tf32(d, dX + ko + lo, dG + ko, id, 1u);
+            const uint64_t dX = mk_desc_mn(sb + (uint32_t)(it & 1) * A.xset);
+            for (int ph = 0; ph < nph; ++ph) {
+                mbar_wait(BAR(ph), it & 1);
+                tc_fence_after();
+                if (lane == 0) {
+                    const int cb = A.T.ph_chunk[ph], ce = A.T.ph_chunk[ph + 1];
+                    for (int ks = 0; ks < TW / 8; ++ks) {
+                        const uint32_t acc0 = (it == 0 && ks == 0) ? 0u : 1u;
+                        const uint64_t ko = (uint64_t)(ks * 64);   // 8 rows x 128 B, in 16-byte units
+                        for (int c0 = cb; c0 < ce; c0 += 8) {
+                            const int nc = min(8, ce - c0);
+                            const uint32_t id = make_idesc_ex(64, 32 * nc, 1, 1);
+                            const uint64_t dG = mk_desc_mn(sb + A.o_gt + (uint32_t)c0 * CHB);
+                            const uint32_t d = tmem_base + 32u * c0;
+                            tc_mma_tf32(d, dX + ko, dG + ko, id, acc0);
+                            tc_mma_tf32(d, dX + ko, dG + ko + log, id, 1u);
+                            tc_mma_tf32(d, dX + ko + lox, dG + ko, id, 1u);
+                        }
                     }
+                    tc_commit(BAR(2 + ph));
                 }
-                tc_commit(BAR(1));
+                __syncwarp();
             }
-            __syncwarp();
         }
-        if (lane == 0) tc_commit(BAR(4));
+        if (lane == 0) tc_commit(BAR(6));
         __syncwarp();
     } else {
         // ================= workers
@@ -197,59 +203,67 @@ __global__ void __launch_bounds__(G_THREADS, 1) o3tp_tc_gw_kernel(const __grid_c
             const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * TW;
             const int b = ns == 2 ? (it & 1) : 0;
             const uint32_t bx = TW * T.D1 * 4, bg = TW * T.Dout * 4, by = TW * T.D2 * 4;
-            mbar_arrive_tx(BAR(2 + b), bx + bg + by);
-            bulk_g2s(sm_u32 + A.o_x + b * A.xb, A.x + row0 * T.D1, bx, BAR(2 + b));
-            bulk_g2s(sm_u32 + A.o_g + b * A.gb, A.g + row0 * T.Dout, bg, BAR(2 + b));
-            bulk_g2s(sm_u32 + A.o_y + b * A.yb, A.y + row0 * T.D2, by, BAR(2 + b));
+            mbar_arrive_tx(BAR(4 + b), bx + bg + by);
+            bulk_g2s(sm_u32 + A.o_x + b * A.xb, A.x + row0 * T.D1, bx, BAR(4 + b));
+            bulk_g2s(sm_u32 + A.o_g + b * A.gb, A.g + row0 * T.Dout, bg, BAR(4 + b));
+            bulk_g2s(sm_u32 + A.o_y + b * A.yb, A.y + row0 * T.D2, by, BAR(4 + b));
         };
         if (nt > 0 && warp == 0 && lane == 0) {
             issue_pf(0);
             if (nt > 1 && ns == 2) issue_pf(1);
         }
         const int xpieces = T.D1 >> 2;     // 16-byte pieces per x row
+        unsigned char* gt = smraw + A.o_gt;
         for (int it = 0; it < nt; ++it) {
             const int b = it & 1, sb = ns == 2 ? b : 0;
-            if (tid == 0) ctr[b ^ 1] = 0;                        // the other counter: last used a tile ago, next used a tile ahead
-            mbar_wait(BAR(2 + sb), ns == 2 ? (it >> 1) & 1 : it & 1);   // staged rows of this tile landed
-            if (it > 0) mbar_wait(BAR(1), (it - 1) & 1);         // the MMAs that read the set are done
+            if (tid == 0) { ctr[b ^ 1] = 0; ctr[2 + (b ^ 1)] = 0; }   // the other parity: last used a tile ago, next used a tile ahead
+            mbar_wait(BAR(4 + sb), ns == 2 ? (it >> 1) & 1 : it & 1);   // staged rows of this tile landed
             const float* xs = reinterpret_cast<const float*>(smraw + A.o_x + sb * A.xb);
             const float* gs = reinterpret_cast<const float*>(smraw + A.o_g + sb * A.gb);
             const float* ys = reinterpret_cast<const float*>(smraw + A.o_y + sb * A.yb);
-            // x rows -> M-side operand: task = (piece, row); a warp covers 8 pieces x 4 rows of one atom (conflict-free)
-            for (int task = tid; task < TW * 8 * ((xpieces + 7) >> 3); task += GWT) {
-                const int pc = task & 7, r4 = (task >> 3) & 3, rq = (task >> 5) & 7, piece = (task >> 8) * 8 + pc, row = rq * 4 + r4;
-                if (piece < xpieces) {
-                    const float4 v = *reinterpret_cast<const float4*>(xs + row * T.D1 + 4 * piece);
-                    st4(smraw, tw_off(piece >> 3, row, 4 * (piece & 7)), A.half, v.x, v.y, v.z, v.w);
+            for (int ph = 0; ph < nph; ++ph) {
+                if (it > 0) mbar_wait(BAR(2 + ph), (it - 1) & 1);    // the MMAs that read this phase's GT columns are done
+                if (ph == 0) {
+                    // x rows -> M-side operand (set it & 1: its readers, the MMAs of tile it - 2, are long done): task =
+                    // (piece, row); a warp covers 8 pieces x 4 rows of one atom (conflict-free)
+                    unsigned char* xset = smraw + b * A.xset;
+                    for (int task = tid; task < TW * 8 * ((xpieces + 7) >> 3); task += GWT) {
+                        const int pc = task & 7, r4 = (task >> 3) & 3, rq = (task >> 5) & 7, piece = (task >> 8) * 8 + pc, row = rq * 4 + r4;
+                        if (piece < xpieces) {
+                            const float4 v = *reinterpret_cast<const float4*>(xs + row * T.D1 + 4 * piece);
+                            st4(xset, tw_off(piece >> 3, row, 4 * (piece & 7)), A.xhalf, v.x, v.y, v.z, v.w);
+                        }
+                    }
                 }
-            }
-            // cotangent rows -> GT (N-side operand): lane = row, warps pull (path, 4 channels) items heaviest first
-            for (;;) {
-                int u = 0;
-                if (lane == 0) u = atomicAdd(&ctr[b], 1);
-                u = __shfl_sync(0xffffffffu, u, 0);
-                if (u >= T.nitem) break;
-                const int code = T.item[u];
-                const PathD& P = T.path[code & 255];
-                const IoD& I = T.io[P.io];
-                const int w0 = code >> 8;
-                const float *grow = gs + lane * T.Dout, *yr = ys + lane * T.D2;
-                switch (I.l) {
-                    case 0: gt_item<0>(P, I, w0, grow, yr, smraw, A.half, nX, lane); break;
-                    case 1: gt_item<1>(P, I, w0, grow, yr, smraw, A.half, nX, lane); break;
-                    default: gt_item<2>(P, I, w0, grow, yr, smraw, A.half, nX, lane); break;
+                // cotangent rows -> GT (N-side operand): lane = row, warps pull (path, 4 channels) items heaviest first
+                const int i0 = T.ph_item[ph], i1 = T.ph_item[ph + 1];
+                for (;;) {
+                    int u = 0;
+                    if (lane == 0) u = atomicAdd(&ctr[2 * ph + b], 1);
+                    u = __shfl_sync(0xffffffffu, u, 0) + i0;
+                    if (u >= i1) break;
+                    const int code = T.item[u];
+                    const PathD& P = T.path[code & 255];
+                    const IoD& I = T.io[P.io];
+                    const int w0 = code >> 8;
+                    const float *grow = gs + lane * T.Dout, *yr = ys + lane * T.D2;
+                    switch (I.l) {
+                        case 0: gt_item<0>(P, I, w0, grow, yr, gt, A.ghalf, 0, lane); break;
+                        case 1: gt_item<1>(P, I, w0, grow, yr, gt, A.ghalf, 0, lane); break;
+                        default: gt_item<2>(P, I, w0, grow, yr, gt, A.ghalf, 0, lane); break;
+                    }
                 }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(ph));
             }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(0));
             named_bar(1, GWT);                                   // every worker is done with this staging buffer
             if (warp == 0 && lane == 0 && it + ns < nt) issue_pf(it + ns);
         }
         // ---------------- final epilogue (warps 0-3): TMEM -> this CTA's partial [64][32 nG]; M = 64: row 16 q + i lives in
         // TMEM lane 32 q + i
         if (warp < 4) {
-            mbar_wait(BAR(4), 0);
+            mbar_wait(BAR(6), 0);
             tc_fence_after();
             const int ntp = 32 * nG;
             float* part = A.partials + (long long)blockIdx.x * 64 * ntp + (long long)(16 * warp + (lane & 15)) * ntp;
@@ -321,28 +335,58 @@ O3TcGw* o3tp_tc_gw_create(const o3::Plan& P) {
     for (auto& ir : P.out) { offo.push_back(acc); acc += ir.mul * (2 * ir.l + 1); }
     T.npath = (int)P.paths.size(); T.nio = (int)P.out.size(); T.D1 = P.D1; T.D2 = P.D2; T.Dout = P.Dout;
     for (size_t io = 0; io < P.out.size(); ++io) T.io[io] = {offo[io], P.out[io].mul, P.out[io].l, P.a[io]};
-    struct It { int code; double cost; };
-    std::vector<It> items;
-    int col = 0;
+    // two phases = two groups of paths (greedy split by padded column count, heaviest path first); each phase's columns
+    // are contiguous and start on a chunk boundary
+    struct Pw { int p, width; };
+    std::vector<Pw> pw;
     for (int p = 0; p < T.npath; ++p) {
         const o3::PathH& h = P.paths[p];
-        const o3::Irrep a = P.in1[h.i1], b = P.in2[h.i2], o = P.out[h.io];
-        const int d1 = 2 * a.l + 1, dout = 2 * o.l + 1;
-        T.path[p] = {off1[h.i1], a.l, a.mul, b.l, off2[h.i2], h.io, col, h.woff};
-        for (int w0 = 0; w0 < o.mul; w0 += CH) {
-            const double cost = 30 + d1 * dout * (a.l && b.l && o.l ? 3.0 : 1.0) + CH * (dout + 2.0 * d1 * dout + 12.0 * d1);
-            items.push_back({p | (w0 << 8), cost});
+        pw.push_back({p, ((P.out[h.io].mul + CH - 1) / CH) * CH * (2 * P.in1[h.i1].l + 1)});
+    }
+    std::vector<Pw> byw = pw;
+    std::stable_sort(byw.begin(), byw.end(), [](const Pw& x, const Pw& y) { return x.width > y.width; });
+    std::vector<int> phase_of(T.npath, 0);
+    int load[2] = {0, 0};
+    for (const Pw& q : byw) {
+        const int k = load[1] < load[0] ? 1 : 0;
+        phase_of[q.p] = k;
+        load[k] += q.width;
+    }
+    int nphase = (load[0] > 0 && load[1] > 0 && T.npath >= 2) ? 2 : 1;
+    if (nphase == 2 && ((load[0] + 31) / 32 + (load[1] + 31) / 32) * 32 > 512) nphase = 1;   // the chunk padding does not fit TMEM
+    if (nphase == 1) std::fill(phase_of.begin(), phase_of.end(), 0);
+    struct It { int code; double cost; };
+    int col = 0, nitem = 0;
+    T.nphase = nphase;
+    for (int ph = 0; ph < nphase; ++ph) {
+        col = (col + 31) & ~31;
+        T.ph_chunk[ph] = col / 32;
+        T.ph_item[ph] = nitem;
+        std::vector<It> items;
+        for (int p = 0; p < T.npath; ++p) {
+            if (phase_of[p] != ph) continue;
+            const o3::PathH& h = P.paths[p];
+            const o3::Irrep a = P.in1[h.i1], b = P.in2[h.i2], o = P.out[h.io];
+            const int d1 = 2 * a.l + 1, dout = 2 * o.l + 1;
+            T.path[p] = {off1[h.i1], a.l, a.mul, b.l, off2[h.i2], h.io, col, h.woff};
+            for (int w0 = 0; w0 < o.mul; w0 += CH) {
+                const double cost = 30 + d1 * dout * (a.l && b.l && o.l ? 3.0 : 1.0) + CH * (dout + 2.0 * d1 * dout + 12.0 * d1);
+                items.push_back({p | (w0 << 8), cost});
+            }
+            col += pw[p].width;    // 4-channel items write whole 16-byte pieces: the path's width is padded to 4 channels
         }
-        col += ((o.mul + CH - 1) / CH) * CH * d1;    // 4-channel items write whole 16-byte pieces: pad the path's width
+        std::stable_sort(items.begin(), items.end(), [](const It& x, const It& y) { return x.cost > y.cost; });
+        if (nitem + (int)items.size() > MAXITEM) { delete S; return nullptr; }
+        for (const It& it : items) T.item[nitem++] = it.code;
     }
     const int nG = (col + 31) / 32;
-    if (nG * 32 > 512 || items.size() > (size_t)MAXITEM || T.npath > 255) { delete S; return nullptr; }
-    std::stable_sort(items.begin(), items.end(), [](const It& x, const It& y) { return x.cost > y.cost; });
-    T.nitem = (int)items.size();
-    for (int i = 0; i < T.nitem; ++i) T.item[i] = items[i].code;
+    T.ph_chunk[nphase] = nG;
+    T.ph_item[nphase] = nitem;
+    if (nG * 32 > 512 || T.npath > 255) { delete S; return nullptr; }
+    T.nitem = nitem;
     T.nX = 2; T.nG = nG;
     GwArgs& A = S->A;
-    A.half = (T.nX + T.nG) * CHB;
+    A.xhalf = T.nX * CHB; A.xset = 2 * A.xhalf; A.o_gt = 2 * A.xset; A.ghalf = T.nG * CHB;
     auto r128 = [](int x) { return (x + 127) & ~127; };
     A.xb = r128(TW * T.D1 * 4); A.gb = r128(TW * T.Dout * 4); A.yb = r128(TW * T.D2 * 4);
     int dev = 0, maxsm = 0;
@@ -350,7 +394,7 @@ O3TcGw* o3tp_tc_gw_create(const o3::Plan& P) {
     cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     for (A.nstage = 2; A.nstage >= 1; --A.nstage) {
         const int n = A.nstage;
-        A.o_x = 2 * A.half; A.o_g = A.o_x + n * A.xb; A.o_y = A.o_g + n * A.gb;
+        A.o_x = A.o_gt + 2 * A.ghalf; A.o_g = A.o_x + n * A.xb; A.o_y = A.o_g + n * A.gb;
         A.o_tab = A.o_y + n * A.yb; A.o_bar = A.o_tab + r128((int)sizeof(Tab));
         S->smem = (size_t)A.o_bar + 128;
         if ((int)S->smem <= maxsm) break;

@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(O3_NT) o3tp_bwd_kernel(const int32_t* __restri
         for (int idx = threadIdx.x; idx < tab[o3::H_NW]; idx += blockDim.x) atomicAdd(gw + idx, gWs[idx]);
 }
 
-__global__ void __launch_bounds__(O3_NT, 2) o3tp_gin_kernel(const int32_t* __restrict__ tab_g, const O3Rows in1,
+__global__ void __launch_bounds__(O3_NT, 3) o3tp_gin_kernel(const int32_t* __restrict__ tab_g, const O3Rows in1,
                                                             const float* __restrict__ in2, const float* __restrict__ w,
                                                             const float* __restrict__ gout, const O3GRows gin1,
                                                             float* __restrict__ gin2, long long rows) {

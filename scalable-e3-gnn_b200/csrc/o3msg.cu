@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(NTH) o3msg_edge_fwd_kernel(const __grid_consta
 // SRC = false: the CSR row of a destination (edges ptr[n] .. ptr[n+1]); also the extras' weight-gradient partials
 // gex[n][gx_off + w slots + s] = sum_e extra[e][s] q_e.  SRC = true: edges perm[ptr[n] .. ptr[n+1]) of a source.
 template <int LO, bool SRC, bool SH>
-__global__ void __launch_bounds__(NTH) o3msg_edge_bwd_kernel(const __grid_constant__ NodeArgs A) {
+__global__ void __launch_bounds__(NTH, 4) o3msg_edge_bwd_kernel(const __grid_constant__ NodeArgs A) {
     constexpr int DO = 2 * LO + 1;
     const int mul = A.io.mul;
     const int nl = (int)((threadIdx.x * A.magic) >> 16), w = threadIdx.x - nl * mul;

@@ -11,7 +11,10 @@
 //   -> edge geometry (rel. position, SH(1), extras) and node attributes.
 // Everything here is HBM-bound integer/byte work: no tensor cores, grids cover the data with
 // coalesced 4/8/16-byte accesses.
+#include <cooperative_groups.h>
+
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -251,11 +254,10 @@ __device__ __forceinline__ int lower_digit(const unsigned long long* keys, int l
     return lo;
 }
 
-__global__ void __launch_bounds__(256) split_count_kernel(TreeP T, int lev) {
-    __shared__ int sm[8];
+__device__ __forceinline__ void split_count_block(const TreeP& T, int lev, int vb, int* sm) {
     const int beg = T.level_ptr[lev], end = T.level_ptr[lev + 1];
-    const int c = beg + blockIdx.x * 256 + threadIdx.x;
-    if (beg + blockIdx.x * 256 >= end) return;
+    const int c = beg + vb * 256 + threadIdx.x;
+    if (beg + vb * 256 >= end) return;
     int nc = 0;
     if (c < end && lev < T.max_depth) {
         const int cnt = T.count[c];
@@ -272,11 +274,14 @@ __global__ void __launch_bounds__(256) split_count_kernel(TreeP T, int lev) {
     if (c < end) T.nchild[c] = nc;
     int tot;
     block_excl_scan_256(nc, sm, tot);
-    if (threadIdx.x == 0) T.bsum[blockIdx.x] = tot;
+    if (threadIdx.x == 0) T.bsum[vb] = tot;
+}
+__global__ void __launch_bounds__(256) split_count_kernel(TreeP T, int lev) {
+    __shared__ int sm[8];
+    split_count_block(T, lev, blockIdx.x, sm);
 }
 
-__global__ void __launch_bounds__(256) split_scan_kernel(TreeP T, int lev) {
-    __shared__ int sm[8];
+__device__ __forceinline__ void split_scan_block(const TreeP& T, int lev, int* sm) {
     const int beg = T.level_ptr[lev], end = T.level_ptr[lev + 1];
     const int nblk = (end - beg + 255) / 256;
     int carry = 0;
@@ -297,18 +302,21 @@ __global__ void __launch_bounds__(256) split_scan_kernel(TreeP T, int lev) {
         for (int l = lev + 2; l <= T.max_depth + 1; ++l) T.level_ptr[l] = end + carry;
     }
 }
-
-__global__ void __launch_bounds__(256) split_emit_kernel(TreeP T, int lev) {
+__global__ void __launch_bounds__(256) split_scan_kernel(TreeP T, int lev) {
     __shared__ int sm[8];
+    split_scan_block(T, lev, sm);
+}
+
+__device__ __forceinline__ void split_emit_block(const TreeP& T, int lev, int vb, int* sm) {
     const int beg = T.level_ptr[lev], end = T.level_ptr[lev + 1];
-    if (beg + blockIdx.x * 256 >= end) return;
+    if (beg + vb * 256 >= end) return;
     if (T.level_ptr[lev + 2] == end) return;  // nothing split (or overflow)
-    const int c = beg + blockIdx.x * 256 + threadIdx.x;
+    const int c = beg + vb * 256 + threadIdx.x;
     const int nc = c < end ? T.nchild[c] : 0;
     int tot;
     const int ex = block_excl_scan_256(nc, sm, tot);
     if (c >= end || nc == 0) return;
-    int child = end + T.bsum[blockIdx.x] + ex;
+    int child = end + T.bsum[vb] + ex;
     T.first_child[c] = child;
     const int s = T.start[c], e = s + T.count[c], shift = 3 * (T.max_depth - lev - 1);
     int prev = s;
@@ -321,6 +329,39 @@ __global__ void __launch_bounds__(256) split_emit_kernel(TreeP T, int lev) {
             ++child;
         }
         prev = b;
+    }
+}
+
+__global__ void __launch_bounds__(256) split_emit_kernel(TreeP T, int lev) {
+    __shared__ int sm[8];
+    split_emit_block(T, lev, blockIdx.x, sm);
+}
+
+// All levels in ONE cooperative launch: count / scan / emit per level separated by grid-wide barriers instead of three
+// launches per level (63 launches of a few microseconds each dominated the build of a 100k-particle cloud), and the loop
+// ends at the first level that holds no cell or splits nothing (every later level is empty by construction).  Blocks
+// stride over the level's 256-cell groups, so the per-cell code is the one of the per-level kernels.
+__global__ void __launch_bounds__(256) split_levels_kernel(TreeP T) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ int sm[8];
+    for (int lev = 0; lev < T.max_depth; ++lev) {
+        const int beg = T.level_ptr[lev], end = T.level_ptr[lev + 1];
+        if (end <= beg) break;                          // grid-uniform: written before the last barrier
+        const int nvb = (end - beg + 255) / 256;
+        for (int vb = blockIdx.x; vb < nvb; vb += gridDim.x) {
+            split_count_block(T, lev, vb, sm);
+            __syncthreads();
+        }
+        grid.sync();
+        if (blockIdx.x == 0) split_scan_block(T, lev, sm);
+        grid.sync();
+        if (T.level_ptr[lev + 2] == end) break;         // nothing split (or capacity overflow): grid-uniform
+        for (int vb = blockIdx.x; vb < nvb; vb += gridDim.x) {
+            split_emit_block(T, lev, vb, sm);
+            __syncthreads();
+        }
+        grid.sync();
     }
 }
 
@@ -705,12 +746,30 @@ extern "C" int se3_octree_build(const float* pos, se3_octree* t, int64_t* m_out,
     T.bsum = bsum; T.flags = flags;
     tree_init_kernel<<<1, 32, 0, st>>>(T); SE3_LAUNCHED();
     const long long lvl_cap = std::min<long long>(t->cell_cap, 8ll * (n / (t->leaf_size + 1) + 1) + 8);
-    for (int lev = 0; lev < t->max_depth; ++lev) {
-        long long ub = lev < 20 ? std::min<long long>(1ll << (3 * lev), lvl_cap) : lvl_cap;
-        const unsigned g = nblk(ub, 256);
-        split_count_kernel<<<g, 256, 0, st>>>(T, lev); SE3_LAUNCHED();
-        split_scan_kernel<<<1, 256, 0, st>>>(T, lev); SE3_LAUNCHED();
-        split_emit_kernel<<<g, 256, 0, st>>>(T, lev); SE3_LAUNCHED();
+    static int coop_blocks = -1;   // resident 256-thread blocks of the all-levels kernel (0: cooperative launch unavailable)
+    if (coop_blocks < 0) {
+        int dev = 0, coop = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        if (coop && !getenv("SE3_OCTREE_LEVEL_LAUNCHES") &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, split_levels_kernel, 256, 0) == cudaSuccess && per_sm > 0)
+            coop_blocks = se3::num_sms() * std::min(per_sm, 4);
+        else
+            coop_blocks = 0;
+    }
+    if (coop_blocks > 0) {
+        const int g = (int)std::min<long long>(coop_blocks, std::max<long long>(1, nblk(lvl_cap, 256)));
+        void* args[] = {(void*)&T};
+        SE3_CUDA_TRY(cudaLaunchCooperativeKernel((void*)split_levels_kernel, dim3(g), dim3(256), args, 0, st));
+        SE3_LAUNCHED();
+    } else {
+        for (int lev = 0; lev < t->max_depth; ++lev) {
+            long long ub = lev < 20 ? std::min<long long>(1ll << (3 * lev), lvl_cap) : lvl_cap;
+            const unsigned g = nblk(ub, 256);
+            split_count_kernel<<<g, 256, 0, st>>>(T, lev); SE3_LAUNCHED();
+            split_scan_kernel<<<1, 256, 0, st>>>(T, lev); SE3_LAUNCHED();
+            split_emit_kernel<<<g, 256, 0, st>>>(T, lev); SE3_LAUNCHED();
+        }
     }
     int h_lp[MAXD + 2];
     int h_flags[2];

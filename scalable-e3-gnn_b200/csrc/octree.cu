@@ -254,7 +254,7 @@ __device__ __forceinline__ int lower_digit(const unsigned long long* keys, int l
     return lo;
 }
 
-__device__ __forceinline__ void split_count_block(const TreeP& T, int lev, int vb, int* sm) {
+__device__ __forceinline__ void split_count_block(const TreeP T, int lev, int vb, int* sm) {
     const int beg = T.level_ptr[lev], end = T.level_ptr[lev + 1];
     const int c = beg + vb * 256 + threadIdx.x;
     if (beg + vb * 256 >= end) return;
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(256) split_count_kernel(TreeP T, int lev) {
     split_count_block(T, lev, blockIdx.x, sm);
 }
 
-__device__ __forceinline__ void split_scan_block(const TreeP& T, int lev, int* sm) {
+__device__ __forceinline__ void split_scan_block(const TreeP T, int lev, int* sm) {
     const int beg = T.level_ptr[lev], end = T.level_ptr[lev + 1];
     const int nblk = (end - beg + 255) / 256;
     int carry = 0;
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(256) split_scan_kernel(TreeP T, int lev) {
     split_scan_block(T, lev, sm);
 }
 
-__device__ __forceinline__ void split_emit_block(const TreeP& T, int lev, int vb, int* sm) {
+__device__ __forceinline__ void split_emit_block(const TreeP T, int lev, int vb, int* sm) {
     const int beg = T.level_ptr[lev], end = T.level_ptr[lev + 1];
     if (beg + vb * 256 >= end) return;
     if (T.level_ptr[lev + 2] == end) return;  // nothing split (or overflow)

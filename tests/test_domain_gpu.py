@@ -93,3 +93,68 @@ def test_cuda_local_graph_equals_torch_twin(n, world):
         tot_own += lg.n_own
         tot_e += lg.e
     assert tot_own == g.n + g.m and tot_e == g.e
+
+
+def _worker_l2(rank, world, port, n, layers, q):
+    """l_max = 2 model on a decomposed graph: message 1 by linearity with halo rows (n_all > n_dst), gate + aggregation
+    over the owned destinations, halo all-to-all per layer (gloo, host staged)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.cuda.set_device(0)
+    from models.segnn.segnn_l2 import SEGNNL2
+    from se3gnn_b200 import capi, domain
+    from se3gnn_b200.octree import build_octree_graph, sh2_attributes
+    from se3gnn_b200.pipeline import synthetic_cloud
+    torch.manual_seed(0)
+    model = SEGNNL2("8x0e+3x1o+2x2e", layers).cuda()
+    pos, vel, mass, target = [torch.from_numpy(a).cuda() for a in synthetic_cloud(n, "plummer", seed=5)]
+    g = build_octree_graph(pos, vel, mass, leaf_size=16)
+    ea, na = sh2_attributes(g)
+    lg = domain.local_graph(rank, world, g.n, g.cell_start, g.leaf_of_rank, g.dst, g.col, rowptr=g.rowptr)
+    domain.exchange_halo_lists(lg)
+    own = lg.own_ids.long()
+    l0 = capi.launch_count()
+    out = model(g.x_in.index_select(0, own), na.index_select(0, own), ea.index_select(0, lg.edge_ids),
+                g.edge_extra.index_select(0, lg.edge_ids), lg.dst, lg.src, halo=lambda x: domain.halo_exchange(x, lg))
+    tgt = target.index_select(0, g.order[lg.part_lo:lg.part_lo + lg.n_part].long())
+    loss = (out[:lg.n_part] - tgt).square().sum() / (3.0 * n)
+    loss.backward()
+    grad = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+    buf = torch.cat([grad, loss.detach().reshape(1)]).cpu()
+    dist.all_reduce(buf)
+    torch.cuda.synchronize()
+    q.put((rank, float(buf[-1]), buf[:-1].numpy(), lg.n_part, lg.n_halo, lg.e, capi.launch_count() - l0))
+    dist.destroy_process_group()
+
+
+def test_two_rank_decomposition_l2_model_matches_single_rank():
+    from conftest import PKG, ROOT
+    from models.segnn.segnn_l2 import SEGNNL2
+    from se3gnn_b200.octree import build_octree_graph, sh2_attributes
+    from se3gnn_b200.pipeline import synthetic_cloud
+    n, layers = 6000, 2
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    os.environ["PYTHONPATH"] = os.pathsep.join([PKG, ROOT, os.path.join(ROOT, "tests"), os.environ.get("PYTHONPATH", "")])
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_l2, args=(r, 2, port, n, layers, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=600) for _ in procs], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+    torch.manual_seed(0)
+    model = SEGNNL2("8x0e+3x1o+2x2e", layers).cuda()
+    pos, vel, mass, target = [torch.from_numpy(a).cuda() for a in synthetic_cloud(n, "plummer", seed=5)]
+    g = build_octree_graph(pos, vel, mass, leaf_size=16)
+    out = model.forward_graph(g, sh2_attributes(g))
+    loss = (out[:n] - target.index_select(0, g.order.long())).square().mean()
+    loss.backward()
+    ref = torch.cat([p.grad.reshape(-1) for p in model.parameters()]).cpu().numpy()
+    assert res[0][3] + res[1][3] == n and res[0][5] + res[1][5] == g.e
+    assert res[0][4] > 0 and res[1][4] > 0 and all(r[6] > 20 for r in res)   # halos exist, CUDA kernels ran
+    scale = np.abs(ref).max()
+    lossf = float(loss.detach())
+    for r in res:
+        assert abs(r[1] - lossf) <= 2e-5 * abs(lossf)
+        assert np.abs(r[2] - ref).max() <= 5e-4 * scale

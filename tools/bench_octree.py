@@ -1,7 +1,11 @@
 #!/usr/bin/env python
 """Octree graph construction only (BASELINE configs[4]): clustered (Plummer / NFW-like) and uniform clouds,
 sweep of sizes on one GPU; edges/s and algorithmic GB/s against the measured HBM peak.  One JSON line per case.
-usage: bench_octree.py [sizes comma-separated] [kinds comma-separated] [reps]"""
+usage: bench_octree.py [sizes comma-separated] [kinds comma-separated] [reps]
+Several GPUs (configs[4] "at 1/8 GPUs"): the build does not shard below one cloud (the decomposed SEGNN step replicates it,
+DESIGN 6), so under torchrun every rank builds its OWN cloud of the given size (replicas only, no collective on the data
+path) and rank 0 prints the aggregate: points and edges of all ranks over the slowest rank's time.
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/bench_octree.py 1e7,1e8 plummer"""
 import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "scalable-e3-gnn_b200")):
@@ -18,11 +22,16 @@ try:
     peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
 except Exception:
     pass
-dev = torch.device("cuda", 0)
+world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+dev = torch.device("cuda", local)
+torch.cuda.set_device(dev)
+if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=dev)
 
 
 def cloud(n, kind):
-    g = torch.Generator(device=dev); g.manual_seed(1)
+    g = torch.Generator(device=dev); g.manual_seed(1 + rank)
     if kind == "uniform":
         return torch.rand((n, 3), device=dev, generator=g)
     d = torch.randn((n, 3), device=dev, generator=g)
@@ -53,10 +62,22 @@ for kind in kinds:
                 best = (ms, prof)
         ms, prof = best
         nb = sum(p[2] for p in prof)
-        line = {"workload": f"octree graph build only, {n} {kind} points, leaf 32", "particles": n, "cells": g.m, "edges": g.e,
-                "levels": g.nlevels, "ms": ms, "edges_per_s": g.e / (ms * 1e-3), "particles_per_s": n / (ms * 1e-3),
-                "algorithmic_GBps": nb / (ms * 1e-3) / 1e9, "hbm_peak_GBps": peak, "frac": nb / (ms * 1e-3) / 1e9 / peak,
-                "stages_ms": {t: round(m_, 4) for t, m_, _, _ in prof}}
-        print(json.dumps(line), flush=True)
+        edges, cells = g.e, g.m
+        if world > 1:   # replicas: totals over the ranks, time of the slowest rank
+            t = torch.tensor([float(edges), float(cells), float(nb)], device=dev, dtype=torch.float64)
+            dist.all_reduce(t)
+            tm = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            edges, cells, nb, ms = int(t[0].item()), int(t[1].item()), float(t[2].item()), float(tm.item())
+        line = {"workload": f"octree graph build only, {n} {kind} points" + (f" per GPU x {world} GPUs (independent clouds)" if world > 1 else "") + ", leaf 32",
+                "n_gpus": world, "particles": n * world, "cells": cells, "edges": edges,
+                "levels": g.nlevels, "ms": ms, "edges_per_s": edges / (ms * 1e-3), "particles_per_s": n * world / (ms * 1e-3),
+                "algorithmic_GBps": nb / (ms * 1e-3) / 1e9, "hbm_peak_GBps": peak * world, "frac": nb / (ms * 1e-3) / 1e9 / (peak * world),
+                "stages_ms": {t_: round(m_, 4) for t_, m_, _, _ in prof}}
+        if rank == 0:
+            print(json.dumps(line), flush=True)
         del g, pos
         torch.cuda.empty_cache()
+
+if world > 1:
+    dist.destroy_process_group()

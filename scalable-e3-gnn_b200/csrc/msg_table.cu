@@ -397,6 +397,57 @@ __global__ void __launch_bounds__(1024) tr_scan_kernel(const int* __restrict__ c
     }
     if (t == 0) ptr[n] = carry_s;
 }
+// Multi-block version of the scan (the single block above walks 1 100 chunks for the nodes of a 1M-particle cloud:
+// 1.4 ms): per-1024-chunk sums, one block scans the chunk sums, every chunk finishes its own scan with its offset.
+__device__ __forceinline__ long long tr_block_scan_1024(long long v, long long* wsum /*[32]*/, long long& total) {
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    long long inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    long long off = 0, tot = 0;
+    for (int w = 0; w < 32; ++w) {
+        const long long x = wsum[w];
+        if (w < warp) off += x;
+        tot += x;
+    }
+    total = tot;
+    __syncthreads();
+    return off + inc - v;     // exclusive
+}
+__global__ void __launch_bounds__(1024) tr_bsum_kernel(const int* __restrict__ cnt, long long n, long long* __restrict__ bsum) {
+    __shared__ long long wsum[32];
+    const long long i = (long long)blockIdx.x * 1024 + threadIdx.x;
+    long long tot;
+    tr_block_scan_1024(i < n ? (long long)cnt[i] : 0, wsum, tot);
+    if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(1024) tr_btop_kernel(long long* __restrict__ bsum, long long nb) {
+    __shared__ long long wsum[32];
+    long long carry = 0;
+    for (long long base = 0; base < nb; base += 1024) {
+        const long long i = base + threadIdx.x;
+        long long tot;
+        const long long ex = tr_block_scan_1024(i < nb ? bsum[i] : 0, wsum, tot);
+        if (i < nb) bsum[i] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) bsum[nb] = carry;
+}
+__global__ void __launch_bounds__(1024) tr_final_kernel(const int* __restrict__ cnt, long long n, const long long* __restrict__ bsum,
+                                                         long long nb, long long* __restrict__ ptr,
+                                                         unsigned long long* __restrict__ cursor) {
+    __shared__ long long wsum[32];
+    const long long i = (long long)blockIdx.x * 1024 + threadIdx.x;
+    long long tot;
+    const long long ex = bsum[blockIdx.x] + tr_block_scan_1024(i < n ? (long long)cnt[i] : 0, wsum, tot);
+    if (i < n) { ptr[i] = ex; cursor[i] = (unsigned long long)ex; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) ptr[n] = bsum[nb];
+}
 __global__ void tr_fill_kernel(const int* __restrict__ src, long long e, unsigned long long* __restrict__ cursor, int* __restrict__ perm) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < e) perm[atomicAdd(cursor + src[i], 1ull)] = (int)i;
@@ -538,7 +589,7 @@ extern "C" int se3_rowptr_from_sorted(int64_t e, int64_t n, const int32_t* idx_s
 
 extern "C" int se3_graph_transpose_work_bytes(int64_t n_src, size_t* bytes) {
     if (n_src < 0 || !bytes) { set_error("graph_transpose: bad argument"); return SE3_ERR_INVALID; }
-    *bytes = (size_t)(n_src + 1) * (sizeof(int) + sizeof(unsigned long long)) + 256;
+    *bytes = (size_t)(n_src + 1) * (sizeof(int) + sizeof(unsigned long long)) + ((size_t)(n_src + 1023) / 1024 + 2) * sizeof(long long) + 256;
     return SE3_OK;
 }
 
@@ -554,7 +605,16 @@ extern "C" int se3_graph_transpose(int64_t e, int64_t n_src, const int32_t* src,
     int* cnt = (int*)(cursor + n_src + 1);
     SE3_CUDA_TRY(cudaMemsetAsync(cnt, 0, sizeof(int) * (size_t)(n_src + 1), st));
     if (e > 0) { tr_count_kernel<<<(unsigned)((e + 255) / 256), 256, 0, st>>>(src, e, cnt); SE3_LAUNCHED(); }
-    tr_scan_kernel<<<1, 1024, 0, st>>>(cnt, n_src, (long long*)tptr, cursor); SE3_LAUNCHED();
+    const long long nb = (n_src + 1023) / 1024;
+    if (nb <= 8) {
+        tr_scan_kernel<<<1, 1024, 0, st>>>(cnt, n_src, (long long*)tptr, cursor); SE3_LAUNCHED();
+    } else {
+        // 8-byte aligned chunk sums behind the counts
+        long long* bsum = (long long*)(((uintptr_t)(cnt + n_src + 1) + 7) & ~(uintptr_t)7);
+        tr_bsum_kernel<<<(unsigned)nb, 1024, 0, st>>>(cnt, n_src, bsum); SE3_LAUNCHED();
+        tr_btop_kernel<<<1, 1024, 0, st>>>(bsum, nb); SE3_LAUNCHED();
+        tr_final_kernel<<<(unsigned)nb, 1024, 0, st>>>(cnt, n_src, bsum, nb, (long long*)tptr, cursor); SE3_LAUNCHED();
+    }
     if (e > 0) {
         tr_fill_kernel<<<(unsigned)((e + 255) / 256), 256, 0, st>>>(src, e, cursor, perm); SE3_LAUNCHED();
         tr_sort_kernel<<<(unsigned)((n_src + 7) / 8), 256, 0, st>>>((const long long*)tptr, n_src, perm); SE3_LAUNCHED();
